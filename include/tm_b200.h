@@ -1,0 +1,275 @@
+/*
+ * tm_b200.h -- C ABI of libtm_b200.so: the B200 (sm_100a) hot path of the multimodal
+ * pre-routing timing predictor (level-wise netlist GNN + layout U-Net + mask fusion).
+ *
+ * The reference (ZeayW/Multimodal-fusion-based-Pre-routing-Timing-Prediction-) has no
+ * FFI/plugin layer: its hot path is Python calling DGL and ATen.  Each entry point below
+ * therefore cites the reference *call site* (src/<file>:<line>) whose library work it
+ * replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (host);
+ *   - no allocation and no ownership transfer inside: the caller passes workspaces;
+ *   - all launches go to the given cudaStream_t (passed as void*), nothing synchronises
+ *     unless stated;
+ *   - return 0 on success, a negative TM_E* for argument errors or a positive cudaError_t;
+ *     tm_last_error() returns a thread-local message for the last failure.
+ * Python binding: multimodal-fusion-based-pre-routing-timing-prediction-_b200/tm_lib.py (ctypes).
+ */
+#ifndef TM_B200_H
+#define TM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TM_OK 0
+#define TM_EINVAL (-1)   /* bad argument                      */
+#define TM_EWORKSPACE (-2) /* workspace too small             */
+#define TM_EUNSUPPORTED (-3)
+
+int tm_version(void);
+const char* tm_last_error(void);
+/* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
+long long tm_launch_count(void);
+int tm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * G1  graph structure: CSR build and level schedule
+ *     replaces dgl.heterograph(...) + the lazy in-edge CSR DGL builds inside graph.pull
+ *     (src/dataset.py:274-278, src/model.py:186-204) and Parser.cal_topo_level
+ *     (src/verilog_parser_asap7.py:1452-1517).
+ * ---------------------------------------------------------------------------------- */
+
+/* Bytes of workspace tm_csr_build needs. */
+size_t tm_csr_build_ws(int64_t n, int64_t e);
+/* CSR keyed on `key` (dst for an in-edge CSR, src for an out-edge CSR):
+ * indptr[n+1], indices[e] = `val` of every edge, ascending inside each row (duplicates kept).
+ * key/val are the int64 edge lists of one edge type as DGL stores them. */
+int tm_csr_build(int64_t n, int64_t e, const int64_t* key, const int64_t* val,
+                 int32_t* indptr, int32_t* indices, void* ws, size_t ws_bytes, void* stream);
+
+size_t tm_levelize_ws(int64_t n);
+/* level[v] = length of the longest walk from the PI set to v (pins not reachable from a PI:
+ * -1), i.e. the last frontier v appears in (verilog_parser_asap7.py:1494-1511).
+ * optr/oidx: out-edge CSR over the union of both edge types.  num_levels: device int32.
+ * Cooperative persistent kernel (frontier BFS + Kahn peeling with grid-wide barriers). */
+int tm_levelize(int64_t n, const int32_t* optr, const int32_t* oidx, const int64_t* pis,
+                int64_t n_pi, int32_t* level, int32_t* num_levels, void* ws, size_t ws_bytes,
+                void* stream);
+
+size_t tm_level_order_ws(int64_t n, int32_t num_levels);
+/* order[] = scheduled pins sorted by (level, pin id); level_ptr[num_levels+1].
+ * Deterministic stable counting sort. */
+int tm_level_order(int64_t n, int32_t num_levels, const int32_t* level, int32_t* order,
+                   int32_t* level_ptr, void* ws, size_t ws_bytes, void* stream);
+
+/* Per-pin auxiliaries of a schedule:
+ * crow[v]   = row of pin v in the compact "cell pin" buffers (pins on even levels > 0), else -1,
+ *             numbered in schedule order;
+ * cell_base[num_levels+1] = first compact row of each level (cell_base[num_levels] = row count);
+ * n_violations (device int32) += number of in-edges whose source is not on an earlier level
+ *             (such a schedule is not a topological one; the caller must refuse it). */
+int tm_schedule_aux(int64_t n, int32_t num_levels, const int32_t* level, const int32_t* order,
+                    const int32_t* level_ptr, const int32_t* net_iptr, const int32_t* net_isrc,
+                    const int32_t* cell_iptr, const int32_t* cell_isrc, int32_t* crow,
+                    int32_t* cell_base, int32_t* n_violations, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * dense fp32 building blocks (replace the cuBLAS SGEMMs behind nn.Linear,
+ * src/model.py:15,23 and every MLP call site model.py:104,141-142,151,272,280,292)
+ * ---------------------------------------------------------------------------------- */
+
+/* epilogue flags for tm_gemm_nn */
+#define TM_EPI_BIAS 1      /* C += bias[col]                                    */
+#define TM_EPI_RELU 2      /* C = max(C,0)                                      */
+#define TM_EPI_MASK 4      /* C *= (mask[row][col] > 0)   (ReLU backward)       */
+#define TM_EPI_ACCUM 8     /* C += old C                                        */
+
+/* C[M,N] = epi( A[M,K] @ B[K,N] ).  Row-major, leading dimensions in elements.
+ * a_rows (optional, int32[M]): gather  A row i from A[a_rows[i]];
+ * c_rows (optional, int32[M]): scatter C row i to   C[c_rows[i]] (mask is indexed like C). */
+int tm_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const int32_t* a_rows,
+               const float* B, int64_t ldb, float* C, int64_t ldc, const int32_t* c_rows,
+               const float* bias, const float* mask, int64_t ldmask, int flags, void* stream);
+
+size_t tm_gemm_tn_ws(int64_t M, int64_t N, int64_t R);
+/* C[M,N] (+)= A[R,M]^T @ B[R,N]  (weight gradients; reduction over the R rows, deterministic
+ * split + fixed-order second pass).  a_rows/b_rows optional row gathers.  Optional bias
+ * gradients: colsum_a[M] (+)= sum_r A[r,:], colsum_b[N] (+)= sum_r B[r,:].
+ * accumulate != 0 adds to C / colsum_*. */
+int tm_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, int64_t lda, const int32_t* a_rows,
+               const float* B, int64_t ldb, const int32_t* b_rows, float* C, int64_t ldc,
+               float* colsum_a, float* colsum_b, int accumulate, void* ws, size_t ws_bytes,
+               void* stream);
+
+/* out[c][r] = in[r][c]  (weight re-layout; in is rows x cols row-major) */
+int tm_transpose(int64_t rows, int64_t cols, const float* in, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * G2/G3  level-wise timing propagation (replaces PathConv.forward, src/model.py:158-213,
+ *        its UDFs :88-116,:138-153 and the autograd backward train.py:553)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n;                 /* pins                                                   */
+  int32_t num_levels;
+  int32_t n_cell_rows;       /* pins on even levels > 0                                */
+  const int32_t* h_level_ptr;/* HOST copy of level_ptr[num_levels+1]                   */
+  const int32_t* order;      /* scheduled pins by (level, id)                          */
+  const int32_t* level;      /* pin -> level                                           */
+  const int32_t* crow;       /* pin -> compact cell row or -1                          */
+  const int32_t* net_iptr;  const int32_t* net_isrc;   /* in-edge CSRs                 */
+  const int32_t* cell_iptr; const int32_t* cell_isrc;
+  const int32_t* net_optr;  const int32_t* net_odst;   /* out-edge CSRs                */
+  const int32_t* cell_optr; const int32_t* cell_odst;
+} tm_schedule;
+
+/* Forward over levels [level_begin, level_end).  D = 128, hidden = 256 (model.py:48).
+ *   H[n,128]   in/out: rows of the processed levels are written, sources are read
+ *              (caller zero-fills before level 0, like train.py:342,559);
+ *   S[n,128]   hoisted self terms fc_cell_self(cell_feat) / fc_net_self(net_feat) incl. bias;
+ *   W1t[128,256], b1[256], W2t[256,128], b2[128]: fc_cell_neigh, weights TRANSPOSED;
+ *   A[n_cell_rows,128], LSE[n_cell_rows,128], HID[n_cell_rows,256]: saved for backward
+ *              (may be NULL for inference). */
+int tm_gnn_forward(const tm_schedule* s, int32_t level_begin, int32_t level_end, float* H,
+                   const float* S, const float* W1t, const float* b1, const float* W2t,
+                   const float* b2, float* A, float* LSE, float* HID, void* stream);
+
+/* Backward over all levels in reverse.
+ *   G[n,128]   in: dLoss/dH contributions from the head (zero elsewhere);
+ *              out: dLoss/d(pre-activation) of every scheduled pin == dLoss/dS;
+ *   W1[256,128], W2[128,256]: fc_cell_neigh weights as stored by nn.Linear;
+ *   GA[n_cell_rows,128] scratch; GHID[n_cell_rows,256], GZC[n_cell_rows,128] out: operands of
+ *   the hoisted weight-gradient GEMMs (dW1 = GHID^T A, dW2 = GZC^T HID). */
+int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, const float* W1,
+                    const float* W2, const float* A, const float* LSE, const float* HID,
+                    float* GA, float* GHID, float* GZC, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * G5  mask fusion (replaces  path_mask.to_dense()*feat_map  and  fcn(path_map),
+ *     src/train.py:500-501 + src/model.py:272)
+ * ---------------------------------------------------------------------------------- */
+/* out[t,0:D] = bias + sum_{j in mask row rows[t]} F[j] * Wt[j,:]     (Wt = fcn.weight^T, [J,D])
+ * rows: optional int32[T] selecting mask rows (NULL = identity). D must be 128.
+ * ld_out: row stride of out (lets the result land inside cat(h_gnn,h_cnn,h_global)). */
+int tm_fuse_forward(int64_t T, int64_t J, int64_t D, const int32_t* mask_indptr,
+                    const int32_t* mask_cols, const int32_t* rows, const float* F,
+                    const float* Wt, const float* bias, float* out, int64_t ld_out, void* stream);
+/* Column-major pull (deterministic, no atomics): csc_ptr[J+1], csc_t[nnz] list the positions t
+ * (0..T-1) whose mask contains column j.
+ *   dWt[j,:] = F[j] * sum_t g[t,:];   dF[j] = sum_t sum_c g[t,c] * Wt[j,c]. */
+int tm_fuse_backward(int64_t T, int64_t J, int64_t D, const int32_t* csc_ptr, const int32_t* csc_t,
+                     const float* g, int64_t ld_g, const float* F, const float* Wt, float* dWt,
+                     float* dF, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * G6  head helpers (src/model.py:280-292, src/train.py:513-522)
+ * ---------------------------------------------------------------------------------- */
+/* dst[i, col0:col0+w] = src[rows ? rows[i] : i, 0:w]   (builds cat(h_gnn,h_cnn,h_global)) */
+int tm_gather_cols(int64_t T, int64_t w, const float* src, int64_t lds, const int32_t* rows,
+                   float* dst, int64_t ldd, int64_t col0, void* stream);
+/* dst[rows[i], 0:w] += src[i, col0:col0+w]  (atomic: rows may repeat) */
+int tm_scatter_add_cols(int64_t T, int64_t w, const float* src, int64_t lds, int64_t col0,
+                        const int32_t* rows, float* dst, int64_t ldd, void* stream);
+/* out[c] (+)= sum_r X[r,c]  (bias gradients; fixed reduction order) */
+int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, float* out, int accumulate,
+              void* stream);
+/* loss[0] = mean((pred-y)^2); grad[i] = 2*(pred[i]-y[i])/T * grad_scale  (nn.MSELoss) */
+int tm_mse(int64_t T, const float* pred, const float* y, float* loss, float* grad,
+           float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * G4  U-Net / LayoutNet image branch, fp32 NHWC (replaces the cuDNN/ATen calls behind
+ *     src/Unet.py:16-21,53,75-77 and src/model.py:227-243)
+ *     Activations are NHWC with an explicit pixel stride `ld` (elements) so that a tensor may
+ *     live inside a wider concat buffer (Unet.py:67 torch.cat becomes free).
+ * ---------------------------------------------------------------------------------- */
+int tm_nchw_to_nhwc(int64_t B, int64_t C, int64_t H, int64_t W, const float* in, float* out,
+                    int64_t ld, void* stream);
+int tm_nhwc_to_nchw(int64_t B, int64_t C, int64_t H, int64_t W, const float* in, int64_t ld,
+                    float* out, void* stream);
+/* Conv2d weight (Cout,Cin,k,k) -> fprop layout wf[k*k][Cin][Cout] and dgrad layout
+ * wb[k*k][Cout][Cin] with flipped taps (either may be NULL). */
+int tm_conv_pack_weight(int64_t Cout, int64_t Cin, int64_t k, const float* w, float* wf, float* wb,
+                        void* stream);
+/* inverse of the fprop layout: dw (Cout,Cin,k,k) = unpack(dwf[k*k][Cin][Cout]) */
+int tm_conv_unpack_wgrad(int64_t Cout, int64_t Cin, int64_t k, const float* dwf, float* dw,
+                         void* stream);
+/* y[b,y,x,co] = bias[co] + sum_{tap,ci} x[b,y+dy,x+dx,ci] * wf[tap][ci][co]; stride 1, pad k/2.
+ * flags: TM_EPI_RELU optional.  The same call with wb computes the data gradient. */
+int tm_conv2d_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k,
+                   const float* x, int64_t ldx, const float* wf, const float* bias, float* y,
+                   int64_t ldy, int flags, void* stream);
+size_t tm_conv2d_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k);
+/* dwf[tap][ci][co] = sum_{b,y,x} x[b,y+dy,x+dx,ci] * dy[b,y,x,co];  dbias[co] = sum dy (optional) */
+int tm_conv2d_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k,
+                         const float* x, int64_t ldx, const float* dy, int64_t lddy, float* dwf,
+                         float* dbias, void* ws, size_t ws_bytes, void* stream);
+
+/* ConvTranspose2d(k=2,s=2) weight (Cin,Cout,2,2) -> wt[Cin][4*Cout] ((dy,dx,co) fastest) and
+ * its transpose wtT[4*Cout][Cin]. */
+int tm_convt_pack_weight(int64_t Cin, int64_t Cout, const float* w, float* wt, float* wtT,
+                         void* stream);
+int tm_convt_unpack_wgrad(int64_t Cin, int64_t Cout, const float* dwt, float* dw, void* stream);
+/* y[b,2y+dy+oy,2x+dx+ox,co] = bias[co] + sum_ci x[b,y,x,ci]*wt[ci][(dy,dx,co)]  (Unet.py:53,57-63)
+ * y is (B,Hy,Wy,*) with pixel stride ldy; (oy,ox) is the F.pad offset. */
+int tm_convt2x2_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, const float* x,
+                     int64_t ldx, const float* wt, const float* bias, float* y, int64_t ldy,
+                     int64_t Hy, int64_t Wy, int64_t oy, int64_t ox, void* stream);
+/* dx[b,y,x,ci] = sum_{dy,dx,co} dyo[b,2y+dy+oy,2x+dx+ox,co] * wtT[(dy,dx,co)][ci] */
+int tm_convt2x2_dgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                           const float* dyo, int64_t lddy, int64_t Hy, int64_t Wy, int64_t oy,
+                           int64_t ox, const float* wtT, float* dx, int64_t lddx, void* stream);
+size_t tm_convt2x2_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
+/* dwt[ci][(dy,dx,co)] = sum x*dyo ; dbias[co] = sum over the 2H x 2W window of dyo */
+int tm_convt2x2_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                           const float* x, int64_t ldx, const float* dyo, int64_t lddy, int64_t Hy,
+                           int64_t Wy, int64_t oy, int64_t ox, float* dwt, float* dbias, void* ws,
+                           size_t ws_bytes, void* stream);
+
+size_t tm_bn_ws(int64_t npix, int64_t C);
+/* Train-mode BatchNorm2d + ReLU (Unet.py:17-18,20-21): batch statistics over B*H*W,
+ * y = relu(gamma*(x-mean)*invstd+beta); running stats updated with `momentum`, unbiased var.
+ * save_mean/save_invstd [C] kept for backward. */
+int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var, float momentum,
+                       float eps, float* y, int64_t ldy, float* save_mean, float* save_invstd,
+                       void* ws, size_t ws_bytes, void* stream);
+/* Backward of the pair: dy is the gradient w.r.t. the ReLU output y.
+ * dx = BN'( dy * (y>0) ), dgamma, dbeta [C]. */
+int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* y,
+                        int64_t ldy, const float* dy, int64_t lddy, const float* gamma,
+                        const float* save_mean, const float* save_invstd, float* dx, int64_t lddx,
+                        float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* 2x2 stride-2 pooling (Unet.py:89-91, model.py:222-224). mode 0 = max (idx: uint8 argmax
+ * saved for backward, first maximum in row-major window order), 1 = avg (idx unused).
+ * flags: TM_EPI_RELU applies ReLU after pooling (OutConv, Unet.py:76-77). */
+int tm_pool2x2_forward(int64_t B, int64_t H, int64_t W, int64_t C, int mode, const float* x,
+                       int64_t ldx, float* y, int64_t ldy, uint8_t* idx, int flags, void* stream);
+/* dx (B,H,W,C) fully written (zeros where no gradient flows; odd trailing row/col get 0).
+ * With TM_EPI_RELU, dy is first masked by (y>0). */
+int tm_pool2x2_backward(int64_t B, int64_t H, int64_t W, int64_t C, int mode, const float* dy,
+                        int64_t lddy, const float* y, int64_t ldy, const uint8_t* idx, float* dx,
+                        int64_t lddx, int flags, void* stream);
+/* dx = dy * (y > 0) * (slope where y <= 0)   elementwise helper for bare ReLU / LeakyReLU layers
+ * (LayoutNet, model.py:219-220).  y is the activation OUTPUT. n elements, contiguous. */
+int tm_leaky_relu_backward(int64_t n, const float* y, const float* dy, float slope, float* dx,
+                           void* stream);
+int tm_leaky_relu_forward(int64_t n, const float* x, float slope, float* y, void* stream);
+/* dst[i*ldd + c] += src[i*lds + c]  for c < C  (adds a gradient living in a strided buffer) */
+int tm_add_strided(int64_t npix, int64_t C, const float* src, int64_t lds, float* dst, int64_t ldd,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * N4  fused Adam (torch.optim.Adam defaults, src/train.py:431-435,555)
+ * ---------------------------------------------------------------------------------- */
+int tm_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TM_B200_H */

@@ -1,0 +1,225 @@
+// G5/G6: mask fusion and head helpers.
+//
+// Fusion in the reference (src/train.py:500-501 + src/model.py:272):
+//     path_map = index_select(path_masks, 0, paths).to_dense() * feat_map      (T, map^2) dense
+//     h_cnn    = fcn(path_map)                                                 Linear(map^2, 128)
+// Here: h_cnn[t] = b + sum_{j in mask_t} F[j] * Wt[j,:]  -- an SpMM of the binary mask CSR with
+// diag(F) * fcn.weight^T.  The dense (T, map^2) operand is never materialised.  Backward pulls per
+// image column through the mask CSC (deterministic, no atomics).
+// Head helpers (src/model.py:280-292, src/train.py:513-522): column-block gather / scatter-add for
+// cat(h_gnn, h_cnn, h_global) and the MSE loss.
+#include "tm_common.cuh"
+
+using namespace tmk;
+
+namespace {
+constexpr int D = 128;
+
+__global__ void __launch_bounds__(128)
+fuse_fwd_kernel(int64_t T, const int* __restrict__ indptr, const int* __restrict__ cols,
+                const int* __restrict__ rows, const float* __restrict__ F, const float* __restrict__ Wt,
+                const float* __restrict__ bias, float* __restrict__ out, int64_t ldo) {
+  __shared__ __align__(16) float part[4][D];
+  const int t = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = rows ? rows[t] : t;
+  const int s = indptr[row], e = indptr[row + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = s + warp * 32; base < e; base += 128) {
+    const int jl = (base + lane < e) ? cols[base + lane] : 0;
+    const float fl = (base + lane < e) ? F[jl] : 0.f;
+    const int n = min(32, e - base);
+    for (int q = 0; q < n; q += 4) {
+      float4 w[4];
+      float f[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = __shfl_sync(0xffffffffu, jl, (q + u) & 31);
+        f[u] = __shfl_sync(0xffffffffu, fl, (q + u) & 31);
+        w[u] = (q + u < n) ? __ldg(reinterpret_cast<const float4*>(Wt + (int64_t)j * D + lane * 4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x = fmaf(f[u], w[u].x, acc.x);
+        acc.y = fmaf(f[u], w[u].y, acc.y);
+        acc.z = fmaf(f[u], w[u].z, acc.z);
+        acc.w = fmaf(f[u], w[u].w, acc.w);
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(&part[warp][lane * 4]) = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float4 r = *reinterpret_cast<const float4*>(&part[0][lane * 4]);
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+      const float4 o = *reinterpret_cast<const float4*>(&part[w][lane * 4]);
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + lane * 4));
+    st4(out + (int64_t)t * ldo + lane * 4, make_float4(r.x + b.x, r.y + b.y, r.z + b.z, r.w + b.w));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fuse_bwd_kernel(int64_t J, const int* __restrict__ cptr, const int* __restrict__ ct,
+                const float* __restrict__ g, int64_t ldg, const float* __restrict__ F,
+                const float* __restrict__ Wt, float* __restrict__ dWt, float* __restrict__ dF) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= J) return;
+  const int s = cptr[j], e = cptr[j + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = s; i < e; i += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      v[q] = (i + q < e) ? __ldg(reinterpret_cast<const float4*>(g + (int64_t)ct[i + q] * ldg + lane * 4))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+  }
+  const float f = F[j];
+  st4(dWt + j * D + lane * 4, make_float4(f * acc.x, f * acc.y, f * acc.z, f * acc.w));
+  float dot = 0.f;
+  if (e > s) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(Wt + j * D + lane * 4));
+    dot = acc.x * w.x + acc.y * w.y + acc.z * w.z + acc.w * w.w;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) dF[j] = dot;
+}
+
+__global__ void gather_cols_kernel(int64_t T, int64_t w, const float* __restrict__ src, int64_t lds,
+                                   const int* __restrict__ rows, float* __restrict__ dst, int64_t ldd,
+                                   int64_t col0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * w) return;
+  const int64_t t = i / w, c = i - t * w;
+  const int64_t r = rows ? rows[t] : t;
+  dst[t * ldd + col0 + c] = src[r * lds + c];
+}
+
+__global__ void scatter_add_cols_kernel(int64_t T, int64_t w, const float* __restrict__ src, int64_t lds,
+                                        int64_t col0, const int* __restrict__ rows, float* __restrict__ dst,
+                                        int64_t ldd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * w) return;
+  const int64_t t = i / w, c = i - t * w;
+  const int64_t r = rows ? rows[t] : t;
+  atomicAdd(&dst[r * ldd + c], src[t * lds + col0 + c]);   // rows may repeat (oversampled paths)
+}
+
+// out[c] (+)= sum_r X[r][c]; one block owns 32 columns, rows reduced in a fixed order
+__global__ void __launch_bounds__(256)
+colsum_kernel(int64_t R, int64_t C, const float* __restrict__ X, int64_t ld, float* __restrict__ out,
+              int accumulate) {
+  __shared__ float part[8][33];
+  const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = threadIdx.y; r < R; r += 8) s += X[r * ld + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) s += part[i][threadIdx.x];
+    out[c] = accumulate ? out[c] + s : s;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+mse_kernel(int64_t T, const float* __restrict__ pred, const float* __restrict__ y, float* __restrict__ loss,
+           float* __restrict__ grad, float gscale) {
+  __shared__ double part[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < T; i += blockDim.x) {
+    const float d = pred[i] - y[i];
+    s += (double)d * (double)d;
+    if (grad) grad[i] = 2.f * d / (float)T * gscale;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = part[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0 && loss) loss[0] = (float)(v / (double)T);
+  }
+}
+
+__global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
+                            float eps, float wd, float bc1, float bc2, float gscale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * gscale;
+  if (wd != 0.f) gi += wd * p[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;   // torch.optim.Adam: (sqrt(v)/sqrt(bc2)) + eps
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+}  // namespace
+
+extern "C" int tm_fuse_forward(int64_t T, int64_t J, int64_t Dd, const int32_t* mask_indptr,
+                               const int32_t* mask_cols, const int32_t* rows, const float* F,
+                               const float* Wt, const float* bias, float* out, int64_t ld_out,
+                               void* stream) {
+  TM_REQUIRE(Dd == D, "tm_fuse_forward: D must be 128");
+  (void)J;
+  if (T <= 0) return 0;
+  fuse_fwd_kernel<<<(unsigned)T, 128, 0, (cudaStream_t)stream>>>(T, mask_indptr, mask_cols, rows, F, Wt, bias, out, ld_out);
+  return check_launch("fuse_fwd");
+}
+
+extern "C" int tm_fuse_backward(int64_t T, int64_t J, int64_t Dd, const int32_t* csc_ptr,
+                                const int32_t* csc_t, const float* g, int64_t ld_g, const float* F,
+                                const float* Wt, float* dWt, float* dF, void* stream) {
+  TM_REQUIRE(Dd == D, "tm_fuse_backward: D must be 128");
+  (void)T;
+  if (J <= 0) return 0;
+  fuse_bwd_kernel<<<(unsigned)cdiv(J * 32, 256), 256, 0, (cudaStream_t)stream>>>(J, csc_ptr, csc_t, g, ld_g, F, Wt, dWt, dF);
+  return check_launch("fuse_bwd");
+}
+
+extern "C" int tm_gather_cols(int64_t T, int64_t w, const float* src, int64_t lds, const int32_t* rows,
+                              float* dst, int64_t ldd, int64_t col0, void* stream) {
+  if (T * w <= 0) return 0;
+  gather_cols_kernel<<<(unsigned)cdiv(T * w, 256), 256, 0, (cudaStream_t)stream>>>(T, w, src, lds, rows, dst, ldd, col0);
+  return check_launch("gather_cols");
+}
+
+extern "C" int tm_scatter_add_cols(int64_t T, int64_t w, const float* src, int64_t lds, int64_t col0,
+                                   const int32_t* rows, float* dst, int64_t ldd, void* stream) {
+  if (T * w <= 0) return 0;
+  scatter_add_cols_kernel<<<(unsigned)cdiv(T * w, 256), 256, 0, (cudaStream_t)stream>>>(T, w, src, lds, col0, rows, dst, ldd);
+  return check_launch("scatter_add_cols");
+}
+
+extern "C" int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, float* out, int accumulate,
+                         void* stream) {
+  if (C <= 0) return 0;
+  colsum_kernel<<<(unsigned)cdiv(C, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(R, C, X, ld, out, accumulate);
+  return check_launch("colsum");
+}
+
+extern "C" int tm_mse(int64_t T, const float* pred, const float* y, float* loss, float* grad,
+                      float grad_scale, void* stream) {
+  TM_REQUIRE(T > 0, "tm_mse: empty batch");
+  mse_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(T, pred, y, loss, grad, grad_scale);
+  return check_launch("mse");
+}
+
+extern "C" int tm_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                            float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  TM_REQUIRE(step >= 1, "tm_adam_step: step starts at 1");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, lr, beta1, beta2, eps,
+                                                                         weight_decay, bc1, bc2, grad_scale);
+  return check_launch("adam");
+}

@@ -1,0 +1,70 @@
+// Dense fp32 entry points: nn.Linear forward/backward building blocks (model.py:15,23 and the
+// MLP call sites model.py:104,141-142,151,272,280,292), weight re-layout, split reduction.
+#include "tm_gemm.cuh"
+
+using namespace tmk;
+
+namespace tmk {
+__global__ void split_reduce_kernel(const float* __restrict__ P, int64_t count, int splits,
+                                    float* __restrict__ C, int64_t N, int64_t ldc, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += P[(int64_t)k * count + i];  // fixed order: deterministic
+  const int64_t m = i / N, n = i - m * N;
+  float* p = C + m * ldc + n;
+  *p = accumulate ? (*p + s) : s;
+}
+}  // namespace tmk
+
+namespace {
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows,
+                                 int64_t cols) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = in[r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+}  // namespace
+
+extern "C" int tm_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                          const int32_t* a_rows, const float* B, int64_t ldb, float* C, int64_t ldc,
+                          const int32_t* c_rows, const float* bias, const float* mask,
+                          int64_t ldmask, int flags, void* stream) {
+  TM_REQUIRE(M >= 0 && N >= 0 && K >= 0, "tm_gemm_nn: negative size");
+  TM_REQUIRE(!(flags & TM_EPI_BIAS) || bias, "tm_gemm_nn: TM_EPI_BIAS without bias");
+  TM_REQUIRE(!(flags & TM_EPI_MASK) || mask, "tm_gemm_nn: TM_EPI_MASK without mask");
+  PlainLoader al{A, lda, a_rows};
+  PlainEpilogue ep{C, ldc, c_rows, bias, mask, ldmask, flags};
+  const bool veca = (lda % 4 == 0) && (K % 4 == 0) && aligned16(A);
+  return launch_gemm_nn(al, veca, B, ldb, ep, M, N, K, (cudaStream_t)stream);
+}
+
+extern "C" size_t tm_gemm_tn_ws(int64_t M, int64_t N, int64_t R) { return tn_ws_bytes(M, N, R); }
+
+extern "C" int tm_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, int64_t lda,
+                          const int32_t* a_rows, const float* B, int64_t ldb, const int32_t* b_rows,
+                          float* C, int64_t ldc, float* colsum_a, float* colsum_b, int accumulate,
+                          void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(M >= 0 && N >= 0 && R >= 0, "tm_gemm_tn: negative size");
+  PlainLoader al{A, lda, a_rows};
+  PlainLoader bl{B, ldb, b_rows};
+  const bool veca = (lda % 4 == 0) && (M % 4 == 0) && aligned16(A);
+  const bool vecb = (ldb % 4 == 0) && (N % 4 == 0) && aligned16(B);
+  return launch_gemm_tn(al, veca, bl, vecb, M, N, R, C, ldc, colsum_a, colsum_b, accumulate, ws, ws_bytes,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int tm_transpose(int64_t rows, int64_t cols, const float* in, float* out, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, rows, cols);
+  return check_launch("transpose");
+}

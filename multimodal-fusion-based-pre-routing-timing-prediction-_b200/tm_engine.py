@@ -1,0 +1,206 @@
+"""Fused design step: U-Net + level-wise GNN + mask fusion + head, forward and backward.
+
+``DesignStep.run(batch)`` performs what one optimisation step of the reference does to one design
+with all sampled endpoints in a batch (src/train.py:465 CNN forward, :490-511 level loop,
+:513-522 MSE on arrival time, :552-553 backward) as a straight sequence of libtm_b200 launches
+with no autograd graph, then leaves the gradients in ``param.grad`` (like ``optim.zero_grad();
+loss.backward()``).  It is numerically the same computation the ``nn.Module`` surface
+(``model.py`` / ``Unet.py``) performs through autograd; tests check both against the oracle.
+
+Data parallelism: designs are independent samples, so ranks own disjoint designs
+and the only exchange is one gradient all-reduce per step.  ``DesignStep`` posts it in three
+buckets on a side stream as soon as each group of gradients exists (head+fusion -> GNN ->
+U-Net), so the NCCL transfers over NVLink overlap the remaining backward kernels.
+"""
+import numpy as np
+import torch
+
+import tm_dp
+import tm_lib
+import tm_ops
+import tm_unet
+from tm_graph import MaskCSR, TimingGraph
+from tm_lib import call, stream
+from tm_ops import D, RELU, gemm_nn, gemm_tn, transpose
+
+
+def build_models(map_size, pooling="max", seed=0, device="cuda"):
+    """Reference wiring (train.py:56-81 with the head sized as model.py:267,280 produce it)."""
+    import model as M
+    import Unet as U
+    torch.manual_seed(seed)
+    gnn = M.PathConv(out_feat_dim=128, hidden_feat_dim=128, cell_feat_dim=36, net_feat_dim=2)
+    fcn = torch.nn.Linear(map_size * map_size, 128)
+    torch.nn.init.xavier_uniform_(fcn.weight, gain=torch.nn.init.calculate_gain("relu"))
+    mdl = M.PathModel(gnn, None, fcn, None, None, M.MLP(128 + 128 + 32, 2 * (128 + 128 + 32), 1))
+    cnn = U.UNet(pooling)
+    return mdl.to(device).train(), cnn.to(device).train()
+
+
+class HostDesign:
+    """A design in pinned host memory: what a data loader hands over each step."""
+
+    FIELDS = ("net_src", "net_dst", "cell_src", "cell_dst", "cell_feat", "net_feat", "pis", "endpoints",
+              "endpoint_level", "arrival_time", "mask_indptr", "mask_cols", "image")
+
+    def __init__(self, d, pin=True):
+        self.n, self.map_size = d.n, d.map_size
+        t = {"net_src": d.net_src, "net_dst": d.net_dst, "cell_src": d.cell_src, "cell_dst": d.cell_dst,
+             "cell_feat": d.cell_feat, "net_feat": d.net_feat, "pis": d.pis, "endpoints": d.endpoints.astype(np.int32),
+             "endpoint_level": d.level[d.endpoints].astype(np.float32), "arrival_time": d.arrival_time,
+             "mask_indptr": d.mask_indptr, "mask_cols": d.mask_cols, "image": d.image}
+        self.t = {}
+        for k, v in t.items():
+            x = torch.from_numpy(np.ascontiguousarray(v))
+            self.t[k] = x.pin_memory() if pin and torch.cuda.is_available() else x
+
+    def nbytes(self, per_step_only=False):
+        keys = ("cell_feat", "net_feat", "endpoints", "endpoint_level", "arrival_time", "mask_indptr",
+                "mask_cols", "image") if per_step_only else self.FIELDS
+        return int(sum(self.t[k].numel() * self.t[k].element_size() for k in keys))
+
+
+class DesignBatch:
+    """Device-resident batch of one design."""
+
+    def __init__(self, graph, mask_csr, endpoints, endpoint_level, arrival_time, image):
+        self.graph, self.mask_csr = graph, mask_csr
+        self.endpoints = endpoints                 # int32 (T,)
+        self.endpoint_level = endpoint_level       # float32 (T,)
+        self.arrival_time = arrival_time           # float32 (T,)
+        self.image = image                         # (C,H,W)
+        self.mask_rows = mask_csr.select(torch.arange(endpoints.numel(), dtype=torch.int32, device=endpoints.device))
+
+    @staticmethod
+    def from_host(h, device, graph=None):
+        """Upload a HostDesign.  With ``graph`` (a TimingGraph already on the device, schedule
+        cached) only the per-step tensors move: features, endpoints, masks, labels, image."""
+        dv = {k: v.to(device, non_blocking=True) for k, v in h.t.items()
+              if graph is None or k not in ("net_src", "net_dst", "cell_src", "cell_dst", "pis")}
+        if graph is None:
+            graph = TimingGraph(h.n, (dv["net_src"], dv["net_dst"]), (dv["cell_src"], dv["cell_dst"]), pis=dv["pis"])
+        graph.ndata["cell_feat"], graph.ndata["net_feat"] = dv["cell_feat"], dv["net_feat"]
+        mask = MaskCSR(dv["mask_indptr"], dv["mask_cols"], h.map_size * h.map_size)
+        return DesignBatch(graph, mask, dv["endpoints"], dv["endpoint_level"], dv["arrival_time"], dv["image"])
+
+    @staticmethod
+    def from_synth(d, device):
+        return DesignBatch.from_host(HostDesign(d, pin=False), device)
+
+
+class DesignStep:
+    def __init__(self, model, cnn, process_group=None, world_size=1):
+        self.model, self.cnn = model, cnn
+        self.pg, self.world = process_group, world_size
+        self.comm_stream = torch.cuda.Stream() if world_size > 1 else None
+        self._pending = []
+        g = model.gnn
+        sd = dict(g.named_parameters())
+        self.gnn_params = [sd[k] for k in tm_ops.GNN_PARAM_NAMES]
+        self.cnn_names = [k for k, _ in cnn.named_parameters()]
+        self.cnn_params = dict(cnn.named_parameters())
+
+    # ---------------------------------------------------------------- forward pieces
+    def _head_forward(self, H, b, feat):
+        m = self.model
+        T = int(b.endpoints.numel())
+        dev = H.device
+        gd = m.global_dim
+        width = D + D + gd
+        X = torch.empty(T, width, dtype=torch.float32, device=dev)
+        call("tm_gather_cols", T, D, H, D, b.endpoints, X, width, 0, stream())
+        wt = tm_ops.fusion_forward(b.mask_rows, feat, m.fcn.weight.detach(), m.fcn.bias.detach(), X[:, D:], width)
+        a0, a2 = m.mlp_alpha.layers[0], m.mlp_alpha.layers[2]
+        lv = b.endpoint_level.reshape(T, 1)
+        ha = tm_ops.mlp2_forward(lv, 1, None, T, a0.weight.detach(), a0.bias.detach(), a2.weight.detach(),
+                                 a2.bias.detach(), X[:, 2 * D:], width)
+        f0, f2 = m.mlp_fuse.layers[0], m.mlp_fuse.layers[2]
+        pred = torch.empty(T, f2.weight.shape[0], dtype=torch.float32, device=dev)
+        hf = tm_ops.mlp2_forward(X, width, None, T, f0.weight.detach(), f0.bias.detach(), f2.weight.detach(),
+                                 f2.bias.detach(), pred, pred.shape[1])
+        return pred, dict(X=X, wt=wt, ha=ha, hf=hf, lv=lv, width=width)
+
+    def forward(self, b):
+        """Inference: predictions for the batch's endpoints (validate(), train.py:137-291)."""
+        fmap, _ = tm_unet.unet_forward(self.cnn, b.image, need_bwd=False, update_stats=self.cnn.training)
+        sched = b.graph.schedule()
+        H, _ = tm_ops.gnn_forward(sched, b.graph.ndata["cell_feat"], b.graph.ndata["net_feat"],
+                                  [p.detach() for p in self.gnn_params], save=False)
+        pred, _ = self._head_forward(H, b, fmap.reshape(-1))
+        return pred.squeeze(-1)
+
+    # ---------------------------------------------------------------- full step
+    def run(self, b, grad_scale=1.0):
+        """Forward + backward.  Returns (loss (1,) device tensor, pred (T,)); fills ``.grad``."""
+        m, cnn = self.model, self.cnn
+        dev = b.image.device
+        fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
+        feat = fmap.reshape(-1)
+        sched = b.graph.schedule()
+        gp = [p.detach() for p in self.gnn_params]
+        H, saved = tm_ops.gnn_forward(sched, b.graph.ndata["cell_feat"], b.graph.ndata["net_feat"], gp, save=True)
+        pred, hs = self._head_forward(H, b, feat)
+        T = int(b.endpoints.numel())
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        gpred = torch.empty(T, 1, dtype=torch.float32, device=dev)
+        call("tm_mse", T, pred, b.arrival_time, loss, gpred, float(grad_scale), stream())
+
+        # ---- head backward
+        width, X = hs["width"], hs["X"]
+        f0, f2 = m.mlp_fuse.layers[0], m.mlp_fuse.layers[2]
+        dw1, db1, dw2, db2, dX = tm_ops.mlp2_backward(X, width, None, T, f0.weight.detach(), f2.weight.detach(),
+                                                      hs["hf"], gpred, 1, need_dx=True)
+        a0, a2 = m.mlp_alpha.layers[0], m.mlp_alpha.layers[2]
+        da1, dab1, da2, dab2, _ = tm_ops.mlp2_backward(hs["lv"], 1, None, T, a0.weight.detach(), a2.weight.detach(),
+                                                       hs["ha"], dX[:, 2 * D:], width)
+        dF, dfw, dfb = tm_ops.fusion_backward(b.mask_rows, feat, hs["wt"], dX[:, D:], width)
+        head = [(f0.weight, dw1), (f0.bias, db1), (f2.weight, dw2), (f2.bias, db2), (a0.weight, da1),
+                (a0.bias, dab1), (a2.weight, da2), (a2.bias, dab2), (m.fcn.weight, dfw), (m.fcn.bias, dfb)]
+        self._assign(head)
+        self._post_allreduce([p for p, _ in head])
+
+        # ---- GNN backward
+        G = torch.zeros(sched.n, D, dtype=torch.float32, device=dev)
+        call("tm_scatter_add_cols", T, D, dX, width, 0, b.endpoints, G, D, stream())
+        ggrads = tm_ops.gnn_backward(sched, saved, gp, G)
+        pairs = list(zip(self.gnn_params, ggrads))
+        self._assign(pairs)
+        self._post_allreduce([p for p, _ in pairs])
+
+        # ---- U-Net backward
+        ug = tm_unet.unet_backward(cnn, ust, dF.reshape(fmap.shape))
+        pairs = [(self.cnn_params[k], ug[k]) for k in self.cnn_names]
+        self._assign(pairs)
+        self._post_allreduce([p for p, _ in pairs])
+        self._wait_allreduce()
+        return loss, pred.squeeze(-1)
+
+    @staticmethod
+    def _assign(pairs):
+        for p, g in pairs:
+            p.grad = g.reshape(p.shape)
+
+    # ---------------------------------------------------------------- data parallel
+    def _post_allreduce(self, params):
+        if self.world <= 1:
+            return
+        bucket = tm_dp.GradBucket(params, self.world, self.pg)
+        self._pending.append((bucket, bucket.post(self.comm_stream)))
+
+    def _wait_allreduce(self):
+        for bucket, work in self._pending:
+            bucket.finish(work)
+        self._pending = []
+
+    def adam_step(self, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """Fused Adam over every parameter that has a gradient (train.py:431-435,555)."""
+        state["step"] = state.get("step", 0) + 1
+        for p in list(self.model.parameters()) + list(self.cnn.parameters()):
+            if p.grad is None:
+                continue
+            st = state.setdefault(id(p), None)
+            if st is None:
+                st = state[id(p)] = (torch.zeros_like(p), torch.zeros_like(p))
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            call("tm_adam_step", p.numel(), p.data, g, st[0], st[1], lr, betas[0], betas[1], eps, weight_decay,
+                 state["step"], 1.0, stream())

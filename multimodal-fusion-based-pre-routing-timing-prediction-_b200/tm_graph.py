@@ -1,0 +1,276 @@
+"""Device-resident graph batch: a DGL-heterograph-shaped container plus its level schedule.
+
+``TimingGraph`` exposes exactly the surface of the DGL graph that the reference touches
+(SURVEY.md 8b): ``ndata``, ``nodes['pin'].data``, ``edges[etype].data``, ``number_of_nodes``,
+``number_of_edges(etype=)``, ``edges(etype=)``, ``to(device)`` -- the batch format produced by
+``src/dataset.py:274-287`` -- so ``src/train.py`` / ``src/test.py`` style loops can hand it to
+``PathModel`` unchanged.  A real ``dgl.DGLGraph`` is accepted too (``as_timing_graph``).
+
+``Schedule`` is what replaces DGL's per-``pull`` graph slicing: in/out CSRs of both edge types,
+pin -> level, pins ordered by (level, id), level offsets -- built ONCE per graph on the GPU by
+``libtm_b200`` (``tm_csr_build``, ``tm_levelize``, ``tm_level_order``, ``tm_schedule_aux``).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+import tm_lib
+
+
+class _View:
+    def __init__(self, data):
+        self.data = data
+
+
+class TimingGraph:
+    def __init__(self, num_nodes, net_edges, cell_edges, pis=None):
+        """``net_edges`` / ``cell_edges``: ``(src, dst)`` int64 tensors or arrays
+        (driver pin -> sink pin; cell input pin -> cell output pin, dataset.py:274-278)."""
+        self._n = int(num_nodes)
+        self._edges = {"net": tuple(torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x,
+                                                    dtype=torch.int64) for x in net_edges),
+                       "cell": tuple(torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x,
+                                                     dtype=torch.int64) for x in cell_edges)}
+        self.pis = None if pis is None else torch.as_tensor(np.asarray(pis) if not torch.is_tensor(pis) else pis,
+                                                            dtype=torch.int64)
+        self.ndata = {}
+        self.nodes = {"pin": _View(self.ndata)}
+        self.edges_data = {"net": {}, "cell": {}}
+        self._topo_levels = None
+        self._schedule = None
+
+    # ---- DGL surface -------------------------------------------------------------------------
+    class _EdgeAccessor:
+        def __init__(self, g):
+            self._g = g
+
+        def __getitem__(self, etype):
+            return _View(self._g.edges_data[etype])
+
+        def __call__(self, etype=None):
+            return self._g._edges[etype]
+
+    @property
+    def edges(self):
+        return TimingGraph._EdgeAccessor(self)
+
+    def number_of_nodes(self):
+        return self._n
+
+    num_nodes = number_of_nodes
+
+    def number_of_edges(self, etype=None):
+        if etype is None:
+            return sum(int(e[0].numel()) for e in self._edges.values())
+        return int(self._edges[etype][0].numel())
+
+    def to(self, device):
+        """Moves edges and every ndata/edata tensor (``graph.to(device)``, train.py:467); in place."""
+        device = torch.device(device)
+        self._edges = {k: tuple(t.to(device, non_blocking=True) for t in v) for k, v in self._edges.items()}
+        if self.pis is not None:
+            self.pis = self.pis.to(device, non_blocking=True)
+        for k in list(self.ndata):
+            self.ndata[k] = self.ndata[k].to(device, non_blocking=True)
+        for et in self.edges_data:
+            for k in list(self.edges_data[et]):
+                self.edges_data[et][k] = self.edges_data[et][k].to(device, non_blocking=True)
+        if self._schedule is not None and self._schedule.device != device:
+            self._schedule = None
+        return self
+
+    @property
+    def device(self):
+        return self._edges["net"][0].device
+
+    # ---- schedule ----------------------------------------------------------------------------
+    def set_topo_levels(self, topo_levels):
+        """Use caller-provided levels (the reference's ``topo_levels``: a list of
+        ``(nodes, targets, path_ids)`` tuples or of plain node lists) instead of recomputing them."""
+        self._topo_levels = [lv[0] if isinstance(lv, (tuple, list)) and len(lv) and
+                             isinstance(lv[0], (list, tuple, np.ndarray, torch.Tensor)) else lv
+                             for lv in topo_levels]
+        self._schedule = None
+
+    def schedule(self):
+        if self._schedule is None:
+            self._schedule = Schedule.build(self)
+        return self._schedule
+
+
+def as_timing_graph(g):
+    """Accept a TimingGraph or anything with DGL's heterograph surface."""
+    if isinstance(g, TimingGraph):
+        return g
+    cached = getattr(g, "_tm_timing_graph", None)
+    if cached is not None:
+        return cached
+    net = g.edges(etype="net")
+    cell = g.edges(etype="cell")
+    tg = TimingGraph(g.number_of_nodes(), (net[0], net[1]), (cell[0], cell[1]))
+    tg.ndata = g.ndata                      # share the frame: features / 'h' live with the caller
+    tg.nodes = {"pin": _View(tg.ndata)}
+    try:
+        g._tm_timing_graph = tg
+    except Exception:
+        pass
+    return tg
+
+
+def build_csr(n, key, val):
+    """-> (indptr int32 [n+1], indices int32 [e]) on ``key.device`` via tm_csr_build."""
+    tm_lib.require_cuda(key, "edge list")
+    e = int(key.numel())
+    dev = key.device
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+    nb = tm_lib.ws_bytes("tm_csr_build_ws", n, e)
+    ws = tm_lib.workspace(nb, dev)
+    tm_lib.call("tm_csr_build", n, e, key.contiguous(), val.contiguous(), indptr, indices, ws, nb,
+                tm_lib.stream())
+    return indptr, indices[:e]
+
+
+class Schedule:
+    """Level schedule + CSRs of one graph, all int32 tensors on the device."""
+
+    @staticmethod
+    def build(g):
+        dev = g.device
+        if dev.type != "cuda":
+            raise RuntimeError("TimingGraph must be moved to a CUDA device first (graph.to('cuda')): "
+                               "there is no CPU path")
+        s = Schedule()
+        s.device = dev
+        n = s.n = g.number_of_nodes()
+        ns, nd = g._edges["net"]
+        cs, cd = g._edges["cell"]
+        s.net_iptr, s.net_isrc = build_csr(n, nd, ns)
+        s.cell_iptr, s.cell_isrc = build_csr(n, cd, cs)
+        s.net_optr, s.net_odst = build_csr(n, ns, nd)
+        s.cell_optr, s.cell_odst = build_csr(n, cs, cd)
+        st = tm_lib.stream()
+        s.level = torch.empty(n, dtype=torch.int32, device=dev)
+        if g._topo_levels is not None:
+            lv = np.full(n, -1, np.int32)
+            for lid, nodes in enumerate(g._topo_levels):
+                lv[np.asarray(nodes, dtype=np.int64)] = lid
+            s.level.copy_(torch.from_numpy(lv))
+            L = len(g._topo_levels)
+        else:
+            src_all, dst_all = torch.cat([ns, cs]), torch.cat([nd, cd])
+            optr, odst = build_csr(n, src_all, dst_all)
+            if g.pis is not None:
+                pis = g.pis.to(dev)
+            else:                                   # pins without any in-edge start the sweep
+                indeg = (s.net_iptr[1:] - s.net_iptr[:-1]) + (s.cell_iptr[1:] - s.cell_iptr[:-1])
+                pis = torch.nonzero(indeg == 0).squeeze(1)
+            nl = torch.zeros(1, dtype=torch.int32, device=dev)
+            nb = tm_lib.ws_bytes("tm_levelize_ws", n)
+            ws = tm_lib.workspace(nb, dev)
+            tm_lib.call("tm_levelize", n, optr, odst, pis.contiguous(), int(pis.numel()), s.level, nl, ws, nb, st)
+            L = int(nl.item())
+        if L <= 0:
+            raise RuntimeError("empty level schedule (no primary inputs?)")
+        s.num_levels = L
+        s.order = torch.empty(n, dtype=torch.int32, device=dev)
+        level_ptr = torch.empty(L + 1, dtype=torch.int32, device=dev)
+        nb = tm_lib.ws_bytes("tm_level_order_ws", n, L)
+        ws = tm_lib.workspace(nb, dev)
+        tm_lib.call("tm_level_order", n, L, s.level, s.order, level_ptr, ws, nb, st)
+        s.crow = torch.empty(n, dtype=torch.int32, device=dev)
+        cell_base = torch.empty(L + 1, dtype=torch.int32, device=dev)
+        viol = torch.zeros(1, dtype=torch.int32, device=dev)
+        tm_lib.call("tm_schedule_aux", n, L, s.level, s.order, level_ptr, s.net_iptr, s.net_isrc,
+                    s.cell_iptr, s.cell_isrc, s.crow, cell_base, viol, st)
+        host = torch.cat([level_ptr, cell_base, viol]).cpu().numpy()          # the one sync
+        s.level_ptr = level_ptr
+        s.h_level_ptr = np.ascontiguousarray(host[:L + 1], dtype=np.int32)
+        s.h_cell_base = np.ascontiguousarray(host[L + 1:2 * L + 2], dtype=np.int32)
+        s.n_sched = int(s.h_level_ptr[L])
+        s.n_cell_rows = int(s.h_cell_base[L])
+        if int(host[-1]) != 0:
+            raise RuntimeError(f"level schedule is not topological: {int(host[-1])} in-edges come from "
+                               "the same or a later level")
+        s.order = s.order[:s.n_sched]
+        # pins grouped by which hoisted self-term MLP feeds them (even levels: fc_cell_self,
+        # odd levels: fc_net_self; model.py:104,141,151)
+        lv_sorted = s.level[s.order.long()]
+        s.cell_class = s.order[(lv_sorted % 2) == 0].contiguous()
+        s.net_class = s.order[(lv_sorted % 2) == 1].contiguous()
+        s.struct = tm_lib.tm_schedule(
+            n=n, num_levels=L, n_cell_rows=s.n_cell_rows,
+            h_level_ptr=s.h_level_ptr.ctypes.data_as(ctypes.c_void_p).value,
+            order=s.order.data_ptr(), level=s.level.data_ptr(), crow=s.crow.data_ptr(),
+            net_iptr=s.net_iptr.data_ptr(), net_isrc=s.net_isrc.data_ptr(),
+            cell_iptr=s.cell_iptr.data_ptr(), cell_isrc=s.cell_isrc.data_ptr(),
+            net_optr=s.net_optr.data_ptr(), net_odst=s.net_odst.data_ptr(),
+            cell_optr=s.cell_optr.data_ptr(), cell_odst=s.cell_odst.data_ptr())
+        return s
+
+    def level_nodes(self, lid):
+        return self.order[int(self.h_level_ptr[lid]):int(self.h_level_ptr[lid + 1])]
+
+    def algorithmic_bytes_fwd(self, D=128):
+        """bytes the forward propagation must move (fp32, int32 indices)."""
+        e = int(self.net_isrc.numel() + self.cell_isrc.numel())
+        n = self.n_sched
+        return 4 * D * e + 4 * D * n + 4 * D * n + 4 * e + 4 * (2 * n + self.num_levels)
+
+    def algorithmic_bytes_bwd(self, D=128):
+        e = int(self.net_isrc.numel() + self.cell_isrc.numel())
+        return 4 * D * (2 * e + 4 * self.n_sched)
+
+
+class MaskCSR:
+    """Sparse path masks (``path_masks``, verilog_parser_asap7.py:1368): CSR over map*map columns."""
+
+    def __init__(self, indptr, cols, width):
+        self.indptr = torch.as_tensor(indptr, dtype=torch.int32)
+        self.cols = torch.as_tensor(cols, dtype=torch.int32)
+        self.width = int(width)
+        self.num_rows = int(self.indptr.numel()) - 1
+
+    @staticmethod
+    def from_sparse_coo(t):
+        """From the reference's ``torch.sparse_coo_tensor`` of int64 ones."""
+        t = t.coalesce()
+        rows, cols = t.indices()
+        order = torch.argsort(rows * t.shape[1] + cols)
+        indptr = torch.zeros(t.shape[0] + 1, dtype=torch.int64)
+        indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=t.shape[0]), 0)
+        return MaskCSR(indptr.to(torch.int32), cols[order].to(torch.int32), t.shape[1])
+
+    def to(self, device):
+        self.indptr = self.indptr.to(device, non_blocking=True)
+        self.cols = self.cols.to(device, non_blocking=True)
+        return self
+
+    def select(self, rows):
+        """-> MaskRows for the given path ids (``th.index_select(path_masks, 0, paths)``, train.py:500)."""
+        return MaskRows(self, rows)
+
+
+class MaskRows:
+    """A row selection of a MaskCSR plus its column-major transpose (built lazily on the GPU)."""
+
+    def __init__(self, csr, rows):
+        self.csr = csr
+        dev = csr.indptr.device
+        self.rows = torch.as_tensor(rows, dtype=torch.int32).to(dev)
+        self.T = int(self.rows.numel())
+        self._csc = None
+
+    def csc(self):
+        if self._csc is None:
+            csr = self.csr
+            rl = self.rows.long()
+            start = csr.indptr[rl].long()
+            deg = csr.indptr[rl + 1].long() - start
+            t_of = torch.repeat_interleave(torch.arange(self.T, device=deg.device), deg)
+            first = torch.cumsum(deg, 0) - deg
+            slot = torch.repeat_interleave(start, deg) + (torch.arange(int(deg.sum()), device=deg.device) - first[t_of])
+            cols = csr.cols[slot].long()
+            self._csc = build_csr(csr.width, cols, t_of)
+        return self._csc

@@ -1,0 +1,313 @@
+"""Host-side operators over ``libtm_b200``: GNN propagation, mask fusion, MLPs.
+
+Two layers:
+
+* plain functions (``gnn_forward`` / ``gnn_backward`` / ``fusion_*`` / ``mlp2_*``) that launch the
+  CUDA kernels on the current stream and return raw tensors -- used by the fused design step
+  (``tm_engine.py``) with no autograd bookkeeping;
+* ``torch.autograd.Function`` wrappers (``GnnPropagateFn``, ``MaskFusionFn``, ``LinearFn``) over the
+  same functions -- used by the drop-in ``nn.Module`` surface (``model.py``) so that the reference's
+  ``train.py`` loop (``loss.backward(retain_graph=True)``, anomaly mode) works unchanged.
+  Saved buffers are never freed or overwritten in ``backward``.
+
+Reference semantics: src/model.py:10-24 (MLP), :88-116,:138-213 (PathConv), :269-292 (PathModel),
+src/train.py:500-501 (mask fusion).
+"""
+import torch
+
+import tm_lib
+from tm_lib import call, stream
+
+D = 128
+BIAS, RELU, MASK, ACCUM = 1, 2, 4, 8
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rowmajor(t):
+    """2-D tensor usable as a strided row-major operand (unit inner stride)."""
+    if t.dtype != torch.float32 or t.stride(-1) != 1:
+        t = t.float().contiguous()
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# thin wrappers
+# --------------------------------------------------------------------------------------------
+def gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, a_rows=None, c_rows=None, bias=None, mask=None, ldmask=0, flags=0):
+    if bias is not None:
+        flags |= BIAS
+    if mask is not None:
+        flags |= MASK
+    call("tm_gemm_nn", M, N, K, A, lda, a_rows, B, ldb, C, ldc, c_rows, bias, mask, ldmask, flags, stream())
+
+
+def gemm_tn(M, N, R, A, lda, B, ldb, C, ldc, a_rows=None, b_rows=None, colsum_a=None, colsum_b=None,
+            accumulate=0):
+    nb = tm_lib.ws_bytes("tm_gemm_tn_ws", M, N, R)
+    ws = tm_lib.workspace(nb, C.device)
+    call("tm_gemm_tn", M, N, R, A, lda, a_rows, B, ldb, b_rows, C, ldc, colsum_a, colsum_b, accumulate,
+         ws, nb, stream())
+
+
+def transpose(w):
+    """(rows, cols) -> (cols, rows), contiguous."""
+    w = _f32c(w)
+    out = torch.empty(w.shape[1], w.shape[0], dtype=torch.float32, device=w.device)
+    call("tm_transpose", w.shape[0], w.shape[1], w, out, stream())
+    return out
+
+
+def colsum(X, R, C, ld, out=None, accumulate=0):
+    if out is None:
+        out = torch.empty(C, dtype=torch.float32, device=X.device)
+    call("tm_colsum", R, C, X, ld, out, accumulate, stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# two-layer MLP (model.py:10-24 with sizes (in, hid, out)):  y = W2 relu(W1 x + b1) + b2
+# --------------------------------------------------------------------------------------------
+def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None):
+    """x rows (optionally gathered by ``rows``) -> out rows (optionally scattered by ``out_rows``).
+    Returns the hidden activations (n_rows, hid) needed by ``mlp2_backward``."""
+    hid, kin = w1.shape
+    nout = w2.shape[0]
+    w1t, w2t = transpose(w1), transpose(w2)
+    h = torch.empty(n_rows, hid, dtype=torch.float32, device=out.device)
+    gemm_nn(n_rows, hid, kin, x, ldx, w1t, hid, h, hid, a_rows=rows, bias=b1, flags=RELU)
+    gemm_nn(n_rows, nout, hid, h, hid, w2t, nout, out, ldo, c_rows=out_rows, bias=b2)
+    return h
+
+
+def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=False):
+    """Gradients of a two-layer MLP.  ``g``: dLoss/d(out) rows (optionally gathered by ``g_rows``).
+    Returns (dw1, db1, dw2, db2, dx or None)."""
+    hid, kin = w1.shape
+    nout = w2.shape[0]
+    dev = h.device
+    dw2 = torch.empty(nout, hid, dtype=torch.float32, device=dev)
+    db2 = torch.empty(nout, dtype=torch.float32, device=dev)
+    dw1 = torch.empty(hid, kin, dtype=torch.float32, device=dev)
+    db1 = torch.empty(hid, dtype=torch.float32, device=dev)
+    if n_rows == 0:
+        for t in (dw1, db1, dw2, db2):
+            t.zero_()
+        return dw1, db1, dw2, db2, None
+    gemm_tn(nout, hid, n_rows, g, ldg, h, hid, dw2, hid, a_rows=g_rows, colsum_a=db2)
+    dh = torch.empty(n_rows, hid, dtype=torch.float32, device=dev)
+    gemm_nn(n_rows, hid, nout, g, ldg, _f32c(w2), hid, dh, hid, a_rows=g_rows, mask=h, ldmask=hid)
+    gemm_tn(hid, kin, n_rows, dh, hid, x, ldx, dw1, kin, b_rows=rows, colsum_a=db1)
+    dx = None
+    if need_dx:
+        dx = torch.empty(n_rows, kin, dtype=torch.float32, device=dev)
+        gemm_nn(n_rows, kin, hid, dh, hid, _f32c(w1), kin, dx, kin)
+    return dw1, db1, dw2, db2, dx
+
+
+# --------------------------------------------------------------------------------------------
+# GNN propagation
+# --------------------------------------------------------------------------------------------
+GNN_PARAM_NAMES = ("fc_cell_self.layers.0.weight", "fc_cell_self.layers.0.bias",
+                   "fc_cell_self.layers.2.weight", "fc_cell_self.layers.2.bias",
+                   "fc_net_self.layers.0.weight", "fc_net_self.layers.0.bias",
+                   "fc_net_self.layers.2.weight", "fc_net_self.layers.2.bias",
+                   "fc_cell_neigh.layers.0.weight", "fc_cell_neigh.layers.0.bias",
+                   "fc_cell_neigh.layers.2.weight", "fc_cell_neigh.layers.2.bias")
+
+
+def gnn_forward(sched, cell_feat, net_feat, params, save=True):
+    """Full propagation over every level.  ``params``: the 12 tensors of GNN_PARAM_NAMES.
+    Returns ``(H, saved)``; H is (N, 128) with zeros on pins outside the schedule."""
+    (cs1w, cs1b, cs2w, cs2b, ns1w, ns1b, ns2w, ns2b, cn1w, cn1b, cn2w, cn2b) = [_f32c(p) for p in params]
+    if cn2w.shape[0] != D or cs2w.shape[0] != D or ns2w.shape[0] != D or cn1w.shape != (256, D):
+        raise RuntimeError("the CUDA propagation kernels are built for out_feat_dim = hidden_feat_dim = 128 "
+                           "with 256-wide MLPs (the reference configuration, options.py:10)")
+    cell_feat, net_feat = _rowmajor(cell_feat), _rowmajor(net_feat)
+    tm_lib.require_cuda(cell_feat, "cell_feat")
+    dev = cell_feat.device
+    n = sched.n
+    S = torch.empty(n, D, dtype=torch.float32, device=dev)
+    nc, nn_ = int(sched.cell_class.numel()), int(sched.net_class.numel())
+    hc = mlp2_forward(cell_feat, cell_feat.stride(0), sched.cell_class, nc, cs1w, cs1b, cs2w, cs2b, S, D,
+                      out_rows=sched.cell_class)
+    hn = mlp2_forward(net_feat, net_feat.stride(0), sched.net_class, nn_, ns1w, ns1b, ns2w, ns2b, S, D,
+                      out_rows=sched.net_class)
+    H = torch.zeros(n, D, dtype=torch.float32, device=dev)
+    ncr = sched.n_cell_rows
+    A = LSE = HID = None
+    if save:
+        A = torch.empty(max(ncr, 1), D, dtype=torch.float32, device=dev)
+        LSE = torch.empty(max(ncr, 1), D, dtype=torch.float32, device=dev)
+        HID = torch.empty(max(ncr, 1), 256, dtype=torch.float32, device=dev)
+    w1t, w2t = transpose(cn1w), transpose(cn2w)
+    call("tm_gnn_forward", sched.struct, 0, sched.num_levels, H, S, w1t, cn1b, w2t, cn2b, A, LSE, HID, stream())
+    saved = dict(H=H, A=A, LSE=LSE, HID=HID, hc=hc, hn=hn, cell_feat=cell_feat, net_feat=net_feat) if save else None
+    return H, saved
+
+
+def gnn_backward(sched, saved, params, G):
+    """``G`` (N,128): dLoss/dH, consumed (overwritten with dLoss/d pre-activation).
+    Returns the 12 parameter gradients in GNN_PARAM_NAMES order."""
+    (cs1w, cs1b, cs2w, cs2b, ns1w, ns1b, ns2w, ns2b, cn1w, cn1b, cn2w, cn2b) = [_f32c(p) for p in params]
+    dev = G.device
+    ncr = sched.n_cell_rows
+    GA = torch.empty(max(ncr, 1), D, dtype=torch.float32, device=dev)
+    GHID = torch.empty(max(ncr, 1), 256, dtype=torch.float32, device=dev)
+    GZC = torch.empty(max(ncr, 1), D, dtype=torch.float32, device=dev)
+    call("tm_gnn_backward", sched.struct, saved["H"], G, cn1w, cn2w, saved["A"], saved["LSE"], saved["HID"],
+         GA, GHID, GZC, stream())
+    dcn2w = torch.empty(D, 256, dtype=torch.float32, device=dev)
+    dcn2b = torch.empty(D, dtype=torch.float32, device=dev)
+    dcn1w = torch.empty(256, D, dtype=torch.float32, device=dev)
+    dcn1b = torch.empty(256, dtype=torch.float32, device=dev)
+    if ncr > 0:
+        gemm_tn(D, 256, ncr, GZC, D, saved["HID"], 256, dcn2w, 256, colsum_a=dcn2b)
+        gemm_tn(256, D, ncr, GHID, 256, saved["A"], D, dcn1w, D, colsum_a=dcn1b)
+    else:
+        for t in (dcn2w, dcn2b, dcn1w, dcn1b):
+            t.zero_()
+    cf, nf = saved["cell_feat"], saved["net_feat"]
+    nc, nn_ = int(sched.cell_class.numel()), int(sched.net_class.numel())
+    dcs1w, dcs1b, dcs2w, dcs2b, _ = mlp2_backward(cf, cf.stride(0), sched.cell_class, nc, cs1w, cs2w,
+                                                  saved["hc"], G, D, g_rows=sched.cell_class)
+    dns1w, dns1b, dns2w, dns2b, _ = mlp2_backward(nf, nf.stride(0), sched.net_class, nn_, ns1w, ns2w,
+                                                  saved["hn"], G, D, g_rows=sched.net_class)
+    return (dcs1w, dcs1b, dcs2w, dcs2b, dns1w, dns1b, dns2w, dns2b, dcn1w, dcn1b, dcn2w, dcn2b)
+
+
+class GnnPropagateFn(torch.autograd.Function):
+    """H = propagate(cell_feat, net_feat; 12 PathConv parameters) over a fixed Schedule."""
+
+    @staticmethod
+    def forward(ctx, sched, cell_feat, net_feat, *params):
+        need = any(p.requires_grad for p in params)
+        H, saved = gnn_forward(sched, cell_feat, net_feat, [p.detach() for p in params], save=need)
+        ctx.sched, ctx.saved = sched, saved
+        ctx.params = [p.detach() for p in params]
+        return H
+
+    @staticmethod
+    def backward(ctx, gH):
+        G = gH.contiguous().clone()                      # consumed in place by the sweep
+        grads = gnn_backward(ctx.sched, ctx.saved, ctx.params, G)
+        return (None, None, None) + tuple(grads)
+
+
+# --------------------------------------------------------------------------------------------
+# mask fusion
+# --------------------------------------------------------------------------------------------
+def fusion_forward(mask_rows, feat, fcn_w, fcn_b, out, ldo):
+    """out[t, 0:128] = fcn(mask_t * feat)  (train.py:501 + model.py:272).  Returns fcn_w^T."""
+    J = int(feat.numel())
+    if fcn_w.shape != (D, J):
+        raise RuntimeError(f"fcn must be Linear({J}, 128); got weight {tuple(fcn_w.shape)}")
+    wt = transpose(fcn_w)
+    csr = mask_rows.csr
+    call("tm_fuse_forward", mask_rows.T, J, D, csr.indptr, csr.cols, mask_rows.rows, feat, wt, _f32c(fcn_b),
+         out, ldo, stream())
+    return wt
+
+
+def fusion_backward(mask_rows, feat, wt, g, ldg):
+    """Returns (dfeat (J,), dfcn_w (128,J), dfcn_b (128,))."""
+    J = int(feat.numel())
+    dev = feat.device
+    cptr, ct = mask_rows.csc()
+    dwt = torch.empty(J, D, dtype=torch.float32, device=dev)
+    dF = torch.empty(J, dtype=torch.float32, device=dev)
+    call("tm_fuse_backward", mask_rows.T, J, D, cptr, ct, g, ldg, feat, wt, dwt, dF, stream())
+    db = colsum(g, mask_rows.T, D, ldg)
+    return dF, transpose(dwt), db
+
+
+class MaskFusionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mask_rows, feat_flat, fcn_w, fcn_b):
+        feat = _f32c(feat_flat.detach()).reshape(-1)
+        out = torch.empty(mask_rows.T, D, dtype=torch.float32, device=feat.device)
+        wt = fusion_forward(mask_rows, feat, fcn_w.detach(), fcn_b.detach(), out, D)
+        ctx.mask_rows, ctx.feat, ctx.wt, ctx.shape = mask_rows, feat, wt, feat_flat.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        dF, dw, db = fusion_backward(ctx.mask_rows, ctx.feat, ctx.wt, g, D)
+        return None, dF.reshape(ctx.shape), dw, db
+
+
+class MaskedFeatureMap:
+    """What the caller may pass as ``path_map`` instead of the dense (T, map^2) product of
+    train.py:500-501: the selected sparse mask rows plus the flattened CNN feature map."""
+
+    def __init__(self, mask_rows, feat_map):
+        self.mask_rows = mask_rows
+        self.feat_map = feat_map
+
+    def to_dense(self):
+        csr = self.mask_rows.csr
+        T, J = self.mask_rows.T, csr.width
+        dense = torch.zeros(T, J, dtype=torch.float32, device=self.feat_map.device)
+        rl = self.mask_rows.rows.long()
+        deg = (csr.indptr[rl + 1] - csr.indptr[rl]).long()
+        t_of = torch.repeat_interleave(torch.arange(T, device=deg.device), deg)
+        first = torch.cumsum(deg, 0) - deg
+        slot = torch.repeat_interleave(csr.indptr[rl].long(), deg) + \
+            (torch.arange(int(deg.sum()), device=deg.device) - first[t_of])
+        dense[t_of, csr.cols[slot].long()] = 1.0
+        return dense * self.feat_map.reshape(1, -1)
+
+
+# --------------------------------------------------------------------------------------------
+# nn.Linear on the fp32 GEMM core (model.py:15; F.linear semantics, optional fused ReLU)
+# --------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        x2 = _rowmajor(x.detach().reshape(-1, x.shape[-1]))
+        tm_lib.require_cuda(x2, "Linear input")
+        M, K = x2.shape
+        N = w.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x2.device)
+        wt = transpose(w.detach())
+        gemm_nn(M, N, K, x2, x2.stride(0), wt, N, y, N, bias=None if b is None else _f32c(b.detach()),
+                flags=RELU if relu else 0)
+        ctx.save = (x2, w.detach(), y if relu else None)
+        ctx.has_bias, ctx.xshape = b is not None, x.shape
+        ctx.need_dx = x.requires_grad
+        return y.reshape(x.shape[:-1] + (N,))
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w, y = ctx.save
+        N, K = w.shape
+        M = x2.shape[0]
+        g2 = _f32c(g.reshape(M, N))
+        if y is not None:                                  # ReLU backward on the incoming gradient
+            gm = torch.empty_like(g2)
+            call("tm_leaky_relu_backward", g2.numel(), y, g2, 0.0, gm, stream())
+            g2 = gm
+        dev = x2.device
+        dw = torch.empty(N, K, dtype=torch.float32, device=dev)
+        db = torch.empty(N, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        if M > 0:
+            gemm_tn(N, K, M, g2, N, x2, x2.stride(0), dw, K, colsum_a=db)
+        else:
+            dw.zero_()
+            if db is not None:
+                db.zero_()
+        dx = None
+        if ctx.need_dx:
+            dx = torch.empty(M, K, dtype=torch.float32, device=dev)
+            gemm_nn(M, K, N, g2, N, _f32c(w), K, dx, K)
+            dx = dx.reshape(ctx.xshape)
+        return dx, dw, db, None
+
+
+def linear(x, w, b=None, relu=False):
+    return LinearFn.apply(x, w, b, relu)

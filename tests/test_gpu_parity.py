@@ -1,0 +1,522 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): bit-exact for level construction, CSR build and indexing;
+rtol 1e-3 (atol scaled to the tensor) for fp32 values and gradients.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLD, assert_close, design_to_oracle, load_golden_step
+from oracle import levelize, restate
+import tm_synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def mods(pkg):
+    import tm_engine, tm_graph, tm_lib, tm_ops, tm_unet  # noqa: E401
+    return dict(engine=tm_engine, graph=tm_graph, lib=tm_lib, ops=tm_ops, unet=tm_unet)
+
+
+def _graph(mods, d, with_pis=True):
+    g = mods["graph"].TimingGraph(d.n, (d.net_src, d.net_dst), (d.cell_src, d.cell_dst),
+                                  pis=d.pis if with_pis else None)
+    g.ndata["cell_feat"] = torch.from_numpy(d.cell_feat)
+    g.ndata["net_feat"] = torch.from_numpy(d.net_feat)
+    return g.to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------
+# integer work: bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["tiny", "c1"])
+def test_schedule_bit_exact(mods, cfg):
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS[cfg])
+    for with_pis in (True, False):
+        s = _graph(mods, d, with_pis).schedule()
+        lv = levelize.node_levels(d.n, np.concatenate([d.net_src, d.cell_src]),
+                                  np.concatenate([d.net_dst, d.cell_dst]), d.pis)
+        assert np.array_equal(s.level.cpu().numpy(), lv)
+        assert s.num_levels == int(lv.max()) + 1
+        order = s.order.cpu().numpy()
+        for lid, nodes in enumerate(d.level_lists()):
+            assert np.array_equal(order[s.h_level_ptr[lid]:s.h_level_ptr[lid + 1]], nodes)   # ascending ids
+        for (ptr, idx), (key, val) in (((s.net_iptr, s.net_isrc), (d.net_dst, d.net_src)),
+                                       ((s.cell_iptr, s.cell_isrc), (d.cell_dst, d.cell_src)),
+                                       ((s.net_optr, s.net_odst), (d.net_src, d.net_dst)),
+                                       ((s.cell_optr, s.cell_odst), (d.cell_src, d.cell_dst))):
+            rp, ri = levelize.in_csr(d.n, val, key)
+            assert np.array_equal(ptr.cpu().numpy(), rp)
+            assert np.array_equal(idx.cpu().numpy(), ri)
+        crow = s.crow.cpu().numpy()
+        cells = np.concatenate([x for i, x in enumerate(d.level_lists()) if i > 0 and i % 2 == 0])
+        assert np.array_equal(crow[cells], np.arange(cells.size))
+        assert (crow[np.setdiff1d(np.arange(d.n), cells)] == -1).all()
+
+
+def test_schedule_golden_levels(mods):
+    """Against the reference's own cal_topo_level output (tests/golden/levels_c1.npz), including
+    the unreachable island it removes."""
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["c1"])
+    z = np.load(os.path.join(GOLD, "levels_c1.npz"))
+    g = mods["graph"].TimingGraph(d.n + 2, (np.concatenate([d.net_src, [d.n]]), np.concatenate([d.net_dst, [d.n + 1]])),
+                                  (d.cell_src, d.cell_dst), pis=d.pis).to(DEV)
+    s = g.schedule()
+    assert np.array_equal(s.level.cpu().numpy(), z["node_level"])
+    assert np.array_equal(np.sort(s.order.cpu().numpy()), z["remaining"])
+
+
+def test_csr_long_rows_and_duplicates(mods):
+    rng = np.random.default_rng(1)
+    n, e = 500, 20000
+    key = rng.integers(0, n, e)
+    key[:3000] = 7                                       # one very long row (bitonic path)
+    key[3000:3040] = 9                                   # a 40-long row
+    val = rng.integers(0, n, e)
+    ptr, idx = mods["graph"].build_csr(n, torch.from_numpy(key).to(DEV), torch.from_numpy(val).to(DEV))
+    rp, ri = levelize.in_csr(n, val, key)
+    assert np.array_equal(ptr.cpu().numpy(), rp)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    ptr, idx = mods["graph"].build_csr(5, torch.zeros(0, dtype=torch.int64, device=DEV),
+                                       torch.zeros(0, dtype=torch.int64, device=DEV))
+    assert ptr.cpu().tolist() == [0] * 6 and idx.numel() == 0
+
+
+def test_schedule_from_topo_levels_and_violation(mods):
+    d = tm_synth.make_design(seed=2, **tm_synth.CONFIGS["tiny"])
+    g = _graph(mods, d)
+    g.set_topo_levels(d.topo_levels())
+    s = g.schedule()
+    assert np.array_equal(s.level.cpu().numpy(), d.level)
+    bad = [list(x) for x in d.level_lists()]
+    bad[1], bad[3] = bad[3], bad[1]                      # not topological any more
+    g2 = _graph(mods, d)
+    g2.set_topo_levels(bad)
+    with pytest.raises(RuntimeError, match="not topological"):
+        g2.schedule()
+
+
+# ---------------------------------------------------------------------------------------------
+# dense building blocks
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (130, 16, 2), (257, 36, 27), (1000, 256, 36), (333, 129, 288),
+                                   (1350, 576, 288), (64, 1, 576)])
+def test_gemm_nn(mods, M, N, K):
+    ops = mods["ops"]
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M + 5, K, device=DEV)
+    B = torch.randn(K, N, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    rows = torch.randperm(M + 5, device=DEV)[:M].to(torch.int32)
+    C = torch.full((M + 5, N), 7.0, device=DEV)
+    ops.gemm_nn(M, N, K, A, K, B, N, C, N, a_rows=rows, c_rows=rows, bias=bias, flags=ops.RELU)
+    ref = torch.relu(A[rows.long()].double() @ B.double() + bias.double())
+    assert_close(C[rows.long()], ref, 1e-4, 1e-5, "gemm_nn gather/scatter")
+    untouched = torch.ones(M + 5, dtype=torch.bool, device=DEV)
+    untouched[rows.long()] = False
+    assert bool((C[untouched] == 7.0).all())
+    mask = torch.randn(M, N, device=DEV)
+    C2 = torch.empty(M, N, device=DEV)
+    ops.gemm_nn(M, N, K, A, K, B, N, C2, N, mask=mask, ldmask=N)
+    assert_close(C2, (A[:M].double() @ B.double()) * (mask > 0), 1e-4, 1e-5, "gemm_nn mask")
+
+
+@pytest.mark.parametrize("M,N,R", [(1, 576, 1350), (128, 256, 5000), (256, 36, 3001), (27, 16, 4096), (256, 2, 777)])
+def test_gemm_tn(mods, M, N, R):
+    ops = mods["ops"]
+    torch.manual_seed(M + N + R)
+    A = torch.randn(R + 3, M, device=DEV)
+    B = torch.randn(R + 3, N, device=DEV)
+    rows = torch.randperm(R + 3, device=DEV)[:R].to(torch.int32)
+    C = torch.empty(M, N, device=DEV)
+    ca, cb = torch.empty(M, device=DEV), torch.empty(N, device=DEV)
+    ops.gemm_tn(M, N, R, A, M, B, N, C, N, a_rows=rows, b_rows=rows, colsum_a=ca, colsum_b=cb)
+    Ag, Bg = A[rows.long()].double(), B[rows.long()].double()
+    assert_close(C, Ag.t() @ Bg, 1e-4, 1e-5, "gemm_tn")
+    assert_close(ca, Ag.sum(0), 1e-4, 1e-5, "colsum_a")
+    assert_close(cb, Bg.sum(0), 1e-4, 1e-5, "colsum_b")
+    C0 = C.clone()
+    ops.gemm_tn(M, N, R, A, M, B, N, C, N, a_rows=rows, b_rows=rows, accumulate=1)
+    assert_close(C, 2 * C0, 1e-5, 1e-6, "gemm_tn accumulate")
+    assert_close(ops.transpose(A), A.t(), 0, 0, "transpose")
+    assert_close(ops.colsum(A, R + 3, M, M), A.double().sum(0), 1e-4, 1e-5, "colsum")
+
+
+def test_linear_fn_autograd(mods):
+    ops = mods["ops"]
+    torch.manual_seed(0)
+    x = torch.randn(77, 36, device=DEV, requires_grad=True)
+    w = torch.randn(256, 36, device=DEV, requires_grad=True)
+    b = torch.randn(256, device=DEV, requires_grad=True)
+    y = ops.linear(x, w, b, relu=True)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr, br = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    yr = torch.relu(F.linear(xr, wr, br))
+    yr.backward(g)
+    assert_close(y, yr, 1e-4, 1e-5, "y")
+    for a, r, n in ((x, xr, "dx"), (w, wr, "dw"), (b, br, "db")):
+        assert_close(a.grad, r.grad, 1e-4, 1e-5, n)
+
+
+# ---------------------------------------------------------------------------------------------
+# GNN propagation forward / backward
+# ---------------------------------------------------------------------------------------------
+def _gnn_params(seed):
+    import model as M
+    torch.manual_seed(seed)
+    return M.PathConv(out_feat_dim=128, hidden_feat_dim=128, cell_feat_dim=36, net_feat_dim=2)
+
+
+@pytest.mark.parametrize("cfg,seed", [("tiny", 0), ("tiny", 5), ("c1", 1)])
+def test_gnn_forward_backward(mods, cfg, seed):
+    ops = mods["ops"]
+    d = tm_synth.make_design(seed=seed, **tm_synth.CONFIGS[cfg])
+    gnn = _gnn_params(seed)
+    sd = {"gnn." + k: v.detach().clone().requires_grad_(True) for k, v in gnn.state_dict().items()}
+    od = design_to_oracle(d)
+    Href = restate.gnn_propagate(sd, "gnn", d.n, od["levels"], od["net_csr"], od["cell_csr"],
+                                 od["cell_feat"], od["net_feat"])
+    torch.manual_seed(seed)
+    Gout = torch.zeros(d.n, 128)
+    ep = torch.from_numpy(d.endpoints)
+    Gout[ep] = torch.randn(ep.numel(), 128)
+    Gout += 0.01 * torch.randn(d.n, 128)                 # every pin receives some gradient
+    names = ["gnn." + k for k in ops.GNN_PARAM_NAMES]
+    gref = torch.autograd.grad(Href, [sd[k] for k in names], Gout)
+
+    gnn = gnn.to(DEV)
+    g = _graph(mods, d)
+    H = gnn.propagate(g)
+    assert_close(H, Href, 1e-3, 1e-4, "H")
+    H.backward(Gout.to(DEV))
+    for k, r in zip(ops.GNN_PARAM_NAMES, gref):
+        assert_close(dict(gnn.named_parameters())[k].grad, r, 1e-3, 1e-4, k)
+    assert gnn.fc_net_drive.layers[0].weight.grad is None and gnn.fc_attn2.weight.grad is None
+    # a second backward through retained buffers gives the same gradients (retain_graph, D9)
+    first = {k: p.grad.clone() for k, p in gnn.named_parameters() if p.grad is not None}
+    gnn.zero_grad()
+    H2 = gnn.propagate(g)
+    H2.backward(Gout.to(DEV), retain_graph=True)
+    for k, p in gnn.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, first[k]), k      # deterministic: bit-identical
+
+
+def test_gnn_zero_indegree_and_duplicate_edges(mods):
+    """Edge cases of the pull: pins with no in-edge of the level's type aggregate 0 (builtin mean /
+    UDF bucketing skip them) and duplicate edges count twice."""
+    ops = mods["ops"]
+    # 0,1: PIs; 2 (sink of 0, twice), 3 (sink of 1); 4 = cell out of (2,3,3); 5: sink of 4 and of 0
+    net = (np.array([0, 0, 1, 4, 0]), np.array([2, 2, 3, 5, 5]))
+    cell = (np.array([2, 3, 3]), np.array([4, 4, 4]))
+    n = 6
+    torch.manual_seed(4)
+    cf, nf = torch.rand(n, 36), torch.rand(n, 2)
+    gnn = _gnn_params(9)
+    sd = {"gnn." + k: v.detach().clone() for k, v in gnn.state_dict().items()}
+    ni, ns = levelize.in_csr(n, net[0], net[1])
+    ci, cs = levelize.in_csr(n, cell[0], cell[1])
+    lv = levelize.node_levels(n, np.concatenate([net[0], cell[0]]), np.concatenate([net[1], cell[1]]), [0, 1])
+    assert lv.tolist() == [0, 0, 1, 1, 2, 3]
+    levels = [torch.from_numpy(np.nonzero(lv == i)[0]) for i in range(4)]
+    t = torch.from_numpy
+    Href = restate.gnn_propagate(sd, "gnn", n, levels, (t(ni).long(), t(ns).long()), (t(ci).long(), t(cs).long()), cf, nf)
+    g = mods["graph"].TimingGraph(n, net, cell, pis=[0, 1])
+    g.ndata["cell_feat"], g.ndata["net_feat"] = cf, nf
+    g.to(DEV)
+    with torch.no_grad():
+        H = gnn.to(DEV).propagate(g)
+    assert_close(H, Href, 1e-4, 1e-5, "H")
+
+
+# ---------------------------------------------------------------------------------------------
+# mask fusion
+# ---------------------------------------------------------------------------------------------
+def test_mask_fusion(mods):
+    ops, G = mods["ops"], mods["graph"]
+    d = tm_synth.make_design(seed=1, **tm_synth.CONFIGS["c1"])
+    J = d.map_size ** 2
+    torch.manual_seed(1)
+    feat = torch.rand(1, J, requires_grad=True)
+    w = (torch.randn(128, J) * 0.05).requires_grad_(True)
+    b = torch.randn(128, requires_grad=True)
+    sel = torch.randperm(d.endpoints.size)[:700]
+    dense = restate.dense_mask_rows(torch.from_numpy(d.mask_indptr).long(), torch.from_numpy(d.mask_cols).long(),
+                                    sel.tolist(), J)
+    ref = F.linear(dense * feat, w, b)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    csr = G.MaskCSR(d.mask_indptr, d.mask_cols, J).to(DEV)
+    rows = csr.select(sel.to(torch.int32))
+    fd, wd, bd = (x.detach().to(DEV).requires_grad_(True) for x in (feat, w, b))
+    out = ops.MaskFusionFn.apply(rows, fd, wd, bd)
+    out.backward(g.to(DEV))
+    assert_close(out, ref, 1e-3, 1e-4, "h_cnn")
+    assert_close(fd.grad, feat.grad, 1e-3, 1e-4, "dfeat")
+    assert_close(wd.grad, w.grad, 1e-3, 1e-4, "dfcn.weight")
+    assert_close(bd.grad, b.grad, 1e-3, 1e-4, "dfcn.bias")
+    # the dense view the reference's caller would build (train.py:500-501)
+    mf = ops.MaskedFeatureMap(rows, fd.detach())
+    assert_close(mf.to_dense(), dense * feat.detach(), 0, 0, "to_dense")
+    # from the reference's sparse COO format
+    rr = np.repeat(np.arange(d.endpoints.size), np.diff(d.mask_indptr))
+    coo = torch.sparse_coo_tensor(np.stack([rr, d.mask_cols.astype(np.int64)]),
+                                  torch.ones(d.mask_cols.size, dtype=torch.int64), (d.endpoints.size, J))
+    c2 = G.MaskCSR.from_sparse_coo(coo)
+    assert torch.equal(c2.indptr, torch.from_numpy(d.mask_indptr)) and torch.equal(c2.cols, torch.from_numpy(d.mask_cols))
+
+
+# ---------------------------------------------------------------------------------------------
+# image branch
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(1, 16, 16, 3, 16, 3), (2, 8, 24, 16, 32, 3), (1, 16, 8, 128, 64, 3),
+                                              (1, 12, 12, 2, 32, 9), (2, 8, 8, 32, 1, 7), (1, 16, 16, 16, 1, 1)])
+def test_conv_kernels(mods, B, H, W, Cin, Cout, k):
+    from tm_lib import call, stream, ws_bytes, workspace
+    torch.manual_seed(B * H + Cin + Cout + k)
+    x = torch.randn(B, Cin, H, W, device=DEV, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, device=DEV) * 0.1).requires_grad_(True)
+    bias = torch.randn(Cout, device=DEV, requires_grad=True)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)
+    g = torch.randn(B, Cout, H, W, device=DEV)
+    gx, gw, gb = torch.autograd.grad(ref, (x, w, bias), g.double())
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous()            # noqa: E731
+    xs, gs = nhwc(x), nhwc(g)
+    wf = torch.empty(k * k * Cin, Cout, device=DEV)
+    wb = torch.empty(k * k * Cout, Cin, device=DEV)
+    call("tm_conv_pack_weight", Cout, Cin, k, w.detach().contiguous(), wf, wb, stream())
+    y = torch.empty(B, H, W, Cout, device=DEV)
+    call("tm_conv2d_nhwc", B, H, W, Cin, Cout, k, xs, Cin, wf, bias.detach(), y, Cout, 0, stream())
+    assert_close(y.permute(0, 3, 1, 2), ref, 1e-3, 1e-4, "fprop")
+    dx = torch.empty(B, H, W, Cin, device=DEV)
+    call("tm_conv2d_nhwc", B, H, W, Cout, Cin, k, gs, Cout, wb, None, dx, Cin, 0, stream())
+    assert_close(dx.permute(0, 3, 1, 2), gx, 1e-3, 1e-4, "dgrad")
+    nb = ws_bytes("tm_conv2d_wgrad_ws", B, H, W, Cin, Cout, k)
+    ws = workspace(nb, xs.device)
+    dwf = torch.empty(k * k * Cin, Cout, device=DEV)
+    db = torch.empty(Cout, device=DEV)
+    call("tm_conv2d_wgrad_nhwc", B, H, W, Cin, Cout, k, xs, Cin, gs, Cout, dwf, db, ws, nb, stream())
+    dw = torch.empty(Cout, Cin, k, k, device=DEV)
+    call("tm_conv_unpack_wgrad", Cout, Cin, k, dwf, dw, stream())
+    assert_close(dw, gw, 1e-3, 1e-4, "wgrad")
+    assert_close(db, gb, 1e-3, 1e-4, "bgrad")
+
+
+@pytest.mark.parametrize("B,H,W,Cin", [(1, 4, 4, 128), (2, 8, 6, 32)])
+def test_convt_kernels(mods, B, H, W, Cin):
+    from tm_lib import call, stream, ws_bytes, workspace
+    Cout = Cin // 2
+    torch.manual_seed(Cin)
+    x = torch.randn(B, Cin, H, W, device=DEV, requires_grad=True)
+    w = (torch.randn(Cin, Cout, 2, 2, device=DEV) * 0.1).requires_grad_(True)
+    bias = torch.randn(Cout, device=DEV, requires_grad=True)
+    ref = F.conv_transpose2d(x.double(), w.double(), bias.double(), stride=2)
+    g = torch.randn_like(ref)
+    gx, gw, gb = torch.autograd.grad(ref, (x, w, bias), g)
+    xs = x.detach().permute(0, 2, 3, 1).contiguous()
+    ld = 2 * Cout                                        # write into the second half of a concat buffer
+    ybuf = torch.zeros(B, 2 * H, 2 * W, ld, device=DEV)
+    wt, wtT = torch.empty(Cin, 4 * Cout, device=DEV), torch.empty(4 * Cout, Cin, device=DEV)
+    call("tm_convt_pack_weight", Cin, Cout, w.detach().contiguous(), wt, wtT, stream())
+    call("tm_convt2x2_nhwc", B, H, W, Cin, Cout, xs, Cin, wt, bias.detach(), ybuf[..., Cout:], ld, 2 * H, 2 * W, 0, 0, stream())
+    assert_close(ybuf[..., Cout:].permute(0, 3, 1, 2), ref, 1e-3, 1e-4, "convT fprop")
+    assert bool((ybuf[..., :Cout] == 0).all())
+    gbuf = torch.zeros(B, 2 * H, 2 * W, ld, device=DEV)
+    gbuf[..., Cout:] = g.float().permute(0, 2, 3, 1)
+    dx = torch.empty(B, H, W, Cin, device=DEV)
+    call("tm_convt2x2_dgrad_nhwc", B, H, W, Cin, Cout, gbuf[..., Cout:], ld, 2 * H, 2 * W, 0, 0, wtT, dx, Cin, stream())
+    assert_close(dx.permute(0, 3, 1, 2), gx, 1e-3, 1e-4, "convT dgrad")
+    nb = ws_bytes("tm_convt2x2_wgrad_ws", B, H, W, Cin, Cout)
+    dwt, dbt = torch.empty(Cin, 4 * Cout, device=DEV), torch.empty(Cout, device=DEV)
+    call("tm_convt2x2_wgrad_nhwc", B, H, W, Cin, Cout, xs, Cin, gbuf[..., Cout:], ld, 2 * H, 2 * W, 0, 0, dwt, dbt,
+         workspace(nb, xs.device), nb, stream())
+    dw = torch.empty(Cin, Cout, 2, 2, device=DEV)
+    call("tm_convt_unpack_wgrad", Cin, Cout, dwt, dw, stream())
+    assert_close(dw, gw, 1e-3, 1e-4, "convT wgrad")
+    assert_close(dbt, gb, 1e-3, 1e-4, "convT bgrad")
+
+
+@pytest.mark.parametrize("pooling", ["max", "avg"])
+def test_unet_vs_oracle(mods, pooling):
+    import Unet as U
+    torch.manual_seed(11)
+    net = U.UNet(pooling).train()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.rand(2, 3, 32, 24)
+    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    ref, stats = restate.unet_forward(P, x, pooling)
+    g = torch.randn_like(ref)
+    names = [k for k, _ in net.named_parameters()]
+    gref = torch.autograd.grad(ref, [P[k] for k in names], g)
+    net = net.to(DEV)
+    out = net(x.to(DEV))
+    assert out.shape == ref.shape
+    assert_close(out, ref, 1e-3, 1e-4, "unet out")
+    out.backward(g.to(DEV))
+    for k, r in zip(names, gref):
+        assert_close(dict(net.named_parameters())[k].grad, r, 1e-3, 2e-4, k)
+    for k, v in stats.items():
+        assert_close(net.state_dict()[k], v, 1e-4, 1e-5, k)
+    assert int(net.inc.double_conv[1].num_batches_tracked) == 1
+    # (C,H,W) input is accepted (train.py:465)
+    with torch.no_grad():
+        o3 = net(x[0].to(DEV))
+    assert o3.shape == (1, 1, 16, 12)
+
+
+def test_layoutnet_vs_golden(mods):
+    import model as M
+    z = np.load(os.path.join(GOLD, "layoutnet.npz"))
+    net = M.LayoutNet("max")
+    net.load_state_dict({k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p.")})
+    net = net.to(DEV)
+    y = net(torch.from_numpy(z["x"]).to(DEV))
+    assert_close(y, z["y"], 1e-3, 1e-4, "layoutnet y")
+    y.square().sum().backward()
+    for k, p in net.named_parameters():
+        assert_close(p.grad, z["g." + k], 1e-3, 2e-4, k)
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole design step
+# ---------------------------------------------------------------------------------------------
+def _load_models(sd_m, sd_c, map_size):
+    import tm_engine
+    model, cnn = tm_engine.build_models(map_size, device="cpu")
+    model.load_state_dict(sd_m)
+    cnn.load_state_dict(sd_c)
+    return model.to(DEV).train(), cnn.to(DEV).train()
+
+
+def _check_step_against_golden(z, model, cnn, pred, loss):
+    assert_close(pred, z["pred"], 1e-3, 1e-4, "pred")
+    assert_close(loss.reshape(()), z["loss"], 1e-3, 1e-4, "loss")
+    for k, p in model.named_parameters():
+        ref = z["grad.model." + k]
+        if ref.size == 0:
+            assert p.grad is None, k
+        else:
+            assert_close(p.grad, ref, 1e-3, 2e-4, "model." + k)
+    for k, p in cnn.named_parameters():
+        assert_close(p.grad, z["grad.cnn." + k], 1e-3, 2e-4, "cnn." + k)
+    for k in z.files:
+        if k.startswith("after.cnn.") and "running" in k:
+            assert_close(cnn.state_dict()[k[len("after.cnn."):]], z[k], 1e-4, 1e-5, k)
+
+
+def test_design_step_vs_golden(mods):
+    """Fused step (tm_engine.DesignStep) against the fixture produced by the UNMODIFIED reference."""
+    eng = mods["engine"]
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["tiny"])
+    z, sd_m, sd_c = load_golden_step("tiny")
+    model, cnn = _load_models(sd_m, sd_c, d.map_size)
+    batch = eng.DesignBatch.from_synth(d, DEV)
+    before = mods["lib"].launch_count()
+    loss, pred = eng.DesignStep(model, cnn).run(batch)
+    assert mods["lib"].launch_count() > before
+    assert_close(batch.graph.schedule().level, d.level, 0, 0, "levels")
+    _check_step_against_golden(z, model, cnn, pred, loss)
+
+
+def test_module_surface_train_loop_vs_golden(mods):
+    """The reference's own loop shape (train.py:465,490-522,552-553) driving the drop-in modules
+    through autograd, with a dense path_map built by the caller exactly like train.py:500-501."""
+    G = mods["graph"]
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["tiny"])
+    z, sd_m, sd_c = load_golden_step("tiny")
+    model, cnn = _load_models(sd_m, sd_c, d.map_size)
+    graph = _graph(mods, d)
+    graph.ndata["h"] = torch.zeros(d.n, 128, device=DEV)
+    rows = np.repeat(np.arange(d.endpoints.size), np.diff(d.mask_indptr))
+    path_masks = torch.sparse_coo_tensor(np.stack([rows, d.mask_cols.astype(np.int64)]),
+                                         torch.ones(d.mask_cols.size, dtype=torch.int64),
+                                         (d.endpoints.size, d.map_size ** 2))
+    feat_map = cnn(torch.from_numpy(d.image).to(DEV)).reshape((1, -1))           # 3-D input, D3
+    label_hats, target_list = None, []
+    for level_id, level in enumerate(d.topo_levels()):
+        nodes, eids = level[:2]
+        targets, paths = level[1], level[2]
+        target_list.extend(targets)
+        if len(paths) == 0:
+            path_map = None
+        else:
+            path_mask = torch.index_select(path_masks, 0, torch.tensor(paths)).to(DEV)
+            path_map = path_mask.to_dense() * feat_map
+        cur = model(graph, nodes, eids, targets, level_id,
+                    torch.tensor(level_id, dtype=torch.float).unsqueeze(0).to(DEV), path_map)
+        if len(paths) == 0:
+            assert cur is None
+            continue
+        label_hats = cur if label_hats is None else torch.cat((label_hats, cur), dim=0)
+    arrival = torch.from_numpy(d.arrival_time).to(DEV)
+    loss = torch.nn.MSELoss()(label_hats, arrival)
+    loss.backward(retain_graph=True)
+    _check_step_against_golden(z, model, cnn, label_hats, loss)
+    assert_close(graph.ndata["h"], z["H"], 1e-3, 1e-4, "ndata['h']")
+
+    # same loop with the sparse fast path for path_map
+    model.zero_grad(); cnn.zero_grad()
+    csr = G.MaskCSR(d.mask_indptr, d.mask_cols, d.map_size ** 2).to(DEV)
+    feat_map = cnn(torch.from_numpy(d.image).unsqueeze(0).to(DEV)).reshape((1, -1))
+    hats = []
+    from tm_ops import MaskedFeatureMap
+    for level_id, (nodes, targets, paths) in enumerate(d.topo_levels()):
+        pm = MaskedFeatureMap(csr.select(paths), feat_map) if paths else None
+        cur = model(graph, nodes, None, targets, level_id, torch.tensor([float(level_id)], device=DEV), pm)
+        if cur is not None:
+            hats.append(cur)
+    loss2 = torch.nn.MSELoss()(torch.cat(hats), arrival)
+    loss2.backward()
+    assert_close(loss2, z["loss"], 1e-3, 1e-4, "loss (sparse path_map)")
+    for k, p in model.named_parameters():
+        if z["grad.model." + k].size:
+            assert_close(p.grad, z["grad.model." + k], 1e-3, 2e-4, "sparse: model." + k)
+
+
+def test_legacy_pathmodel_constructor(mods):
+    """train.py:81 calls PathModel(gnn, fcn, mlp) with a 320-wide head (D1/D2)."""
+    import model as M
+    gnn = M.PathConv(out_feat_dim=128, hidden_feat_dim=128, cell_feat_dim=36, net_feat_dim=2)
+    fcn = torch.nn.Linear(64, 128)
+    mlp = M.MLP(128 + 128 + 64, (128 + 128 + 64) * 2, 1)
+    pm = M.PathModel(gnn, fcn, mlp)
+    assert pm.fcn is fcn and pm.mlp_fuse is mlp and pm.cnn is None and pm.global_dim == 64
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["tiny"])
+    pm = pm.to(DEV)
+    graph = _graph(mods, d)
+    lv = d.topo_levels()
+    with torch.no_grad():
+        out = None
+        for level_id, (nodes, targets, paths) in enumerate(lv):
+            pmap = torch.rand(len(targets), 64, device=DEV) if targets else None
+            out = pm(graph, nodes, targets, targets, level_id, torch.tensor([float(level_id)], device=DEV), pmap)
+            if targets:
+                assert out.shape == (len(targets),)
+
+
+def test_adam_matches_torch(mods):
+    from tm_lib import call, stream
+    torch.manual_seed(0)
+    p = torch.randn(1000, device=DEV)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(1000, device=DEV)
+        ref.grad = g.clone()
+        opt.step()
+        call("tm_adam_step", 1000, p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.0, step, 1.0, stream())
+    assert_close(p, ref, 1e-5, 1e-6, "adam")
+
+
+def test_cpu_inputs_fail_loudly(mods):
+    import model as M
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.MLP(4, 8, 2)(torch.randn(3, 4))
