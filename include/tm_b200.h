@@ -35,6 +35,26 @@ const char* tm_last_error(void);
 long long tm_launch_count(void);
 int tm_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* The level schedule of one graph (all device arrays int32 unless noted).  Built by the G1
+ * entry points below, consumed by the G2/G3 propagation kernels. */
+typedef struct {
+  int64_t n;                 /* pins                                                   */
+  int32_t num_levels;
+  int32_t n_cell_rows;       /* pins on even levels > 0                                */
+  const int32_t* h_level_ptr;/* HOST copy of level_ptr[num_levels+1]                   */
+  const int32_t* order;      /* scheduled pins by (level, id)                          */
+  const int32_t* level;      /* pin -> level                                           */
+  const int32_t* crow;       /* pin -> compact cell row or -1                          */
+  const int32_t* net_iptr;  const int32_t* net_isrc;   /* in-edge CSRs                 */
+  const int32_t* cell_iptr; const int32_t* cell_isrc;
+  const int32_t* net_optr;  const int32_t* net_odst;   /* out-edge CSRs                */
+  const int32_t* cell_optr; const int32_t* cell_odst;
+  /* level-ordered edge lists (tm_schedule_edges), indexed by schedule position            */
+  const int32_t* f_ptr;  const int32_t* f_src;         /* forward gather sources           */
+  const int32_t* bn_ptr; const int32_t* bn_dst; const float* bn_w;   /* backward, net edges */
+  const int32_t* bc_ptr; const int32_t* bc_row;        /* backward, cell edges (compact row) */
+} tm_schedule;
+
 /* ------------------------------------------------------------------------------------
  * G1  graph structure: CSR build and level schedule
  *     replaces dgl.heterograph(...) + the lazy in-edge CSR DGL builds inside graph.pull
@@ -76,6 +96,14 @@ int tm_schedule_aux(int64_t n, int32_t num_levels, const int32_t* level, const i
                     const int32_t* cell_iptr, const int32_t* cell_isrc, int32_t* crow,
                     int32_t* cell_base, int32_t* n_violations, void* stream);
 
+size_t tm_schedule_edges_ws(int64_t n_sched);
+/* Level-ordered edge lists for the propagation kernels (see tm_schedule): f_ptr/bn_ptr/bc_ptr
+ * [n_sched+1]; f_src [E_net+E_cell]; bn_dst, bn_w [E_net]; bc_row [E_cell] (upper bounds).
+ * `s` needs order, level, crow and the four CSRs filled in. */
+int tm_schedule_edges(const tm_schedule* s, int64_t n_sched, int32_t* f_ptr, int32_t* f_src,
+                      int32_t* bn_ptr, int32_t* bn_dst, float* bn_w, int32_t* bc_ptr,
+                      int32_t* bc_row, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * dense fp32 building blocks (replace the cuBLAS SGEMMs behind nn.Linear,
  * src/model.py:15,23 and every MLP call site model.py:104,141-142,151,272,280,292)
@@ -111,19 +139,6 @@ int tm_transpose(int64_t rows, int64_t cols, const float* in, float* out, void* 
  * G2/G3  level-wise timing propagation (replaces PathConv.forward, src/model.py:158-213,
  *        its UDFs :88-116,:138-153 and the autograd backward train.py:553)
  * ---------------------------------------------------------------------------------- */
-typedef struct {
-  int64_t n;                 /* pins                                                   */
-  int32_t num_levels;
-  int32_t n_cell_rows;       /* pins on even levels > 0                                */
-  const int32_t* h_level_ptr;/* HOST copy of level_ptr[num_levels+1]                   */
-  const int32_t* order;      /* scheduled pins by (level, id)                          */
-  const int32_t* level;      /* pin -> level                                           */
-  const int32_t* crow;       /* pin -> compact cell row or -1                          */
-  const int32_t* net_iptr;  const int32_t* net_isrc;   /* in-edge CSRs                 */
-  const int32_t* cell_iptr; const int32_t* cell_isrc;
-  const int32_t* net_optr;  const int32_t* net_odst;   /* out-edge CSRs                */
-  const int32_t* cell_optr; const int32_t* cell_odst;
-} tm_schedule;
 
 /* Forward over levels [level_begin, level_end).  D = 128, hidden = 256 (model.py:48).
  *   H[n,128]   in/out: rows of the processed levels are written, sources are read

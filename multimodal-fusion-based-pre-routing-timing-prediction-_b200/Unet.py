@@ -88,4 +88,6 @@ class UNet(nn.Module):
             self.pooling = "avg" if isinstance(self.outc.conv[1], nn.AvgPool2d) else "max"
 
     def forward(self, x):
-        return tm_unet.UNetFn.apply(self, x, *self.parameters())
+        params = list(self.parameters())
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return tm_unet.UNetFn.apply(self, x, need, *params)

@@ -65,7 +65,7 @@ __global__ void fold4_kernel(int64_t Cout, const float* __restrict__ cs, float* 
 
 // ------------------------------------------------------------------------------ batch norm
 // block = 32 channels x 8 pixel lanes; grid.x = pixel chunks, grid.y = channel groups of 32
-constexpr int BN_PIX_PER_BLOCK = 1024;
+constexpr int BN_PIX_PER_BLOCK = 128;
 
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(int64_t npix, int64_t C, const float* __restrict__ x, int64_t ldx, double* __restrict__ part) {
@@ -94,10 +94,14 @@ __global__ void bn_finalize_kernel(int64_t npix, int64_t C, int nblk, const doub
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float momentum, float eps, float* __restrict__ save_mean,
                                    float* __restrict__ save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
   if (c >= C) return;
   double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblk; ++i) { a += part[((int64_t)i * C + c) * 2]; b += part[((int64_t)i * C + c) * 2 + 1]; }
+  for (int i = lane; i < nblk; i += 32) { a += part[((int64_t)i * C + c) * 2]; b += part[((int64_t)i * C + c) * 2 + 1]; }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane != 0) return;
   const double mean = a / (double)npix;
   double var = b / (double)npix - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -151,12 +155,14 @@ bn_bwd_stats_kernel(int64_t npix, int64_t C, const float* __restrict__ x, int64_
 
 __global__ void bn_bwd_finalize_kernel(int64_t C, int nblk, const double* __restrict__ part,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
   if (c >= C) return;
   double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblk; ++i) { a += part[((int64_t)i * C + c) * 2]; b += part[((int64_t)i * C + c) * 2 + 1]; }
-  dbeta[c] = (float)a;
-  dgamma[c] = (float)b;
+  for (int i = lane; i < nblk; i += 32) { a += part[((int64_t)i * C + c) * 2]; b += part[((int64_t)i * C + c) * 2 + 1]; }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { dbeta[c] = (float)a; dgamma[c] = (float)b; }
 }
 
 __global__ void bn_bwd_apply_kernel(int64_t npix, int64_t C, const float* __restrict__ x, int64_t ldx,
@@ -354,7 +360,7 @@ extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64
   double* part = (double*)ws;
   bn_stats_kernel<<<dim3(nblk, (unsigned)cdiv(C, 32)), dim3(32, 8), 0, ST>>>(npix, C, x, ldx, part);
   TM_TRY(check_launch("bn_stats"));
-  bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, ST>>>(npix, C, nblk, part, running_mean, running_var,
+  bn_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(npix, C, nblk, part, running_mean, running_var,
                                                              momentum, eps, save_mean, save_invstd);
   TM_TRY(check_launch("bn_finalize"));
   bn_relu_apply_kernel<<<blocks_for(npix * C), 256, 0, ST>>>(npix, C, x, ldx, gamma, beta, save_mean,
@@ -375,7 +381,7 @@ extern "C" int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int6
                                                                                  lddy, save_mean, save_invstd,
                                                                                  part);
   TM_TRY(check_launch("bn_bwd_stats"));
-  bn_bwd_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, ST>>>(C, nblk, part, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(C, nblk, part, dgamma, dbeta);
   TM_TRY(check_launch("bn_bwd_finalize"));
   bn_bwd_apply_kernel<<<blocks_for(npix * C), 256, 0, ST>>>(npix, C, x, ldx, y, ldy, dy, lddy, gamma, save_mean,
                                                             save_invstd, dgamma, dbeta, dx, lddx);

@@ -25,7 +25,7 @@ namespace {
 constexpr int D = 128;     // out_feat_dim (model.py:43, options.py:10)
 constexpr int HID = 256;   // MLP hidden width (model.py:48)
 constexpr int TILE = 16;   // pins per CTA on a cell level
-constexpr int CT = 256;    // threads per CTA
+constexpr int CT = 128;    // threads per CTA on a cell level
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -35,88 +35,139 @@ __device__ __forceinline__ float4 f4relu(float4 a) { return make_float4(fmaxf(a.
 // forward, level 0 and odd (net) levels: one warp per pin
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gnn_net_fwd_kernel(const int* __restrict__ order, int p0, int cnt, const int* __restrict__ iptr,
-                   const int* __restrict__ isrc, const float* __restrict__ S, float* H, int level0) {
+gnn_net_fwd_kernel(const int* __restrict__ order, int p0, int cnt, const int* __restrict__ f_ptr,
+                   const int* __restrict__ f_src, const float* __restrict__ S, float* H) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= cnt) return;
-  const int v = order[p0 + w];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!level0) {
-    const int s = iptr[v], e = iptr[v + 1];
-    for (int i = s; i < e; i += 4) {
-      float4 m[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        m[q] = (i + q < e) ? ld4(H + (int64_t)isrc[i + q] * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc = f4add(acc, m[q]);
-    }
-    if (e > s) acc = f4scale(acc, 1.f / (float)(e - s));
-  }
+  const int p = p0 + w;
+  const int v = order[p];
+  const int s = f_ptr[p], e = f_ptr[p + 1];          // level 0: empty range
   const float4 sv = ld4_stream(S + (int64_t)v * D + lane * 4);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = s; i < e; i += 4) {
+    float4 m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      m[q] = (i + q < e) ? ld4(H + (int64_t)f_src[i + q] * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc = f4add(acc, m[q]);
+  }
+  if (e > s) acc = f4scale(acc, 1.f / (float)(e - s));
   st4(H + (int64_t)v * D + lane * 4, f4relu(f4add(sv, acc)));
 }
 
 // ---------------------------------------------------------------------------------------------
-// tile MLP pieces shared by forward and backward (fp32 FFMA, weights streamed through L1/L2)
-//   gemm_128x256: out[16][256] = in[16][128] @ Wk[128][256]     thread -> 4 rows x 4 cols
-//   gemm_256x128: out[16][128] = in[16][256] @ Wk[256][128]     thread -> 2 rows x 4 cols
+// tile MLP shared by forward and backward: out = epi2( epi1(in @ Wa) @ Wb ) for a 16-row tile,
+//   Wa: [128][256] row-major (k-major), Wb: [256][128] row-major.
+// The 256 KB of weights do not fit in shared memory next to the tiles, so they are STREAMED:
+// 16 chunks of 16 KB (8 of Wa, 8 of Wb; each chunk is a contiguous run of k-rows) flow through a
+// 3-stage cp.async ring, so the L2->SM weight traffic is bandwidth- not latency-bound and overlaps
+// the FFMA work.  128 threads; GEMM1 thread tile 8 rows x 4 cols, GEMM2 thread tile 4 rows x 4 cols;
+// tile rows are read as warp-wide broadcasts, weights as conflict-free 128-bit LDS.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gemm_128x256(const float (*in)[D], const float* __restrict__ Wk,
-                                             int rg, int cg, float (&acc)[4][4]) {
+constexpr int CHUNK = 4096;       // floats per weight chunk (16 KB)
+constexpr int NSTAGE = 3;
+constexpr int NCHUNK = 16;
+constexpr size_t CELL_SMEM = (size_t)(TILE * D + TILE * HID + NSTAGE * CHUNK) * sizeof(float) + TILE * sizeof(int);
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void issue_chunk(float* wbuf, const float* __restrict__ Wa,
+                                            const float* __restrict__ Wb, int c, int tid) {
+  if (c < NCHUNK) {
+    const float* src = (c < 8) ? Wa + (size_t)c * CHUNK : Wb + (size_t)(c - 8) * CHUNK;
+    float* dst = wbuf + (c % NSTAGE) * CHUNK;
+#pragma unroll
+    for (int i = 0; i < CHUNK / 4 / CT; ++i) cp_async16(dst + (tid + i * CT) * 4, src + (tid + i * CT) * 4);
+  }
+  cp_async_commit();   // always commit (possibly empty) so that wait_group<1> means "chunk c landed"
+}
+
+// Call order inside a kernel:  mlp_prologue() -> fill in_s -> mlp_tile()
+__device__ __forceinline__ void mlp_prologue(float* wbuf, const float* Wa, const float* Wb, int tid) {
+  issue_chunk(wbuf, Wa, Wb, 0, tid);
+  issue_chunk(wbuf, Wa, Wb, 1, tid);
+}
+
+template <class Epi1, class Epi2>
+__device__ __forceinline__ void mlp_tile(const float (*in_s)[D], float (*mid_s)[HID], float* wbuf,
+                                         const float* Wa, const float* Wb, int tid, Epi1 epi1, Epi2 epi2) {
+  const int cg1 = tid & 63, rg1 = tid >> 6;   // GEMM1: cols 4*cg1.., rows 8*rg1..
+  const int cg2 = tid & 31, rg2 = tid >> 5;   // GEMM2: cols 4*cg2.., rows 4*rg2..
+  float acc1[8][4], acc2[4][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc1[r][c] = 0.f;
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-#pragma unroll 2
-  for (int k = 0; k < D; k += 4) {
-    float4 a[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(&in[rg * 4 + r][k]);
-    float4 wv[4];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) wv[kk] = __ldg(reinterpret_cast<const float4*>(Wk + (int64_t)(k + kk) * HID + cg * 4));
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float av[4] = {a[r].x, a[r].y, a[r].z, a[r].w};
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        acc[r][0] = fmaf(av[kk], wv[kk].x, acc[r][0]);
-        acc[r][1] = fmaf(av[kk], wv[kk].y, acc[r][1]);
-        acc[r][2] = fmaf(av[kk], wv[kk].z, acc[r][2]);
-        acc[r][3] = fmaf(av[kk], wv[kk].w, acc[r][3]);
-      }
-    }
-  }
-}
+    for (int c = 0; c < 4; ++c) acc2[r][c] = 0.f;
 
-__device__ __forceinline__ void gemm_256x128(const float (*in)[HID], const float* __restrict__ Wk,
-                                             int rg, int cg, float (&acc)[2][4]) {
+  for (int c = 0; c < NCHUNK; ++c) {
+    cp_async_wait<1>();
+    __syncthreads();                      // chunk c visible; buffer of chunk c-1 free; tiles visible
+    issue_chunk(wbuf, Wa, Wb, c + 2, tid);
+    const float* w = wbuf + (c % NSTAGE) * CHUNK;
+    if (c < 8) {                          // GEMM1: k rows 16c .. 16c+15 of Wa, 256 columns
+      const int kb = c * 16;
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+      for (int kk = 0; kk < 16; kk += 4) {
+        float4 a[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-#pragma unroll 2
-  for (int k = 0; k < HID; k += 4) {
-    float4 a[2];
+        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float4*>(&in_s[rg1 * 8 + r][kb + kk]);
 #pragma unroll
-    for (int r = 0; r < 2; ++r) a[r] = *reinterpret_cast<const float4*>(&in[rg * 2 + r][k]);
-    float4 wv[4];
+        for (int j = 0; j < 4; ++j) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + (kk + j) * HID + cg1 * 4);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) wv[kk] = __ldg(reinterpret_cast<const float4*>(Wk + (int64_t)(k + kk) * D + cg * 4));
+          for (int r = 0; r < 8; ++r) {
+            const float av = (j == 0) ? a[r].x : (j == 1) ? a[r].y : (j == 2) ? a[r].z : a[r].w;
+            acc1[r][0] = fmaf(av, wv.x, acc1[r][0]);
+            acc1[r][1] = fmaf(av, wv.y, acc1[r][1]);
+            acc1[r][2] = fmaf(av, wv.z, acc1[r][2]);
+            acc1[r][3] = fmaf(av, wv.w, acc1[r][3]);
+          }
+        }
+      }
+      if (c == 7) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const float av[4] = {a[r].x, a[r].y, a[r].z, a[r].w};
+        for (int r = 0; r < 8; ++r) {
+          const float4 o = epi1(rg1 * 8 + r, cg1 * 4, make_float4(acc1[r][0], acc1[r][1], acc1[r][2], acc1[r][3]));
+          *reinterpret_cast<float4*>(&mid_s[rg1 * 8 + r][cg1 * 4]) = o;
+        }
+      }
+    } else {                              // GEMM2: k rows 32(c-8) .. +31 of Wb, 128 columns
+      const int kb = (c - 8) * 32;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        acc[r][0] = fmaf(av[kk], wv[kk].x, acc[r][0]);
-        acc[r][1] = fmaf(av[kk], wv[kk].y, acc[r][1]);
-        acc[r][2] = fmaf(av[kk], wv[kk].z, acc[r][2]);
-        acc[r][3] = fmaf(av[kk], wv[kk].w, acc[r][3]);
+      for (int kk = 0; kk < 32; kk += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(&mid_s[rg2 * 4 + r][kb + kk]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + (kk + j) * D + cg2 * 4);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float av = (j == 0) ? a[r].x : (j == 1) ? a[r].y : (j == 2) ? a[r].z : a[r].w;
+            acc2[r][0] = fmaf(av, wv.x, acc2[r][0]);
+            acc2[r][1] = fmaf(av, wv.y, acc2[r][1]);
+            acc2[r][2] = fmaf(av, wv.z, acc2[r][2]);
+            acc2[r][3] = fmaf(av, wv.w, acc2[r][3]);
+          }
+        }
       }
     }
   }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    epi2(rg2 * 4 + r, cg2 * 4, make_float4(acc2[r][0], acc2[r][1], acc2[r][2], acc2[r][3]));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -124,42 +175,72 @@ __device__ __forceinline__ void gemm_256x128(const float (*in)[HID], const float
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CT)
 gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
-                    const int* __restrict__ iptr, const int* __restrict__ isrc,
+                    const int* __restrict__ f_ptr, const int* __restrict__ f_src,
                     const float* __restrict__ S, float* H, const float* __restrict__ W1t,
                     const float* __restrict__ b1, const float* __restrict__ W2t,
                     const float* __restrict__ b2, float* __restrict__ A, float* __restrict__ LSE,
                     float* __restrict__ HIDb) {
-  __shared__ __align__(16) float a_s[TILE][D];
-  __shared__ __align__(16) float hid_s[TILE][HID];
-  __shared__ int v_s[TILE];
+  extern __shared__ __align__(16) float smem[];
+  float (*a_s)[D] = reinterpret_cast<float (*)[D]>(smem);
+  float (*hid_s)[HID] = reinterpret_cast<float (*)[HID]>(smem + TILE * D);
+  float* wbuf = smem + TILE * D + TILE * HID;
+  int* v_s = reinterpret_cast<int*>(wbuf + NSTAGE * CHUNK);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * TILE;
+  mlp_prologue(wbuf, W1t, W2t, tid);
 
-  // phase 1: each warp aggregates two pins (online softmax per channel, single pass over edges)
+  // phase 1: each warp aggregates PPW consecutive pins.  Their in-edges are one contiguous range of
+  // the level-ordered edge list, walked once with warp-uniform pin boundaries; eight source rows
+  // are in flight per step (online softmax per channel, lane = 4 channels).
+  constexpr int PPW = TILE / (CT / 32);
+  {
+    const int r0 = warp * PPW;
+    const int npin = min(PPW, cnt - (t0 + r0));                  // may be <= 0 on the tail tile
+    const int pb = p0 + t0 + r0;
+    int ptrs = 0, vv = -1;
+    if (npin > 0) {
+      if (lane <= npin) ptrs = f_ptr[pb + lane];
+      if (lane < npin) vv = order[pb + lane];
+    }
+    if (lane < PPW) v_s[r0 + lane] = vv;
+    int q = 0;
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    float sm[4] = {0.f, 0.f, 0.f, 0.f}, tw[4] = {0.f, 0.f, 0.f, 0.f};
+    auto finish_pin = [&]() {                                    // writes pin q, resets the state
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f), lse = av;
+      if (sm[0] > 0.f) {                                         // at least one in-edge
+        av = make_float4(tw[0] / sm[0], tw[1] / sm[1], tw[2] / sm[2], tw[3] / sm[3]);
+        lse = make_float4(mx[0] + logf(sm[0]), mx[1] + logf(sm[1]), mx[2] + logf(sm[2]), mx[3] + logf(sm[3]));
+      }
+      *reinterpret_cast<float4*>(&a_s[r0 + q][lane * 4]) = av;
+      if (A) {
+        st4(A + (int64_t)(crow0 + t0 + r0 + q) * D + lane * 4, av);
+        st4(LSE + (int64_t)(crow0 + t0 + r0 + q) * D + lane * 4, lse);
+      }
 #pragma unroll
-  for (int rr = 0; rr < TILE / (CT / 32); ++rr) {
-    const int r = warp * (TILE / (CT / 32)) + rr;
-    const int p = t0 + r;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), lse = av;
-    int v = -1;
-    if (p < cnt) {
-      v = order[p0 + p];
-      const int s = iptr[v], e = iptr[v + 1];
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      float sm[4] = {0.f, 0.f, 0.f, 0.f}, tw[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int i = s; i < e; i += 4) {
-        float4 m[4];
+      for (int c = 0; c < 4; ++c) { mx[c] = -INFINITY; sm[c] = 0.f; tw[c] = 0.f; }
+      ++q;
+    };
+    if (npin > 0) {
+      const int E0 = __shfl_sync(0xffffffffu, ptrs, 0), E1 = __shfl_sync(0xffffffffu, ptrs, npin);
+      int bnd = __shfl_sync(0xffffffffu, ptrs, 1);               // end of pin q's range
+      for (int i = E0; i < E1; i += 8) {
+        const int idx = (i + (lane & 7) < E1) ? f_src[i + (lane & 7)] : 0;
+        float4 m[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (i + q < e) m[q] = ld4(H + (int64_t)isrc[i + q] * D + lane * 4);
+        for (int u = 0; u < 8; ++u) {
+          const int src = __shfl_sync(0xffffffffu, idx, u);
+          if (i + u < E1) m[u] = ld4(H + (int64_t)src * D + lane * 4);
+        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (i + q < e) {
-            const float mv[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
+        for (int u = 0; u < 8; ++u) {
+          if (i + u < E1) {
+            while (i + u >= bnd) { finish_pin(); bnd = __shfl_sync(0xffffffffu, ptrs, q + 1); }
+            const float mv[4] = {m[u].x, m[u].y, m[u].z, m[u].w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float nm = fmaxf(mx[c], mv[c]);
-              const float sc = expf(mx[c] - nm);      // exp(-inf) = 0 on the first edge
+              const float sc = expf(mx[c] - nm);                 // exp(-inf) = 0 on the first edge
               const float ex = expf(mv[c] - nm);
               sm[c] = sm[c] * sc + ex;
               tw[c] = tw[c] * sc + mv[c] * ex;
@@ -168,53 +249,30 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
           }
         }
       }
-      if (e > s) {
-        av = make_float4(tw[0] / sm[0], tw[1] / sm[1], tw[2] / sm[2], tw[3] / sm[3]);
-        lse = make_float4(mx[0] + logf(sm[0]), mx[1] + logf(sm[1]), mx[2] + logf(sm[2]), mx[3] + logf(sm[3]));
-      }
-      if (A) {
-        st4(A + (int64_t)(crow0 + p) * D + lane * 4, av);
-        st4(LSE + (int64_t)(crow0 + p) * D + lane * 4, lse);
-      }
+      while (q < npin) finish_pin();
     }
-    *reinterpret_cast<float4*>(&a_s[r][lane * 4]) = av;
-    if (lane == 0) v_s[r] = v;
+    for (int r = max(npin, 0); r < PPW; ++r)                     // rows past the end of the level
+      *reinterpret_cast<float4*>(&a_s[r0 + r][lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  __syncthreads();
 
-  // phase 2: hidden = relu(a @ W1t + b1)
-  {
-    const int cg = tid & 63, rg = tid >> 6;
-    float acc[4][4];
-    gemm_128x256(a_s, W1t, rg, cg, acc);
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + cg * 4));
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float4 o = f4relu(make_float4(acc[r][0] + bb.x, acc[r][1] + bb.y, acc[r][2] + bb.z, acc[r][3] + bb.w));
-      *reinterpret_cast<float4*>(&hid_s[rg * 4 + r][cg * 4]) = o;
-      const int p = t0 + rg * 4 + r;
-      if (HIDb && p < cnt) st4(HIDb + (int64_t)(crow0 + p) * HID + cg * 4, o);
+  // phases 2+3: hidden = relu(a @ W1t + b1);  h = relu(S + hidden @ W2t + b2)
+  auto epi1 = [&](int row, int col, float4 acc) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + col));
+    const float4 o = f4relu(make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w));
+    const int p = t0 + row;
+    if (HIDb && p < cnt) st4(HIDb + (int64_t)(crow0 + p) * HID + col, o);
+    return o;
+  };
+  auto epi2 = [&](int row, int col, float4 acc) {
+    const int v = v_s[row];
+    if (v >= 0) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col));
+      const float4 sv = ld4_stream(S + (int64_t)v * D + col);
+      st4(H + (int64_t)v * D + col,
+          f4relu(make_float4(acc.x + bb.x + sv.x, acc.y + bb.y + sv.y, acc.z + bb.z + sv.z, acc.w + bb.w + sv.w)));
     }
-  }
-  __syncthreads();
-
-  // phase 3: h = relu(S + hidden @ W2t + b2)
-  {
-    const int cg = tid & 31, rg = tid >> 5;
-    float acc[2][4];
-    gemm_256x128(hid_s, W2t, rg, cg, acc);
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + cg * 4));
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int v = v_s[rg * 2 + r];
-      if (v >= 0) {
-        const float4 sv = ld4_stream(S + (int64_t)v * D + cg * 4);
-        float4 o = make_float4(acc[r][0] + bb.x + sv.x, acc[r][1] + bb.y + sv.y, acc[r][2] + bb.z + sv.z,
-                               acc[r][3] + bb.w + sv.w);
-        st4(H + (int64_t)v * D + cg * 4, f4relu(o));
-      }
-    }
-  }
+  };
+  mlp_tile(a_s, hid_s, wbuf, W1t, W2t, tid, epi1, epi2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -226,46 +284,22 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
 // ---------------------------------------------------------------------------------------------
 struct SchedDev {
   const int* order;
-  const int* level;
-  const int* crow;
-  const int* net_iptr;
-  const int* net_optr;
-  const int* net_odst;
-  const int* cell_optr;
-  const int* cell_odst;
+  const int* bn_ptr;
+  const int* bn_dst;
+  const float* bn_w;
+  const int* bc_ptr;
+  const int* bc_row;
 };
 
-__device__ __forceinline__ float4 pull_gz(const SchedDev& s, int v, int lane, const float* __restrict__ H,
-                                          const float* G, const float* __restrict__ GA,
-                                          const float* __restrict__ A, const float* __restrict__ LSE) {
-  const int64_t off = (int64_t)v * D + lane * 4;
-  float4 g = ld4(G + off);
-  const float4 hv = ld4(H + off);
-  const int lv = s.level[v];
-  for (int e = s.net_optr[v], e1 = s.net_optr[v + 1]; e < e1; ++e) {
-    const int u = s.net_odst[e];
-    const int lu = s.level[u];
-    if ((lu & 1) && lu > lv) {
-      const float inv = 1.f / (float)(s.net_iptr[u + 1] - s.net_iptr[u]);
-      g = f4add(g, f4scale(ld4(G + (int64_t)u * D + lane * 4), inv));
-    }
-  }
-  for (int e = s.cell_optr[v], e1 = s.cell_optr[v + 1]; e < e1; ++e) {
-    const int u = s.cell_odst[e];
-    const int lu = s.level[u];
-    if (lu > 0 && !(lu & 1) && lu > lv) {
-      const int64_t co = (int64_t)s.crow[u] * D + lane * 4;
-      const float4 ga = ld4(GA + co), ls = ld4(LSE + co), aa = ld4(A + co);
-      g.x += ga.x * expf(hv.x - ls.x) * (1.f + hv.x - aa.x);
-      g.y += ga.y * expf(hv.y - ls.y) * (1.f + hv.y - aa.y);
-      g.z += ga.z * expf(hv.z - ls.z) * (1.f + hv.z - aa.z);
-      g.w += ga.w * expf(hv.w - ls.w) * (1.f + hv.w - aa.w);
-    }
-  }
-  return make_float4(hv.x > 0.f ? g.x : 0.f, hv.y > 0.f ? g.y : 0.f, hv.z > 0.f ? g.z : 0.f,
-                     hv.w > 0.f ? g.w : 0.f);
+__device__ __forceinline__ float4 cell_edge_grad(float4 hv, float4 ga, float4 ls, float4 aa) {
+  return make_float4(ga.x * expf(hv.x - ls.x) * (1.f + hv.x - aa.x), ga.y * expf(hv.y - ls.y) * (1.f + hv.y - aa.y),
+                     ga.z * expf(hv.z - ls.z) * (1.f + hv.z - aa.z), ga.w * expf(hv.w - ls.w) * (1.f + hv.w - aa.w));
+}
+__device__ __forceinline__ float4 relu_mask(float4 hv, float4 g) {
+  return make_float4(hv.x > 0.f ? g.x : 0.f, hv.y > 0.f ? g.y : 0.f, hv.z > 0.f ? g.z : 0.f, hv.w > 0.f ? g.w : 0.f);
 }
 
+// one warp per pin (level 0 and odd levels)
 __global__ void __launch_bounds__(256)
 gnn_net_bwd_kernel(SchedDev s, int p0, int cnt, const float* __restrict__ H, float* G,
                    const float* __restrict__ GA, const float* __restrict__ A,
@@ -273,9 +307,37 @@ gnn_net_bwd_kernel(SchedDev s, int p0, int cnt, const float* __restrict__ H, flo
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= cnt) return;
-  const int v = s.order[p0 + w];
-  const float4 gz = pull_gz(s, v, lane, H, G, GA, A, LSE);
-  st4(G + (int64_t)v * D + lane * 4, gz);
+  const int p = p0 + w;
+  const int v = s.order[p];
+  const int ns = s.bn_ptr[p], ne = s.bn_ptr[p + 1], cs = s.bc_ptr[p], ce = s.bc_ptr[p + 1];
+  const int64_t off = (int64_t)v * D + lane * 4;
+  float4 g = ld4(G + off);
+  const float4 hv = ld4(H + off);
+  for (int i = ns; i < ne; i += 4) {
+    float4 m[4];
+    float wq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      wq[q] = 0.f;
+      m[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i + q < ne) { wq[q] = s.bn_w[i + q]; m[q] = ld4(G + (int64_t)s.bn_dst[i + q] * D + lane * 4); }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g = f4add(g, f4scale(m[q], wq[q]));
+  }
+  for (int i = cs; i < ce; i += 2) {
+    float4 ga[2], ls[2], aa[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (i + q < ce) {
+        const int64_t co = (int64_t)s.bc_row[i + q] * D + lane * 4;
+        ga[q] = ld4(GA + co); ls[q] = ld4(LSE + co); aa[q] = ld4(A + co);
+      }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (i + q < ce) g = f4add(g, cell_edge_grad(hv, ga[q], ls[q], aa[q]));
+  }
+  st4(G + off, relu_mask(hv, g));
 }
 
 __global__ void __launch_bounds__(CT)
@@ -283,53 +345,120 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
                     const float* __restrict__ W1, const float* __restrict__ W2, float* GA,
                     const float* __restrict__ A, const float* __restrict__ LSE,
                     const float* __restrict__ HIDb, float* __restrict__ GHID, float* __restrict__ GZC) {
-  __shared__ __align__(16) float gz_s[TILE][D];
-  __shared__ __align__(16) float gh_s[TILE][HID];
+  extern __shared__ __align__(16) float smem[];
+  float (*gz_s)[D] = reinterpret_cast<float (*)[D]>(smem);
+  float (*gh_s)[HID] = reinterpret_cast<float (*)[HID]>(smem + TILE * D);
+  float* wbuf = smem + TILE * D + TILE * HID;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * TILE;
-#pragma unroll
-  for (int rr = 0; rr < TILE / (CT / 32); ++rr) {
-    const int r = warp * (TILE / (CT / 32)) + rr;
-    const int p = t0 + r;
-    float4 gz = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p < cnt) {
-      const int v = s.order[p0 + p];
-      gz = pull_gz(s, v, lane, H, G, GA, A, LSE);
-      st4(G + (int64_t)v * D + lane * 4, gz);
-      st4(GZC + (int64_t)(crow0 + p) * D + lane * 4, gz);
+  // g_hid = (g_z @ W2) * (hid > 0): W2 is [128][256] as stored by nn.Linear(256,128)  -> "Wa"
+  // g_a   =  g_hid @ W1:            W1 is [256][128] as stored by nn.Linear(128,256)  -> "Wb"
+  mlp_prologue(wbuf, W2, W1, tid);
+
+  // phase 1: each warp pulls the gradient of PPW consecutive pins.  gz_s accumulates, the first
+  // 128 columns of gh_s hold the pins' own h rows until the MLP overwrites them.
+  constexpr int PPW = TILE / (CT / 32);
+  {
+    const int r0 = warp * PPW;
+    const int npin = min(PPW, cnt - (t0 + r0));
+    const int pb = p0 + t0 + r0;
+    int nptr = 0, cptr = 0, vv = 0;
+    if (npin > 0) {
+      if (lane <= npin) { nptr = s.bn_ptr[pb + lane]; cptr = s.bc_ptr[pb + lane]; }
+      if (lane < npin) vv = s.order[pb + lane];
     }
-    *reinterpret_cast<float4*>(&gz_s[r][lane * 4]) = gz;
-  }
-  __syncthreads();
-  {  // g_hid = (g_z @ W2) * (hid > 0);  W2 is [128][256] as stored by nn.Linear(256,128)
-    const int cg = tid & 63, rg = tid >> 6;
-    float acc[4][4];
-    gemm_128x256(gz_s, W2, rg, cg, acc);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int p = t0 + rg * 4 + r;
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p < cnt) {
-        const float4 hd = ld4(HIDb + (int64_t)(crow0 + p) * HID + cg * 4);
-        o = make_float4(hd.x > 0.f ? acc[r][0] : 0.f, hd.y > 0.f ? acc[r][1] : 0.f,
-                        hd.z > 0.f ? acc[r][2] : 0.f, hd.w > 0.f ? acc[r][3] : 0.f);
-        st4(GHID + (int64_t)(crow0 + p) * HID + cg * 4, o);
+    for (int r = 0; r < PPW; ++r) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f), hv = g;
+      if (r < npin) {
+        const int64_t off = (int64_t)__shfl_sync(0xffffffffu, vv, r) * D + lane * 4;
+        g = ld4(G + off);
+        hv = ld4(H + off);
       }
-      *reinterpret_cast<float4*>(&gh_s[rg * 4 + r][cg * 4]) = o;
+      *reinterpret_cast<float4*>(&gz_s[r0 + r][lane * 4]) = g;
+      *reinterpret_cast<float4*>(&gh_s[r0 + r][lane * 4]) = hv;
     }
-  }
-  __syncthreads();
-  {  // g_a = g_hid @ W1;  W1 is [256][128] as stored by nn.Linear(128,256)
-    const int cg = tid & 31, rg = tid >> 5;
-    float acc[2][4];
-    gemm_256x128(gh_s, W1, rg, cg, acc);
+    if (npin > 0) {
+      {  // net out-edges: one contiguous range for the warp's pins
+        const int E0 = __shfl_sync(0xffffffffu, nptr, 0), E1 = __shfl_sync(0xffffffffu, nptr, npin);
+        int q = 0, bnd = __shfl_sync(0xffffffffu, nptr, 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto flush = [&]() {
+          float4* dst = reinterpret_cast<float4*>(&gz_s[r0 + q][lane * 4]);
+          *dst = f4add(*dst, acc);
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          ++q;
+        };
+        for (int i = E0; i < E1; i += 8) {
+          const bool ok = i + (lane & 7) < E1;
+          const int idx = ok ? s.bn_dst[i + (lane & 7)] : 0;
+          const float wt = ok ? s.bn_w[i + (lane & 7)] : 0.f;
+          float4 m[8];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int p = t0 + rg * 2 + r;
-      if (p < cnt)
-        st4(GA + (int64_t)(crow0 + p) * D + cg * 4, make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+          for (int u = 0; u < 8; ++u) {
+            const int dst = __shfl_sync(0xffffffffu, idx, u);
+            if (i + u < E1) m[u] = ld4(G + (int64_t)dst * D + lane * 4);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float wu = __shfl_sync(0xffffffffu, wt, u);
+            if (i + u < E1) {
+              while (i + u >= bnd) { flush(); bnd = __shfl_sync(0xffffffffu, nptr, q + 1); }
+              acc = f4add(acc, f4scale(m[u], wu));
+            }
+          }
+        }
+        if (q < npin) flush();
+      }
+      {  // cell out-edges (rare on cell levels)
+        const int E0 = __shfl_sync(0xffffffffu, cptr, 0), E1 = __shfl_sync(0xffffffffu, cptr, npin);
+        int q = 0, bnd = __shfl_sync(0xffffffffu, cptr, 1);
+        for (int i = E0; i < E1; ++i) {
+          while (i >= bnd) { ++q; bnd = __shfl_sync(0xffffffffu, cptr, q + 1); }
+          const int64_t co = (int64_t)s.bc_row[i] * D + lane * 4;
+          const float4 hv = *reinterpret_cast<const float4*>(&gh_s[r0 + q][lane * 4]);
+          float4* dst = reinterpret_cast<float4*>(&gz_s[r0 + q][lane * 4]);
+          *dst = f4add(*dst, cell_edge_grad(hv, ld4(GA + co), ld4(LSE + co), ld4(A + co)));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < PPW; ++r) {
+      if (r < npin) {
+        const float4 hv = *reinterpret_cast<const float4*>(&gh_s[r0 + r][lane * 4]);
+        const float4 gz = relu_mask(hv, *reinterpret_cast<const float4*>(&gz_s[r0 + r][lane * 4]));
+        *reinterpret_cast<float4*>(&gz_s[r0 + r][lane * 4]) = gz;
+        st4(G + (int64_t)__shfl_sync(0xffffffffu, vv, r) * D + lane * 4, gz);
+        st4(GZC + (int64_t)(crow0 + t0 + r0 + r) * D + lane * 4, gz);
+      }
     }
   }
+  auto epi1 = [&](int row, int col, float4 acc) {
+    const int p = t0 + row;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p < cnt) {
+      const float4 hd = ld4(HIDb + (int64_t)(crow0 + p) * HID + col);
+      o = make_float4(hd.x > 0.f ? acc.x : 0.f, hd.y > 0.f ? acc.y : 0.f, hd.z > 0.f ? acc.z : 0.f,
+                      hd.w > 0.f ? acc.w : 0.f);
+      st4(GHID + (int64_t)(crow0 + p) * HID + col, o);
+    }
+    return o;
+  };
+  auto epi2 = [&](int row, int col, float4 acc) {
+    const int p = t0 + row;
+    if (p < cnt) st4(GA + (int64_t)(crow0 + p) * D + col, acc);
+  };
+  mlp_tile(gz_s, gh_s, wbuf, W2, W1, tid, epi1, epi2);
+}
+
+int cell_smem_optin() {
+  static bool done = false;   // per process; the attribute is per function and device
+  if (!done) {
+    TM_CUDA(cudaFuncSetAttribute(gnn_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
+    TM_CUDA(cudaFuncSetAttribute(gnn_cell_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
+    done = true;
+  }
+  return 0;
 }
 
 int cell_base_of(const tm_schedule* s, int level) {
@@ -342,23 +471,23 @@ int cell_base_of(const tm_schedule* s, int level) {
 extern "C" int tm_gnn_forward(const tm_schedule* s, int32_t lb, int32_t le, float* H, const float* S,
                               const float* W1t, const float* b1, const float* W2t, const float* b2,
                               float* A, float* LSE, float* HIDb, void* stream) {
+  TM_REQUIRE(s && s->f_ptr && s->f_src, "tm_gnn_forward: schedule lacks the level-ordered edge lists");
   TM_REQUIRE(s && s->h_level_ptr && lb >= 0 && le <= s->num_levels && lb <= le, "tm_gnn_forward: bad level range");
   TM_REQUIRE((A == nullptr) == (LSE == nullptr) && (A == nullptr) == (HIDb == nullptr),
              "tm_gnn_forward: A, LSE, HID must be all set or all NULL");
   cudaStream_t st = (cudaStream_t)stream;
+  TM_TRY(cell_smem_optin());
   int crow0 = cell_base_of(s, lb + (lb & 1));
   for (int l = lb; l < le; ++l) {
     const int p0 = s->h_level_ptr[l], cnt = s->h_level_ptr[l + 1] - p0;
     const bool cell = (l > 0) && !(l & 1);
     if (cnt > 0) {
       if (!cell) {
-        gnn_net_fwd_kernel<<<(unsigned)cdiv(cnt, 8), 256, 0, st>>>(s->order, p0, cnt, s->net_iptr, s->net_isrc,
-                                                                  S, H, l == 0);
+        gnn_net_fwd_kernel<<<(unsigned)cdiv(cnt, 8), 256, 0, st>>>(s->order, p0, cnt, s->f_ptr, s->f_src, S, H);
         TM_TRY(check_launch("gnn_net_fwd"));
       } else {
-        gnn_cell_fwd_kernel<<<(unsigned)cdiv(cnt, TILE), CT, 0, st>>>(s->order, p0, cnt, crow0, s->cell_iptr,
-                                                                     s->cell_isrc, S, H, W1t, b1, W2t, b2, A,
-                                                                     LSE, HIDb);
+        gnn_cell_fwd_kernel<<<(unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st>>>(s->order, p0, cnt, crow0, s->f_ptr, s->f_src, S,
+                                                                             H, W1t, b1, W2t, b2, A, LSE, HIDb);
         TM_TRY(check_launch("gnn_cell_fwd"));
       }
     }
@@ -370,9 +499,10 @@ extern "C" int tm_gnn_forward(const tm_schedule* s, int32_t lb, int32_t le, floa
 extern "C" int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, const float* W1,
                                const float* W2, const float* A, const float* LSE, const float* HIDb,
                                float* GA, float* GHID, float* GZC, void* stream) {
-  TM_REQUIRE(s && s->h_level_ptr, "tm_gnn_backward: bad schedule");
+  TM_REQUIRE(s && s->h_level_ptr && s->bn_ptr && s->bc_ptr, "tm_gnn_backward: bad schedule");
   cudaStream_t st = (cudaStream_t)stream;
-  SchedDev d{s->order, s->level, s->crow, s->net_iptr, s->net_optr, s->net_odst, s->cell_optr, s->cell_odst};
+  TM_TRY(cell_smem_optin());
+  SchedDev d{s->order, s->bn_ptr, s->bn_dst, s->bn_w, s->bc_ptr, s->bc_row};
   int crow_end = cell_base_of(s, s->num_levels + (s->num_levels & 1));  // total cell rows
   for (int l = s->num_levels - 1; l >= 0; --l) {
     const int p0 = s->h_level_ptr[l], cnt = s->h_level_ptr[l + 1] - p0;
@@ -383,7 +513,7 @@ extern "C" int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, c
       gnn_net_bwd_kernel<<<(unsigned)cdiv(cnt, 8), 256, 0, st>>>(d, p0, cnt, H, G, GA, A, LSE);
       TM_TRY(check_launch("gnn_net_bwd"));
     } else {
-      gnn_cell_bwd_kernel<<<(unsigned)cdiv(cnt, TILE), CT, 0, st>>>(d, p0, cnt, crow_end, H, G, W1, W2, GA, A,
+      gnn_cell_bwd_kernel<<<(unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st>>>(d, p0, cnt, crow_end, H, G, W1, W2, GA, A,
                                                                    LSE, HIDb, GHID, GZC);
       TM_TRY(check_launch("gnn_cell_bwd"));
     }

@@ -441,3 +441,88 @@ extern "C" int tm_schedule_aux(int64_t n, int32_t L, const int32_t* level, const
                                                      net_isrc, cell_iptr, cell_isrc, crow, n_violations);
   return check_launch("sched_aux");
 }
+
+// ------------------------------------------------------------------------------------------
+// level-ordered edge lists: the gather structures of the propagation kernels.
+// For schedule position p (pin v = order[p], level l):
+//   forward   f_ptr/f_src : sources of the in-edges pulled on v's level (net if l odd, cell if
+//                           l even > 0, none on level 0);
+//   backward  bn_ptr/bn_dst/bn_w : net out-edges v->u that carry gradient (u on a later odd
+//                           level) with weight 1/indeg_net(u);
+//             bc_ptr/bc_row : cell out-edges v->u that carry gradient (u on a later even level),
+//                           stored as the compact row crow[u].
+// Positions are contiguous per level, so a warp that owns consecutive pins reads one contiguous
+// edge range: the dependent-load chain of a gather is ptr -> src -> row (3 deep).
+// ------------------------------------------------------------------------------------------
+namespace {
+struct EdgeIn {
+  const int* order; const int* level; const int* crow;
+  const int* net_iptr; const int* net_isrc; const int* cell_iptr; const int* cell_isrc;
+  const int* net_optr; const int* net_odst; const int* cell_optr; const int* cell_odst;
+};
+
+__global__ void sched_edges_count_kernel(EdgeIn g, int64_t n_sched, int* __restrict__ cf,
+                                         int* __restrict__ cbn, int* __restrict__ cbc) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > n_sched) return;
+  if (p == n_sched) { cf[p] = 0; cbn[p] = 0; cbc[p] = 0; return; }
+  const int v = g.order[p], l = g.level[v];
+  cf[p] = (l & 1) ? g.net_iptr[v + 1] - g.net_iptr[v] : (l > 0 ? g.cell_iptr[v + 1] - g.cell_iptr[v] : 0);
+  int a = 0, b = 0;
+  for (int e = g.net_optr[v]; e < g.net_optr[v + 1]; ++e) { const int lu = g.level[g.net_odst[e]]; a += ((lu & 1) && lu > l); }
+  for (int e = g.cell_optr[v]; e < g.cell_optr[v + 1]; ++e) { const int lu = g.level[g.cell_odst[e]]; b += (lu > 0 && !(lu & 1) && lu > l); }
+  cbn[p] = a;
+  cbc[p] = b;
+}
+
+__global__ void sched_edges_fill_kernel(EdgeIn g, int64_t n_sched, const int* __restrict__ f_ptr,
+                                        int* __restrict__ f_src, const int* __restrict__ bn_ptr,
+                                        int* __restrict__ bn_dst, float* __restrict__ bn_w,
+                                        const int* __restrict__ bc_ptr, int* __restrict__ bc_row) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sched) return;
+  const int v = g.order[p], l = g.level[v];
+  int o = f_ptr[p];
+  if (l & 1) { for (int e = g.net_iptr[v]; e < g.net_iptr[v + 1]; ++e) f_src[o++] = g.net_isrc[e]; }
+  else if (l > 0) { for (int e = g.cell_iptr[v]; e < g.cell_iptr[v + 1]; ++e) f_src[o++] = g.cell_isrc[e]; }
+  o = bn_ptr[p];
+  for (int e = g.net_optr[v]; e < g.net_optr[v + 1]; ++e) {
+    const int u = g.net_odst[e], lu = g.level[u];
+    if ((lu & 1) && lu > l) { bn_dst[o] = u; bn_w[o] = 1.f / (float)(g.net_iptr[u + 1] - g.net_iptr[u]); ++o; }
+  }
+  o = bc_ptr[p];
+  for (int e = g.cell_optr[v]; e < g.cell_optr[v + 1]; ++e) {
+    const int u = g.cell_odst[e], lu = g.level[u];
+    if (lu > 0 && !(lu & 1) && lu > l) bc_row[o++] = g.crow[u];
+  }
+}
+}  // namespace
+
+extern "C" size_t tm_schedule_edges_ws(int64_t n_sched) {
+  return (size_t)(3 * (n_sched + 1) + 3 * (int64_t)scan_ws_ints(n_sched + 1)) * sizeof(int) + 8 * 256;
+}
+
+extern "C" int tm_schedule_edges(const tm_schedule* s, int64_t n_sched, int32_t* f_ptr, int32_t* f_src,
+                                 int32_t* bn_ptr, int32_t* bn_dst, float* bn_w, int32_t* bc_ptr,
+                                 int32_t* bc_row, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(s && n_sched > 0, "tm_schedule_edges: bad schedule");
+  TM_REQUIRE(ws_bytes >= tm_schedule_edges_ws(n_sched), "tm_schedule_edges: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(ws);
+  int* cf = c.take<int>(n_sched + 1);
+  int* cbn = c.take<int>(n_sched + 1);
+  int* cbc = c.take<int>(n_sched + 1);
+  int* b0 = c.take<int>(scan_ws_ints(n_sched + 1));
+  int* b1 = c.take<int>(scan_ws_ints(n_sched + 1));
+  int* b2 = c.take<int>(scan_ws_ints(n_sched + 1));
+  EdgeIn g{s->order, s->level, s->crow, s->net_iptr, s->net_isrc, s->cell_iptr, s->cell_isrc,
+           s->net_optr, s->net_odst, s->cell_optr, s->cell_odst};
+  const unsigned blocks = (unsigned)cdiv(n_sched + 1, 256);
+  sched_edges_count_kernel<<<blocks, 256, 0, st>>>(g, n_sched, cf, cbn, cbc);
+  TM_TRY(check_launch("sched_edges_count"));
+  TM_TRY(exclusive_scan(cf, f_ptr, n_sched + 1, b0, 0, 0, 0, st));
+  TM_TRY(exclusive_scan(cbn, bn_ptr, n_sched + 1, b1, 0, 0, 0, st));
+  TM_TRY(exclusive_scan(cbc, bc_ptr, n_sched + 1, b2, 0, 0, 0, st));
+  sched_edges_fill_kernel<<<blocks, 256, 0, st>>>(g, n_sched, f_ptr, f_src, bn_ptr, bn_dst, bn_w, bc_ptr, bc_row);
+  return check_launch("sched_edges_fill");
+}

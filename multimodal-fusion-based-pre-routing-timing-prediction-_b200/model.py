@@ -114,7 +114,9 @@ class PathConv(nn.Module):
                                       "(the only configuration the reference constructs, train.py:56-63)")
         g = as_timing_graph(graph)
         sched = g.schedule()
-        H = tm_ops.GnnPropagateFn.apply(sched, g.ndata['cell_feat'], g.ndata['net_feat'], *self._params())
+        params = self._params()
+        need = th.is_grad_enabled() and any(p.requires_grad for p in params)
+        H = tm_ops.GnnPropagateFn.apply(sched, g.ndata['cell_feat'], g.ndata['net_feat'], need, *params)
         self._prop = (g, sched, H)
         g.ndata['h'] = H                                          # what model.py:208 leaves behind
         return H
@@ -151,7 +153,9 @@ class LayoutNet(nn.Module):
             nn.Conv2d(32, 1, 7, 1, 3), nn.LeakyReLU(negative_slope=0.1))
 
     def forward(self, x):
-        return tm_unet.LayoutNetFn.apply(self, x, *self.parameters())
+        params = list(self.parameters())
+        need = th.is_grad_enabled() and any(p.requires_grad for p in params)
+        return tm_unet.LayoutNetFn.apply(self, x, need, *params)
 
 
 class PathModel(nn.Module):

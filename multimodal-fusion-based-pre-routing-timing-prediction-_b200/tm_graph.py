@@ -207,6 +207,22 @@ class Schedule:
             cell_iptr=s.cell_iptr.data_ptr(), cell_isrc=s.cell_isrc.data_ptr(),
             net_optr=s.net_optr.data_ptr(), net_odst=s.net_odst.data_ptr(),
             cell_optr=s.cell_optr.data_ptr(), cell_odst=s.cell_odst.data_ptr())
+        # level-ordered edge lists: what the propagation kernels actually walk
+        e_net, e_cell = int(s.net_isrc.numel()), int(s.cell_isrc.numel())
+        ns1 = s.n_sched + 1
+        s.f_ptr = torch.empty(ns1, dtype=torch.int32, device=dev)
+        s.f_src = torch.empty(max(e_net + e_cell, 1), dtype=torch.int32, device=dev)
+        s.bn_ptr = torch.empty(ns1, dtype=torch.int32, device=dev)
+        s.bn_dst = torch.empty(max(e_net, 1), dtype=torch.int32, device=dev)
+        s.bn_w = torch.empty(max(e_net, 1), dtype=torch.float32, device=dev)
+        s.bc_ptr = torch.empty(ns1, dtype=torch.int32, device=dev)
+        s.bc_row = torch.empty(max(e_cell, 1), dtype=torch.int32, device=dev)
+        nb = tm_lib.ws_bytes("tm_schedule_edges_ws", s.n_sched)
+        ws = tm_lib.workspace(nb, dev)
+        tm_lib.call("tm_schedule_edges", s.struct, s.n_sched, s.f_ptr, s.f_src, s.bn_ptr, s.bn_dst, s.bn_w,
+                    s.bc_ptr, s.bc_row, ws, nb, st)
+        for k in ("f_ptr", "f_src", "bn_ptr", "bn_dst", "bn_w", "bc_ptr", "bc_row"):
+            setattr(s.struct, k, getattr(s, k).data_ptr())
         return s
 
     def level_nodes(self, lid):

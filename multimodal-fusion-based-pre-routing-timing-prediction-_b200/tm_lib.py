@@ -26,7 +26,10 @@ class tm_schedule(ctypes.Structure):
                 ("crow", ctypes.c_void_p), ("net_iptr", ctypes.c_void_p), ("net_isrc", ctypes.c_void_p),
                 ("cell_iptr", ctypes.c_void_p), ("cell_isrc", ctypes.c_void_p),
                 ("net_optr", ctypes.c_void_p), ("net_odst", ctypes.c_void_p),
-                ("cell_optr", ctypes.c_void_p), ("cell_odst", ctypes.c_void_p)]
+                ("cell_optr", ctypes.c_void_p), ("cell_odst", ctypes.c_void_p),
+                ("f_ptr", ctypes.c_void_p), ("f_src", ctypes.c_void_p),
+                ("bn_ptr", ctypes.c_void_p), ("bn_dst", ctypes.c_void_p), ("bn_w", ctypes.c_void_p),
+                ("bc_ptr", ctypes.c_void_p), ("bc_row", ctypes.c_void_p)]
 
 
 def parse_header(path=HEADER_PATH):

@@ -184,8 +184,7 @@ class GnnPropagateFn(torch.autograd.Function):
     """H = propagate(cell_feat, net_feat; 12 PathConv parameters) over a fixed Schedule."""
 
     @staticmethod
-    def forward(ctx, sched, cell_feat, net_feat, *params):
-        need = any(p.requires_grad for p in params)
+    def forward(ctx, sched, cell_feat, net_feat, need, *params):
         H, saved = gnn_forward(sched, cell_feat, net_feat, [p.detach() for p in params], save=need)
         ctx.sched, ctx.saved = sched, saved
         ctx.params = [p.detach() for p in params]
@@ -195,7 +194,7 @@ class GnnPropagateFn(torch.autograd.Function):
     def backward(ctx, gH):
         G = gH.contiguous().clone()                      # consumed in place by the sweep
         grads = gnn_backward(ctx.sched, ctx.saved, ctx.params, G)
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 # --------------------------------------------------------------------------------------------

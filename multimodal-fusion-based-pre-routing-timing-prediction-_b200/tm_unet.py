@@ -254,8 +254,8 @@ def unet_param_names(net):
 
 class UNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, net, x, *params):
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, net, x, need, *params):
+        # `need` is decided by the caller: grad mode is always off inside Function.forward
         out, st = unet_forward(net, x, need_bwd=need, update_stats=net.training)
         ctx.net, ctx.st = net, st
         ctx.names = unet_param_names(net)
@@ -264,7 +264,7 @@ class UNetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         grads = unet_backward(ctx.net, ctx.st, gout)
-        return (None, None) + tuple(grads[k] for k in ctx.names)
+        return (None, None, None) + tuple(grads[k] for k in ctx.names)
 
 
 # --------------------------------------------------------------------------------------------
@@ -346,8 +346,7 @@ def layoutnet_backward(net, st, gout):
 
 class LayoutNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, net, x, *params):
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, net, x, need, *params):
         out, st = layoutnet_forward(net, x, need_bwd=need)
         ctx.net, ctx.st = net, st
         ctx.names = [k for k, _ in net.named_parameters()]
@@ -356,4 +355,4 @@ class LayoutNetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         grads = layoutnet_backward(ctx.net, ctx.st, gout)
-        return (None, None) + tuple(grads[k] for k in ctx.names)
+        return (None, None, None) + tuple(grads[k] for k in ctx.names)
