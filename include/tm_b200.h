@@ -187,9 +187,10 @@ int tm_gather_cols(int64_t T, int64_t w, const float* src, int64_t lds, const in
 /* dst[rows[i], 0:w] += src[i, col0:col0+w]  (atomic: rows may repeat) */
 int tm_scatter_add_cols(int64_t T, int64_t w, const float* src, int64_t lds, int64_t col0,
                         const int32_t* rows, float* dst, int64_t ldd, void* stream);
-/* out[c] (+)= sum_r X[r,c]  (bias gradients; fixed reduction order) */
-int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, float* out, int accumulate,
-              void* stream);
+/* out[c] (+)= sum_r X[rows ? rows[r] : r, c]  (bias gradients; fixed reduction order) */
+size_t tm_colsum_ws(int64_t R, int64_t C);
+int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, const int32_t* rows, float* out,
+              int accumulate, void* ws, size_t ws_bytes, void* stream);
 /* loss[0] = mean((pred-y)^2); grad[i] = 2*(pred[i]-y[i])/T * grad_scale  (nn.MSELoss) */
 int tm_mse(int64_t T, const float* pred, const float* y, float* loss, float* grad,
            float grad_scale, void* stream);
@@ -276,6 +277,32 @@ int tm_leaky_relu_forward(int64_t n, const float* x, float slope, float* y, void
 /* dst[i*ldd + c] += src[i*lds + c]  for c < C  (adds a gradient living in a strided buffer) */
 int tm_add_strided(int64_t npix, int64_t C, const float* src, int64_t lds, float* dst, int64_t ldd,
                    void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Tensor-core variants (tcgen05.mma kind::f16, accumulator in TMEM) of the dense contractions.
+ * Same meaning as tm_gemm_nn / tm_gemm_tn / tm_conv2d_nhwc / tm_conv2d_wgrad_nhwc above.
+ *   precision 0: operands rounded to bf16 (fp32 accumulate)            -- rtol 2e-2 class
+ *   precision 1: operands split into two bf16 terms, three MMAs        -- ~16-bit products
+ *   precision 2: operands split into three bf16 terms (24 bits), six MMAs -- fp32-class (rtol 1e-3 path)
+ *   err: optional device int32, set to 1 if a tensor-core barrier timed out (never expected).
+ * tm_tc_gemm_nn: b_is_nk != 0 means B is given as [N,K] row-major (an nn.Linear weight as
+ * stored), otherwise [K,N] row-major like tm_gemm_nn.
+ * ---------------------------------------------------------------------------------- */
+int tm_tc_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const int32_t* a_rows,
+                  const float* B, int64_t ldb, int b_is_nk, float* C, int64_t ldc,
+                  const int32_t* c_rows, const float* bias, const float* mask, int64_t ldmask,
+                  int flags, int precision, int* err, void* stream);
+size_t tm_tc_gemm_tn_ws(int64_t M, int64_t N, int64_t R);
+int tm_tc_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, int64_t lda, const int32_t* a_rows,
+                  const float* B, int64_t ldb, const int32_t* b_rows, float* C, int64_t ldc,
+                  int accumulate, int precision, void* ws, size_t ws_bytes, int* err, void* stream);
+int tm_tc_conv2d_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k,
+                      const float* x, int64_t ldx, const float* wf, const float* bias, float* y,
+                      int64_t ldy, int flags, int precision, int* err, void* stream);
+size_t tm_tc_conv2d_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k);
+int tm_tc_conv2d_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k,
+                            const float* x, int64_t ldx, const float* dy, int64_t lddy, float* dwf,
+                            int precision, void* ws, size_t ws_bytes, int* err, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * N4  fused Adam (torch.optim.Adam defaults, src/train.py:431-435,555)

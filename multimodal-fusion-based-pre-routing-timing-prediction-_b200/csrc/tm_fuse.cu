@@ -111,21 +111,33 @@ __global__ void scatter_add_cols_kernel(int64_t T, int64_t w, const float* __res
   atomicAdd(&dst[r * ldd + c], src[t * lds + col0 + c]);   // rows may repeat (oversampled paths)
 }
 
-// out[c] (+)= sum_r X[r][c]; one block owns 32 columns, rows reduced in a fixed order
+// out[c] (+)= sum_r X[rows ? rows[r] : r][c]: grid = (column groups of 32, row chunks); partial sums
+// per chunk, then a fixed-order second pass (deterministic).
+constexpr int CS_ROWS = 2048;   // rows per chunk
 __global__ void __launch_bounds__(256)
-colsum_kernel(int64_t R, int64_t C, const float* __restrict__ X, int64_t ld, float* __restrict__ out,
-              int accumulate) {
-  __shared__ float part[8][33];
+colsum_partial_kernel(int64_t R, int64_t C, const float* __restrict__ X, int64_t ld, const int* __restrict__ rows,
+                      float* __restrict__ part) {
+  __shared__ float sm[8][33];
   const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
+  const int64_t r1 = (r0 + CS_ROWS < R) ? r0 + CS_ROWS : R;
   float s = 0.f;
   if (c < C)
-    for (int64_t r = threadIdx.y; r < R; r += 8) s += X[r * ld + c];
-  part[threadIdx.y][threadIdx.x] = s;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += X[(rows ? (int64_t)rows[r] : r) * ld + c];
+  sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) s += part[i][threadIdx.x];
-    out[c] = accumulate ? out[c] + s : s;
+    for (int i = 1; i < 8; ++i) s += sm[i][threadIdx.x];
+    part[(int64_t)blockIdx.y * C + c] = s;
   }
+}
+__global__ void colsum_final_kernel(int64_t C, int nchunk, const float* __restrict__ part, float* __restrict__ out,
+                                    int accumulate) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int i = 0; i < nchunk; ++i) s += part[(int64_t)i * C + c];
+  out[c] = accumulate ? out[c] + s : s;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -199,11 +211,18 @@ extern "C" int tm_scatter_add_cols(int64_t T, int64_t w, const float* src, int64
   return check_launch("scatter_add_cols");
 }
 
-extern "C" int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, float* out, int accumulate,
-                         void* stream) {
+extern "C" size_t tm_colsum_ws(int64_t R, int64_t C) { return (size_t)cdiv(R > 0 ? R : 1, CS_ROWS) * C * sizeof(float) + 256; }
+
+extern "C" int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, const int32_t* rows, float* out,
+                         int accumulate, void* ws, size_t ws_bytes, void* stream) {
   if (C <= 0) return 0;
-  colsum_kernel<<<(unsigned)cdiv(C, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(R, C, X, ld, out, accumulate);
-  return check_launch("colsum");
+  TM_REQUIRE(ws_bytes >= tm_colsum_ws(R, C), "tm_colsum: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunk = (int)cdiv(R > 0 ? R : 1, CS_ROWS);
+  colsum_partial_kernel<<<dim3((unsigned)cdiv(C, 32), (unsigned)nchunk), dim3(32, 8), 0, st>>>(R, C, X, ld, rows, (float*)ws);
+  TM_TRY(check_launch("colsum_partial"));
+  colsum_final_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(C, nchunk, (const float*)ws, out, accumulate);
+  return check_launch("colsum_final");
 }
 
 extern "C" int tm_mse(int64_t T, const float* pred, const float* y, float* loss, float* grad,

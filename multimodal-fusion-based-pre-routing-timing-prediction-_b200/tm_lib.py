@@ -107,6 +107,24 @@ def workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+_err_flags = {}
+
+
+def err_flag(device):
+    """Per-device int32 the tensor-core kernels set to 1 if one of their barriers ever timed out."""
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _err_flags:
+        _err_flags[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _err_flags[key]
+
+
+def check_err_flags():
+    for key, t in _err_flags.items():
+        if int(t.item()) != 0:
+            raise RuntimeError(f"tensor-core barrier timeout reported on {key}")
+
+
 def launch_count():
     return int(lib().tm_launch_count())
 

@@ -13,6 +13,8 @@ Two layers:
 Reference semantics: src/model.py:10-24 (MLP), :88-116,:138-213 (PathConv), :269-292 (PathModel),
 src/train.py:500-501 (mask fusion).
 """
+import os
+
 import torch
 
 import tm_lib
@@ -20,6 +22,27 @@ from tm_lib import call, stream
 
 D = 128
 BIAS, RELU, MASK, ACCUM = 1, 2, 4, 8
+
+# Arithmetic of the dense contractions (MLPs, weight gradients):
+#   "tc6"  tcgen05 tensor cores, operands split into three bf16 terms (24 bits), 6 MMAs, fp32
+#          accumulate in TMEM -- fp32-class accuracy, the default for the rtol 1e-3 path;
+#   "tc3"  two bf16 terms, 3 MMAs (~16-bit products);
+#   "bf16" tcgen05 with plain bf16 operands (rtol 2e-2 class);
+#   "fp32" the CUDA-core FFMA kernels (tm_gemm_nn / tm_gemm_tn).
+MATH = os.environ.get("TM_MATH", "tc6")
+TC_MIN_K = 16          # contractions shorter than this stay on the CUDA-core kernel (K = 1, 2: pure bandwidth)
+
+
+def _precision(math=None):
+    m = math or MATH
+    if m not in ("tc6", "tc3", "bf16", "fp32"):
+        raise ValueError(f"unknown math mode {m!r}")
+    return {"tc6": 2, "tc3": 1, "bf16": 0, "fp32": None}[m]
+
+
+def _colsum(R, C, X, ld, rows, out, accumulate):
+    nb = tm_lib.ws_bytes("tm_colsum_ws", R, C)
+    call("tm_colsum", R, C, X, ld, rows, out, accumulate, tm_lib.workspace(nb, out.device), nb, stream())
 
 
 def _f32c(t):
@@ -38,20 +61,41 @@ def _rowmajor(t):
 # --------------------------------------------------------------------------------------------
 # thin wrappers
 # --------------------------------------------------------------------------------------------
-def gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, a_rows=None, c_rows=None, bias=None, mask=None, ldmask=0, flags=0):
+def gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, a_rows=None, c_rows=None, bias=None, mask=None, ldmask=0, flags=0,
+            b_is_nk=False, math=None):
+    """C = epi(A @ B).  B is [K,N] row-major, or [N,K] (an nn.Linear weight as stored) with b_is_nk."""
     if bias is not None:
         flags |= BIAS
     if mask is not None:
         flags |= MASK
-    call("tm_gemm_nn", M, N, K, A, lda, a_rows, B, ldb, C, ldc, c_rows, bias, mask, ldmask, flags, stream())
+    prec = _precision(math)
+    if prec is None or K < TC_MIN_K:
+        if b_is_nk:
+            B, ldb = transpose(B[:, :K] if B.shape[1] != K else B), N
+        call("tm_gemm_nn", M, N, K, A, lda, a_rows, B, ldb, C, ldc, c_rows, bias, mask, ldmask, flags, stream())
+    else:
+        call("tm_tc_gemm_nn", M, N, K, A, lda, a_rows, B, ldb, 1 if b_is_nk else 0, C, ldc, c_rows, bias, mask,
+             ldmask, flags, prec, tm_lib.err_flag(C.device), stream())
 
 
 def gemm_tn(M, N, R, A, lda, B, ldb, C, ldc, a_rows=None, b_rows=None, colsum_a=None, colsum_b=None,
-            accumulate=0):
-    nb = tm_lib.ws_bytes("tm_gemm_tn_ws", M, N, R)
+            accumulate=0, math=None):
+    """C (+)= A^T @ B over the R rows; optional column sums of A / B (bias gradients)."""
+    prec = _precision(math)
+    if prec is None or (M < TC_MIN_K and N < TC_MIN_K):
+        nb = tm_lib.ws_bytes("tm_gemm_tn_ws", M, N, R)
+        ws = tm_lib.workspace(nb, C.device)
+        call("tm_gemm_tn", M, N, R, A, lda, a_rows, B, ldb, b_rows, C, ldc, colsum_a, colsum_b, accumulate,
+             ws, nb, stream())
+        return
+    nb = tm_lib.ws_bytes("tm_tc_gemm_tn_ws", M, N, R)
     ws = tm_lib.workspace(nb, C.device)
-    call("tm_gemm_tn", M, N, R, A, lda, a_rows, B, ldb, b_rows, C, ldc, colsum_a, colsum_b, accumulate,
-         ws, nb, stream())
+    call("tm_tc_gemm_tn", M, N, R, A, lda, a_rows, B, ldb, b_rows, C, ldc, accumulate, prec, ws, nb,
+         tm_lib.err_flag(C.device), stream())
+    if colsum_a is not None:
+        _colsum(R, M, A, lda, a_rows, colsum_a, accumulate)
+    if colsum_b is not None:
+        _colsum(R, N, B, ldb, b_rows, colsum_b, accumulate)
 
 
 def transpose(w):
@@ -65,7 +109,7 @@ def transpose(w):
 def colsum(X, R, C, ld, out=None, accumulate=0):
     if out is None:
         out = torch.empty(C, dtype=torch.float32, device=X.device)
-    call("tm_colsum", R, C, X, ld, out, accumulate, stream())
+    _colsum(R, C, X, ld, None, out, accumulate)
     return out
 
 
@@ -77,10 +121,9 @@ def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None):
     Returns the hidden activations (n_rows, hid) needed by ``mlp2_backward``."""
     hid, kin = w1.shape
     nout = w2.shape[0]
-    w1t, w2t = transpose(w1), transpose(w2)
     h = torch.empty(n_rows, hid, dtype=torch.float32, device=out.device)
-    gemm_nn(n_rows, hid, kin, x, ldx, w1t, hid, h, hid, a_rows=rows, bias=b1, flags=RELU)
-    gemm_nn(n_rows, nout, hid, h, hid, w2t, nout, out, ldo, c_rows=out_rows, bias=b2)
+    gemm_nn(n_rows, hid, kin, x, ldx, _f32c(w1), kin, h, hid, a_rows=rows, bias=b1, flags=RELU, b_is_nk=True)
+    gemm_nn(n_rows, nout, hid, h, hid, _f32c(w2), hid, out, ldo, c_rows=out_rows, bias=b2, b_is_nk=True)
     return h
 
 
@@ -273,9 +316,8 @@ class LinearFn(torch.autograd.Function):
         M, K = x2.shape
         N = w.shape[0]
         y = torch.empty(M, N, dtype=torch.float32, device=x2.device)
-        wt = transpose(w.detach())
-        gemm_nn(M, N, K, x2, x2.stride(0), wt, N, y, N, bias=None if b is None else _f32c(b.detach()),
-                flags=RELU if relu else 0)
+        gemm_nn(M, N, K, x2, x2.stride(0), _f32c(w.detach()), K, y, N,
+                bias=None if b is None else _f32c(b.detach()), flags=RELU if relu else 0, b_is_nk=True)
         ctx.save = (x2, w.detach(), y if relu else None)
         ctx.has_bias, ctx.xshape = b is not None, x.shape
         ctx.need_dx = x.requires_grad

@@ -31,16 +31,46 @@ class _Ws:
         return self.buf
 
 
-def _conv(x, ldx, B, H, W, cin, cout, k, wf, bias, y, ldy, flags=0):
-    call("tm_conv2d_nhwc", B, H, W, cin, cout, k, x, ldx, wf, bias, y, ldy, flags, stream())
+# arithmetic of the convolutions: "tc3" (split-bf16 x3 on tcgen05, fp32-class), "bf16" (tcgen05,
+# plain bf16 operands) or "fp32" (CUDA-core implicit GEMM).  Per network: net.math overrides.
+MATH = None            # None -> follow tm_ops.MATH
+_CUR = None            # math mode of the network currently being run (net.math)
 
 
-def _conv_wgrad(ws, x, ldx, dy, lddy, B, H, W, cin, cout, k, want_bias):
+def _prec(math):
+    import tm_ops
+    return tm_ops._precision(math or _CUR or MATH or tm_ops.MATH)
+
+
+def _enter(net):
+    global _CUR
+    _CUR = getattr(net, "math", None)
+
+
+def _conv(x, ldx, B, H, W, cin, cout, k, wf, bias, y, ldy, flags=0, math=None):
+    prec = _prec(math)
+    if prec is None:
+        call("tm_conv2d_nhwc", B, H, W, cin, cout, k, x, ldx, wf, bias, y, ldy, flags, stream())
+    else:
+        call("tm_tc_conv2d_nhwc", B, H, W, cin, cout, k, x, ldx, wf, bias, y, ldy, flags, prec,
+             tm_lib.err_flag(y.device), stream())
+
+
+def _conv_wgrad(ws, x, ldx, dy, lddy, B, H, W, cin, cout, k, want_bias, math=None):
     dev = dy.device
     dwf = _empty(k * k * cin, cout, dev=dev)
     dbias = _empty(cout, dev=dev) if want_bias else None
-    nb = tm_lib.ws_bytes("tm_conv2d_wgrad_ws", B, H, W, cin, cout, k)
-    call("tm_conv2d_wgrad_nhwc", B, H, W, cin, cout, k, x, ldx, dy, lddy, dwf, dbias, ws.get(nb), nb, stream())
+    prec = _prec(math)
+    if prec is None:
+        nb = tm_lib.ws_bytes("tm_conv2d_wgrad_ws", B, H, W, cin, cout, k)
+        call("tm_conv2d_wgrad_nhwc", B, H, W, cin, cout, k, x, ldx, dy, lddy, dwf, dbias, ws.get(nb), nb, stream())
+    else:
+        nb = tm_lib.ws_bytes("tm_tc_conv2d_wgrad_ws", B, H, W, cin, cout, k)
+        call("tm_tc_conv2d_wgrad_nhwc", B, H, W, cin, cout, k, x, ldx, dy, lddy, dwf, prec, ws.get(nb), nb,
+             tm_lib.err_flag(dev), stream())
+        if want_bias:
+            nbc = tm_lib.ws_bytes("tm_colsum_ws", B * H * W, cout)
+            call("tm_colsum", B * H * W, cout, dy, lddy, None, dbias, 0, tm_lib.workspace(nbc, dev), nbc, stream())
     dw = _empty(cout, cin, k, k, dev=dev)
     call("tm_conv_unpack_wgrad", cout, cin, k, dwf, dw, stream())
     return dw, dbias
@@ -130,6 +160,7 @@ def _dc_mods(dc):
 def unet_forward(net, x, need_bwd=True, update_stats=True):
     """``net``: the UNet module (parameter container).  x: (B,3,H,W) or (3,H,W) on a CUDA device.
     Returns (out (B,1,H/2,W/2), state)."""
+    _enter(net)
     if x.dim() == 3:                                   # train.py:465 passes (C,H,W)
         x = x.unsqueeze(0)
     x = x.detach().float().contiguous()
@@ -193,6 +224,7 @@ def unet_forward(net, x, need_bwd=True, update_stats=True):
 
 def unet_backward(net, st, gout):
     """gout: (B,1,H/2,W/2).  Returns {state_dict-style name: gradient} for every parameter."""
+    _enter(net)
     B, H, W, mode = st["B"], st["H"], st["W"], st["mode"]
     ws, chans, Hs, Ws_, cat = st["ws"], st["chans"], st["Hs"], st["Ws"], st["cat"]
     dev = gout.device
@@ -275,6 +307,7 @@ LAYOUT_SPEC = [(0, 2, 32, 9, True), (3, 32, 64, 7, True), (6, 64, 32, 9, False),
 
 
 def layoutnet_forward(net, x, need_bwd=True):
+    _enter(net)
     squeeze = x.dim() == 3
     if squeeze:
         x = x.unsqueeze(0)
@@ -315,6 +348,7 @@ def layoutnet_forward(net, x, need_bwd=True):
 
 
 def layoutnet_backward(net, st, gout):
+    _enter(net)
     B, mode, ws = st["B"], st["mode"], st["ws"]
     dev = gout.device
     g = gout.detach().float().contiguous().reshape(-1, 1)

@@ -21,7 +21,17 @@ DEV = "cuda"
 @pytest.fixture(scope="module")
 def mods(pkg):
     import tm_engine, tm_graph, tm_lib, tm_ops, tm_unet  # noqa: E401
-    return dict(engine=tm_engine, graph=tm_graph, lib=tm_lib, ops=tm_ops, unet=tm_unet)
+    yield dict(engine=tm_engine, graph=tm_graph, lib=tm_lib, ops=tm_ops, unet=tm_unet)
+    tm_lib.check_err_flags()                     # no tensor-core barrier ever timed out
+
+
+@pytest.fixture(params=["tc6", "fp32"])
+def math_mode(request, mods):
+    """Run a test under both fp32-class arithmetic modes (tensor-core split-bf16 x3, CUDA cores)."""
+    old = mods["ops"].MATH
+    mods["ops"].MATH = request.param
+    yield request.param
+    mods["ops"].MATH = old
 
 
 def _graph(mods, d, with_pis=True):
@@ -107,7 +117,7 @@ def test_schedule_from_topo_levels_and_violation(mods):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (130, 16, 2), (257, 36, 27), (1000, 256, 36), (333, 129, 288),
                                    (1350, 576, 288), (64, 1, 576)])
-def test_gemm_nn(mods, M, N, K):
+def test_gemm_nn(mods, math_mode, M, N, K):
     ops = mods["ops"]
     torch.manual_seed(M + N + K)
     A = torch.randn(M + 5, K, device=DEV)
@@ -128,7 +138,7 @@ def test_gemm_nn(mods, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,R", [(1, 576, 1350), (128, 256, 5000), (256, 36, 3001), (27, 16, 4096), (256, 2, 777)])
-def test_gemm_tn(mods, M, N, R):
+def test_gemm_tn(mods, math_mode, M, N, R):
     ops = mods["ops"]
     torch.manual_seed(M + N + R)
     A = torch.randn(R + 3, M, device=DEV)
@@ -175,7 +185,7 @@ def _gnn_params(seed):
 
 
 @pytest.mark.parametrize("cfg,seed", [("tiny", 0), ("tiny", 5), ("c1", 1)])
-def test_gnn_forward_backward(mods, cfg, seed):
+def test_gnn_forward_backward(mods, math_mode, cfg, seed):
     ops = mods["ops"]
     d = tm_synth.make_design(seed=seed, **tm_synth.CONFIGS[cfg])
     gnn = _gnn_params(seed)
@@ -344,7 +354,7 @@ def test_convt_kernels(mods, B, H, W, Cin):
 
 
 @pytest.mark.parametrize("pooling", ["max", "avg"])
-def test_unet_vs_oracle(mods, pooling):
+def test_unet_vs_oracle(mods, math_mode, pooling):
     import Unet as U
     torch.manual_seed(11)
     net = U.UNet(pooling).train()
@@ -371,7 +381,7 @@ def test_unet_vs_oracle(mods, pooling):
     assert o3.shape == (1, 1, 16, 12)
 
 
-def test_layoutnet_vs_golden(mods):
+def test_layoutnet_vs_golden(mods, math_mode):
     import model as M
     z = np.load(os.path.join(GOLD, "layoutnet.npz"))
     net = M.LayoutNet("max")
@@ -411,7 +421,7 @@ def _check_step_against_golden(z, model, cnn, pred, loss):
             assert_close(cnn.state_dict()[k[len("after.cnn."):]], z[k], 1e-4, 1e-5, k)
 
 
-def test_design_step_vs_golden(mods):
+def test_design_step_vs_golden(mods, math_mode):
     """Fused step (tm_engine.DesignStep) against the fixture produced by the UNMODIFIED reference."""
     eng = mods["engine"]
     d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["tiny"])
