@@ -283,7 +283,10 @@ int tm_add_strided(int64_t npix, int64_t C, const float* src, int64_t lds, float
  * Same meaning as tm_gemm_nn / tm_gemm_tn / tm_conv2d_nhwc / tm_conv2d_wgrad_nhwc above.
  *   precision 0: operands rounded to bf16 (fp32 accumulate)            -- rtol 2e-2 class
  *   precision 1: operands split into two bf16 terms, three MMAs        -- ~16-bit products
- *   precision 2: operands split into three bf16 terms (24 bits), six MMAs -- fp32-class (rtol 1e-3 path)
+ *   precision 2: operands split into three bf16 terms (24 bits), six MMAs -- fp32-class
+ *   precision 3: 3xTF32 -- kind::tf32 on the raw fp32 words (hi) plus the residual x - trunc_tf32(x) (lo),
+ *                hi*hi + hi*lo + lo*hi, ~21-bit products -- fp32-class, the default rtol 1e-3 path
+ *   precision 4: single-pass TF32
  *   err: optional device int32, set to 1 if a tensor-core barrier timed out (never expected).
  * tm_tc_gemm_nn: b_is_nk != 0 means B is given as [N,K] row-major (an nn.Linear weight as
  * stored), otherwise [K,N] row-major like tm_gemm_nn.

@@ -9,9 +9,17 @@
 using namespace tmk;
 
 namespace {
+// widest vector load the operand rows allow: 2 = 256-bit, 1 = 128-bit, 0 = scalar
+inline int vec_mode(const void* p, int64_t ld) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  if ((ld % 8 == 0) && (a % 32 == 0)) return 2;
+  if ((ld % 4 == 0) && (a % 16 == 0)) return 1;
+  return 0;
+}
+// splits of the reduction dimension so that (tiles x splits) fills the persistent grid once
 inline void tn_split(int64_t M, int64_t N, int64_t R, int bn, int* splits, int64_t* k_per_split) {
   const int64_t tiles = cdiv(M, tc::BM) * cdiv(N, bn);
-  int64_t want = cdiv(2 * (int64_t)sm_count(), tiles);
+  int64_t want = (int64_t)sm_count() / tiles;
   const int64_t cap = cdiv(R, 4 * tc::BK);
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -29,21 +37,25 @@ extern "C" int tm_tc_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, in
   TM_REQUIRE(!(flags & TM_EPI_BIAS) || bias, "tm_tc_gemm_nn: TM_EPI_BIAS without bias");
   TM_REQUIRE(!(flags & TM_EPI_MASK) || mask, "tm_tc_gemm_nn: TM_EPI_MASK without mask");
   cudaStream_t st = (cudaStream_t)stream;
-  tc::RowLoader al{A, lda, a_rows, M, K, (lda % 4 == 0) && aligned16(A)};
+  tc::RowLoader al{A, lda, a_rows, M, K, vec_mode(A, lda)};
   PlainEpilogue ep{C, ldc, c_rows, bias, mask, ldmask, flags};
   if (b_is_nk) {
-    tc::RowLoader bl{B, ldb, nullptr, N, K, (ldb % 4 == 0) && aligned16(B)};
+    tc::RowLoader bl{B, ldb, nullptr, N, K, vec_mode(B, ldb)};
     return tc::launch(al, bl, ep, M, N, K, 1, K > 0 ? cdiv(K, tc::BK) * tc::BK : tc::BK, precision, err, st);
   }
-  tc::ColLoader bl{B, ldb, nullptr, N, K};
+  tc::ColLoader bl{B, ldb, nullptr, N, K, vec_mode(B, ldb)};
   return tc::launch(al, bl, ep, M, N, K, 1, K > 0 ? cdiv(K, tc::BK) * tc::BK : tc::BK, precision, err, st);
 }
 
 extern "C" size_t tm_tc_gemm_tn_ws(int64_t M, int64_t N, int64_t R) {
-  int splits;
-  int64_t kps;
-  tn_split(M, N, R, tc::pick_bn(N), &splits, &kps);
-  return (size_t)splits * M * N * sizeof(float) + 256;
+  size_t worst = 0;                       // the N tile depends on the precision chosen at launch
+  for (int prec = 0; prec < 5; ++prec) {
+    int splits;
+    int64_t kps;
+    tn_split(M, N, R, tc::pick_bn(N, prec), &splits, &kps);
+    if ((size_t)splits > worst) worst = (size_t)splits;
+  }
+  return worst * M * N * sizeof(float) + 256;
 }
 
 extern "C" int tm_tc_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, int64_t lda,
@@ -56,9 +68,9 @@ extern "C" int tm_tc_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, in
   cudaStream_t st = (cudaStream_t)stream;
   int splits;
   int64_t kps;
-  tn_split(M, N, R, tc::pick_bn(N), &splits, &kps);
-  tc::ColLoader al{A, lda, a_rows, M, R};
-  tc::ColLoader bl{B, ldb, b_rows, N, R};
+  tn_split(M, N, R, tc::pick_bn(N, precision), &splits, &kps);
+  tc::ColLoader al{A, lda, a_rows, M, R, vec_mode(A, lda)};
+  tc::ColLoader bl{B, ldb, b_rows, N, R, vec_mode(B, ldb)};
   tc::PartialEpilogue ep{(float*)ws, M, N};
   TM_TRY(tc::launch(al, bl, ep, M, N, R, splits, kps, precision, err, st));
   split_reduce_kernel<<<(unsigned)cdiv(M * N, 256), 256, 0, st>>>((const float*)ws, M * N, splits, C, N, ldc, accumulate);
@@ -71,8 +83,8 @@ extern "C" int tm_tc_conv2d_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, i
   TM_REQUIRE(k >= 1 && (k & 1), "tm_tc_conv2d_nhwc: odd kernel sizes only");
   const int64_t M = B * H * W, K = k * k * Cin;
   tc::Im2colLoader8 al{x, ldx, (int)H, (int)W, (int)Cin, (int)k, (int)(k / 2), M, K,
-                       (Cin % 8 == 0) && (ldx % 4 == 0) && aligned16(x)};
-  tc::ColLoader bl{wf, Cout, nullptr, Cout, K};
+                       (Cin % 4 == 0) ? vec_mode(x, ldx) : 0};
+  tc::ColLoader bl{wf, Cout, nullptr, Cout, K, vec_mode(wf, Cout)};
   PlainEpilogue ep{y, ldy, nullptr, bias, nullptr, 0, (flags & TM_EPI_RELU) | (bias ? TM_EPI_BIAS : 0)};
   return tc::launch(al, bl, ep, M, Cout, K, 1, cdiv(K, tc::BK) * tc::BK, precision, err, (cudaStream_t)stream);
 }
@@ -89,9 +101,9 @@ extern "C" int tm_tc_conv2d_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t 
   cudaStream_t st = (cudaStream_t)stream;
   int splits;
   int64_t kps;
-  tn_split(M, N, R, tc::pick_bn(N), &splits, &kps);
-  tc::Im2colColLoader al{x, ldx, (int)H, (int)W, (int)Cin, (int)k, (int)(k / 2), M, R};
-  tc::ColLoader bl{dy, lddy, nullptr, N, R};
+  tn_split(M, N, R, tc::pick_bn(N, precision), &splits, &kps);
+  tc::Im2colColLoader al{x, ldx, (int)H, (int)W, (int)Cin, (int)k, (int)(k / 2), M, R, (Cin % 4 == 0) ? vec_mode(x, ldx) : 0};
+  tc::ColLoader bl{dy, lddy, nullptr, N, R, vec_mode(dy, lddy)};
   tc::PartialEpilogue ep{(float*)ws, M, N};
   TM_TRY(tc::launch(al, bl, ep, M, N, R, splits, kps, precision, err, st));
   split_reduce_kernel<<<(unsigned)cdiv(M * N, 256), 256, 0, st>>>((const float*)ws, M * N, splits, dwf, N, N, 0);

@@ -10,13 +10,22 @@
 // Staging through threads (instead of TMA) keeps row gathers, transposed operands (weight
 // gradients) and im2col (convolutions) one template parameter away.
 //
-// Tile: BM = 128 rows, BN in {32,64,128} columns, BK = 32; 2-stage smem ring fed one k-block
-// ahead through registers; one elected thread issues the MMAs, tcgen05.commit arrives on an
-// mbarrier per stage; the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 bit),
-// transposes it through shared memory and writes 128-bit row-contiguous stores.  Two or three
-// CTAs are resident per SM so staging, MMA and epilogue of different tiles overlap.
+// Persistent, warp-specialised CTA (one per SM), tiles of BM = 128 rows x BN in {32,64,128,256}
+// columns, k-blocks of BK = 32:
+//   warps 5..12  producers: cp.async of raw fp32 k-blocks ND ahead (across tile boundaries) into a
+//                raw ring; once landed: raw -> registers -> bf16 split -> ring of NS stages in the
+//                UMMA layout; arrive on full[stage].  K-contiguous operands are copied and
+//                converted by the SAME thread (no barrier, warps drift apart and overlap their
+//                copy / convert phases); transposed operands are copied cooperatively.
+//   warp  4      one elected thread issues the tcgen05.mma's of a stage, tcgen05.commit releases
+//                the stage (empty[stage]) and, after a tile's last k-block, publishes the
+//                accumulator (acc_full[buf]); the accumulator is double-buffered in TMEM
+//   warps 0..3   epilogue: tcgen05.ld of the finished accumulator (lane = tile row), transpose
+//                through shared memory, fused bias / ReLU / mask / accumulate, 128-bit stores,
+//                then acc_empty[buf] -- overlapping the next tile's main loop.
 #pragma once
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "tm_gemm.cuh"
 
@@ -25,17 +34,27 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int THREADS = 256;
+constexpr int EPI_WARPS = 4;        // warps 0..3: TMEM lane group = warp index
+constexpr int MMA_WARP = 4;
+constexpr int PROD_WARP0 = 5;
+constexpr int PROD_WARPS = 8;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;   // 416
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-// Bounded wait: a tensor-core fault must not turn into a hung GPU.  Returns false on timeout.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a tensor-core fault must not turn into a hung GPU.  Returns false on timeout or
+// when another role of the CTA already gave up (*abort != 0).
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    if ((spin & 1023u) == 1023u && *abort) return false;
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -94,9 +113,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// cp.async (LDGSTS): global -> shared without a register round trip; bytes past `nbytes` are
+// zero-filled, so out-of-matrix elements need no branch in the consumer
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int nbytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------
-// operand loaders: v[0..7] = operand(row, k0 .. k0+7), zero outside the matrix
-// kTransposed selects the lane mapping of the staging loop (which index is contiguous in HBM)
+// operand loaders.  Operands are fp32 in HBM; a k-block of a tile is first copied RAW into shared
+// memory by cp.async in 16-byte chunks (4 floats), several k-blocks ahead of its use.
+//   kTransposed == false: k is contiguous in HBM.  chunk = 4 consecutive k of one row.
+//        St begin(row)            resolves what depends on the row once per tile
+//        copy4(dst, st, k)        operand(row, k..k+3) -> 16 bytes at dst (zero outside the matrix)
+//   kTransposed == true: the row index is contiguous in HBM.  chunk = 4 consecutive rows, one k.
+//        St begin(row4)           (row4 % 4 == 0)
+//        copy4(dst, st, k)        operand(row4..row4+3, k) -> 16 bytes at dst
 // ---------------------------------------------------------------------------------------------
 struct RowLoader {      // element(row, k) = A[rows ? rows[row] : row][k]   (k contiguous)
   static constexpr bool kTransposed = false;
@@ -104,19 +141,22 @@ struct RowLoader {      // element(row, k) = A[rows ? rows[row] : row][k]   (k c
   int64_t ld;
   const int32_t* rows;
   int64_t nrows, K;
-  bool vec;             // ld % 4 == 0 && 16-byte aligned base
-  __device__ __forceinline__ void load8(int64_t row, int64_t k0, float (&v)[8]) const {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (row >= nrows || k0 >= K) return;
-    const float* p = A + (rows ? (int64_t)rows[row] : row) * ld + k0;
-    if (vec && k0 + 8 <= K) {
-      const float4 a = ld4(p), b = ld4(p + 4);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  int vec;              // != 0: ld % 4 == 0 and 16-byte aligned base
+  struct St { const float* p; };
+  __device__ __forceinline__ St begin(int64_t row) const {
+    St s;
+    s.p = nullptr;
+    if (row < nrows) s.p = A + (rows ? (int64_t)rows[row] : row) * ld;
+    return s;
+  }
+  __device__ __forceinline__ void copy4(uint32_t dst, const St& s, int64_t k) const {
+    const int64_t rem = s.p ? K - k : 0;             // valid elements from k on
+    const float* src = (rem > 0) ? s.p + k : A;
+    if (vec) {
+      cp_async16(dst, src, rem >= 4 ? 16 : (rem > 0 ? (int)rem * 4 : 0));
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (k0 + i < K) v[i] = p[i];
+      for (int i = 0; i < 4; ++i) cp_async4(dst + 4 * i, rem > i ? src + i : A, rem > i ? 4 : 0);
     }
   }
 };
@@ -127,11 +167,23 @@ struct ColLoader {      // element(row, k) = A[krows ? krows[k] : k][row]   (row
   int64_t ld;
   const int32_t* krows;
   int64_t nrows, K;
-  __device__ __forceinline__ void load8(int64_t row, int64_t k0, float (&v)[8]) const {
+  int vec;              // != 0: ld % 4 == 0 and 16-byte aligned base
+  struct St { int64_t row4; int nr; };
+  __device__ __forceinline__ St begin(int64_t row4) const {
+    St s;
+    s.row4 = row4;
+    const int64_t nr = nrows - row4;
+    s.nr = nr >= 4 ? 4 : (nr > 0 ? (int)nr : 0);
+    return s;
+  }
+  __device__ __forceinline__ void copy4(uint32_t dst, const St& s, int64_t k) const {
+    const int nr = (k < K) ? s.nr : 0;
+    const float* src = nr ? A + (krows ? (int64_t)krows[k] : k) * ld + s.row4 : A;
+    if (vec) {
+      cp_async16(dst, src, nr * 4);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[i] = 0.f;
-      if (row < nrows && k0 + i < K) v[i] = A[(krows ? (int64_t)krows[k0 + i] : k0 + i) * ld + row];
+      for (int i = 0; i < 4; ++i) cp_async4(dst + 4 * i, nr > i ? src + i : A, nr > i ? 4 : 0);
     }
   }
 };
@@ -143,34 +195,38 @@ struct Im2colLoader8 {
   int64_t ldx;
   int H, W, Cin, ks, pad;
   int64_t nrows, K;
-  bool vec;             // Cin % 8 == 0 && ldx % 4 == 0 && aligned
-  __device__ __forceinline__ void load8(int64_t row, int64_t k0, float (&v)[8]) const {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (row >= nrows || k0 >= K) return;
-    const int hw = H * W;
-    const int b = (int)(row / hw);
-    const int rem = (int)(row - (int64_t)b * hw);
-    const int y = rem / W, x = rem - y * W;
-    if (vec) {
-      const int tap = (int)(k0 / Cin), ci = (int)(k0 - (int64_t)tap * Cin);
-      const int ty = tap / ks, tx = tap - ty * ks;
-      const int yy = y + ty - pad, xx = x + tx - pad;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const float* p = X + (((int64_t)b * H + yy) * W + xx) * ldx + ci;
-        const float4 a = ld4(p), c = ld4(p + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-      }
+  int vec;              // != 0: Cin % 4 == 0, ldx % 4 == 0, 16-byte aligned base
+  struct St { const float* p; int y, x; };
+  __device__ __forceinline__ St begin(int64_t row) const {
+    St s;
+    s.p = nullptr; s.y = 0; s.x = 0;
+    if (row < nrows) {
+      const uint32_t r = (uint32_t)row, hw = (uint32_t)(H * W);
+      const uint32_t rem = r % hw;
+      s.y = (int)(rem / (uint32_t)W);
+      s.x = (int)(rem - (uint32_t)s.y * (uint32_t)W);
+      s.p = X + row * ldx;                       // pixel (b, y, x)
+    }
+    return s;
+  }
+  __device__ __forceinline__ const float* tap_ptr(const St& s, int tap) const {   // nullptr: padding
+    const int ty = tap / ks, tx = tap - ty * ks;
+    const int yy = s.y + ty - pad, xx = s.x + tx - pad;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) return nullptr;
+    return s.p + ((int64_t)(ty - pad) * W + (tx - pad)) * ldx;
+  }
+  __device__ __forceinline__ void copy4(uint32_t dst, const St& s, int64_t k) const {
+    const bool on = s.p && k < K;
+    int tap = on ? (int)((uint32_t)k / (uint32_t)Cin) : 0, ci = on ? (int)k - tap * Cin : 0;
+    if (vec) {                                   // the 4 elements share a tap
+      const float* p = on ? tap_ptr(s, tap) : nullptr;
+      cp_async16(dst, p ? p + ci : X, p ? 16 : 0);
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t k = k0 + i;
-        if (k < K) {
-          const int tap = (int)(k / Cin), ci = (int)(k - (int64_t)tap * Cin);
-          const int ty = tap / ks, tx = tap - ty * ks;
-          const int yy = y + ty - pad, xx = x + tx - pad;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[i] = X[(((int64_t)b * H + yy) * W + xx) * ldx + ci];
-        }
+      for (int i = 0; i < 4; ++i) {
+        const float* p = (on && k + i < K) ? tap_ptr(s, tap) : nullptr;
+        cp_async4(dst + 4 * i, p ? p + ci : X, p ? 4 : 0);
+        if (++ci == Cin) { ci = 0; ++tap; }
       }
     }
   }
@@ -183,22 +239,38 @@ struct Im2colColLoader {
   int64_t ldx;
   int H, W, Cin, ks, pad;
   int64_t nrows, K;     // nrows = ks*ks*Cin, K = number of pixels
-  __device__ __forceinline__ void load8(int64_t row, int64_t k0, float (&v)[8]) const {
+  int vec;              // != 0: Cin % 4 == 0, ldx % 4 == 0, 16-byte aligned base
+  struct St { int row4, nr; };
+  __device__ __forceinline__ St begin(int64_t row4) const {
+    St s;
+    s.row4 = (int)row4;
+    const int64_t nr = nrows - row4;
+    s.nr = nr >= 4 ? 4 : (nr > 0 ? (int)nr : 0);
+    return s;
+  }
+  __device__ __forceinline__ void copy4(uint32_t dst, const St& s, int64_t k) const {
+    const bool on = s.nr > 0 && k < K;
+    int y = 0, x = 0;
+    if (on) {
+      const uint32_t rem = (uint32_t)k % (uint32_t)(H * W);
+      y = (int)(rem / (uint32_t)W);
+      x = (int)(rem - (uint32_t)y * (uint32_t)W);
+    }
+    int tap = on ? s.row4 / Cin : 0, ci = on ? s.row4 - tap * Cin : 0;
+    const float* px = X + k * ldx;               // pixel k itself
+    if (vec) {                                   // the 4 rows share a tap
+      const int ty = tap / ks, tx = tap - ty * ks;
+      const int yy = y + ty - pad, xx = x + tx - pad;
+      const bool inb = on && yy >= 0 && yy < H && xx >= 0 && xx < W;
+      cp_async16(dst, inb ? px + ((int64_t)(ty - pad) * W + (tx - pad)) * ldx + ci : X, inb ? 16 : 0);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (row >= nrows) return;
-    const int tap = (int)(row / Cin), ci = (int)(row - (int64_t)tap * Cin);
-    const int ty = tap / ks, tx = tap - ty * ks;
-    const int hw = H * W;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t px = k0 + i;
-      if (px < K) {
-        const int b = (int)(px / hw);
-        const int rem = (int)(px - (int64_t)b * hw);
-        const int y = rem / W, x = rem - y * W;
+      for (int i = 0; i < 4; ++i) {
+        const int ty = tap / ks, tx = tap - ty * ks;
         const int yy = y + ty - pad, xx = x + tx - pad;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[i] = X[(((int64_t)b * H + yy) * W + xx) * ldx + ci];
+        const bool inb = on && i < s.nr && yy >= 0 && yy < H && xx >= 0 && xx < W;
+        cp_async4(dst + 4 * i, inb ? px + ((int64_t)(ty - pad) * W + (tx - pad)) * ldx + ci : X, inb ? 4 : 0);
+        if (++ci == Cin) { ci = 0; ++tap; }
       }
     }
   }
@@ -207,8 +279,7 @@ struct Im2colColLoader {
 // ---------------------------------------------------------------------------------------------
 // staging: fp32 -> bf16 parts into the UMMA K-major no-swizzle layout (BK = 32: 4 k-groups of 8)
 //   byte offset of (row, kgroup) = (row / 8) * 512 + kgroup * 128 + (row % 8) * 16
-// A warp-level work unit covers 32 (row, kgroup) items; global loads are issued one k-block ahead
-// into registers (prefetch) and converted / stored after the previous MMAs released the stage.
+// A warp-level work unit covers 32 (row, kgroup) items.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -230,12 +301,11 @@ __device__ __forceinline__ void split_store(float (&v)[8], uint8_t* base, uint32
     h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]); h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
     *reinterpret_cast<uint4*>(base + (size_t)part * pstride + off) = h;
     if (part + 1 < PARTS) {
-      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+      const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(hp[i]);
-        v[2 * i] -= f.x;                 // exact: the residual is representable in fp32
-        v[2 * i + 1] -= f.y;
+      for (int i = 0; i < 4; ++i) {            // exact: the residual is representable in fp32
+        v[2 * i] -= __uint_as_float(hh[i] << 16);
+        v[2 * i + 1] -= __uint_as_float(hh[i] & 0xFFFF0000u);
       }
     }
   }
@@ -247,257 +317,918 @@ __device__ __forceinline__ void split_store(float (&v)[8], uint8_t* base, uint32
 struct PartialEpilogue {
   float* P;
   int64_t M, N;
-  struct Row { int64_t r; };
-  __device__ __forceinline__ Row row(int64_t m) const { return Row{m}; }
-  __device__ __forceinline__ void store(const Row& rw, int64_t n, float v) const {
-    P[((int64_t)blockIdx.z * M + rw.r) * N + n] = v;
-  }
+  struct Row { float* p; };
 };
 
 template <class EP>
-__device__ __forceinline__ void store4(const EP& ep, const typename EP::Row& rw, int64_t n, int64_t N, const float (&v)[4]) {
+__device__ __forceinline__ typename EP::Row epi_row(const EP& ep, int64_t m, int z) { return ep.row(m); }
+template <>
+__device__ __forceinline__ PartialEpilogue::Row epi_row<PartialEpilogue>(const PartialEpilogue& ep, int64_t m, int z) {
+  return PartialEpilogue::Row{ep.P + ((int64_t)z * ep.M + m) * ep.N};
+}
+
+// Column-only epilogue terms (bias) are fetched once per 32-column chunk, row handles once per tile:
+// a load issued after a store to memory that may alias it cannot be hoisted by the compiler and
+// would otherwise serialise one L2 round trip per store.
+template <class EP>
+__device__ __forceinline__ float4 epi_bias4(const EP& ep, int64_t n, int64_t N) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <>
+__device__ __forceinline__ float4 epi_bias4<PlainEpilogue>(const PlainEpilogue& ep, int64_t n, int64_t N) {
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.flags & TM_EPI_BIAS) {
+    if (n < N) b.x = ep.bias[n];
+    if (n + 1 < N) b.y = ep.bias[n + 1];
+    if (n + 2 < N) b.z = ep.bias[n + 2];
+    if (n + 3 < N) b.w = ep.bias[n + 3];
+  }
+  return b;
+}
+
+// Row operands of the epilogue (ReLU-backward mask, old C for accumulation) are fetched for all 8
+// store passes of a chunk BEFORE the first store, for the same reason.
+struct EpiAux { float4 mask, old; };
+template <class EP>
+__device__ __forceinline__ EpiAux epi_aux(const EP& ep, const typename EP::Row& rw, int64_t n, int64_t N) { return EpiAux{}; }
+template <>
+__device__ __forceinline__ EpiAux epi_aux<PlainEpilogue>(const PlainEpilogue& ep, const PlainEpilogue::Row& rw, int64_t n, int64_t N) {
+  EpiAux a;
+  a.mask = make_float4(1.f, 1.f, 1.f, 1.f);
+  a.old = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.flags & TM_EPI_MASK) {
+    const float* mp = ep.mask + rw.r * ep.ldmask + n;
+    if ((n + 4 <= N) && ((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0)) a.mask = ld4(mp);
+    else {
+      if (n < N) a.mask.x = mp[0];
+      if (n + 1 < N) a.mask.y = mp[1];
+      if (n + 2 < N) a.mask.z = mp[2];
+      if (n + 3 < N) a.mask.w = mp[3];
+    }
+  }
+  if (ep.flags & TM_EPI_ACCUM) {
+    const float* cp = ep.C + rw.r * ep.ldc + n;
+    if ((n + 4 <= N) && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0)) a.old = ld4(cp);
+    else {
+      if (n < N) a.old.x = cp[0];
+      if (n + 1 < N) a.old.y = cp[1];
+      if (n + 2 < N) a.old.z = cp[2];
+      if (n + 3 < N) a.old.w = cp[3];
+    }
+  }
+  return a;
+}
+
+template <class EP>
+__device__ __forceinline__ void store4(const EP& ep, const typename EP::Row& rw, int64_t n, int64_t N, const float (&v)[4],
+                                       const float4& b4, const EpiAux& ax) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (n + i < N) ep.store(rw, n + i, v[i]);
 }
-// PlainEpilogue fast path: one 128-bit store per lane when rows are 16-byte aligned
 template <>
-__device__ __forceinline__ void store4<PlainEpilogue>(const PlainEpilogue& ep, const PlainEpilogue::Row& rw, int64_t n,
-                                                      int64_t N, const float (&v)[4]) {
-  const bool vec = (n + 4 <= N) && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
-                   (!(ep.flags & TM_EPI_MASK) || (((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0)));
-  if (!vec) {
+__device__ __forceinline__ void store4<PartialEpilogue>(const PartialEpilogue& ep, const PartialEpilogue::Row& rw, int64_t n,
+                                                        int64_t N, const float (&v)[4], const float4& b4, const EpiAux& ax) {
+  if (n + 4 <= N && (N & 3) == 0) {
+    st4(rw.p + n, make_float4(v[0], v[1], v[2], v[3]));
+  } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (n + i < N) ep.store(rw, n + i, v[i]);
-    return;
+      if (n + i < N) rw.p[n + i] = v[i];
   }
-  float4 o = make_float4(v[0], v[1], v[2], v[3]);
-  if (ep.flags & TM_EPI_BIAS) { o.x += ep.bias[n]; o.y += ep.bias[n + 1]; o.z += ep.bias[n + 2]; o.w += ep.bias[n + 3]; }
-  float* p = ep.C + rw.r * ep.ldc + n;
-  if (ep.flags & TM_EPI_ACCUM) { const float4 c = ld4(p); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+}
+// PlainEpilogue: one 128-bit store per lane when rows are 16-byte aligned
+template <>
+__device__ __forceinline__ void store4<PlainEpilogue>(const PlainEpilogue& ep, const PlainEpilogue::Row& rw, int64_t n,
+                                                      int64_t N, const float (&v)[4], const float4& b4, const EpiAux& ax) {
+  float4 o = make_float4(v[0] + b4.x + ax.old.x, v[1] + b4.y + ax.old.y, v[2] + b4.z + ax.old.z, v[3] + b4.w + ax.old.w);
   if (ep.flags & TM_EPI_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
   if (ep.flags & TM_EPI_MASK) {
-    const float4 mk = ld4(ep.mask + rw.r * ep.ldmask + n);
-    o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f; o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+    o.x = ax.mask.x > 0.f ? o.x : 0.f; o.y = ax.mask.y > 0.f ? o.y : 0.f; o.z = ax.mask.z > 0.f ? o.z : 0.f; o.w = ax.mask.w > 0.f ? o.w : 0.f;
   }
-  st4(p, o);
+  float* p = ep.C + rw.r * ep.ldc + n;
+  if ((n + 4 <= N) && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0)) {
+    st4(p, o);
+  } else {
+    if (n < N) p[0] = o.x;
+    if (n + 1 < N) p[1] = o.y;
+    if (n + 2 < N) p[2] = o.z;
+    if (n + 3 < N) p[3] = o.w;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel.  grid = (m tiles, n tiles, k splits)
+// kernel configuration
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int parts_of(int split) { return split == 1 ? 1 : (split == 3 ? 2 : 3); }
-constexpr int EPI_SCRATCH = 8 * 32 * 33 * 4;            // one 32 x 33 fp32 tile per warp
+constexpr uint32_t EPI_SCRATCH = EPI_WARPS * 32 * 33 * 4;   // one 32 x 33 fp32 transpose tile per epilogue warp
+constexpr uint32_t SMEM_BUDGET = 218 * 1024;
+constexpr int MAX_STAGES = 8;
 
 template <int BN, int SPLIT>
-constexpr size_t smem_bytes() {
-  size_t ring = (size_t)2 * (BM + BN) * BK * 2 * parts_of(SPLIT);
-  return (ring > EPI_SCRATCH ? ring : EPI_SCRATCH) + 1024 /*alignment slack*/;
-}
+struct Cfg {
+  static constexpr int PARTS = parts_of(SPLIT);
+  static constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE = (A_BYTES + B_BYTES) * PARTS;      // one k-block of bf16 parts (UMMA layout)
+  static constexpr int A_UNITS = BM / 8, B_UNITS = BN / 8;          // 32-item conversion units per stage
+  static constexpr int A_PER = A_UNITS / PROD_WARPS;                // 2
+  static constexpr int B_PER = (B_UNITS + PROD_WARPS - 1) / PROD_WARPS;   // 1..4
+  // raw fp32 k-block (cp.async target): thread-private items of 32 bytes, 256 threads (transposed
+  // operands use the same area as a [k][row] tile image, which is never larger)
+  static constexpr uint32_t RAW_A = A_PER * 32 * PROD_THREADS, RAW_B = B_PER * 32 * PROD_THREADS;
+  static constexpr uint32_t RAW = RAW_A + RAW_B;
+  static constexpr uint32_t RING = SMEM_BUDGET - EPI_SCRATCH - 1024;
+  static constexpr int NS = (PARTS == 3 || 3 * STAGE + 2 * RAW > RING) ? 2 : 3;          // bf16 stages
+  static constexpr int ND_RAW = (int)((RING - NS * STAGE) / RAW);
+  static constexpr int ND = ND_RAW > 6 ? 6 : ND_RAW;                  // raw k-blocks in flight
+  static_assert(ND >= 2, "shared-memory budget too small for this tile");
+  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators, power of two
+  static constexpr size_t SMEM = (size_t)NS * STAGE + (size_t)ND * RAW + EPI_SCRATCH + 1024 /*alignment slack*/;
+  static constexpr int A_CH = BM * BK / 4 / PROD_THREADS;           // 16-byte copy chunks per thread (4)
+  static constexpr int B_CH = (BN * BK / 4 + PROD_THREADS - 1) / PROD_THREADS;   // 1..8
+};
 
-template <int CW>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
-  if (CW == 32) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-  } else {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-  }
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// tile index -> (m tile, n tile, k split): splits fastest, then n, so that concurrently running
+// CTAs share A rows through L2
+struct TileMap {
+  int64_t total, K, k_per_split;
+  int nt, z;
+  long long* trace;   // TM_TC_TRACE: clock64 stamps of CTA 0 (producer warp 0 / MMA thread / epilogue warp 0)
+  int dbg;    // TM_TC_DEBUG bits (bottleneck bisection): 1 no epilogue stores, 2 no global loads, 4 no staging, 8 no MMA
+  // nq = n tile INDEX (the kernel scales it by its BN)
+  __device__ __forceinline__ void decode(int64_t t, int64_t& m0, int64_t& nq, int& zi, int64_t& kbeg, int& nkb) const {
+    zi = (int)(t % z);
+    const int64_t q = t / z;
+    nq = q % nt;
+    m0 = (q / nt) * BM;
+    kbeg = (int64_t)zi * k_per_split;
+    const int64_t kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+    const int64_t nb = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
+    nkb = nb > 0 ? (int)nb : 1;                  // K == 0 still produces a (zero) accumulator
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// the kernel.  grid = min(#tiles, #SMs) persistent CTAs
+// ---------------------------------------------------------------------------------------------
 template <class AL, class BL, class EP, int BN, int SPLIT>
-__global__ void __launch_bounds__(THREADS)
-tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, int64_t K, int64_t k_per_split, int* __restrict__ err) {
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __restrict__ err) {
+  using C = Cfg<BN, SPLIT>;
+  constexpr int PARTS = C::PARTS, NS = C::NS, A_PER = C::A_PER, B_PER = C::B_PER;
+  constexpr uint32_t A_BYTES = C::A_BYTES, B_BYTES = C::B_BYTES, STAGE = C::STAGE;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int PARTS = parts_of(SPLIT);
-  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-  constexpr uint32_t STAGE = (A_BYTES + B_BYTES) * PARTS;
-  constexpr int A_UNITS = BM / 8, B_UNITS = BN / 8;                 // 32-item work units per tile
-  constexpr int NWARP = THREADS / 32;
-  constexpr int A_PER = A_UNITS / NWARP;                            // units per warp (2)
-  constexpr int B_PER = (B_UNITS + NWARP - 1) / NWARP;              // 1..4
-  __shared__ __align__(8) uint64_t mma_done[2];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* rawring = ring + (size_t)NS * STAGE;
+  float* scratch = reinterpret_cast<float*>(rawring + (size_t)C::ND * C::RAW);
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int abort_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
-  const int64_t k_begin = (int64_t)blockIdx.z * k_per_split;
-  const int64_t k_end = (k_begin + k_per_split < K) ? k_begin + k_per_split : K;
-  const int nkb = (k_end > k_begin) ? (int)((k_end - k_begin + BK - 1) / BK) : 0;
 
-  if (warp == 0) tmem_alloc(&tmem_base_s, BN);
-  if (tid == 32) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], PROD_WARPS); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], EPI_WARPS); mbar_init(&acc_empty[1], EPI_WARPS);
+    abort_s = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = tmem_base_s;
-  constexpr uint32_t idesc = make_idesc(BN);
+  const uint32_t tmem_base = tmem_base_s;
+  volatile int* abortp = &abort_s;
   bool ok = true;
+  const int64_t G = gridDim.x;
 
-  float pa[A_PER][8], pb[B_PER][8];
-  auto prefetch = [&](int kb) {
-    const int64_t k0 = k_begin + (int64_t)kb * BK;
+  if (warp >= PROD_WARP0) {
+    // ======================= producers =======================
+    constexpr int ND = C::ND, A_CH = C::A_CH, B_CH = C::B_CH;
+    constexpr uint32_t RAW = C::RAW, RAW_A = C::RAW_A;
+    constexpr bool COOP = AL::kTransposed || BL::kTransposed;       // any cooperative copy -> producer-wide barriers
+    const int pw = warp - PROD_WARP0;
+    const int ptid = tid - PROD_WARP0 * 32;
+    // ---- conversion items (fixed per thread): (row, k group) of the tile, 8 consecutive k each
+    int a_row[A_PER], a_kg[A_PER], b_row[B_PER], b_kg[B_PER];
+    uint32_t a_off[A_PER], b_off[B_PER];
+    bool b_on[B_PER];
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
-      int row, kg;
-      unit_coords<AL::kTransposed>(warp * A_PER + i, lane, row, kg);
-      al.load8(m0 + row, k0 + kg * 8, pa[i]);
+      unit_coords<AL::kTransposed>(pw * A_PER + i, lane, a_row[i], a_kg[i]);
+      a_off[i] = (uint32_t)(a_row[i] >> 3) * 512u + (uint32_t)a_kg[i] * 128u + (uint32_t)(a_row[i] & 7) * 16u;
     }
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
-      const int u = warp * B_PER + i;
-      if (u < B_UNITS) {
-        int row, kg;
-        unit_coords<BL::kTransposed>(u, lane, row, kg);
-        bl.load8(n0 + row, k0 + kg * 8, pb[i]);
+      const int u = pw * B_PER + i;
+      b_on[i] = u < C::B_UNITS;
+      unit_coords<BL::kTransposed>(b_on[i] ? u : 0, lane, b_row[i], b_kg[i]);
+      b_off[i] = (uint32_t)(b_row[i] >> 3) * 512u + (uint32_t)b_kg[i] * 128u + (uint32_t)(b_row[i] & 7) * 16u;
+    }
+    // raw layouts.  K-contiguous operand: thread-private, item i half h at ((2i + h) * 256 + ptid) * 16
+    // (conflict-free for the warp's 128-bit accesses).  Transposed operand: tile image [k][row].
+    auto priv = [&](int i, int h) { return (uint32_t)((2 * i + h) * PROD_THREADS + ptid) * 16u; };
+    // ---- load cursor (ND k-blocks ahead of the conversion, across tile boundaries)
+    constexpr int A_NST = AL::kTransposed ? 1 : A_PER;
+    constexpr int B_NST = BL::kTransposed ? 1 : B_PER;
+    typename AL::St ast[A_NST];
+    typename BL::St bst[B_NST];
+    int64_t lt = blockIdx.x, lk = 0;
+    int lkb = 0, lnkb = 0;
+    bool lvalid = false;
+    uint32_t total = 0;
+    for (int64_t t = blockIdx.x; t < tm.total; t += G) {
+      int64_t m0, nq, kb0; int zi, nkb;
+      tm.decode(t, m0, nq, zi, kb0, nkb);
+      total += (uint32_t)nkb;
+    }
+    auto open_tile = [&]() {
+      lvalid = lt < tm.total;
+      if (!lvalid) return;
+      int64_t m0, nq; int zi;
+      tm.decode(lt, m0, nq, zi, lk, lnkb);
+      lkb = 0;
+      if (AL::kTransposed) { ast[0] = al.begin(m0 + (ptid & (BM / 4 - 1)) * 4); }
+      else {
+#pragma unroll
+        for (int i = 0; i < A_NST; ++i) ast[i] = al.begin(m0 + a_row[i]);
       }
-    }
-  };
-  auto commit_stage = [&](uint8_t* a_base, uint8_t* b_base) {
+      if (BL::kTransposed) { bst[0] = bl.begin(nq * BN + (ptid & (BN / 4 - 1)) * 4); }
+      else {
 #pragma unroll
-    for (int i = 0; i < A_PER; ++i) {
-      int row, kg;
-      unit_coords<AL::kTransposed>(warp * A_PER + i, lane, row, kg);
-      split_store<PARTS>(pa[i], a_base, (uint32_t)(row >> 3) * 512u + (uint32_t)kg * 128u + (uint32_t)(row & 7) * 16u, A_BYTES);
-    }
-#pragma unroll
-    for (int i = 0; i < B_PER; ++i) {
-      const int u = warp * B_PER + i;
-      if (u < B_UNITS) {
-        int row, kg;
-        unit_coords<BL::kTransposed>(u, lane, row, kg);
-        split_store<PARTS>(pb[i], b_base, (uint32_t)(row >> 3) * 512u + (uint32_t)kg * 128u + (uint32_t)(row & 7) * 16u, B_BYTES);
+        for (int i = 0; i < B_NST; ++i) bst[i] = bl.begin(nq * BN + b_row[i]);
       }
-    }
-  };
-
-  if (nkb > 0) prefetch(0);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
-    if (kb >= 2) ok = mbar_wait(&mma_done[s], (uint32_t)((kb >> 1) - 1) & 1u) && ok;   // stage free again
-    uint8_t* a_base = smem + (size_t)s * STAGE;
-    uint8_t* b_base = a_base + A_BYTES * PARTS;
-    commit_stage(a_base, b_base);
-    if (kb + 1 < nkb) prefetch(kb + 1);                 // in flight while the MMAs below are issued
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t sa = smem_u32(a_base), sb = smem_u32(b_base);
+    };
+    uint32_t ls = 0;                                               // raw slot of the next k-block to load
+    auto issue = [&]() {                                           // always commits exactly one group
+      if (lvalid && !(tm.dbg & 2)) {
+        const uint32_t ra = smem_u32(rawring + (size_t)ls * RAW), rb = ra + RAW_A;
+        if (AL::kTransposed) {
 #pragma unroll
-      for (int ks = 0; ks < BK / 16; ++ks) {
-        const uint32_t koff = (uint32_t)ks * 256u;      // two 128-byte core matrices per K = 16
-        uint64_t da[PARTS], db[PARTS];
+          for (int j = 0; j < A_CH; ++j) {
+            const int q = j * PROD_THREADS + ptid, kk = q / (BM / 4), rc = q % (BM / 4);
+            al.copy4(ra + (uint32_t)(kk * BM + rc * 4) * 4u, ast[0], lk + kk);
+          }
+        } else {
 #pragma unroll
-        for (int p = 0; p < PARTS; ++p) {
-          da[p] = make_desc(sa + p * A_BYTES + koff, 128, 512);
-          db[p] = make_desc(sb + p * B_BYTES + koff, 128, 512);
+          for (int i = 0; i < A_PER; ++i) {
+            al.copy4(ra + priv(i, 0), ast[i], lk + a_kg[i] * 8);
+            al.copy4(ra + priv(i, 1), ast[i], lk + a_kg[i] * 8 + 4);
+          }
         }
-        // products in decreasing magnitude; parts: 0 = hi, 1 = mid, 2 = lo
-        umma(tmem_d, da[0], db[0], idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-        if (PARTS >= 2) { umma(tmem_d, da[0], db[1], idesc, 1u); umma(tmem_d, da[1], db[0], idesc, 1u); }
-        if (PARTS >= 3) {
-          umma(tmem_d, da[1], db[1], idesc, 1u);
-          umma(tmem_d, da[0], db[2], idesc, 1u);
-          umma(tmem_d, da[2], db[0], idesc, 1u);
+        if (BL::kTransposed) {
+#pragma unroll
+          for (int j = 0; j < B_CH; ++j) {
+            const int q = j * PROD_THREADS + ptid, kk = q / (BN / 4), rc = q % (BN / 4);
+            if (kk < BK) bl.copy4(rb + (uint32_t)(kk * BN + rc * 4) * 4u, bst[0], lk + kk);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < B_PER; ++i) {
+            if (b_on[i]) {
+              bl.copy4(rb + priv(i, 0), bst[i < B_NST ? i : 0], lk + b_kg[i] * 8);
+              bl.copy4(rb + priv(i, 1), bst[i < B_NST ? i : 0], lk + b_kg[i] * 8 + 4);
+            }
+          }
         }
       }
-      umma_commit(&mma_done[s]);
-    }
-  }
-  if (nkb > 0) {
-    const int last = nkb - 1;                           // the last commit covers every earlier MMA
-    ok = mbar_wait(&mma_done[last & 1], (uint32_t)(last >> 1) & 1u) && ok;
-  }
-  tc_fence_after();
-  if (!ok && err) atomicExch(err, 1);
-  __syncthreads();                                      // every warp is done with the smem ring
-
-  // epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (= tile rows) and one half of the columns.
-  // TMEM -> registers -> 32x33 smem tile (transpose) -> 128-bit row-contiguous global stores.
-  {
-    constexpr int CW = (BN / 2 >= 32) ? 32 : 16;        // columns per chunk
-    constexpr int LPR = CW / 4;                         // lanes per row when storing
-    constexpr int RPI = 32 / LPR;                       // rows per store instruction
-    float* scr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-    const int lane_grp = warp & 3;
-    const int c_half = (warp >> 2) * (BN / 2);
-#pragma unroll 1
-    for (int c = c_half; c < c_half + BN / 2; c += CW) {
-      float v[32];
-      if (nkb > 0) {
-        tmem_ld_cols<CW>(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c, v);
+      if (lvalid) {
+        lk += BK;
+        if (++lkb == lnkb) { lt += G; open_tile(); }
+      }
+      cp_async_commit();
+      if (++ls == (uint32_t)ND) ls = 0;
+    };
+    auto read_item = [&](bool transposed, const uint8_t* raw, int i, int row, int kg, int rows, float (&v)[8]) {
+      if (transposed) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float*>(raw + (uint32_t)((kg * 8 + e) * rows + row) * 4u);
       } else {
-#pragma unroll
-        for (int i = 0; i < CW; ++i) v[i] = 0.f;
+        const float4 x = *reinterpret_cast<const float4*>(raw + priv(i, 0));
+        const float4 y = *reinterpret_cast<const float4*>(raw + priv(i, 1));
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
       }
+    };
+    open_tile();
+#pragma unroll 1
+    for (int d = 0; d < ND; ++d) issue();
+
+    uint32_t s = 0, ph = 0, rs = 0;
+    uint32_t tr_n = 0;
+    const bool tr_on = tm.trace && blockIdx.x == 0 && pw == 0 && lane == 0;
+#pragma unroll 1
+    for (uint32_t g = 0; g < total; ++g) {
+      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 0] = clock64();
+      cp_async_wait<ND - 1>();                                         // my copies of k-block g have landed
+      if (!mbar_wait(&empty_bar[s], ph ^ 1u, abortp)) abort_s = 1;    // MMAs that read this stage are done
+      if (COOP) asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory");   // everybody's copies landed
+      else __syncwarp();
+      if (*abortp) { ok = false; break; }                              // (uniform across the barrier)
+      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 1] = clock64();
+      const uint8_t* raw_a = rawring + (size_t)rs * RAW;
+      const uint8_t* raw_b = raw_a + RAW_A;
+      uint8_t* a_base = ring + (size_t)s * STAGE;
+      uint8_t* b_base = a_base + A_BYTES * PARTS;
+      if (!(tm.dbg & 4)) {
 #pragma unroll
-      for (int i = 0; i < CW; ++i) scr[lane * 33 + i] = v[i];
-      __syncwarp();
+        for (int i = 0; i < A_PER; ++i) {
+          float v[8];
+          read_item(AL::kTransposed, raw_a, i, a_row[i], a_kg[i], BM, v);
+          split_store<PARTS>(v, a_base, a_off[i], A_BYTES);
+        }
 #pragma unroll
-      for (int it = 0; it < 32 / RPI; ++it) {
-        const int r = it * RPI + lane / LPR, cq = (lane % LPR) * 4;
-        const int64_t m = m0 + lane_grp * 32 + r;
-        const int64_t n = n0 + c + cq;
-        if (m < M && n < N) {
-          const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
-          const typename EP::Row rw = ep.row(m);
-          store4<EP>(ep, rw, n, N, o);
+        for (int i = 0; i < B_PER; ++i) {
+          if (b_on[i]) {
+            float v[8];
+            read_item(BL::kTransposed, raw_b, i, b_row[i], b_kg[i], BN, v);
+            split_store<PARTS>(v, b_base, b_off[i], B_BYTES);
+          }
         }
       }
-      __syncwarp();
+      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 2] = clock64();
+      fence_async_smem();                                              // generic-proxy stores -> async proxy (UMMA)
+      if (COOP) asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory");   // everyone is done reading raw slot rs
+      else __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);                        // one arrival per producer warp
+      if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+      if (++rs == (uint32_t)ND) rs = 0;
+      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 3] = clock64();
+      ++tr_n;
+      issue();                                                         // refill the slot just freed (k-block g + ND)
     }
+    cp_async_wait<0>();
+  } else if (warp == MMA_WARP) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t s = 0, ph = 0;
+      int li = 0;
+      for (int64_t t = blockIdx.x; t < tm.total && ok; t += G, ++li) {
+        const int buf = li & 1;
+        const uint32_t aph = (uint32_t)(li >> 1) & 1u;
+        ok = mbar_wait(&acc_empty[buf], aph ^ 1u, abortp);               // epilogue drained this accumulator
+        if (!ok) break;
+        tc_fence_after();
+        int64_t m0, nq, kb0; int zi, nkb;
+        tm.decode(t, m0, nq, zi, kb0, nkb);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const bool tr_on = tm.trace && blockIdx.x == 0 && li == 0 + (kb >> 6) && kb < 64;
+          if (tr_on) tm.trace[256 + kb * 4 + 0] = clock64();
+          ok = mbar_wait(&full_bar[s], ph, abortp);
+          if (!ok) break;
+          tc_fence_after();
+          if (tr_on) tm.trace[256 + kb * 4 + 1] = clock64();
+          const uint32_t sa = smem_u32(ring + (size_t)s * STAGE), sb = sa + A_BYTES * PARTS;
+          if (!(tm.dbg & 8))
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint32_t koff = (uint32_t)ks * 256u;                   // two 128-byte core matrices per K = 16
+            uint64_t da[PARTS], db[PARTS];
+#pragma unroll
+            for (int p = 0; p < PARTS; ++p) {
+              da[p] = make_desc(sa + p * A_BYTES + koff, 128, 512);
+              db[p] = make_desc(sb + p * B_BYTES + koff, 128, 512);
+            }
+            // products in decreasing magnitude; parts: 0 = hi, 1 = mid, 2 = lo
+            umma(tmem_d, da[0], db[0], idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            if (PARTS >= 2) { umma(tmem_d, da[0], db[1], idesc, 1u); umma(tmem_d, da[1], db[0], idesc, 1u); }
+            if (PARTS >= 3) {
+              umma(tmem_d, da[1], db[1], idesc, 1u);
+              umma(tmem_d, da[0], db[2], idesc, 1u);
+              umma(tmem_d, da[2], db[0], idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);                                    // stage reusable once these MMAs retire
+          if (tr_on) tm.trace[256 + kb * 4 + 2] = clock64();
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(&acc_full[buf]);                                     // covers every MMA of the tile
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue =======================
+    float* scr = scratch + warp * (32 * 33);
+    int li = 0;
+    for (int64_t t = blockIdx.x; t < tm.total && ok; t += G, ++li) {
+      const int buf = li & 1;
+      const uint32_t aph = (uint32_t)(li >> 1) & 1u;
+      const bool tr_on = tm.trace && blockIdx.x == 0 && warp == 0 && lane == 0 && li < 16;
+      if (tr_on) tm.trace[512 + li * 4 + 0] = clock64();
+      ok = mbar_wait(&acc_full[buf], aph, abortp);
+      if (!ok) break;
+      tc_fence_after();
+      if (tr_on) tm.trace[512 + li * 4 + 1] = clock64();
+      int64_t m0, nq, kb0; int zi, nkb;
+      tm.decode(t, m0, nq, zi, kb0, nkb);
+      const int64_t n0 = nq * BN;
+      typename EP::Row rws[8];                                            // this lane's rows of the 8 store passes
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
+        rws[pass] = epi_row<EP>(ep, m < M ? m : M - 1, zi);
+      }
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= N) break;
+        const float4 b4 = epi_bias4<EP>(ep, n0 + c + (lane & 7) * 4, N);
+        float v[32];
+        tmem_ld32(trow + (uint32_t)c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+        __syncwarp();
+        EpiAux aux[8];
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {                            // row operands first (loads in flight together)
+          const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
+          const int64_t n = n0 + c + (lane & 7) * 4;
+          aux[pass] = (m < M && n < N) ? epi_aux<EP>(ep, rws[pass], n, N) : EpiAux{};
+        }
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {                            // 8 lanes x 4 columns per row, 4 rows per pass
+          const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
+          const int64_t m = m0 + warp * 32 + r;
+          const int64_t n = n0 + c + cq;
+          if (m < M && n < N && !(tm.dbg & 1)) {
+            const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
+            store4<EP>(ep, rws[pass], n, N, o, b4, aux[pass]);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (tr_on) tm.trace[512 + li * 4 + 2] = clock64();
+    }
+  }
+  if (!ok) {
+    abort_s = 1;
+    if (err) atomicExch(err, 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, BN);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-// N tile: at most 128 so that two or three CTAs share an SM (one CTA's staging / epilogue overlaps
-// another's MMAs); wider outputs use grid.y.
-inline int pick_bn(int64_t N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
+// =============================================================================================
+// 3xTF32 kernel (precision 3, the default fp32-class mode; precision 4 = single-pass TF32).
+//
+// tcgen05.mma.kind::tf32 reads fp32 words from shared memory and uses their upper 19 bits, so the
+// RAW fp32 k-block that cp.async drops into the stage *is* the "hi" operand -- no conversion and
+// no second staging buffer.  Only the residual  lo = x - trunc_tf32(x)  (exact in fp32) is
+// computed, elementwise and layout-preserving, by the thread that copied the chunk (no barrier
+// between producer warps).  Products hi*hi + hi*lo + lo*hi keep ~21 mantissa bits.
+//
+// Shared-memory layouts (per operand plane, ROWS x 32 fp32 = ROWS*128 bytes, 1024-byte aligned):
+//   K-contiguous operand  -> K-major SWIZZLE_128B:  off(row, c) = row*128 + ((c ^ (row&7)) << 4),
+//                            c = 16-byte chunk (4 consecutive k)
+//   transposed operand    -> MN-major SWIZZLE_128B_BASE32B (the only MN-major layout of 32-bit
+//                            operands): atoms of 4 k x 128 bytes (32 rows), the 32-byte chunk index
+//                            XOR-ed with k & 3.  chunk = 4 consecutive rows (16-byte index rc) of one k:
+//                            off(k, rc) = (rc>>3)*4096 + (k>>2)*512 + (k&3)*128 + (((((rc&7)>>1) ^ (k&3)) << 1 | (rc&1)) << 4)
+// Both are written directly by 16-byte cp.async's (whole 128-byte lines per quarter warp in HBM
+// and in shared memory), so weight gradients (both operands transposed) need no transposition.
+// =============================================================================================
+constexpr uint32_t TF32_MASK = 0xFFFFE000u;
+
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// swizzled descriptor, version 1; layout type (bits [61,64)): 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t type = 2) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46) | ((uint64_t)type << 61);
+}
+// byte offset of the 16-byte chunk (k, rc) of an MN-major plane
+__device__ __forceinline__ uint32_t mn_chunk_off(int k, int rc) {
+  const uint32_t j = (uint32_t)(rc & 7), k4 = (uint32_t)(k & 3);
+  return (uint32_t)(rc >> 3) * 4096u + (uint32_t)(k >> 2) * 512u + k4 * 128u + (((((j >> 1) ^ k4) << 1) | (j & 1u)) << 4);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+template <int BN, int PLANES>
+struct TfCfg {
+  static constexpr uint32_t PLANE_A = BM * BK * 4, PLANE_B = BN * BK * 4;
+  static constexpr uint32_t SLOT = (PLANE_A + PLANE_B) * PLANES;
+  static constexpr uint32_t RING = SMEM_BUDGET - EPI_SCRATCH - 1024;
+  static constexpr int ND_RAW = (int)(RING / SLOT);
+  static constexpr int ND = ND_RAW > MAX_STAGES ? MAX_STAGES : ND_RAW;
+  static_assert(ND >= 2, "shared-memory budget too small for this tile");
+  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr size_t SMEM = (size_t)ND * SLOT + EPI_SCRATCH + 1024;
+  static constexpr int A_CH = BM * 8 / PROD_THREADS;                          // 16-byte chunks per thread (4)
+  static constexpr int B_CH = (BN * 8 + PROD_THREADS - 1) / PROD_THREADS;     // 1..8
+};
+
+template <class AL, class BL, class EP, int BN, int PLANES>
+__global__ void __launch_bounds__(THREADS, 1)
+tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __restrict__ err) {
+  using C = TfCfg<BN, PLANES>;
+  constexpr int ND = C::ND, A_CH = C::A_CH, B_CH = C::B_CH;
+  constexpr uint32_t PLANE_A = C::PLANE_A, PLANE_B = C::PLANE_B, SLOT = C::SLOT;
+  constexpr uint32_t OFF_AHI = 0, OFF_ALO = PLANE_A, OFF_BHI = PLANE_A * PLANES, OFF_BLO = PLANE_A * PLANES + PLANE_B;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* scratch = reinterpret_cast<float*>(ring + (size_t)ND * SLOT);
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int abort_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < ND; ++i) { mbar_init(&full_bar[i], PROD_WARPS); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], EPI_WARPS); mbar_init(&acc_empty[1], EPI_WARPS);
+    abort_s = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  volatile int* abortp = &abort_s;
+  bool ok = true;
+  const int64_t G = gridDim.x;
+
+  if (warp >= PROD_WARP0) {
+    // ======================= producers =======================
+    const int ptid = tid - PROD_WARP0 * 32;
+    // chunk j of this thread -> byte offset inside the operand plane (same for hi and lo)
+    uint32_t a_o[A_CH], b_o[B_CH];
+    bool b_on[B_CH];
+#pragma unroll
+    for (int j = 0; j < A_CH; ++j) {
+      const int q = j * PROD_THREADS + ptid;
+      if (AL::kTransposed) {
+        const int rc = q % (BM / 4), k = q / (BM / 4);
+        a_o[j] = mn_chunk_off(k, rc);
+      } else {
+        const int row = q >> 3, c = q & 7;
+        a_o[j] = (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < B_CH; ++j) {
+      const int q = j * PROD_THREADS + ptid;
+      b_on[j] = q < BN * 8;
+      if (BL::kTransposed) {
+        const int rc = q % (BN / 4), k = q / (BN / 4);
+        b_o[j] = mn_chunk_off(k, rc);
+      } else {
+        const int row = q >> 3, c = q & 7;
+        b_o[j] = (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+      }
+    }
+    constexpr int A_NST = AL::kTransposed ? 1 : A_CH;
+    constexpr int B_NST = BL::kTransposed ? 1 : B_CH;
+    typename AL::St ast[A_NST];
+    typename BL::St bst[B_NST];
+    int64_t lt = blockIdx.x, lk = 0;
+    int lkb = 0, lnkb = 0;
+    bool lvalid = false;
+    uint32_t total = 0;
+    for (int64_t t = blockIdx.x; t < tm.total; t += G) {
+      int64_t m0, nq, kb0; int zi, nkb;
+      tm.decode(t, m0, nq, zi, kb0, nkb);
+      total += (uint32_t)nkb;
+    }
+    auto open_tile = [&]() {
+      lvalid = lt < tm.total;
+      if (!lvalid) return;
+      int64_t m0, nq; int zi;
+      tm.decode(lt, m0, nq, zi, lk, lnkb);
+      lkb = 0;
+      if (AL::kTransposed) { ast[0] = al.begin(m0 + (ptid % (BM / 4)) * 4); }
+      else {
+#pragma unroll
+        for (int j = 0; j < A_NST; ++j) ast[j] = al.begin(m0 + j * (PROD_THREADS / 8) + (ptid >> 3));
+      }
+      if (BL::kTransposed) { bst[0] = bl.begin(nq * BN + (ptid % (BN / 4)) * 4); }
+      else {
+#pragma unroll
+        for (int j = 0; j < B_NST; ++j) bst[j] = bl.begin(nq * BN + j * (PROD_THREADS / 8) + (ptid >> 3));
+      }
+    };
+    uint32_t ls = 0, lph = 0;                                        // slot / phase of the next k-block to load
+    auto issue = [&]() -> bool {                                     // always commits exactly one group
+      if (lvalid) {
+        if (!mbar_wait(&empty_bar[ls], lph ^ 1u, abortp)) return false;   // MMAs that read this slot are done
+        if (!(tm.dbg & 2)) {
+          const uint32_t base = smem_u32(ring + (size_t)ls * SLOT);
+#pragma unroll
+          for (int j = 0; j < A_CH; ++j) {
+            if (AL::kTransposed) al.copy4(base + OFF_AHI + a_o[j], ast[0], lk + (j * PROD_THREADS + ptid) / (BM / 4));
+            else al.copy4(base + OFF_AHI + a_o[j], ast[j], lk + (ptid & 7) * 4);
+          }
+#pragma unroll
+          for (int j = 0; j < B_CH; ++j) {
+            if (b_on[j]) {
+              if (BL::kTransposed) bl.copy4(base + OFF_BHI + b_o[j], bst[0], lk + (j * PROD_THREADS + ptid) / (BN / 4));
+              else bl.copy4(base + OFF_BHI + b_o[j], bst[j < B_NST ? j : 0], lk + (ptid & 7) * 4);
+            }
+          }
+        }
+        lk += BK;
+        if (++lkb == lnkb) { lt += G; open_tile(); }
+        if (++ls == (uint32_t)ND) { ls = 0; lph ^= 1u; }
+      }
+      cp_async_commit();
+      return true;
+    };
+    constexpr int D = ND - 1;                                        // k-blocks in flight
+    open_tile();
+#pragma unroll 1
+    for (int d = 0; d < D && ok; ++d) ok = issue();
+
+    uint32_t s = 0;
+    uint32_t tr_n = 0;
+    const bool tr_on = tm.trace && blockIdx.x == 0 && warp == PROD_WARP0 && lane == 0;
+#pragma unroll 1
+    for (uint32_t g = 0; g < total && ok; ++g) {
+      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 0] = clock64();
+      cp_async_wait<D - 1>();                                          // my chunks of k-block g have landed
+      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 1] = clock64();
+      if (PLANES == 2 && !(tm.dbg & 4)) {
+        uint8_t* base = ring + (size_t)s * SLOT;
+        auto residual = [&](uint32_t hi_off, uint32_t lo_off) {
+          const float4 x = *reinterpret_cast<const float4*>(base + hi_off);
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & TF32_MASK);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & TF32_MASK);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & TF32_MASK);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & TF32_MASK);
+          *reinterpret_cast<float4*>(base + lo_off) = l;
+        };
+#pragma unroll
+        for (int j = 0; j < A_CH; ++j) residual(OFF_AHI + a_o[j], OFF_ALO + a_o[j]);
+#pragma unroll
+        for (int j = 0; j < B_CH; ++j)
+          if (b_on[j]) residual(OFF_BHI + b_o[j], OFF_BLO + b_o[j]);
+      }
+      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 2] = clock64();
+      fence_async_smem();                                              // cp.async + generic stores -> async proxy (UMMA)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);                        // one arrival per producer warp
+      if (++s == (uint32_t)ND) s = 0;
+      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 3] = clock64();
+      ++tr_n;
+      ok = issue();                                                    // k-block g + D
+    }
+    cp_async_wait<0>();
+  } else if (warp == MMA_WARP) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BN, AL::kTransposed, BL::kTransposed);
+      // per MMA (K = 8): K-major advances 32 bytes inside the swizzle atom, MN-major two 512-byte k groups
+      constexpr uint32_t A_KSTEP = AL::kTransposed ? 1024u : 32u, B_KSTEP = BL::kTransposed ? 1024u : 32u;
+      constexpr uint32_t A_LBO = AL::kTransposed ? 4096u : 16u, B_LBO = BL::kTransposed ? 4096u : 16u;
+      constexpr uint32_t A_SBO = AL::kTransposed ? 512u : 1024u, B_SBO = BL::kTransposed ? 512u : 1024u;
+      constexpr uint32_t A_TY = AL::kTransposed ? 1u : 2u, B_TY = BL::kTransposed ? 1u : 2u;
+      uint32_t s = 0, ph = 0;
+      int li = 0;
+      for (int64_t t = blockIdx.x; t < tm.total && ok; t += G, ++li) {
+        const int buf = li & 1;
+        const uint32_t aph = (uint32_t)(li >> 1) & 1u;
+        ok = mbar_wait(&acc_empty[buf], aph ^ 1u, abortp);               // epilogue drained this accumulator
+        if (!ok) break;
+        tc_fence_after();
+        int64_t m0, nq, kb0; int zi, nkb;
+        tm.decode(t, m0, nq, zi, kb0, nkb);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const bool tr_on = tm.trace && blockIdx.x == 0 && li == 0 && kb < 64;
+          if (tr_on) tm.trace[256 + kb * 4 + 0] = clock64();
+          ok = mbar_wait(&full_bar[s], ph, abortp);
+          if (!ok) break;
+          tc_fence_after();
+          if (tr_on) tm.trace[256 + kb * 4 + 1] = clock64();
+          const uint32_t base = smem_u32(ring + (size_t)s * SLOT);
+          if (!(tm.dbg & 8))
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t ah = make_desc_sw128(base + OFF_AHI + ks * A_KSTEP, A_LBO, A_SBO, A_TY);
+            const uint64_t bh = make_desc_sw128(base + OFF_BHI + ks * B_KSTEP, B_LBO, B_SBO, B_TY);
+            umma_tf32(tmem_d, ah, bh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            if (PLANES == 2) {
+              const uint64_t alo = make_desc_sw128(base + OFF_ALO + ks * A_KSTEP, A_LBO, A_SBO, A_TY);
+              const uint64_t blo = make_desc_sw128(base + OFF_BLO + ks * B_KSTEP, B_LBO, B_SBO, B_TY);
+              umma_tf32(tmem_d, ah, blo, idesc, 1u);
+              umma_tf32(tmem_d, alo, bh, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);                                    // slot reusable once these MMAs retire
+          if (tr_on) tm.trace[256 + kb * 4 + 2] = clock64();
+          if (++s == (uint32_t)ND) { s = 0; ph ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(&acc_full[buf]);                                     // covers every MMA of the tile
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue =======================
+    float* scr = scratch + warp * (32 * 33);
+    int li = 0;
+    for (int64_t t = blockIdx.x; t < tm.total && ok; t += G, ++li) {
+      const int buf = li & 1;
+      const uint32_t aph = (uint32_t)(li >> 1) & 1u;
+      ok = mbar_wait(&acc_full[buf], aph, abortp);
+      if (!ok) break;
+      tc_fence_after();
+      int64_t m0, nq, kb0; int zi, nkb;
+      tm.decode(t, m0, nq, zi, kb0, nkb);
+      const int64_t n0 = nq * BN;
+      typename EP::Row rws[8];                                            // this lane's rows of the 8 store passes
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
+        rws[pass] = epi_row<EP>(ep, m < M ? m : M - 1, zi);
+      }
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= N) break;
+        const float4 b4 = epi_bias4<EP>(ep, n0 + c + (lane & 7) * 4, N);
+        float v[32];
+        tmem_ld32(trow + (uint32_t)c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+        __syncwarp();
+        EpiAux aux[8];
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {                            // row operands first (loads in flight together)
+          const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
+          const int64_t n = n0 + c + (lane & 7) * 4;
+          aux[pass] = (m < M && n < N) ? epi_aux<EP>(ep, rws[pass], n, N) : EpiAux{};
+        }
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {                            // 8 lanes x 4 columns per row, 4 rows per pass
+          const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
+          const int64_t m = m0 + warp * 32 + r;
+          const int64_t n = n0 + c + cq;
+          if (m < M && n < N && !(tm.dbg & 1)) {
+            const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
+            store4<EP>(ep, rws[pass], n, N, o, b4, aux[pass]);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  if (!ok) {
+    abort_s = 1;
+    if (err) atomicExch(err, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// N tile: as wide as the accumulator / staging budget allows, so the A operand is staged once
+inline int pick_bn(int64_t N, int precision) {
+  if (precision >= 3) return N > 64 ? 128 : (N > 32 ? 64 : 32);
+  if (N > 128 && precision != 2) return 256;
+  return N > 64 ? 128 : (N > 32 ? 64 : 32);
+}
 
 template <class AL, class BL, class EP, int BN, int SPLIT>
 int launch_one(const AL& al, const BL& bl, const EP& ep, int64_t M, int64_t N, int64_t K, int splits,
                int64_t k_per_split, int* err, cudaStream_t st) {
   auto kern = tc_gemm_kernel<AL, BL, EP, BN, SPLIT>;
-  constexpr size_t sm = smem_bytes<BN, SPLIT>();
+  constexpr size_t sm = Cfg<BN, SPLIT>::SMEM;
   static bool optin = false;
   if (!optin) {
     TM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     optin = true;
   }
-  dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, BN), (unsigned)splits);
-  kern<<<grid, THREADS, sm, st>>>(al, bl, ep, M, N, K, k_per_split, err);
+  TileMap tm;
+  tm.nt = (int)cdiv(N, BN);
+  tm.z = splits < 1 ? 1 : splits;
+  tm.total = cdiv(M, BM) * tm.nt * tm.z;
+  tm.K = K;
+  tm.k_per_split = k_per_split;
+  static const int dbg = getenv("TM_TC_DEBUG") ? atoi(getenv("TM_TC_DEBUG")) : 0;
+  tm.dbg = dbg;
+  tm.trace = nullptr;
+  static const bool trace_on = getenv("TM_TC_TRACE") != nullptr;
+  static long long* trace_buf = nullptr;
+  if (trace_on) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 1024 * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, 1024 * sizeof(long long), st);
+    tm.trace = trace_buf;
+  }
+  const int64_t grid = tm.total < sm_count() ? tm.total : sm_count();
+  kern<<<(unsigned)grid, THREADS, sm, st>>>(al, bl, ep, M, N, tm, err);
+  if (trace_on) {
+    static long long h[1024];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    long long t0 = h[0];
+    fprintf(stderr, "[tc trace] BN=%d SPLIT=%d NS=%d tiles=%lld grid=%lld\n", BN, SPLIT, Cfg<BN, SPLIT>::NS, (long long)tm.total, (long long)grid);
+    for (int i = 0; i < 40; ++i)
+      fprintf(stderr, "  prod %2d: start %7lld  got-empty %7lld  stored %7lld  arrived %7lld | mma: wait %7lld full %7lld issued %7lld\n", i,
+              h[i * 4] - t0, h[i * 4 + 1] - t0, h[i * 4 + 2] - t0, h[i * 4 + 3] - t0, h[256 + i * 4] - t0, h[256 + i * 4 + 1] - t0,
+              h[256 + i * 4 + 2] - t0);
+    for (int i = 0; i < 6; ++i)
+      fprintf(stderr, "  epi %2d: wait %7lld full %7lld done %7lld\n", i, h[512 + i * 4] - t0, h[512 + i * 4 + 1] - t0, h[512 + i * 4 + 2] - t0);
+  }
   return check_launch("tc_gemm");
+}
+
+template <class AL, class BL, class EP, int BN, int PLANES>
+int launch_tf(const AL& al, const BL& bl, const EP& ep, int64_t M, int64_t N, int64_t K, int splits,
+              int64_t k_per_split, int* err, cudaStream_t st) {
+  auto kern = tf_gemm_kernel<AL, BL, EP, BN, PLANES>;
+  constexpr size_t sm = TfCfg<BN, PLANES>::SMEM;
+  static bool optin = false;
+  if (!optin) {
+    TM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    optin = true;
+  }
+  TileMap tm;
+  tm.nt = (int)cdiv(N, BN);
+  tm.z = splits < 1 ? 1 : splits;
+  tm.total = cdiv(M, BM) * tm.nt * tm.z;
+  tm.K = K;
+  tm.k_per_split = k_per_split;
+  static const int dbg = getenv("TM_TC_DEBUG") ? atoi(getenv("TM_TC_DEBUG")) : 0;
+  tm.dbg = dbg;
+  tm.trace = nullptr;
+  static const bool trace_on = getenv("TM_TC_TRACE") != nullptr;
+  static long long* trace_buf = nullptr;
+  if (trace_on) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 1024 * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, 1024 * sizeof(long long), st);
+    tm.trace = trace_buf;
+  }
+  const int64_t grid = tm.total < sm_count() ? tm.total : sm_count();
+  kern<<<(unsigned)grid, THREADS, sm, st>>>(al, bl, ep, M, N, tm, err);
+  if (trace_on) {
+    static long long h[1024];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    long long t0 = h[0];
+    fprintf(stderr, "[tf trace] BN=%d PLANES=%d ND=%d tiles=%lld grid=%lld\n", BN, PLANES, TfCfg<BN, PLANES>::ND, (long long)tm.total, (long long)grid);
+    for (int i = 0; i < 40; ++i)
+      fprintf(stderr, "  prod %2d: start %7lld  landed %7lld  lo-done %7lld  arrived %7lld | mma: wait %7lld full %7lld issued %7lld\n", i,
+              h[i * 4] - t0, h[i * 4 + 1] - t0, h[i * 4 + 2] - t0, h[i * 4 + 3] - t0, h[256 + i * 4] - t0, h[256 + i * 4 + 1] - t0,
+              h[256 + i * 4 + 2] - t0);
+  }
+  return check_launch("tf_gemm");
 }
 
 template <class AL, class BL, class EP>
 int launch(const AL& al, const BL& bl, const EP& ep, int64_t M, int64_t N, int64_t K, int splits,
            int64_t k_per_split, int precision, int* err, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
-  const int bn = pick_bn(N);
+  const int bn = pick_bn(N, precision);
+  if (precision >= 3) {
+#define TM_TF_CASE(BN_)                                                                                  \
+  return precision == 3 ? launch_tf<AL, BL, EP, BN_, 2>(al, bl, ep, M, N, K, splits, k_per_split, err, st) \
+                        : launch_tf<AL, BL, EP, BN_, 1>(al, bl, ep, M, N, K, splits, k_per_split, err, st)
+    switch (bn) {
+      case 128: TM_TF_CASE(128);
+      case 64: TM_TF_CASE(64);
+      default: TM_TF_CASE(32);
+    }
+#undef TM_TF_CASE
+  }
 #define TM_TC_CASE(BN_)                                                                                 \
   return precision == 2   ? launch_one<AL, BL, EP, BN_, 6>(al, bl, ep, M, N, K, splits, k_per_split, err, st) \
          : precision == 1 ? launch_one<AL, BL, EP, BN_, 3>(al, bl, ep, M, N, K, splits, k_per_split, err, st) \
                           : launch_one<AL, BL, EP, BN_, 1>(al, bl, ep, M, N, K, splits, k_per_split, err, st)
   switch (bn) {
+    case 256:
+      return precision == 1 ? launch_one<AL, BL, EP, 256, 3>(al, bl, ep, M, N, K, splits, k_per_split, err, st)
+                            : launch_one<AL, BL, EP, 256, 1>(al, bl, ep, M, N, K, splits, k_per_split, err, st);
     case 128: TM_TC_CASE(128);
     case 64: TM_TC_CASE(64);
     default: TM_TC_CASE(32);

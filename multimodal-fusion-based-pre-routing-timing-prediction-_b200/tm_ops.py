@@ -24,20 +24,22 @@ D = 128
 BIAS, RELU, MASK, ACCUM = 1, 2, 4, 8
 
 # Arithmetic of the dense contractions (MLPs, weight gradients):
-#   "tc6"  tcgen05 tensor cores, operands split into three bf16 terms (24 bits), 6 MMAs, fp32
-#          accumulate in TMEM -- fp32-class accuracy, the default for the rtol 1e-3 path;
-#   "tc3"  two bf16 terms, 3 MMAs (~16-bit products);
+#   "tf32x3" tcgen05 kind::tf32, x = hi + lo with hi = the fp32 word itself (the tensor core reads its
+#          upper 19 bits) and lo = x - trunc(x); hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM:
+#          ~21-bit products, fp32-class accuracy -- the default for the rtol 1e-3 path;
+#   "tf32" single-pass TF32 (11-bit operands);
+#   "tc6"  bf16 operands split into three terms (24 bits), 6 MMAs;  "tc3": two terms, 3 MMAs;
 #   "bf16" tcgen05 with plain bf16 operands (rtol 2e-2 class);
 #   "fp32" the CUDA-core FFMA kernels (tm_gemm_nn / tm_gemm_tn).
-MATH = os.environ.get("TM_MATH", "tc6")
+MATH = os.environ.get("TM_MATH", "tf32x3")
 TC_MIN_K = 16          # contractions shorter than this stay on the CUDA-core kernel (K = 1, 2: pure bandwidth)
 
 
 def _precision(math=None):
     m = math or MATH
-    if m not in ("tc6", "tc3", "bf16", "fp32"):
+    if m not in ("tf32x3", "tf32", "tc6", "tc3", "bf16", "fp32"):
         raise ValueError(f"unknown math mode {m!r}")
-    return {"tc6": 2, "tc3": 1, "bf16": 0, "fp32": None}[m]
+    return {"tf32x3": 3, "tf32": 4, "tc6": 2, "tc3": 1, "bf16": 0, "fp32": None}[m]
 
 
 def _colsum(R, C, X, ld, rows, out, accumulate):
@@ -74,6 +76,10 @@ def gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, a_rows=None, c_rows=None, bias=None
             B, ldb = transpose(B[:, :K] if B.shape[1] != K else B), N
         call("tm_gemm_nn", M, N, K, A, lda, a_rows, B, ldb, C, ldc, c_rows, bias, mask, ldmask, flags, stream())
     else:
+        if not b_is_nk and B.dim() == 2 and B.is_contiguous() and B.shape == (K, N) and B.numel() <= (1 << 22):
+            # a [K,N] weight: hand the tensor cores the K-major [N,K] form (one tiny transpose
+            # instead of an MN-major operand re-staged by every CTA)
+            B, ldb, b_is_nk = transpose(B), K, True
         call("tm_tc_gemm_nn", M, N, K, A, lda, a_rows, B, ldb, 1 if b_is_nk else 0, C, ldc, c_rows, bias, mask,
              ldmask, flags, prec, tm_lib.err_flag(C.device), stream())
 
@@ -116,14 +122,21 @@ def colsum(X, R, C, ld, out=None, accumulate=0):
 # --------------------------------------------------------------------------------------------
 # two-layer MLP (model.py:10-24 with sizes (in, hid, out)):  y = W2 relu(W1 x + b1) + b2
 # --------------------------------------------------------------------------------------------
-def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None):
+def _recurrence_math():
+    """Arithmetic of the hoisted self-term MLPs.  Their output S seeds the 101-level recurrence, whose
+    ReLU masks turn forward rounding differences into gradient differences, so they keep 24-bit
+    products ("tc6") when the default mode is one of the ~21-bit / 16-bit ones."""
+    return "tc6" if MATH in ("tf32x3", "tf32", "tc3") else None
+
+
+def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, math=None):
     """x rows (optionally gathered by ``rows``) -> out rows (optionally scattered by ``out_rows``).
     Returns the hidden activations (n_rows, hid) needed by ``mlp2_backward``."""
     hid, kin = w1.shape
     nout = w2.shape[0]
     h = torch.empty(n_rows, hid, dtype=torch.float32, device=out.device)
-    gemm_nn(n_rows, hid, kin, x, ldx, _f32c(w1), kin, h, hid, a_rows=rows, bias=b1, flags=RELU, b_is_nk=True)
-    gemm_nn(n_rows, nout, hid, h, hid, _f32c(w2), hid, out, ldo, c_rows=out_rows, bias=b2, b_is_nk=True)
+    gemm_nn(n_rows, hid, kin, x, ldx, _f32c(w1), kin, h, hid, a_rows=rows, bias=b1, flags=RELU, b_is_nk=True, math=math)
+    gemm_nn(n_rows, nout, hid, h, hid, _f32c(w2), hid, out, ldo, c_rows=out_rows, bias=b2, b_is_nk=True, math=math)
     return h
 
 
@@ -177,9 +190,9 @@ def gnn_forward(sched, cell_feat, net_feat, params, save=True):
     S = torch.empty(n, D, dtype=torch.float32, device=dev)
     nc, nn_ = int(sched.cell_class.numel()), int(sched.net_class.numel())
     hc = mlp2_forward(cell_feat, cell_feat.stride(0), sched.cell_class, nc, cs1w, cs1b, cs2w, cs2b, S, D,
-                      out_rows=sched.cell_class)
+                      out_rows=sched.cell_class, math=_recurrence_math())
     hn = mlp2_forward(net_feat, net_feat.stride(0), sched.net_class, nn_, ns1w, ns1b, ns2w, ns2b, S, D,
-                      out_rows=sched.net_class)
+                      out_rows=sched.net_class, math=_recurrence_math())
     H = torch.zeros(n, D, dtype=torch.float32, device=dev)
     ncr = sched.n_cell_rows
     A = LSE = HID = None

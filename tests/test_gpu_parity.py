@@ -25,7 +25,7 @@ def mods(pkg):
     tm_lib.check_err_flags()                     # no tensor-core barrier ever timed out
 
 
-@pytest.fixture(params=["tc6", "fp32"])
+@pytest.fixture(params=["tf32x3", "tc6", "fp32"])
 def math_mode(request, mods):
     """Run a test under both fp32-class arithmetic modes (tensor-core split-bf16 x3, CUDA cores)."""
     old = mods["ops"].MATH
