@@ -25,7 +25,7 @@ namespace {
 constexpr int D = 128;     // out_feat_dim (model.py:43, options.py:10)
 constexpr int HID = 256;   // MLP hidden width (model.py:48)
 constexpr int TILE = 16;   // pins per CTA on a cell level
-constexpr int CT = 128;    // threads per CTA on a cell level
+constexpr int CT = 256;    // threads per CTA on a cell level (8 warps: two per scheduler hide the ALU latency)
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -58,18 +58,28 @@ gnn_net_fwd_kernel(const int* __restrict__ order, int p0, int cnt, const int* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// tile MLP shared by forward and backward: out = epi2( epi1(in @ Wa) @ Wb ) for a 16-row tile,
+// tile MLP shared by forward and backward: out = (epi1(in @ Wa)) @ Wb for a 16-row tile,
 //   Wa: [128][256] row-major (k-major), Wb: [256][128] row-major.
+// A level holds only a few thousand pins and the next level needs all of them, so the tile is 16
+// rows and every SM gets one: the MLP runs on the warp-level tensor-core path (mma.sync m16n8k8,
+// whose M = 16 is exactly the tile; tcgen05's M >= 64 would idle 3/4 of every instruction here) in
+// 3xTF32: x = hi + lo with hi = rna_tf32(x), lo = x - hi (exact); lo*hi + hi*lo + hi*hi accumulated
+// in fp32 keeps ~22 mantissa bits per product -- the fp32-class accuracy the 101-level recurrence needs.
 // The 256 KB of weights do not fit in shared memory next to the tiles, so they are STREAMED:
 // 16 chunks of 16 KB (8 of Wa, 8 of Wb; each chunk is a contiguous run of k-rows) flow through a
-// 3-stage cp.async ring, so the L2->SM weight traffic is bandwidth- not latency-bound and overlaps
-// the FFMA work.  128 threads; GEMM1 thread tile 8 rows x 4 cols, GEMM2 thread tile 4 rows x 4 cols;
-// tile rows are read as warp-wide broadcasts, weights as conflict-free 128-bit LDS.
+// 3-stage cp.async ring.  Row strides are padded (IN_LD, MID_LD, chunk rows + 8 floats) so that the
+// mma fragment loads hit 32 distinct banks.  256 threads = 8 warps; warp w owns hidden columns
+// 32w..32w+31 in GEMM1 and output columns 16w..16w+15 in GEMM2.
 // ---------------------------------------------------------------------------------------------
-constexpr int CHUNK = 4096;       // floats per weight chunk (16 KB)
+constexpr int CHUNK = 4096;       // floats per weight chunk in HBM (16 KB)
 constexpr int NSTAGE = 3;
 constexpr int NCHUNK = 16;
-constexpr size_t CELL_SMEM = (size_t)(TILE * D + TILE * HID + NSTAGE * CHUNK) * sizeof(float) + TILE * sizeof(int);
+constexpr int IN_LD = D + 4;      // 132: bank(g*132 + t) = 4g + t   -> conflict-free A fragments
+constexpr int MID_LD = HID + 4;   // 260
+constexpr int WA_LD = HID + 8;    // 264: bank(t*264 + g) = 8t + g   -> conflict-free B fragments
+constexpr int WB_LD = D + 8;      // 136
+constexpr int SLOT = 32 * WB_LD;  // 4352 floats >= 16 * WA_LD (4224)
+constexpr size_t CELL_SMEM = (size_t)(TILE * IN_LD + TILE * MID_LD + NSTAGE * SLOT) * sizeof(float) + TILE * sizeof(int);
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -82,10 +92,22 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void issue_chunk(float* wbuf, const float* __restrict__ Wa,
                                             const float* __restrict__ Wb, int c, int tid) {
   if (c < NCHUNK) {
-    const float* src = (c < 8) ? Wa + (size_t)c * CHUNK : Wb + (size_t)(c - 8) * CHUNK;
-    float* dst = wbuf + (c % NSTAGE) * CHUNK;
+    float* dst = wbuf + (c % NSTAGE) * SLOT;
+    if (c < 8) {                      // 16 rows x 256 floats of Wa
+      const float* src = Wa + (size_t)c * CHUNK;
 #pragma unroll
-    for (int i = 0; i < CHUNK / 4 / CT; ++i) cp_async16(dst + (tid + i * CT) * 4, src + (tid + i * CT) * 4);
+      for (int i = 0; i < CHUNK / 4 / CT; ++i) {
+        const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
+        cp_async16(dst + row * WA_LD + c4, src + row * HID + c4);
+      }
+    } else {                          // 32 rows x 128 floats of Wb
+      const float* src = Wb + (size_t)(c - 8) * CHUNK;
+#pragma unroll
+      for (int i = 0; i < CHUNK / 4 / CT; ++i) {
+        const int q = tid + i * CT, row = q >> 5, c4 = (q & 31) * 4;
+        cp_async16(dst + row * WB_LD + c4, src + row * D + c4);
+      }
+    }
   }
   cp_async_commit();   // always commit (possibly empty) so that wait_group<1> means "chunk c landed"
 }
@@ -96,78 +118,83 @@ __device__ __forceinline__ void mlp_prologue(float* wbuf, const float* Wa, const
   issue_chunk(wbuf, Wa, Wb, 1, tid);
 }
 
-template <class Epi1, class Epi2>
-__device__ __forceinline__ void mlp_tile(const float (*in_s)[D], float (*mid_s)[HID], float* wbuf,
-                                         const float* Wa, const float* Wb, int tid, Epi1 epi1, Epi2 epi2) {
-  const int cg1 = tid & 63, rg1 = tid >> 6;   // GEMM1: cols 4*cg1.., rows 8*rg1..
-  const int cg2 = tid & 31, rg2 = tid >> 5;   // GEMM2: cols 4*cg2.., rows 4*rg2..
-  float acc1[8][4], acc2[4][4];
+// hi = x rounded to 11 significant bits (round half away: add half an ulp_tf32, clear the low 13
+// bits -- two integer ops; cvt.rna.tf32 expands to a much longer sequence), lo = x - hi (exact)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// one k-step (8) of a 16 x (8*NT) product: A fragment from a padded row-major tile, B from a chunk
+template <int NT>
+__device__ __forceinline__ void mma_kstep(float (&acc)[NT][4], const float* a_tile, int a_ld, int ka,
+                                          const float* w, int w_ld, int kw, int n_base, int g, int t) {
+  uint32_t ah[4], al[4];
+  split_tf32(a_tile[g * a_ld + ka + t], ah[0], al[0]);
+  split_tf32(a_tile[(g + 8) * a_ld + ka + t], ah[1], al[1]);
+  split_tf32(a_tile[g * a_ld + ka + t + 4], ah[2], al[2]);
+  split_tf32(a_tile[(g + 8) * a_ld + ka + t + 4], ah[3], al[3]);
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+  for (int j = 0; j < NT; ++j) {
+    uint32_t bh0, bl0, bh1, bl1;
+    split_tf32(w[(kw + t) * w_ld + n_base + j * 8 + g], bh0, bl0);
+    split_tf32(w[(kw + t + 4) * w_ld + n_base + j * 8 + g], bh1, bl1);
+    mma_tf32(acc[j], al, bh0, bh1);        // small terms first
+    mma_tf32(acc[j], ah, bl0, bl1);
+    mma_tf32(acc[j], ah, bh0, bh1);
+  }
+}
+
+// in_s: [TILE][IN_LD], mid_s: [TILE][MID_LD] (receives epi1 of the first product), out_s: [TILE][IN_LD]
+// (raw second product; may alias in_s).  epi1(row, col, v0, v1) -> float2 for columns col, col+1.
+// Ends with a __syncthreads(): mid_s and out_s are complete and visible to the whole CTA.
+template <class Epi1>
+__device__ __forceinline__ void mlp_tile(const float* in_s, float* mid_s, float* out_s, float* wbuf,
+                                         const float* Wa, const float* Wb, int tid, Epi1 epi1) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  constexpr int NT1 = HID / 8 / (CT / 32), NT2 = D / 8 / (CT / 32);   // n-tiles per warp: 4 and 2
+  float acc1[NT1][4], acc2[NT2][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc1[r][c] = 0.f;
+  for (int j = 0; j < NT1; ++j)
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) acc1[j][c] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc2[r][c] = 0.f;
+  for (int j = 0; j < NT2; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc2[j][c] = 0.f;
 
   for (int c = 0; c < NCHUNK; ++c) {
     cp_async_wait<1>();
     __syncthreads();                      // chunk c visible; buffer of chunk c-1 free; tiles visible
     issue_chunk(wbuf, Wa, Wb, c + 2, tid);
-    const float* w = wbuf + (c % NSTAGE) * CHUNK;
-    if (c < 8) {                          // GEMM1: k rows 16c .. 16c+15 of Wa, 256 columns
-      const int kb = c * 16;
+    const float* w = wbuf + (c % NSTAGE) * SLOT;
+    if (c < 8) {                          // GEMM1: k rows 16c .. 16c+15 of Wa
 #pragma unroll
-      for (int kk = 0; kk < 16; kk += 4) {
-        float4 a[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float4*>(&in_s[rg1 * 8 + r][kb + kk]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 wv = *reinterpret_cast<const float4*>(w + (kk + j) * HID + cg1 * 4);
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const float av = (j == 0) ? a[r].x : (j == 1) ? a[r].y : (j == 2) ? a[r].z : a[r].w;
-            acc1[r][0] = fmaf(av, wv.x, acc1[r][0]);
-            acc1[r][1] = fmaf(av, wv.y, acc1[r][1]);
-            acc1[r][2] = fmaf(av, wv.z, acc1[r][2]);
-            acc1[r][3] = fmaf(av, wv.w, acc1[r][3]);
-          }
-        }
-      }
+      for (int ks = 0; ks < 2; ++ks) mma_kstep<NT1>(acc1, in_s, IN_LD, c * 16 + ks * 8, w, WA_LD, ks * 8, warp * NT1 * 8, g, t);
       if (c == 7) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float4 o = epi1(rg1 * 8 + r, cg1 * 4, make_float4(acc1[r][0], acc1[r][1], acc1[r][2], acc1[r][3]));
-          *reinterpret_cast<float4*>(&mid_s[rg1 * 8 + r][cg1 * 4]) = o;
+        for (int j = 0; j < NT1; ++j) {
+          const int col = warp * NT1 * 8 + j * 8 + 2 * t;
+          *reinterpret_cast<float2*>(&mid_s[g * MID_LD + col]) = epi1(g, col, acc1[j][0], acc1[j][1]);
+          *reinterpret_cast<float2*>(&mid_s[(g + 8) * MID_LD + col]) = epi1(g + 8, col, acc1[j][2], acc1[j][3]);
         }
       }
-    } else {                              // GEMM2: k rows 32(c-8) .. +31 of Wb, 128 columns
-      const int kb = (c - 8) * 32;
+    } else {                              // GEMM2: k rows 32(c-8) .. +31 of Wb
 #pragma unroll
-      for (int kk = 0; kk < 32; kk += 4) {
-        float4 a[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(&mid_s[rg2 * 4 + r][kb + kk]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 wv = *reinterpret_cast<const float4*>(w + (kk + j) * D + cg2 * 4);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const float av = (j == 0) ? a[r].x : (j == 1) ? a[r].y : (j == 2) ? a[r].z : a[r].w;
-            acc2[r][0] = fmaf(av, wv.x, acc2[r][0]);
-            acc2[r][1] = fmaf(av, wv.y, acc2[r][1]);
-            acc2[r][2] = fmaf(av, wv.z, acc2[r][2]);
-            acc2[r][3] = fmaf(av, wv.w, acc2[r][3]);
-          }
-        }
-      }
+      for (int ks = 0; ks < 4; ++ks) mma_kstep<NT2>(acc2, mid_s, MID_LD, (c - 8) * 32 + ks * 8, w, WB_LD, ks * 8, warp * NT2 * 8, g, t);
     }
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-    epi2(rg2 * 4 + r, cg2 * 4, make_float4(acc2[r][0], acc2[r][1], acc2[r][2], acc2[r][3]));
+  for (int j = 0; j < NT2; ++j) {
+    const int col = warp * NT2 * 8 + j * 8 + 2 * t;
+    *reinterpret_cast<float2*>(&out_s[g * IN_LD + col]) = make_float2(acc2[j][0], acc2[j][1]);
+    *reinterpret_cast<float2*>(&out_s[(g + 8) * IN_LD + col]) = make_float2(acc2[j][2], acc2[j][3]);
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -181,10 +208,10 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
                     const float* __restrict__ b2, float* __restrict__ A, float* __restrict__ LSE,
                     float* __restrict__ HIDb) {
   extern __shared__ __align__(16) float smem[];
-  float (*a_s)[D] = reinterpret_cast<float (*)[D]>(smem);
-  float (*hid_s)[HID] = reinterpret_cast<float (*)[HID]>(smem + TILE * D);
-  float* wbuf = smem + TILE * D + TILE * HID;
-  int* v_s = reinterpret_cast<int*>(wbuf + NSTAGE * CHUNK);
+  float (*a_s)[IN_LD] = reinterpret_cast<float (*)[IN_LD]>(smem);
+  float (*hid_s)[MID_LD] = reinterpret_cast<float (*)[MID_LD]>(smem + TILE * IN_LD);
+  float* wbuf = smem + TILE * IN_LD + TILE * MID_LD;
+  int* v_s = reinterpret_cast<int*>(wbuf + NSTAGE * SLOT);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * TILE;
   mlp_prologue(wbuf, W1t, W2t, tid);
@@ -256,23 +283,31 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
   }
 
   // phases 2+3: hidden = relu(a @ W1t + b1);  h = relu(S + hidden @ W2t + b2)
-  auto epi1 = [&](int row, int col, float4 acc) {
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + col));
-    const float4 o = f4relu(make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w));
-    const int p = t0 + row;
-    if (HIDb && p < cnt) st4(HIDb + (int64_t)(crow0 + p) * HID + col, o);
-    return o;
+  auto epi1 = [&](int row, int col, float v0, float v1) {
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(b1 + col));
+    return make_float2(fmaxf(v0 + bb.x, 0.f), fmaxf(v1 + bb.y, 0.f));
   };
-  auto epi2 = [&](int row, int col, float4 acc) {
+  mlp_tile(&a_s[0][0], &hid_s[0][0], &a_s[0][0], wbuf, W1t, W2t, tid, epi1);
+  // coalesced epilogues from shared memory: hidden rows (saved for backward), then h rows
+  if (HIDb) {
+#pragma unroll
+    for (int i = 0; i < TILE * HID / 4 / CT; ++i) {
+      const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
+      if (t0 + row < cnt) st4(HIDb + (int64_t)(crow0 + t0 + row) * HID + c4, *reinterpret_cast<const float4*>(&hid_s[row][c4]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TILE * D / 4 / CT; ++i) {
+    const int q = tid + i * CT, row = q >> 5, c4 = (q & 31) * 4;
     const int v = v_s[row];
     if (v >= 0) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col));
-      const float4 sv = ld4_stream(S + (int64_t)v * D + col);
-      st4(H + (int64_t)v * D + col,
+      const float4 acc = *reinterpret_cast<const float4*>(&a_s[row][c4]);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c4));
+      const float4 sv = ld4_stream(S + (int64_t)v * D + c4);
+      st4(H + (int64_t)v * D + c4,
           f4relu(make_float4(acc.x + bb.x + sv.x, acc.y + bb.y + sv.y, acc.z + bb.z + sv.z, acc.w + bb.w + sv.w)));
     }
-  };
-  mlp_tile(a_s, hid_s, wbuf, W1t, W2t, tid, epi1, epi2);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -346,9 +381,9 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
                     const float* __restrict__ A, const float* __restrict__ LSE,
                     const float* __restrict__ HIDb, float* __restrict__ GHID, float* __restrict__ GZC) {
   extern __shared__ __align__(16) float smem[];
-  float (*gz_s)[D] = reinterpret_cast<float (*)[D]>(smem);
-  float (*gh_s)[HID] = reinterpret_cast<float (*)[HID]>(smem + TILE * D);
-  float* wbuf = smem + TILE * D + TILE * HID;
+  float (*gz_s)[IN_LD] = reinterpret_cast<float (*)[IN_LD]>(smem);
+  float (*gh_s)[MID_LD] = reinterpret_cast<float (*)[MID_LD]>(smem + TILE * IN_LD);
+  float* wbuf = smem + TILE * IN_LD + TILE * MID_LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * TILE;
   // g_hid = (g_z @ W2) * (hid > 0): W2 is [128][256] as stored by nn.Linear(256,128)  -> "Wa"
@@ -433,22 +468,27 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
       }
     }
   }
-  auto epi1 = [&](int row, int col, float4 acc) {
+  // g_hid = (g_z @ W2) * (hid > 0);  g_a = g_hid @ W1
+  auto epi1 = [&](int row, int col, float v0, float v1) {
     const int p = t0 + row;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 o = make_float2(0.f, 0.f);
     if (p < cnt) {
-      const float4 hd = ld4(HIDb + (int64_t)(crow0 + p) * HID + col);
-      o = make_float4(hd.x > 0.f ? acc.x : 0.f, hd.y > 0.f ? acc.y : 0.f, hd.z > 0.f ? acc.z : 0.f,
-                      hd.w > 0.f ? acc.w : 0.f);
-      st4(GHID + (int64_t)(crow0 + p) * HID + col, o);
+      const float2 hd = *reinterpret_cast<const float2*>(HIDb + (int64_t)(crow0 + p) * HID + col);
+      o = make_float2(hd.x > 0.f ? v0 : 0.f, hd.y > 0.f ? v1 : 0.f);
     }
     return o;
   };
-  auto epi2 = [&](int row, int col, float4 acc) {
-    const int p = t0 + row;
-    if (p < cnt) st4(GA + (int64_t)(crow0 + p) * D + col, acc);
-  };
-  mlp_tile(gz_s, gh_s, wbuf, W2, W1, tid, epi1, epi2);
+  mlp_tile(&gz_s[0][0], &gh_s[0][0], &gz_s[0][0], wbuf, W2, W1, tid, epi1);
+#pragma unroll
+  for (int i = 0; i < TILE * HID / 4 / CT; ++i) {
+    const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
+    if (t0 + row < cnt) st4(GHID + (int64_t)(crow0 + t0 + row) * HID + c4, *reinterpret_cast<const float4*>(&gh_s[row][c4]));
+  }
+#pragma unroll
+  for (int i = 0; i < TILE * D / 4 / CT; ++i) {
+    const int q = tid + i * CT, row = q >> 5, c4 = (q & 31) * 4;
+    if (t0 + row < cnt) st4(GA + (int64_t)(crow0 + t0 + row) * D + c4, *reinterpret_cast<const float4*>(&gz_s[row][c4]));
+  }
 }
 
 int cell_smem_optin() {

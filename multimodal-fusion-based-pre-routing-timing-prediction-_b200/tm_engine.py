@@ -93,6 +93,10 @@ class DesignStep:
         self.model, self.cnn = model, cnn
         self.pg, self.world = process_group, world_size
         self.comm_stream = torch.cuda.Stream() if world_size > 1 else None
+        # The image branch (U-Net) and the netlist branch (GNN) are independent until the fusion, and
+        # both are chains of small latency-bound kernels: they run on two streams, forward and backward.
+        self.image_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.overlap = True
         self._pending = []
         g = model.gnn
         sd = dict(g.named_parameters())
@@ -134,11 +138,17 @@ class DesignStep:
         """Forward + backward.  Returns (loss (1,) device tensor, pred (T,)); fills ``.grad``."""
         m, cnn = self.model, self.cnn
         dev = b.image.device
-        fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
-        feat = fmap.reshape(-1)
+        main = torch.cuda.current_stream()
+        side = self.image_stream if (self.overlap and self.image_stream is not None) else main
+        side.wait_stream(main)                               # fork: inputs / parameters are ready on `main`
         sched = b.graph.schedule()
         gp = [p.detach() for p in self.gnn_params]
+        # the longer chain is enqueued first so the host's launch time for the other one overlaps it
         H, saved = tm_ops.gnn_forward(sched, b.graph.ndata["cell_feat"], b.graph.ndata["net_feat"], gp, save=True)
+        with torch.cuda.stream(side):
+            fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
+            feat = fmap.reshape(-1)
+        main.wait_stream(side)                               # join: the fusion needs the feature map
         pred, hs = self._head_forward(H, b, feat)
         T = int(b.endpoints.numel())
         loss = torch.empty(1, dtype=torch.float32, device=dev)
@@ -159,21 +169,49 @@ class DesignStep:
         self._assign(head)
         self._post_allreduce([p for p, _ in head])
 
-        # ---- GNN backward
+        # ---- GNN backward (main stream) next to the U-Net backward (image stream)
+        side.wait_stream(main)                               # dF is ready
         G = torch.zeros(sched.n, D, dtype=torch.float32, device=dev)
         call("tm_scatter_add_cols", T, D, dX, width, 0, b.endpoints, G, D, stream())
         ggrads = tm_ops.gnn_backward(sched, saved, gp, G)
         pairs = list(zip(self.gnn_params, ggrads))
         self._assign(pairs)
         self._post_allreduce([p for p, _ in pairs])
-
-        # ---- U-Net backward
-        ug = tm_unet.unet_backward(cnn, ust, dF.reshape(fmap.shape))
-        pairs = [(self.cnn_params[k], ug[k]) for k in self.cnn_names]
-        self._assign(pairs)
-        self._post_allreduce([p for p, _ in pairs])
+        with torch.cuda.stream(side):
+            ug = tm_unet.unet_backward(cnn, ust, dF.reshape(fmap.shape))
+            upairs = [(self.cnn_params[k], ug[k]) for k in self.cnn_names]
+            self._assign(upairs)
+            self._post_allreduce([p for p, _ in upairs])
+        main.wait_stream(side)                               # join: every gradient exists on `main`
         self._wait_allreduce()
         return loss, pred.squeeze(-1)
+
+    # ---------------------------------------------------------------- CUDA graph
+    def capture(self, b, warmup=2):
+        """Capture ``run(b)`` (about 500 launches on two streams) into one CUDA graph.  The batch's
+        tensors become the graph's static inputs: refresh them in place (``tensor.copy_``) and call
+        the returned function, which replays the graph and returns the same (loss, pred) tensors;
+        ``param.grad`` tensors are rewritten in place by every replay.  Single-GPU only: the NCCL
+        all-reduce of the data-parallel path stays outside graphs."""
+        if self.world > 1:
+            raise RuntimeError("DesignStep.capture: graphs are not used on the data-parallel path")
+        cur = torch.cuda.current_stream()
+        s = torch.cuda.Stream()
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.run(b)
+        cur.wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss, pred = self.run(b)
+
+        def replay():
+            g.replay()
+            return loss, pred
+        replay.graph = g
+        return replay
 
     @staticmethod
     def _assign(pairs):

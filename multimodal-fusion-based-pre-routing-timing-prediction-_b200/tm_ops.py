@@ -47,6 +47,41 @@ def _colsum(R, C, X, ld, rows, out, accumulate):
     call("tm_colsum", R, C, X, ld, rows, out, accumulate, tm_lib.workspace(nb, out.device), nb, stream())
 
 
+class _Aux:
+    """Helper stream for bandwidth-bound side work (bias-gradient column sums) that is independent of
+    the tensor-core GEMM enqueued next to it: the persistent GEMM CTAs fill the shared memory of every
+    SM but leave thread / register room, so a plain streaming kernel co-resides with them."""
+    stream = None
+    pending = []
+
+    @classmethod
+    def run(cls, fn, *tensors):
+        if not torch.cuda.is_available():
+            return fn()
+        if cls.stream is None:
+            cls.stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        if torch.cuda.is_current_stream_capturing() or cur == cls.stream:
+            return fn()
+        # every tensor passed in stays referenced by the caller until its aux_join(), so no
+        # record_stream (which would stall the caching allocator's reuse of these large buffers)
+        cls.stream.wait_stream(cur)
+        with torch.cuda.stream(cls.stream):
+            fn()
+        cls.pending.append(cur)
+
+    @classmethod
+    def join(cls):
+        """Make the current stream wait for everything posted from it."""
+        if cls.stream is not None and cls.pending:
+            torch.cuda.current_stream().wait_stream(cls.stream)
+            cls.pending = []
+
+
+def aux_join():
+    _Aux.join()
+
+
 def _f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
@@ -96,12 +131,12 @@ def gemm_tn(M, N, R, A, lda, B, ldb, C, ldc, a_rows=None, b_rows=None, colsum_a=
         return
     nb = tm_lib.ws_bytes("tm_tc_gemm_tn_ws", M, N, R)
     ws = tm_lib.workspace(nb, C.device)
+    if colsum_a is not None:
+        _Aux.run(lambda: _colsum(R, M, A, lda, a_rows, colsum_a, accumulate), A, colsum_a, a_rows)
+    if colsum_b is not None:
+        _Aux.run(lambda: _colsum(R, N, B, ldb, b_rows, colsum_b, accumulate), B, colsum_b, b_rows)
     call("tm_tc_gemm_tn", M, N, R, A, lda, a_rows, B, ldb, b_rows, C, ldc, accumulate, prec, ws, nb,
          tm_lib.err_flag(C.device), stream())
-    if colsum_a is not None:
-        _colsum(R, M, A, lda, a_rows, colsum_a, accumulate)
-    if colsum_b is not None:
-        _colsum(R, N, B, ldb, b_rows, colsum_b, accumulate)
 
 
 def transpose(w):
@@ -162,6 +197,7 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
     if need_dx:
         dx = torch.empty(n_rows, kin, dtype=torch.float32, device=dev)
         gemm_nn(n_rows, kin, hid, dh, hid, _f32c(w1), kin, dx, kin)
+    aux_join()
     return dw1, db1, dw2, db2, dx
 
 
@@ -224,6 +260,7 @@ def gnn_backward(sched, saved, params, G):
     if ncr > 0:
         gemm_tn(D, 256, ncr, GZC, D, saved["HID"], 256, dcn2w, 256, colsum_a=dcn2b)
         gemm_tn(256, D, ncr, GHID, 256, saved["A"], D, dcn1w, D, colsum_a=dcn1b)
+        aux_join()
     else:
         for t in (dcn2w, dcn2b, dcn1w, dcn1b):
             t.zero_()
@@ -351,6 +388,7 @@ class LinearFn(torch.autograd.Function):
         db = torch.empty(N, dtype=torch.float32, device=dev) if ctx.has_bias else None
         if M > 0:
             gemm_tn(N, K, M, g2, N, x2, x2.stride(0), dw, K, colsum_a=db)
+            aux_join()
         else:
             dw.zero_()
             if db is not None:

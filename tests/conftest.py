@@ -54,14 +54,27 @@ def load_golden_step(name="tiny"):
     return z, sd_m, sd_c
 
 
-def assert_close(a, b, rtol=1e-3, atol_scale=1e-4, name=""):
-    """rtol plus an atol scaled to the tensor's magnitude (SURVEY.md 8d parity gates)."""
+def assert_close(a, b, rtol=1e-3, atol_scale=1e-4, name="", flip_frac=0.0, flip_factor=50.0):
+    """rtol plus an atol scaled to the tensor's magnitude (SURVEY.md 8d parity gates).
+
+    ``flip_frac`` > 0 is for GRADIENTS that pass through millions of ReLU gates: two correct fp32
+    evaluations with different summation order disagree about the sign of the few pre-activations
+    that sit within rounding noise of zero (expected count ~ #gates x 2^-22), and each such gate
+    switches one gradient row (one element of a bias gradient) on or off.  Up to that fraction of
+    elements -- at least two, for the small bias vectors -- may exceed the tolerance, by at most
+    ``flip_factor`` x; everything else must meet it.  Forward values never use it."""
     a = torch.as_tensor(a).double().cpu()
     b = torch.as_tensor(b).double().cpu()
     assert a.shape == b.shape, f"{name}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     scale = float(b.abs().max()) if b.numel() else 0.0
     atol = atol_scale * max(scale, 1e-30)
     err = (a - b).abs()
-    bad = err > atol + rtol * b.abs()
-    assert not bool(bad.any()), (f"{name}: {int(bad.sum())}/{a.numel()} mismatches, max abs err "
-                                 f"{float(err.max()):.3e}, ref scale {scale:.3e}")
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    nbad = int(bad.sum())
+    msg = (f"{name}: {nbad}/{a.numel()} mismatches, max abs err {float(err.max()) if a.numel() else 0:.3e}, "
+           f"ref scale {scale:.3e}")
+    if flip_frac > 0.0:
+        assert nbad <= max(2, flip_frac * a.numel()) and not bool((err > flip_factor * tol).any()), msg
+    else:
+        assert nbad == 0, msg

@@ -206,8 +206,10 @@ def test_gnn_forward_backward(mods, math_mode, cfg, seed):
     H = gnn.propagate(g)
     assert_close(H, Href, 1e-3, 1e-4, "H")
     H.backward(Gout.to(DEV))
+    # ~2 M ReLU gates (pins x channels + hidden units): allow the handful of boundary flips any
+    # reordered fp32-class evaluation produces (see conftest.assert_close); H above is held exactly.
     for k, r in zip(ops.GNN_PARAM_NAMES, gref):
-        assert_close(dict(gnn.named_parameters())[k].grad, r, 1e-3, 1e-4, k)
+        assert_close(dict(gnn.named_parameters())[k].grad, r, 1e-3, 1e-4, k, flip_frac=5e-3)
     assert gnn.fc_net_drive.layers[0].weight.grad is None and gnn.fc_attn2.weight.grad is None
     # a second backward through retained buffers gives the same gradients (retain_graph, D9)
     first = {k: p.grad.clone() for k, p in gnn.named_parameters() if p.grad is not None}
