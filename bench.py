@@ -278,11 +278,13 @@ def main():
         H, saved = tm_ops.gnn_forward(sched, cf, nf, gp, save=True)
         S = torch.empty(sched.n, 128, device=dev)
         w1t, w2t = tm_ops.transpose(gp[8]), tm_ops.transpose(gp[10])
+        gnb = tm_lib.ws_bytes("tm_gnn_ws_bytes")
+        gws = tm_lib.workspace(gnb, dev)
 
         def prop_only():
             H.zero_()
             tm_lib.call("tm_gnn_forward", sched.struct, 0, sched.num_levels, H, S, w1t, gp[9], w2t, gp[11],
-                        saved["A"], saved["LSE"], saved["HID"], tm_lib.stream())
+                        saved["A"], saved["LSE"], saved["HID"], gws, gnb, tm_lib.stream())
 
         S.copy_(torch.rand_like(S))
         t_zero = timed(lambda: H.zero_())
@@ -292,7 +294,7 @@ def main():
 
         def bwd_only():
             tm_lib.call("tm_gnn_backward", sched.struct, H, G, gp[8], gp[10], saved["A"], saved["LSE"], saved["HID"],
-                        GA, GH, GZ, tm_lib.stream())
+                        GA, GH, GZ, gws, gnb, tm_lib.stream())
 
         t_bwd = timed(bwd_only)
         t_gnn_f = timed(lambda: tm_ops.gnn_forward(sched, cf, nf, gp, save=True))

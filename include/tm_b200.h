@@ -147,9 +147,12 @@ int tm_transpose(int64_t rows, int64_t cols, const float* in, float* out, void* 
  *   W1t[128,256], b1[256], W2t[256,128], b2[128]: fc_cell_neigh, weights TRANSPOSED;
  *   A[n_cell_rows,128], LSE[n_cell_rows,128], HID[n_cell_rows,256]: saved for backward
  *              (may be NULL for inference). */
+size_t tm_gnn_ws_bytes(void);   /* workspace of tm_gnn_forward / tm_gnn_backward: the weights re-packed
+                                 * (padded rows, 3xTF32 hi/lo pre-split) for the tile MLP */
 int tm_gnn_forward(const tm_schedule* s, int32_t level_begin, int32_t level_end, float* H,
                    const float* S, const float* W1t, const float* b1, const float* W2t,
-                   const float* b2, float* A, float* LSE, float* HID, void* stream);
+                   const float* b2, float* A, float* LSE, float* HID, void* ws, size_t ws_bytes,
+                   void* stream);
 
 /* Backward over all levels in reverse.
  *   G[n,128]   in: dLoss/dH contributions from the head (zero elsewhere);
@@ -159,7 +162,7 @@ int tm_gnn_forward(const tm_schedule* s, int32_t level_begin, int32_t level_end,
  *   the hoisted weight-gradient GEMMs (dW1 = GHID^T A, dW2 = GZC^T HID). */
 int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, const float* W1,
                     const float* W2, const float* A, const float* LSE, const float* HID,
-                    float* GA, float* GHID, float* GZC, void* stream);
+                    float* GA, float* GHID, float* GZC, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * G5  mask fusion (replaces  path_mask.to_dense()*feat_map  and  fcn(path_map),

@@ -59,102 +59,148 @@ gnn_net_fwd_kernel(const int* __restrict__ order, int p0, int cnt, const int* __
 
 // ---------------------------------------------------------------------------------------------
 // tile MLP shared by forward and backward: out = (epi1(in @ Wa)) @ Wb for a 16-row tile,
-//   Wa: [128][256] row-major (k-major), Wb: [256][128] row-major.
+//   Wa: [128][256] (k-major), Wb: [256][128].
 // A level holds only a few thousand pins and the next level needs all of them, so the tile is 16
 // rows and every SM gets one: the MLP runs on the warp-level tensor-core path (mma.sync m16n8k8,
 // whose M = 16 is exactly the tile; tcgen05's M >= 64 would idle 3/4 of every instruction here) in
-// 3xTF32: x = hi + lo with hi = rna_tf32(x), lo = x - hi (exact); lo*hi + hi*lo + hi*hi accumulated
-// in fp32 keeps ~22 mantissa bits per product -- the fp32-class accuracy the 101-level recurrence needs.
-// The 256 KB of weights do not fit in shared memory next to the tiles, so they are STREAMED:
-// 16 chunks of 16 KB (8 of Wa, 8 of Wb; each chunk is a contiguous run of k-rows) flow through a
-// 3-stage cp.async ring.  Row strides are padded (IN_LD, MID_LD, chunk rows + 8 floats) so that the
-// mma fragment loads hit 32 distinct banks.  256 threads = 8 warps; warp w owns hidden columns
-// 32w..32w+31 in GEMM1 and output columns 16w..16w+15 in GEMM2.
+// 3xTF32: x = hi + lo with hi = x rounded to 11 bits, lo = x - hi (exact); lo*hi + hi*lo + hi*hi
+// accumulated in fp32 keeps ~22 mantissa bits per product -- the fp32-class accuracy the 101-level
+// recurrence needs.
+//   * weights: re-packed once per call (gnn_pack_kernel) into padded rows, so the 256 KB stream
+//     through shared memory as 16 contiguous chunks moved by ONE cp.async.bulk each.  The stream is
+//     latency-bound (every CTA pulls the same lines out of L2), so the ring is 8 slots deep: all of
+//     Wa is requested at kernel entry and lands while the tile is being gathered; Wb chunks follow
+//     into the slots GEMM1 frees.  (Pre-splitting the weights into hi/lo rows would double this
+//     L2 traffic -- 32 MB per level for config 2 -- for a few ALU ops per fragment; measured slower.)
+//     B fragments are conflict-free LDS + an on-the-fly split;
+//   * tiles: the input / hidden tiles are stored pre-split (hi and lo arrays), so A fragments are
+//     plain LDS as well and every element is split exactly once.
+// 256 threads = 8 warps; warp w owns hidden columns 32w..32w+31 in GEMM1 and output columns
+// 16w..16w+15 in GEMM2.
 // ---------------------------------------------------------------------------------------------
-constexpr int CHUNK = 4096;       // floats per weight chunk in HBM (16 KB)
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 8;
 constexpr int NCHUNK = 16;
 constexpr int IN_LD = D + 4;      // 132: bank(g*132 + t) = 4g + t   -> conflict-free A fragments
 constexpr int MID_LD = HID + 4;   // 260
-constexpr int WA_LD = HID + 8;    // 264: bank(t*264 + g) = 8t + g   -> conflict-free B fragments
-constexpr int WB_LD = D + 8;      // 136
-constexpr int SLOT = 32 * WB_LD;  // 4352 floats >= 16 * WA_LD (4224)
-constexpr size_t CELL_SMEM = (size_t)(TILE * IN_LD + TILE * MID_LD + NSTAGE * SLOT) * sizeof(float) + TILE * sizeof(int);
+constexpr int WA_ROW = HID + 8;   // 264 floats per packed k-row of Wa: bank(t*264 + g) = 8t + g -> conflict-free B fragments
+constexpr int WB_ROW = D + 8;     // 136
+constexpr int CHUNK_A = 16 * WA_ROW;    // floats per chunk of Wa (16 k-rows)  = 4224
+constexpr int CHUNK_B = 32 * WB_ROW;    // floats per chunk of Wb (32 k-rows)  = 4352
+constexpr int SLOT = CHUNK_B > CHUNK_A ? CHUNK_B : CHUNK_A;
+constexpr size_t PACK_FLOATS = (size_t)D * WA_ROW + (size_t)HID * WB_ROW;   // one (Wa, Wb) pair
+constexpr int TILE_FLOATS = 3 * TILE * IN_LD + 2 * TILE * MID_LD;
+constexpr size_t CELL_SMEM = (size_t)(TILE_FLOATS + NSTAGE * SLOT) * sizeof(float) + TILE * sizeof(int) + 64;
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-__device__ __forceinline__ void issue_chunk(float* wbuf, const float* __restrict__ Wa,
-                                            const float* __restrict__ Wb, int c, int tid) {
-  if (c < NCHUNK) {
-    float* dst = wbuf + (c % NSTAGE) * SLOT;
-    if (c < 8) {                      // 16 rows x 256 floats of Wa
-      const float* src = Wa + (size_t)c * CHUNK;
-#pragma unroll
-      for (int i = 0; i < CHUNK / 4 / CT; ++i) {
-        const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
-        cp_async16(dst + row * WA_LD + c4, src + row * HID + c4);
-      }
-    } else {                          // 32 rows x 128 floats of Wb
-      const float* src = Wb + (size_t)(c - 8) * CHUNK;
-#pragma unroll
-      for (int i = 0; i < CHUNK / 4 / CT; ++i) {
-        const int q = tid + i * CT, row = q >> 5, c4 = (q & 31) * 4;
-        cp_async16(dst + row * WB_LD + c4, src + row * D + c4);
-      }
-    }
+struct Tiles {                    // shared-memory carve-up of one CTA
+  float* scr;                     // [TILE][IN_LD]  fp32 scratch / raw GEMM2 output
+  float* in_hi;                   // [TILE][IN_LD]
+  float* in_lo;
+  float* mid_hi;                  // [TILE][MID_LD]
+  float* mid_lo;
+  float* wbuf;                    // NSTAGE x SLOT
+  int* v_s;                       // [TILE]
+  uint64_t* wfull;                // [NSTAGE] mbarriers
+  __device__ explicit Tiles(float* smem) {
+    scr = smem;
+    in_hi = scr + TILE * IN_LD;
+    in_lo = in_hi + TILE * IN_LD;
+    mid_hi = in_lo + TILE * IN_LD;
+    mid_lo = mid_hi + TILE * MID_LD;
+    wbuf = mid_lo + TILE * MID_LD;
+    v_s = reinterpret_cast<int*>(wbuf + NSTAGE * SLOT);
+    wfull = reinterpret_cast<uint64_t*>(v_s + TILE);
   }
-  cp_async_commit();   // always commit (possibly empty) so that wait_group<1> means "chunk c landed"
-}
-
-// Call order inside a kernel:  mlp_prologue() -> fill in_s -> mlp_tile()
-__device__ __forceinline__ void mlp_prologue(float* wbuf, const float* Wa, const float* Wb, int tid) {
-  issue_chunk(wbuf, Wa, Wb, 0, tid);
-  issue_chunk(wbuf, Wa, Wb, 1, tid);
-}
+};
 
 // hi = x rounded to 11 significant bits (round half away: add half an ulp_tf32, clear the low 13
 // bits -- two integer ops; cvt.rna.tf32 expands to a much longer sequence), lo = x - hi (exact)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
 }
+__device__ __forceinline__ void split4(float4 x, float4& hi, float4& lo) {
+  split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+}
+
+// src [R][C] row-major -> dst [R][C + 8] (row padding only)
+__global__ void gnn_pack_kernel(const float* __restrict__ src, int R, int C, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * (C + 8)) return;
+  const int r = i / (C + 8), c = i - r * (C + 8);
+  dst[i] = (c < C) ? src[(size_t)r * C + c] : 0.f;
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one elected thread: chunk c of the packed weights -> ring slot c % NSTAGE, completion on wfull
+__device__ __forceinline__ void issue_chunk(const Tiles& T, const float* __restrict__ Wa,
+                                            const float* __restrict__ Wb, int c) {
+  if (c >= NCHUNK) return;
+  const float* src = (c < 8) ? Wa + (size_t)c * CHUNK_A : Wb + (size_t)(c - 8) * CHUNK_B;
+  const uint32_t bytes = (uint32_t)((c < 8 ? CHUNK_A : CHUNK_B) * sizeof(float));
+  const uint32_t bar = smem_addr(&T.wfull[c % NSTAGE]), dst = smem_addr(T.wbuf + (c % NSTAGE) * SLOT);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void wait_chunk(const Tiles& T, int c) {
+  const uint32_t bar = smem_addr(&T.wfull[c % NSTAGE]), parity = (uint32_t)(c / NSTAGE) & 1u;
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 24)) __trap();      // a lost bulk copy must fail the launch, not hang the GPU
+  }
+}
+
+// Call order inside a kernel:  mlp_prologue() -> fill in_hi / in_lo -> mlp_tile()
+__device__ __forceinline__ void mlp_prologue(const Tiles& T, const float* Wa, const float* Wb, int tid) {
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NSTAGE; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&T.wfull[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < NSTAGE - 1; ++c) issue_chunk(T, Wa, Wb, c);
+  }
+}
+
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// one k-step (8) of a 16 x (8*NT) product: A fragment from a padded row-major tile, B from a chunk
+// one k-step (8) of a 16 x (8*NT) product: A fragments from the pre-split tile, B from a packed chunk
 template <int NT>
-__device__ __forceinline__ void mma_kstep(float (&acc)[NT][4], const float* a_tile, int a_ld, int ka,
-                                          const float* w, int w_ld, int kw, int n_base, int g, int t) {
+__device__ __forceinline__ void mma_kstep(float (&acc)[NT][4], const float* a_hi, const float* a_lo, int a_ld, int ka,
+                                          const float* w, int w_row, int kw, int n_base, int g, int t) {
   uint32_t ah[4], al[4];
-  split_tf32(a_tile[g * a_ld + ka + t], ah[0], al[0]);
-  split_tf32(a_tile[(g + 8) * a_ld + ka + t], ah[1], al[1]);
-  split_tf32(a_tile[g * a_ld + ka + t + 4], ah[2], al[2]);
-  split_tf32(a_tile[(g + 8) * a_ld + ka + t + 4], ah[3], al[3]);
+  const int i0 = g * a_ld + ka + t, i1 = (g + 8) * a_ld + ka + t;
+  ah[0] = __float_as_uint(a_hi[i0]); ah[1] = __float_as_uint(a_hi[i1]);
+  ah[2] = __float_as_uint(a_hi[i0 + 4]); ah[3] = __float_as_uint(a_hi[i1 + 4]);
+  al[0] = __float_as_uint(a_lo[i0]); al[1] = __float_as_uint(a_lo[i1]);
+  al[2] = __float_as_uint(a_lo[i0 + 4]); al[3] = __float_as_uint(a_lo[i1 + 4]);
+  const float* w0 = w + (kw + t) * w_row + n_base + g;
+  const float* w1 = w0 + 4 * w_row;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
-    uint32_t bh0, bl0, bh1, bl1;
-    split_tf32(w[(kw + t) * w_ld + n_base + j * 8 + g], bh0, bl0);
-    split_tf32(w[(kw + t + 4) * w_ld + n_base + j * 8 + g], bh1, bl1);
+    float h0, l0, h1, l1;
+    split_tf32(w0[j * 8], h0, l0);
+    split_tf32(w1[j * 8], h1, l1);
+    const uint32_t bh0 = __float_as_uint(h0), bh1 = __float_as_uint(h1), bl0 = __float_as_uint(l0), bl1 = __float_as_uint(l1);
     mma_tf32(acc[j], al, bh0, bh1);        // small terms first
     mma_tf32(acc[j], ah, bl0, bl1);
     mma_tf32(acc[j], ah, bh0, bh1);
   }
 }
 
-// in_s: [TILE][IN_LD], mid_s: [TILE][MID_LD] (receives epi1 of the first product), out_s: [TILE][IN_LD]
-// (raw second product; may alias in_s).  epi1(row, col, v0, v1) -> float2 for columns col, col+1.
-// Ends with a __syncthreads(): mid_s and out_s are complete and visible to the whole CTA.
+// T.in_hi/in_lo: the pre-split input tile; T.mid_hi/mid_lo receive epi1 of the first product
+// (epi1(row, col, v0, v1) -> float2 for columns col, col+1); T.scr receives the raw second product.
+// Ends with a __syncthreads(): mid and scr are complete and visible to the whole CTA.
 template <class Epi1>
-__device__ __forceinline__ void mlp_tile(const float* in_s, float* mid_s, float* out_s, float* wbuf,
-                                         const float* Wa, const float* Wb, int tid, Epi1 epi1) {
+__device__ __forceinline__ void mlp_tile(const Tiles& T, const float* Wa, const float* Wb, int tid, Epi1 epi1) {
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   constexpr int NT1 = HID / 8 / (CT / 32), NT2 = D / 8 / (CT / 32);   // n-tiles per warp: 4 and 2
   float acc1[NT1][4], acc2[NT2][4];
@@ -168,31 +214,39 @@ __device__ __forceinline__ void mlp_tile(const float* in_s, float* mid_s, float*
     for (int c = 0; c < 4; ++c) acc2[j][c] = 0.f;
 
   for (int c = 0; c < NCHUNK; ++c) {
-    cp_async_wait<1>();
-    __syncthreads();                      // chunk c visible; buffer of chunk c-1 free; tiles visible
-    issue_chunk(wbuf, Wa, Wb, c + 2, tid);
-    const float* w = wbuf + (c % NSTAGE) * SLOT;
+    __syncthreads();                      // everybody is done with chunk c-1 (its slot is free); tiles visible
+    if (tid == 0) issue_chunk(T, Wa, Wb, c + NSTAGE - 1);
+    wait_chunk(T, c);
+    const float* w = T.wbuf + (c % NSTAGE) * SLOT;
     if (c < 8) {                          // GEMM1: k rows 16c .. 16c+15 of Wa
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) mma_kstep<NT1>(acc1, in_s, IN_LD, c * 16 + ks * 8, w, WA_LD, ks * 8, warp * NT1 * 8, g, t);
+      for (int ks = 0; ks < 2; ++ks)
+        mma_kstep<NT1>(acc1, T.in_hi, T.in_lo, IN_LD, c * 16 + ks * 8, w, WA_ROW, ks * 8, warp * NT1 * 8, g, t);
       if (c == 7) {
 #pragma unroll
         for (int j = 0; j < NT1; ++j) {
           const int col = warp * NT1 * 8 + j * 8 + 2 * t;
-          *reinterpret_cast<float2*>(&mid_s[g * MID_LD + col]) = epi1(g, col, acc1[j][0], acc1[j][1]);
-          *reinterpret_cast<float2*>(&mid_s[(g + 8) * MID_LD + col]) = epi1(g + 8, col, acc1[j][2], acc1[j][3]);
+          float2 h0, l0, h1, l1;
+          const float2 e0 = epi1(g, col, acc1[j][0], acc1[j][1]), e1 = epi1(g + 8, col, acc1[j][2], acc1[j][3]);
+          split_tf32(e0.x, h0.x, l0.x); split_tf32(e0.y, h0.y, l0.y);
+          split_tf32(e1.x, h1.x, l1.x); split_tf32(e1.y, h1.y, l1.y);
+          *reinterpret_cast<float2*>(&T.mid_hi[g * MID_LD + col]) = h0;
+          *reinterpret_cast<float2*>(&T.mid_lo[g * MID_LD + col]) = l0;
+          *reinterpret_cast<float2*>(&T.mid_hi[(g + 8) * MID_LD + col]) = h1;
+          *reinterpret_cast<float2*>(&T.mid_lo[(g + 8) * MID_LD + col]) = l1;
         }
       }
     } else {                              // GEMM2: k rows 32(c-8) .. +31 of Wb
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_kstep<NT2>(acc2, mid_s, MID_LD, (c - 8) * 32 + ks * 8, w, WB_LD, ks * 8, warp * NT2 * 8, g, t);
+      for (int ks = 0; ks < 4; ++ks)
+        mma_kstep<NT2>(acc2, T.mid_hi, T.mid_lo, MID_LD, (c - 8) * 32 + ks * 8, w, WB_ROW, ks * 8, warp * NT2 * 8, g, t);
     }
   }
 #pragma unroll
   for (int j = 0; j < NT2; ++j) {
     const int col = warp * NT2 * 8 + j * 8 + 2 * t;
-    *reinterpret_cast<float2*>(&out_s[g * IN_LD + col]) = make_float2(acc2[j][0], acc2[j][1]);
-    *reinterpret_cast<float2*>(&out_s[(g + 8) * IN_LD + col]) = make_float2(acc2[j][2], acc2[j][3]);
+    *reinterpret_cast<float2*>(&T.scr[g * IN_LD + col]) = make_float2(acc2[j][0], acc2[j][1]);
+    *reinterpret_cast<float2*>(&T.scr[(g + 8) * IN_LD + col]) = make_float2(acc2[j][2], acc2[j][3]);
   }
   __syncthreads();
 }
@@ -208,13 +262,11 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
                     const float* __restrict__ b2, float* __restrict__ A, float* __restrict__ LSE,
                     float* __restrict__ HIDb) {
   extern __shared__ __align__(16) float smem[];
-  float (*a_s)[IN_LD] = reinterpret_cast<float (*)[IN_LD]>(smem);
-  float (*hid_s)[MID_LD] = reinterpret_cast<float (*)[MID_LD]>(smem + TILE * IN_LD);
-  float* wbuf = smem + TILE * IN_LD + TILE * MID_LD;
-  int* v_s = reinterpret_cast<int*>(wbuf + NSTAGE * SLOT);
+  const Tiles T(smem);
+  int* v_s = T.v_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * TILE;
-  mlp_prologue(wbuf, W1t, W2t, tid);
+  mlp_prologue(T, W1t, W2t, tid);
 
   // phase 1: each warp aggregates PPW consecutive pins.  Their in-edges are one contiguous range of
   // the level-ordered edge list, walked once with warp-uniform pin boundaries; eight source rows
@@ -239,7 +291,10 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
         av = make_float4(tw[0] / sm[0], tw[1] / sm[1], tw[2] / sm[2], tw[3] / sm[3]);
         lse = make_float4(mx[0] + logf(sm[0]), mx[1] + logf(sm[1]), mx[2] + logf(sm[2]), mx[3] + logf(sm[3]));
       }
-      *reinterpret_cast<float4*>(&a_s[r0 + q][lane * 4]) = av;
+      float4 avh, avl;
+      split4(av, avh, avl);
+      *reinterpret_cast<float4*>(&T.in_hi[(r0 + q) * IN_LD + lane * 4]) = avh;
+      *reinterpret_cast<float4*>(&T.in_lo[(r0 + q) * IN_LD + lane * 4]) = avl;
       if (A) {
         st4(A + (int64_t)(crow0 + t0 + r0 + q) * D + lane * 4, av);
         st4(LSE + (int64_t)(crow0 + t0 + r0 + q) * D + lane * 4, lse);
@@ -278,8 +333,10 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
       }
       while (q < npin) finish_pin();
     }
-    for (int r = max(npin, 0); r < PPW; ++r)                     // rows past the end of the level
-      *reinterpret_cast<float4*>(&a_s[r0 + r][lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = max(npin, 0); r < PPW; ++r) {                   // rows past the end of the level
+      *reinterpret_cast<float4*>(&T.in_hi[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(&T.in_lo[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 
   // phases 2+3: hidden = relu(a @ W1t + b1);  h = relu(S + hidden @ W2t + b2)
@@ -287,13 +344,15 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
     const float2 bb = __ldg(reinterpret_cast<const float2*>(b1 + col));
     return make_float2(fmaxf(v0 + bb.x, 0.f), fmaxf(v1 + bb.y, 0.f));
   };
-  mlp_tile(&a_s[0][0], &hid_s[0][0], &a_s[0][0], wbuf, W1t, W2t, tid, epi1);
-  // coalesced epilogues from shared memory: hidden rows (saved for backward), then h rows
+  mlp_tile(T, W1t, W2t, tid, epi1);
+  // coalesced epilogues from shared memory: hidden rows (saved for backward; hi + lo is exact), then h rows
   if (HIDb) {
 #pragma unroll
     for (int i = 0; i < TILE * HID / 4 / CT; ++i) {
       const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
-      if (t0 + row < cnt) st4(HIDb + (int64_t)(crow0 + t0 + row) * HID + c4, *reinterpret_cast<const float4*>(&hid_s[row][c4]));
+      if (t0 + row < cnt)
+        st4(HIDb + (int64_t)(crow0 + t0 + row) * HID + c4,
+            f4add(*reinterpret_cast<const float4*>(&T.mid_hi[row * MID_LD + c4]), *reinterpret_cast<const float4*>(&T.mid_lo[row * MID_LD + c4])));
     }
   }
 #pragma unroll
@@ -301,7 +360,7 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
     const int q = tid + i * CT, row = q >> 5, c4 = (q & 31) * 4;
     const int v = v_s[row];
     if (v >= 0) {
-      const float4 acc = *reinterpret_cast<const float4*>(&a_s[row][c4]);
+      const float4 acc = *reinterpret_cast<const float4*>(&T.scr[row * IN_LD + c4]);
       const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c4));
       const float4 sv = ld4_stream(S + (int64_t)v * D + c4);
       st4(H + (int64_t)v * D + c4,
@@ -381,14 +440,14 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
                     const float* __restrict__ A, const float* __restrict__ LSE,
                     const float* __restrict__ HIDb, float* __restrict__ GHID, float* __restrict__ GZC) {
   extern __shared__ __align__(16) float smem[];
-  float (*gz_s)[IN_LD] = reinterpret_cast<float (*)[IN_LD]>(smem);
-  float (*gh_s)[MID_LD] = reinterpret_cast<float (*)[MID_LD]>(smem + TILE * IN_LD);
-  float* wbuf = smem + TILE * IN_LD + TILE * MID_LD;
+  const Tiles T(smem);
+  float (*gz_s)[IN_LD] = reinterpret_cast<float (*)[IN_LD]>(T.scr);          // gradient accumulation scratch
+  float (*gh_s)[MID_LD] = reinterpret_cast<float (*)[MID_LD]>(T.mid_hi);     // the pins' own h rows until the MLP runs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * TILE;
   // g_hid = (g_z @ W2) * (hid > 0): W2 is [128][256] as stored by nn.Linear(256,128)  -> "Wa"
   // g_a   =  g_hid @ W1:            W1 is [256][128] as stored by nn.Linear(128,256)  -> "Wb"
-  mlp_prologue(wbuf, W2, W1, tid);
+  mlp_prologue(T, W2, W1, tid);
 
   // phase 1: each warp pulls the gradient of PPW consecutive pins.  gz_s accumulates, the first
   // 128 columns of gh_s hold the pins' own h rows until the MLP overwrites them.
@@ -462,9 +521,15 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
       if (r < npin) {
         const float4 hv = *reinterpret_cast<const float4*>(&gh_s[r0 + r][lane * 4]);
         const float4 gz = relu_mask(hv, *reinterpret_cast<const float4*>(&gz_s[r0 + r][lane * 4]));
-        *reinterpret_cast<float4*>(&gz_s[r0 + r][lane * 4]) = gz;
+        float4 gzh, gzl;
+        split4(gz, gzh, gzl);
+        *reinterpret_cast<float4*>(&T.in_hi[(r0 + r) * IN_LD + lane * 4]) = gzh;
+        *reinterpret_cast<float4*>(&T.in_lo[(r0 + r) * IN_LD + lane * 4]) = gzl;
         st4(G + (int64_t)__shfl_sync(0xffffffffu, vv, r) * D + lane * 4, gz);
         st4(GZC + (int64_t)(crow0 + t0 + r0 + r) * D + lane * 4, gz);
+      } else {
+        *reinterpret_cast<float4*>(&T.in_hi[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(&T.in_lo[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
@@ -478,11 +543,13 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
     }
     return o;
   };
-  mlp_tile(&gz_s[0][0], &gh_s[0][0], &gz_s[0][0], wbuf, W2, W1, tid, epi1);
+  mlp_tile(T, W2, W1, tid, epi1);
 #pragma unroll
   for (int i = 0; i < TILE * HID / 4 / CT; ++i) {
     const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
-    if (t0 + row < cnt) st4(GHID + (int64_t)(crow0 + t0 + row) * HID + c4, *reinterpret_cast<const float4*>(&gh_s[row][c4]));
+    if (t0 + row < cnt)
+      st4(GHID + (int64_t)(crow0 + t0 + row) * HID + c4,
+          f4add(*reinterpret_cast<const float4*>(&T.mid_hi[row * MID_LD + c4]), *reinterpret_cast<const float4*>(&T.mid_lo[row * MID_LD + c4])));
   }
 #pragma unroll
   for (int i = 0; i < TILE * D / 4 / CT; ++i) {
@@ -508,15 +575,35 @@ int cell_base_of(const tm_schedule* s, int level) {
 }
 }  // namespace
 
+extern "C" size_t tm_gnn_ws_bytes() { return PACK_FLOATS * sizeof(float) + 256; }
+
+namespace {
+// (Wa [128][256], Wb [256][128]) -> padded, hi/lo pre-split rows in the caller's workspace
+int pack_pair(const float* Wa, const float* Wb, void* ws, size_t ws_bytes, const float** pa, const float** pb, cudaStream_t st) {
+  TM_REQUIRE(ws && ws_bytes >= tm_gnn_ws_bytes(), "tm_gnn: workspace too small (tm_gnn_ws_bytes)");
+  float* a = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* b = a + (size_t)D * WA_ROW;
+  gnn_pack_kernel<<<(D * WA_ROW + 255) / 256, 256, 0, st>>>(Wa, D, HID, a);
+  TM_TRY(check_launch("gnn_pack(Wa)"));
+  gnn_pack_kernel<<<(HID * WB_ROW + 255) / 256, 256, 0, st>>>(Wb, HID, D, b);
+  TM_TRY(check_launch("gnn_pack(Wb)"));
+  *pa = a;
+  *pb = b;
+  return 0;
+}
+}  // namespace
+
 extern "C" int tm_gnn_forward(const tm_schedule* s, int32_t lb, int32_t le, float* H, const float* S,
-                              const float* W1t, const float* b1, const float* W2t, const float* b2,
-                              float* A, float* LSE, float* HIDb, void* stream) {
+                              const float* W1t_in, const float* b1, const float* W2t_in, const float* b2,
+                              float* A, float* LSE, float* HIDb, void* ws, size_t ws_bytes, void* stream) {
   TM_REQUIRE(s && s->f_ptr && s->f_src, "tm_gnn_forward: schedule lacks the level-ordered edge lists");
   TM_REQUIRE(s && s->h_level_ptr && lb >= 0 && le <= s->num_levels && lb <= le, "tm_gnn_forward: bad level range");
   TM_REQUIRE((A == nullptr) == (LSE == nullptr) && (A == nullptr) == (HIDb == nullptr),
              "tm_gnn_forward: A, LSE, HID must be all set or all NULL");
   cudaStream_t st = (cudaStream_t)stream;
   TM_TRY(cell_smem_optin());
+  const float *W1t = nullptr, *W2t = nullptr;
+  TM_TRY(pack_pair(W1t_in, W2t_in, ws, ws_bytes, &W1t, &W2t, st));
   int crow0 = cell_base_of(s, lb + (lb & 1));
   for (int l = lb; l < le; ++l) {
     const int p0 = s->h_level_ptr[l], cnt = s->h_level_ptr[l + 1] - p0;
@@ -536,12 +623,15 @@ extern "C" int tm_gnn_forward(const tm_schedule* s, int32_t lb, int32_t le, floa
   return 0;
 }
 
-extern "C" int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, const float* W1,
-                               const float* W2, const float* A, const float* LSE, const float* HIDb,
-                               float* GA, float* GHID, float* GZC, void* stream) {
+extern "C" int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, const float* W1_in,
+                               const float* W2_in, const float* A, const float* LSE, const float* HIDb,
+                               float* GA, float* GHID, float* GZC, void* ws, size_t ws_bytes, void* stream) {
   TM_REQUIRE(s && s->h_level_ptr && s->bn_ptr && s->bc_ptr, "tm_gnn_backward: bad schedule");
   cudaStream_t st = (cudaStream_t)stream;
   TM_TRY(cell_smem_optin());
+  // backward products: g_hid = g_z @ W2 (W2 [128][256] is "Wa"), g_a = g_hid @ W1 (W1 [256][128] is "Wb")
+  const float *W2 = nullptr, *W1 = nullptr;
+  TM_TRY(pack_pair(W2_in, W1_in, ws, ws_bytes, &W2, &W1, st));
   SchedDev d{s->order, s->bn_ptr, s->bn_dst, s->bn_w, s->bc_ptr, s->bc_row};
   int crow_end = cell_base_of(s, s->num_levels + (s->num_levels & 1));  // total cell rows
   for (int l = s->num_levels - 1; l >= 0; --l) {

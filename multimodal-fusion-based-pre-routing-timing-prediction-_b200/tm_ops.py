@@ -237,7 +237,9 @@ def gnn_forward(sched, cell_feat, net_feat, params, save=True):
         LSE = torch.empty(max(ncr, 1), D, dtype=torch.float32, device=dev)
         HID = torch.empty(max(ncr, 1), 256, dtype=torch.float32, device=dev)
     w1t, w2t = transpose(cn1w), transpose(cn2w)
-    call("tm_gnn_forward", sched.struct, 0, sched.num_levels, H, S, w1t, cn1b, w2t, cn2b, A, LSE, HID, stream())
+    nb = tm_lib.ws_bytes("tm_gnn_ws_bytes")
+    call("tm_gnn_forward", sched.struct, 0, sched.num_levels, H, S, w1t, cn1b, w2t, cn2b, A, LSE, HID,
+         tm_lib.workspace(nb, dev), nb, stream())
     saved = dict(H=H, A=A, LSE=LSE, HID=HID, hc=hc, hn=hn, cell_feat=cell_feat, net_feat=net_feat) if save else None
     return H, saved
 
@@ -251,8 +253,9 @@ def gnn_backward(sched, saved, params, G):
     GA = torch.empty(max(ncr, 1), D, dtype=torch.float32, device=dev)
     GHID = torch.empty(max(ncr, 1), 256, dtype=torch.float32, device=dev)
     GZC = torch.empty(max(ncr, 1), D, dtype=torch.float32, device=dev)
+    nb = tm_lib.ws_bytes("tm_gnn_ws_bytes")
     call("tm_gnn_backward", sched.struct, saved["H"], G, cn1w, cn2w, saved["A"], saved["LSE"], saved["HID"],
-         GA, GHID, GZC, stream())
+         GA, GHID, GZC, tm_lib.workspace(nb, dev), nb, stream())
     dcn2w = torch.empty(D, 256, dtype=torch.float32, device=dev)
     dcn2b = torch.empty(D, dtype=torch.float32, device=dev)
     dcn1w = torch.empty(256, D, dtype=torch.float32, device=dev)
