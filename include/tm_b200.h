@@ -174,6 +174,14 @@ int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, const float*
 int tm_fuse_forward(int64_t T, int64_t J, int64_t D, const int32_t* mask_indptr,
                     const int32_t* mask_cols, const int32_t* rows, const float* F,
                     const float* Wt, const float* bias, float* out, int64_t ld_out, void* stream);
+/* The same forward from the RUN-LENGTH form of the selected mask rows: endpoint t owns runs
+ * run_ptr[t]..run_ptr[t+1], run r covers columns [run_lo[r], run_hi[r]).  Builds the fp64 prefix table
+ * P[j] = sum_{i<j} F[i]*Wt[i,:] in ws (tm_fuse_runs_ws(J) bytes) and sums P[hi]-P[lo] per run:
+ * 2 table rows per run instead of one weight row per column. */
+size_t tm_fuse_runs_ws(int64_t J);
+int tm_fuse_forward_runs(int64_t T, int64_t J, int64_t D, const int32_t* run_ptr, const int32_t* run_lo,
+                         const int32_t* run_hi, const float* F, const float* Wt, const float* bias,
+                         float* out, int64_t ld_out, void* ws, size_t ws_bytes, void* stream);
 /* Column-major pull (deterministic, no atomics): csc_ptr[J+1], csc_t[nnz] list the positions t
  * (0..T-1) whose mask contains column j.
  *   dWt[j,:] = F[j] * sum_t g[t,:];   dF[j] = sum_t sum_c g[t,c] * Wt[j,c]. */

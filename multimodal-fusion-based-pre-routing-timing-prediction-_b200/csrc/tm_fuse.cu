@@ -62,6 +62,67 @@ fuse_fwd_kernel(int64_t T, const int* __restrict__ indptr, const int* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Run-length formulation of the forward.  A path mask is a union of bin bounding boxes
+// (verilog_parser_asap7.py:1315-1333), i.e. a few dozen RUNS of consecutive columns per endpoint
+// (config 2: 1050 columns but 30 runs on average).  With the prefix table
+//     P[j] = sum_{i<j} F[i] * Wt[i,:]            (J+1 rows, fp64 so that differences are exact to fp32)
+// the masked sum of an endpoint is  sum_runs (P[hi] - P[lo]):  two table rows per run instead of one
+// weight row per column -- 35x less L2 traffic for the same result.
+// ---------------------------------------------------------------------------------------------
+constexpr int PB = 128;   // table rows per block of the two-pass scan
+
+__global__ void __launch_bounds__(D)
+prefix_local_kernel(int64_t J, const float* __restrict__ F, const float* __restrict__ Wt,
+                    double* __restrict__ P, double* __restrict__ tot) {
+  const int c = threadIdx.x;
+  const int64_t j0 = (int64_t)blockIdx.x * PB;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int i = 0; i < PB; ++i) {
+    const int64_t j = j0 + i;
+    if (j < J) {
+      acc += (double)F[j] * (double)Wt[j * D + c];
+      P[(j + 1) * D + c] = acc;
+    }
+  }
+  tot[(int64_t)blockIdx.x * D + c] = acc;
+  if (blockIdx.x == 0) P[c] = 0.0;
+}
+
+__global__ void __launch_bounds__(D)
+prefix_offset_kernel(int64_t J, double* __restrict__ P, const double* __restrict__ tot) {
+  const int c = threadIdx.x, b = blockIdx.x;
+  if (b == 0) return;
+  double off = 0.0;
+  for (int i = 0; i < b; ++i) off += tot[(int64_t)i * D + c];      // fixed order: deterministic
+  const int64_t j0 = (int64_t)b * PB;
+#pragma unroll 8
+  for (int i = 0; i < PB; ++i) {
+    const int64_t j = j0 + i;
+    if (j < J) P[(j + 1) * D + c] += off;
+  }
+}
+
+__global__ void __launch_bounds__(D)
+fuse_fwd_runs_kernel(const int* __restrict__ run_ptr, const int* __restrict__ run_lo, const int* __restrict__ run_hi,
+                     const double* __restrict__ P, const float* __restrict__ bias, float* __restrict__ out, int64_t ldo) {
+  const int t = blockIdx.x, c = threadIdx.x;
+  const int s = run_ptr[t], e = run_ptr[t + 1];
+  double acc = 0.0;
+  for (int r = s; r < e; r += 4) {
+    double hi[4], lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      hi[u] = 0.0; lo[u] = 0.0;
+      if (r + u < e) { hi[u] = P[(int64_t)run_hi[r + u] * D + c]; lo[u] = P[(int64_t)run_lo[r + u] * D + c]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += hi[u] - lo[u];
+  }
+  out[(int64_t)t * ldo + c] = (float)acc + bias[c];
+}
+
 __global__ void __launch_bounds__(256)
 fuse_bwd_kernel(int64_t J, const int* __restrict__ cptr, const int* __restrict__ ct,
                 const float* __restrict__ g, int64_t ldg, const float* __restrict__ F,
@@ -185,6 +246,30 @@ extern "C" int tm_fuse_forward(int64_t T, int64_t J, int64_t Dd, const int32_t* 
   if (T <= 0) return 0;
   fuse_fwd_kernel<<<(unsigned)T, 128, 0, (cudaStream_t)stream>>>(T, mask_indptr, mask_cols, rows, F, Wt, bias, out, ld_out);
   return check_launch("fuse_fwd");
+}
+
+extern "C" size_t tm_fuse_runs_ws(int64_t J) {
+  return (size_t)((J + 1) * D + cdiv(J, PB) * D) * sizeof(double) + 256;
+}
+
+extern "C" int tm_fuse_forward_runs(int64_t T, int64_t J, int64_t Dd, const int32_t* run_ptr, const int32_t* run_lo,
+                                    const int32_t* run_hi, const float* F, const float* Wt, const float* bias,
+                                    float* out, int64_t ld_out, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(Dd == D, "tm_fuse_forward_runs: D must be 128");
+  TM_REQUIRE(ws && ws_bytes >= tm_fuse_runs_ws(J), "tm_fuse_forward_runs: workspace too small");
+  if (T <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* P = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  double* tot = P + (J + 1) * D;
+  const unsigned nb = (unsigned)cdiv(J, PB);
+  if (nb > 0) {
+    prefix_local_kernel<<<nb, D, 0, st>>>(J, F, Wt, P, tot);
+    TM_TRY(check_launch("fuse_prefix_local"));
+    prefix_offset_kernel<<<nb, D, 0, st>>>(J, P, tot);
+    TM_TRY(check_launch("fuse_prefix_offset"));
+  }
+  fuse_fwd_runs_kernel<<<(unsigned)T, D, 0, st>>>(run_ptr, run_lo, run_hi, P, bias, out, ld_out);
+  return check_launch("fuse_fwd_runs");
 }
 
 extern "C" int tm_fuse_backward(int64_t T, int64_t J, int64_t Dd, const int32_t* csc_ptr,

@@ -63,13 +63,17 @@ class HostDesign:
 class DesignBatch:
     """Device-resident batch of one design."""
 
-    def __init__(self, graph, mask_csr, endpoints, endpoint_level, arrival_time, image):
+    def __init__(self, graph, mask_csr, endpoints, endpoint_level, arrival_time, image, cell_feat=None, net_feat=None):
         self.graph, self.mask_csr = graph, mask_csr
+        # per-batch feature tensors (a prefetched batch must not disturb the one in flight through
+        # the shared graph object); default: whatever the graph carries
+        self.cell_feat = cell_feat if cell_feat is not None else graph.ndata["cell_feat"]
+        self.net_feat = net_feat if net_feat is not None else graph.ndata["net_feat"]
         self.endpoints = endpoints                 # int32 (T,)
         self.endpoint_level = endpoint_level       # float32 (T,)
         self.arrival_time = arrival_time           # float32 (T,)
         self.image = image                         # (C,H,W)
-        self.mask_rows = mask_csr.select(torch.arange(endpoints.numel(), dtype=torch.int32, device=endpoints.device))
+        self.mask_rows = mask_csr.select_all()
 
     @staticmethod
     def from_host(h, device, graph=None):
@@ -79,9 +83,10 @@ class DesignBatch:
               if graph is None or k not in ("net_src", "net_dst", "cell_src", "cell_dst", "pis")}
         if graph is None:
             graph = TimingGraph(h.n, (dv["net_src"], dv["net_dst"]), (dv["cell_src"], dv["cell_dst"]), pis=dv["pis"])
-        graph.ndata["cell_feat"], graph.ndata["net_feat"] = dv["cell_feat"], dv["net_feat"]
+            graph.ndata["cell_feat"], graph.ndata["net_feat"] = dv["cell_feat"], dv["net_feat"]
         mask = MaskCSR(dv["mask_indptr"], dv["mask_cols"], h.map_size * h.map_size)
-        return DesignBatch(graph, mask, dv["endpoints"], dv["endpoint_level"], dv["arrival_time"], dv["image"])
+        return DesignBatch(graph, mask, dv["endpoints"], dv["endpoint_level"], dv["arrival_time"], dv["image"],
+                           cell_feat=dv["cell_feat"], net_feat=dv["net_feat"])
 
     @staticmethod
     def from_synth(d, device):
@@ -128,7 +133,7 @@ class DesignStep:
         """Inference: predictions for the batch's endpoints (validate(), train.py:137-291)."""
         fmap, _ = tm_unet.unet_forward(self.cnn, b.image, need_bwd=False, update_stats=self.cnn.training)
         sched = b.graph.schedule()
-        H, _ = tm_ops.gnn_forward(sched, b.graph.ndata["cell_feat"], b.graph.ndata["net_feat"],
+        H, _ = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat,
                                   [p.detach() for p in self.gnn_params], save=False)
         pred, _ = self._head_forward(H, b, fmap.reshape(-1))
         return pred.squeeze(-1)
@@ -144,7 +149,7 @@ class DesignStep:
         sched = b.graph.schedule()
         gp = [p.detach() for p in self.gnn_params]
         # the longer chain is enqueued first so the host's launch time for the other one overlaps it
-        H, saved = tm_ops.gnn_forward(sched, b.graph.ndata["cell_feat"], b.graph.ndata["net_feat"], gp, save=True)
+        H, saved = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat, gp, save=True)
         with torch.cuda.stream(side):
             fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
             feat = fmap.reshape(-1)

@@ -267,16 +267,59 @@ class MaskCSR:
         """-> MaskRows for the given path ids (``th.index_select(path_masks, 0, paths)``, train.py:500)."""
         return MaskRows(self, rows)
 
+    def select_all(self):
+        """Every row, in order (one design's endpoints in one batch, test.py:176)."""
+        dev = self.indptr.device
+        return MaskRows(self, torch.arange(self.num_rows, dtype=torch.int32, device=dev), identity=True)
+
 
 class MaskRows:
     """A row selection of a MaskCSR plus its column-major transpose (built lazily on the GPU)."""
 
-    def __init__(self, csr, rows):
+    def __init__(self, csr, rows, identity=False):
         self.csr = csr
         dev = csr.indptr.device
         self.rows = torch.as_tensor(rows, dtype=torch.int32).to(dev)
         self.T = int(self.rows.numel())
+        self.identity = bool(identity)        # rows == arange(num_rows): skip the gather when building runs
         self._csc = None
+        self._runs = None
+
+    def runs(self):
+        """Run-length form of the selected rows: (run_ptr int32[T+1], run_lo, run_hi int32[<= nnz]) with
+        run r = columns [run_lo[r], run_hi[r]).  Needs ascending columns inside a row (the CSR
+        convention); built with asynchronous device ops only when the selection is the identity,
+        otherwise the rows are gathered first.  A row boundary always starts a new run; two adjacent
+        runs that touch are harmless (their prefix differences add up to the same sum)."""
+        if self._runs is None:
+            csr = self.csr
+            dev = csr.indptr.device
+            if self.identity:
+                indptr, cols = csr.indptr.long(), csr.cols.long()
+            else:
+                rl = self.rows.long()
+                start = csr.indptr[rl].long()
+                deg = csr.indptr[rl + 1].long() - start
+                indptr = torch.zeros(self.T + 1, dtype=torch.int64, device=dev)
+                indptr[1:] = torch.cumsum(deg, 0)
+                t_of = torch.repeat_interleave(torch.arange(self.T, device=dev), deg)
+                slot = torch.repeat_interleave(start, deg) + (torch.arange(int(deg.sum()), device=dev) - indptr[:-1][t_of])
+                cols = csr.cols[slot].long()
+            nnz = int(cols.numel())
+            if nnz == 0:
+                z = torch.zeros(1, dtype=torch.int32, device=dev)
+                self._runs = (torch.zeros(self.T + 1, dtype=torch.int32, device=dev), z, z)
+                return self._runs
+            brk = torch.ones(nnz, dtype=torch.int64, device=dev)
+            brk[1:] = (cols[1:] != cols[:-1] + 1).long()
+            brk.index_fill_(0, indptr[:-1].clamp(max=nnz - 1), 1)          # every row starts a run
+            ridx = torch.cumsum(brk, 0) - 1                                  # run index of every entry
+            run_lo = torch.full((nnz,), 1 << 30, dtype=torch.int64, device=dev).scatter_reduce_(0, ridx, cols, "amin")
+            run_hi = torch.full((nnz,), -1, dtype=torch.int64, device=dev).scatter_reduce_(0, ridx, cols + 1, "amax")
+            excl = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(brk, 0)])
+            run_ptr = excl[indptr]                                           # runs before the row's first entry
+            self._runs = (run_ptr.to(torch.int32), run_lo.to(torch.int32), run_hi.to(torch.int32))
+        return self._runs
 
     def csc(self):
         if self._csc is None:

@@ -32,6 +32,7 @@ BIAS, RELU, MASK, ACCUM = 1, 2, 4, 8
 #   "bf16" tcgen05 with plain bf16 operands (rtol 2e-2 class);
 #   "fp32" the CUDA-core FFMA kernels (tm_gemm_nn / tm_gemm_tn).
 MATH = os.environ.get("TM_MATH", "tf32x3")
+FUSE_RUNS = os.environ.get("TM_FUSE_RUNS", "1") != "0"    # run-length / prefix-table mask fusion forward
 TC_MIN_K = 16          # contractions shorter than this stay on the CUDA-core kernel (K = 1, 2: pure bandwidth)
 
 
@@ -302,9 +303,15 @@ def fusion_forward(mask_rows, feat, fcn_w, fcn_b, out, ldo):
     if fcn_w.shape != (D, J):
         raise RuntimeError(f"fcn must be Linear({J}, 128); got weight {tuple(fcn_w.shape)}")
     wt = transpose(fcn_w)
-    csr = mask_rows.csr
-    call("tm_fuse_forward", mask_rows.T, J, D, csr.indptr, csr.cols, mask_rows.rows, feat, wt, _f32c(fcn_b),
-         out, ldo, stream())
+    if FUSE_RUNS:
+        run_ptr, run_lo, run_hi = mask_rows.runs()
+        nb = tm_lib.ws_bytes("tm_fuse_runs_ws", J)
+        call("tm_fuse_forward_runs", mask_rows.T, J, D, run_ptr, run_lo, run_hi, feat, wt, _f32c(fcn_b), out, ldo,
+             tm_lib.workspace(nb, feat.device), nb, stream())
+    else:
+        csr = mask_rows.csr
+        call("tm_fuse_forward", mask_rows.T, J, D, csr.indptr, csr.cols, mask_rows.rows, feat, wt, _f32c(fcn_b),
+             out, ldo, stream())
     return wt
 
 

@@ -285,6 +285,52 @@ def test_mask_fusion(mods):
     assert torch.equal(c2.indptr, torch.from_numpy(d.mask_indptr)) and torch.equal(c2.cols, torch.from_numpy(d.mask_cols))
 
 
+@pytest.mark.parametrize("identity", [True, False])
+def test_mask_fusion_runs_vs_csr(mods, identity):
+    """The run-length / prefix-table forward equals the per-column CSR forward and the dense oracle;
+    the run decomposition itself is checked bit-exactly against a host walk of the CSR (incl. an
+    empty row and touching runs)."""
+    ops, G = mods["ops"], mods["graph"]
+    d = tm_synth.make_design(seed=2, **tm_synth.CONFIGS["c1"])
+    J = d.map_size ** 2
+    indptr, cols = d.mask_indptr.copy(), d.mask_cols.copy()
+    # make row 3 empty
+    lo, hi = indptr[3], indptr[4]
+    cols = np.concatenate([cols[:lo], cols[hi:]])
+    indptr[4:] -= (hi - lo)
+    csr = G.MaskCSR(indptr, cols, J).to(DEV)
+    T = indptr.size - 1
+    if identity:
+        rows, sel = csr.select_all(), np.arange(T)
+    else:
+        sel = np.random.default_rng(0).permutation(T)[:300]
+        rows = csr.select(torch.from_numpy(sel.astype(np.int32)))
+    run_ptr, run_lo, run_hi = (x.cpu().numpy() for x in rows.runs())
+    for t, r in enumerate(sel):                                   # host walk: union of runs == the row's columns
+        c = cols[indptr[r]:indptr[r + 1]]
+        got = np.concatenate([np.arange(run_lo[q], run_hi[q]) for q in range(run_ptr[t], run_ptr[t + 1])]) \
+            if run_ptr[t + 1] > run_ptr[t] else np.zeros(0, np.int64)
+        assert np.array_equal(got, c), f"row {r}"
+    torch.manual_seed(3)
+    feat = torch.rand(J, device=DEV)
+    w = torch.randn(128, J, device=DEV) * 0.05
+    b = torch.randn(128, device=DEV)
+    out_runs = torch.empty(rows.T, 128, device=DEV)
+    out_csr = torch.empty(rows.T, 128, device=DEV)
+    old = ops.FUSE_RUNS
+    try:
+        ops.FUSE_RUNS = True
+        ops.fusion_forward(rows, feat, w, b, out_runs, 128)
+        ops.FUSE_RUNS = False
+        ops.fusion_forward(rows, feat, w, b, out_csr, 128)
+    finally:
+        ops.FUSE_RUNS = old
+    dense = restate.dense_mask_rows(torch.from_numpy(indptr).long(), torch.from_numpy(cols).long(), sel.tolist(), J)
+    ref = F.linear(dense.double() * feat.cpu().double(), w.cpu().double(), b.cpu().double())
+    assert_close(out_runs, ref, 1e-4, 1e-5, "runs vs fp64 dense")
+    assert_close(out_csr, ref, 1e-3, 1e-4, "csr vs fp64 dense")
+
+
 # ---------------------------------------------------------------------------------------------
 # image branch
 # ---------------------------------------------------------------------------------------------
