@@ -17,6 +17,8 @@
 // A warp owns a pin (lane = 4 channels, 128-bit loads); cell levels are processed in 16-pin tiles:
 // the aggregated rows are staged in shared memory and pushed through the 128->256->128 MLP by the
 // same CTA, so `a` and the hidden layer never round-trip through HBM on the forward critical path.
+#include <stdlib.h>
+
 #include "tm_common.cuh"
 
 using namespace tmk;
@@ -26,6 +28,13 @@ constexpr int D = 128;     // out_feat_dim (model.py:43, options.py:10)
 constexpr int HID = 256;   // MLP hidden width (model.py:48)
 constexpr int TILE = 16;   // pins per CTA on a cell level
 constexpr int CT = 256;    // threads per CTA on a cell level (8 warps: two per scheduler hide the ALU latency)
+
+// Programmatic dependent launch: consecutive level kernels are chained so that a kernel's CTAs may
+// start while the previous level is still running -- everything that does not read the previous
+// level's output (weight-chunk prefetch, schedule lookups) overlaps it; pdl_wait() then blocks until
+// the previous grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -39,11 +48,13 @@ gnn_net_fwd_kernel(const int* __restrict__ order, int p0, int cnt, const int* __
                    const int* __restrict__ f_src, const float* __restrict__ S, float* H) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= cnt) return;
+  pdl_launch_dependents();
+  if (w >= cnt) { pdl_wait(); return; }
   const int p = p0 + w;
   const int v = order[p];
   const int s = f_ptr[p], e = f_ptr[p + 1];          // level 0: empty range
   const float4 sv = ld4_stream(S + (int64_t)v * D + lane * 4);
+  pdl_wait();                                        // H rows of earlier levels are read from here on
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = s; i < e; i += 4) {
     float4 m[4];
@@ -267,6 +278,7 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * TILE;
   mlp_prologue(T, W1t, W2t, tid);
+  pdl_wait();                                        // (the weight prefetch above overlaps the previous level)
 
   // phase 1: each warp aggregates PPW consecutive pins.  Their in-edges are one contiguous range of
   // the level-ordered edge list, walked once with warp-uniform pin boundaries; eight source rows
@@ -345,6 +357,7 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
     return make_float2(fmaxf(v0 + bb.x, 0.f), fmaxf(v1 + bb.y, 0.f));
   };
   mlp_tile(T, W1t, W2t, tid, epi1);
+  pdl_launch_dependents();                           // the next level may be scheduled while the epilogue drains
   // coalesced epilogues from shared memory: hidden rows (saved for backward; hi + lo is exact), then h rows
   if (HIDb) {
 #pragma unroll
@@ -400,10 +413,12 @@ gnn_net_bwd_kernel(SchedDev s, int p0, int cnt, const float* __restrict__ H, flo
                    const float* __restrict__ LSE) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= cnt) return;
+  pdl_launch_dependents();
+  if (w >= cnt) { pdl_wait(); return; }
   const int p = p0 + w;
   const int v = s.order[p];
   const int ns = s.bn_ptr[p], ne = s.bn_ptr[p + 1], cs = s.bc_ptr[p], ce = s.bc_ptr[p + 1];
+  pdl_wait();
   const int64_t off = (int64_t)v * D + lane * 4;
   float4 g = ld4(G + off);
   const float4 hv = ld4(H + off);
@@ -448,6 +463,7 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
   // g_hid = (g_z @ W2) * (hid > 0): W2 is [128][256] as stored by nn.Linear(256,128)  -> "Wa"
   // g_a   =  g_hid @ W1:            W1 is [256][128] as stored by nn.Linear(128,256)  -> "Wb"
   mlp_prologue(T, W2, W1, tid);
+  pdl_wait();
 
   // phase 1: each warp pulls the gradient of PPW consecutive pins.  gz_s accumulates, the first
   // 128 columns of gh_s hold the pins' own h rows until the MLP overwrites them.
@@ -544,6 +560,7 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
     return o;
   };
   mlp_tile(T, W2, W1, tid, epi1);
+  pdl_launch_dependents();
 #pragma unroll
   for (int i = 0; i < TILE * HID / 4 / CT; ++i) {
     const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
@@ -556,6 +573,26 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
     const int q = tid + i * CT, row = q >> 5, c4 = (q & 31) * 4;
     if (t0 + row < cnt) st4(GA + (int64_t)(crow0 + t0 + row) * D + c4, *reinterpret_cast<const float4*>(&gz_s[row][c4]));
   }
+}
+
+// launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself)
+template <class... KArgs, class... Args>
+int launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const char* what, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int pdl = getenv("TM_GNN_PDL") ? atoi(getenv("TM_GNN_PDL")) : 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
 }
 
 int cell_smem_optin() {
@@ -610,12 +647,11 @@ extern "C" int tm_gnn_forward(const tm_schedule* s, int32_t lb, int32_t le, floa
     const bool cell = (l > 0) && !(l & 1);
     if (cnt > 0) {
       if (!cell) {
-        gnn_net_fwd_kernel<<<(unsigned)cdiv(cnt, 8), 256, 0, st>>>(s->order, p0, cnt, s->f_ptr, s->f_src, S, H);
-        TM_TRY(check_launch("gnn_net_fwd"));
+        TM_TRY(launch_pdl(gnn_net_fwd_kernel, (unsigned)cdiv(cnt, 8), 256, 0, st, "gnn_net_fwd", s->order, p0, cnt, s->f_ptr,
+                          s->f_src, S, H));
       } else {
-        gnn_cell_fwd_kernel<<<(unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st>>>(s->order, p0, cnt, crow0, s->f_ptr, s->f_src, S,
-                                                                             H, W1t, b1, W2t, b2, A, LSE, HIDb);
-        TM_TRY(check_launch("gnn_cell_fwd"));
+        TM_TRY(launch_pdl(gnn_cell_fwd_kernel, (unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st, "gnn_cell_fwd", s->order, p0, cnt,
+                          crow0, s->f_ptr, s->f_src, S, H, W1t, b1, W2t, b2, A, LSE, HIDb));
       }
     }
     if (cell) crow0 += cnt;
@@ -640,12 +676,10 @@ extern "C" int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, c
     if (cell) crow_end -= cnt;
     if (cnt <= 0) continue;
     if (!cell) {
-      gnn_net_bwd_kernel<<<(unsigned)cdiv(cnt, 8), 256, 0, st>>>(d, p0, cnt, H, G, GA, A, LSE);
-      TM_TRY(check_launch("gnn_net_bwd"));
+      TM_TRY(launch_pdl(gnn_net_bwd_kernel, (unsigned)cdiv(cnt, 8), 256, 0, st, "gnn_net_bwd", d, p0, cnt, H, G, (const float*)GA, A, LSE));
     } else {
-      gnn_cell_bwd_kernel<<<(unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st>>>(d, p0, cnt, crow_end, H, G, W1, W2, GA, A,
-                                                                   LSE, HIDb, GHID, GZC);
-      TM_TRY(check_launch("gnn_cell_bwd"));
+      TM_TRY(launch_pdl(gnn_cell_bwd_kernel, (unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st, "gnn_cell_bwd", d, p0, cnt, crow_end, H,
+                        G, W1, W2, GA, A, LSE, HIDb, GHID, GZC));
     }
   }
   return 0;

@@ -753,21 +753,26 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
 #pragma unroll
         for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
         __syncwarp();
-        EpiAux aux[8];
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {                            // row operands first (loads in flight together)
-          const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
-          const int64_t n = n0 + c + (lane & 7) * 4;
-          aux[pass] = (m < M && n < N) ? epi_aux<EP>(ep, rws[pass], n, N) : EpiAux{};
-        }
+        for (int half = 0; half < 2; ++half) {
+          EpiAux aux[4];
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {                            // 8 lanes x 4 columns per row, 4 rows per pass
-          const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
-          const int64_t m = m0 + warp * 32 + r;
-          const int64_t n = n0 + c + cq;
-          if (m < M && n < N && !(tm.dbg & 1)) {
-            const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
-            store4<EP>(ep, rws[pass], n, N, o, b4, aux[pass]);
+          for (int q = 0; q < 4; ++q) {                                   // row operands first (loads in flight together)
+            const int pass = half * 4 + q;
+            const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
+            const int64_t n = n0 + c + (lane & 7) * 4;
+            aux[q] = (m < M && n < N) ? epi_aux<EP>(ep, rws[pass], n, N) : EpiAux{};
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                                   // 8 lanes x 4 columns per row, 4 rows per pass
+            const int pass = half * 4 + q;
+            const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
+            const int64_t m = m0 + warp * 32 + r;
+            const int64_t n = n0 + c + cq;
+            if (m < M && n < N && !(tm.dbg & 1)) {
+              const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
+              store4<EP>(ep, rws[pass], n, N, o, b4, aux[q]);
+            }
           }
         }
         __syncwarp();
@@ -807,6 +812,11 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
 // and in shared memory), so weight gradients (both operands transposed) need no transposition.
 // =============================================================================================
 constexpr uint32_t TF32_MASK = 0xFFFFE000u;
+// 16 producer warps: the copy phase is bound by cp.async issue and the lo pass by ALU latency, both of
+// which scale with the number of warps in flight (the kernel needs < 64 registers per thread)
+constexpr int TF_PROD_WARPS = 16;
+constexpr int TF_PROD_THREADS = TF_PROD_WARPS * 32;
+constexpr int TF_THREADS = (EPI_WARPS + 1 + TF_PROD_WARPS) * 32;   // 672
 
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -840,12 +850,12 @@ struct TfCfg {
   static_assert(ND >= 2, "shared-memory budget too small for this tile");
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr size_t SMEM = (size_t)ND * SLOT + EPI_SCRATCH + 1024;
-  static constexpr int A_CH = BM * 8 / PROD_THREADS;                          // 16-byte chunks per thread (4)
-  static constexpr int B_CH = (BN * 8 + PROD_THREADS - 1) / PROD_THREADS;     // 1..8
+  static constexpr int A_CH = BM * 8 / TF_PROD_THREADS;                          // 16-byte chunks per thread (4)
+  static constexpr int B_CH = (BN * 8 + TF_PROD_THREADS - 1) / TF_PROD_THREADS;     // 1..8
 };
 
 template <class AL, class BL, class EP, int BN, int PLANES>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(TF_THREADS, 1)
 tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __restrict__ err) {
   using C = TfCfg<BN, PLANES>;
   constexpr int ND = C::ND, A_CH = C::A_CH, B_CH = C::B_CH;
@@ -860,7 +870,7 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < ND; ++i) { mbar_init(&full_bar[i], PROD_WARPS); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < ND; ++i) { mbar_init(&full_bar[i], TF_PROD_WARPS); mbar_init(&empty_bar[i], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_empty[0], EPI_WARPS); mbar_init(&acc_empty[1], EPI_WARPS);
     abort_s = 0;
@@ -883,7 +893,7 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
     bool b_on[B_CH];
 #pragma unroll
     for (int j = 0; j < A_CH; ++j) {
-      const int q = j * PROD_THREADS + ptid;
+      const int q = j * TF_PROD_THREADS + ptid;
       if (AL::kTransposed) {
         const int rc = q % (BM / 4), k = q / (BM / 4);
         a_o[j] = mn_chunk_off(k, rc);
@@ -894,7 +904,7 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
     }
 #pragma unroll
     for (int j = 0; j < B_CH; ++j) {
-      const int q = j * PROD_THREADS + ptid;
+      const int q = j * TF_PROD_THREADS + ptid;
       b_on[j] = q < BN * 8;
       if (BL::kTransposed) {
         const int rc = q % (BN / 4), k = q / (BN / 4);
@@ -926,12 +936,12 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
       if (AL::kTransposed) { ast[0] = al.begin(m0 + (ptid % (BM / 4)) * 4); }
       else {
 #pragma unroll
-        for (int j = 0; j < A_NST; ++j) ast[j] = al.begin(m0 + j * (PROD_THREADS / 8) + (ptid >> 3));
+        for (int j = 0; j < A_NST; ++j) ast[j] = al.begin(m0 + j * (TF_PROD_THREADS / 8) + (ptid >> 3));
       }
       if (BL::kTransposed) { bst[0] = bl.begin(nq * BN + (ptid % (BN / 4)) * 4); }
       else {
 #pragma unroll
-        for (int j = 0; j < B_NST; ++j) bst[j] = bl.begin(nq * BN + j * (PROD_THREADS / 8) + (ptid >> 3));
+        for (int j = 0; j < B_NST; ++j) bst[j] = bl.begin(nq * BN + j * (TF_PROD_THREADS / 8) + (ptid >> 3));
       }
     };
     uint32_t ls = 0, lph = 0;                                        // slot / phase of the next k-block to load
@@ -942,13 +952,13 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
           const uint32_t base = smem_u32(ring + (size_t)ls * SLOT);
 #pragma unroll
           for (int j = 0; j < A_CH; ++j) {
-            if (AL::kTransposed) al.copy4(base + OFF_AHI + a_o[j], ast[0], lk + (j * PROD_THREADS + ptid) / (BM / 4));
+            if (AL::kTransposed) al.copy4(base + OFF_AHI + a_o[j], ast[0], lk + (j * TF_PROD_THREADS + ptid) / (BM / 4));
             else al.copy4(base + OFF_AHI + a_o[j], ast[j], lk + (ptid & 7) * 4);
           }
 #pragma unroll
           for (int j = 0; j < B_CH; ++j) {
             if (b_on[j]) {
-              if (BL::kTransposed) bl.copy4(base + OFF_BHI + b_o[j], bst[0], lk + (j * PROD_THREADS + ptid) / (BN / 4));
+              if (BL::kTransposed) bl.copy4(base + OFF_BHI + b_o[j], bst[0], lk + (j * TF_PROD_THREADS + ptid) / (BN / 4));
               else bl.copy4(base + OFF_BHI + b_o[j], bst[j < B_NST ? j : 0], lk + (ptid & 7) * 4);
             }
           }
@@ -1079,21 +1089,26 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
 #pragma unroll
         for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
         __syncwarp();
-        EpiAux aux[8];
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {                            // row operands first (loads in flight together)
-          const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
-          const int64_t n = n0 + c + (lane & 7) * 4;
-          aux[pass] = (m < M && n < N) ? epi_aux<EP>(ep, rws[pass], n, N) : EpiAux{};
-        }
+        for (int half = 0; half < 2; ++half) {
+          EpiAux aux[4];
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {                            // 8 lanes x 4 columns per row, 4 rows per pass
-          const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
-          const int64_t m = m0 + warp * 32 + r;
-          const int64_t n = n0 + c + cq;
-          if (m < M && n < N && !(tm.dbg & 1)) {
-            const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
-            store4<EP>(ep, rws[pass], n, N, o, b4, aux[pass]);
+          for (int q = 0; q < 4; ++q) {                                   // row operands first (loads in flight together)
+            const int pass = half * 4 + q;
+            const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
+            const int64_t n = n0 + c + (lane & 7) * 4;
+            aux[q] = (m < M && n < N) ? epi_aux<EP>(ep, rws[pass], n, N) : EpiAux{};
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                                   // 8 lanes x 4 columns per row, 4 rows per pass
+            const int pass = half * 4 + q;
+            const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
+            const int64_t m = m0 + warp * 32 + r;
+            const int64_t n = n0 + c + cq;
+            if (m < M && n < N && !(tm.dbg & 1)) {
+              const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
+              store4<EP>(ep, rws[pass], n, N, o, b4, aux[q]);
+            }
           }
         }
         __syncwarp();
@@ -1190,7 +1205,7 @@ int launch_tf(const AL& al, const BL& bl, const EP& ep, int64_t M, int64_t N, in
     tm.trace = trace_buf;
   }
   const int64_t grid = tm.total < sm_count() ? tm.total : sm_count();
-  kern<<<(unsigned)grid, THREADS, sm, st>>>(al, bl, ep, M, N, tm, err);
+  kern<<<(unsigned)grid, TF_THREADS, sm, st>>>(al, bl, ep, M, N, tm, err);
   if (trace_on) {
     static long long h[1024];
     cudaStreamSynchronize(st);
