@@ -242,29 +242,51 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
 
-    # ---- end to end from pinned host memory: every step uploads its own inputs (features, image,
-    # masks, labels, endpoints) and reads its loss back.  The upload of step i+1 is issued on a copy
-    # stream before step i computes (a data loader's prefetch), all inside the timed region.
+    # ---- end to end from pinned host memory through the public API: every step copies its inputs
+    # host -> device and reads its loss back.  The upload of step i+1 is issued on a copy stream before
+    # step i computes (a data loader's prefetch), all inside the timed region.
     graph = batch.graph
     copy_stream = torch.cuda.Stream()
+    if use_graph:
+        # DesignStep.prepare(): structure resident + captured step; per-step VALUES (features, image,
+        # labels) are re-uploaded into the graph's static inputs.  Two prepared copies alternate so that
+        # the upload of the next step overlaps the replay of the current one.
+        preps = [step.prepare(host, dev, graph=graph) for _ in range(2)]
+        e2e_h2d = preps[0].nbytes()
+        e2e_note = ("DesignStep.prepare(): netlist / endpoint / mask structure resident, step replayed as a CUDA graph; "
+                    "per step: features + image + labels uploaded (prefetched on a copy stream), loss read back")
 
-    def upload():
-        with torch.cuda.stream(copy_stream):
-            b = tm_engine.DesignBatch.from_host(host, dev, graph=graph)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return b, ev
+        def e2e_loop(n):
+            ev = [torch.cuda.Event(), torch.cuda.Event()]
+            preps[0].upload(host, copy_stream); ev[0].record(copy_stream)
+            out = 0.0
+            for i in range(n):
+                if i + 1 < n:
+                    preps[(i + 1) & 1].upload(host, copy_stream); ev[(i + 1) & 1].record(copy_stream)
+                torch.cuda.current_stream().wait_event(ev[i & 1])
+                out = float(preps[i & 1].step()[0].item())           # D2H read of the step's loss
+            return out
+    else:
+        e2e_h2d = host.nbytes(per_step_only=True)
+        e2e_note = "graph structure + level schedule cached per design; the next step's upload is prefetched on a copy stream"
 
-    def e2e_loop(n):
-        nxt = upload()
-        out = 0.0
-        for i in range(n):
-            b2, ev = nxt
-            if i + 1 < n:
-                nxt = upload()
-            torch.cuda.current_stream().wait_event(ev)
-            out = float(step.run(b2)[0].item())          # D2H read of the step's loss
-        return out
+        def upload():
+            with torch.cuda.stream(copy_stream):
+                b = tm_engine.DesignBatch.from_host(host, dev, graph=graph)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return b, ev
+
+        def e2e_loop(n):
+            nxt = upload()
+            out = 0.0
+            for i in range(n):
+                b2, ev = nxt
+                if i + 1 < n:
+                    nxt = upload()
+                torch.cuda.current_stream().wait_event(ev)
+                out = float(step.run(b2)[0].item())          # D2H read of the step's loss
+            return out
 
     e2e_loop(2)
     sync_all()
@@ -367,7 +389,7 @@ def main():
             extra["cpu_baseline"] = None
 
     if rank == 0:
-        h2d = host.nbytes(per_step_only=True)
+        h2d = e2e_h2d
         line = {"metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": "designs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -377,7 +399,7 @@ def main():
                            "resident_loop": "CUDA graph replay of the two-stream step" if use_graph else "eager launches",
                            "l2": "working set per step (~1.5 GB of activations) exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": world * args.steps / e2e_s, "unit": "designs/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": 4, "note": "graph structure + level schedule cached per design; the next step's upload is prefetched on a copy stream"},
+                        "d2h_bytes_per_step": 4, "note": e2e_note},
                 "gpu_launches": launches, "clocks": clocks, "loss": lv}
         line.update(extra)
         print(json.dumps(line), flush=True)

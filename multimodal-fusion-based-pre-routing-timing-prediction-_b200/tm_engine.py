@@ -93,6 +93,32 @@ class DesignBatch:
         return DesignBatch.from_host(HostDesign(d, pin=False), device)
 
 
+class PreparedDesign:
+    VALUE_FIELDS = ("cell_feat", "net_feat", "image", "arrival_time")
+
+    def __init__(self, step, host, device, graph=None):
+        self.batch = DesignBatch.from_host(host, device, graph=graph)
+        self.static = {"cell_feat": self.batch.cell_feat, "net_feat": self.batch.net_feat,
+                       "image": self.batch.image, "arrival_time": self.batch.arrival_time}
+        torch.cuda.synchronize()
+        self.replay = step.capture(self.batch)
+
+    def upload(self, host, stream=None):
+        """Host -> device copy of the per-step values into the graph's static inputs."""
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            for k in self.VALUE_FIELDS:
+                self.static[k].copy_(host.t[k], non_blocking=True)
+
+    def nbytes(self):
+        return int(sum(t.numel() * t.element_size() for t in self.static.values()))
+
+    def step(self, host=None):
+        if host is not None:
+            self.upload(host)
+        return self.replay()
+
+
 class DesignStep:
     def __init__(self, model, cnn, process_group=None, world_size=1):
         self.model, self.cnn = model, cnn
@@ -211,12 +237,23 @@ class DesignStep:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             loss, pred = self.run(b)
+        grads = [(p, p.grad) for p in list(self.model.parameters()) + list(self.cnn.parameters()) if p.grad is not None]
 
         def replay():
             g.replay()
+            for p, gr in grads:                      # several captured steps may coexist: re-point .grad
+                p.grad = gr
             return loss, pred
         replay.graph = g
         return replay
+
+    def prepare(self, host, device, graph=None):
+        """A design made resident for repeated steps: uploads everything once, builds the structure
+        that depends only on the netlist and the endpoint batch (level schedule, CSRs, mask runs / CSC)
+        and captures the step as a CUDA graph.  Returns a ``PreparedDesign``; its ``step(host)``
+        refreshes the per-step VALUES (features, image, labels) from pinned host memory and replays.
+        The structure (edges, endpoints, masks) must be the one given here."""
+        return PreparedDesign(self, host, device, graph)
 
     @staticmethod
     def _assign(pairs):
