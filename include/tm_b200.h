@@ -190,6 +190,24 @@ int tm_fuse_backward(int64_t T, int64_t J, int64_t D, const int32_t* csc_ptr, co
                      float* dF, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * N2  path-mask rasteriser (replaces the host code that builds `path_masks`:
+ *     find_critical_path, verilog_parser_asap7.py:1433-1450, and the bounding-box rasterisation,
+ *     :1302-1369).  src/dst: ALL pin-graph edges in insertion order (the order networkx iterates
+ *     predecessors in); level: longest-path levels (tm_levelize / cal_topo_level); pin_xy: int32 [n][2]
+ *     bins; endpoints: int32 [T].  Row t of the result = ascending columns x*map_size+y covered by the
+ *     union of the bounding boxes of consecutive pins on endpoint t's critical path.
+ *     tm_mask_count -> counts[t] (-1: a pin on the path has no predecessor one level below, where the
+ *     reference would loop forever); the caller builds indptr = exclusive scan(counts) and sizes cols;
+ *     tm_mask_fill writes cols.  Both use the same workspace (tm_mask_ws_bytes), untouched in between.
+ * ---------------------------------------------------------------------------------- */
+size_t tm_mask_ws_bytes(int64_t n, int64_t T, int64_t map_size);
+int tm_mask_count(int64_t n, int64_t E, const int32_t* src, const int32_t* dst, const int32_t* level,
+                  int64_t T, const int32_t* endpoints, const int32_t* pin_xy, int64_t map_size,
+                  int32_t* counts, void* ws, size_t ws_bytes, void* stream);
+int tm_mask_fill(int64_t n, int64_t T, int64_t map_size, const int32_t* indptr, int32_t* cols, void* ws,
+                 size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * G6  head helpers (src/model.py:280-292, src/train.py:513-522)
  * ---------------------------------------------------------------------------------- */
 /* dst[i, col0:col0+w] = src[rows ? rows[i] : i, 0:w]   (builds cat(h_gnn,h_cnn,h_global)) */

@@ -32,6 +32,27 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
     if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][i];
   }
 }
+// K <= 4 (fc_net_self layer 1: K = 2, model.py:50): pure streaming -- one thread per 4 outputs,
+// 128-bit stores, the K x N weight stays in L1
+__global__ void __launch_bounds__(256)
+gemm_small_k_kernel(int64_t M, int64_t N, int K, const float* __restrict__ A, int64_t lda,
+                    const int32_t* __restrict__ a_rows, const float* __restrict__ B, int64_t ldb,
+                    float* __restrict__ C, int64_t ldc, const int32_t* __restrict__ c_rows,
+                    const float* __restrict__ bias, int flags) {
+  const int64_t n4s = N >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * n4s) return;
+  const int64_t m = i / n4s, n = (i - m * n4s) << 2;
+  const float* a = A + (a_rows ? (int64_t)a_rows[m] : m) * lda;
+  float4 acc = (flags & TM_EPI_BIAS) ? __ldg(reinterpret_cast<const float4*>(bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < K; ++k) {
+    const float av = a[k];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(B + (int64_t)k * ldb + n));
+    acc.x = fmaf(av, b.x, acc.x); acc.y = fmaf(av, b.y, acc.y); acc.z = fmaf(av, b.z, acc.z); acc.w = fmaf(av, b.w, acc.w);
+  }
+  if (flags & TM_EPI_RELU) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+  st4(C + (c_rows ? (int64_t)c_rows[m] : m) * ldc + n, acc);
+}
 }  // namespace
 
 extern "C" int tm_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
@@ -41,6 +62,12 @@ extern "C" int tm_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, int64
   TM_REQUIRE(M >= 0 && N >= 0 && K >= 0, "tm_gemm_nn: negative size");
   TM_REQUIRE(!(flags & TM_EPI_BIAS) || bias, "tm_gemm_nn: TM_EPI_BIAS without bias");
   TM_REQUIRE(!(flags & TM_EPI_MASK) || mask, "tm_gemm_nn: TM_EPI_MASK without mask");
+  if (K >= 1 && K <= 4 && M > 0 && N > 0 && (N % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && aligned16(B) && aligned16(C) &&
+      (!bias || aligned16(bias)) && !(flags & (TM_EPI_MASK | TM_EPI_ACCUM))) {
+    gemm_small_k_kernel<<<(unsigned)cdiv(M * (N / 4), 256), 256, 0, (cudaStream_t)stream>>>(M, N, (int)K, A, lda, a_rows, B, ldb, C,
+                                                                                         ldc, c_rows, bias, flags);
+    return check_launch("gemm_small_k");
+  }
   PlainLoader al{A, lda, a_rows};
   PlainEpilogue ep{C, ldc, c_rows, bias, mask, ldmask, flags};
   const bool veca = (lda % 4 == 0) && (K % 4 == 0) && aligned16(A);

@@ -273,6 +273,36 @@ class MaskCSR:
         return MaskRows(self, torch.arange(self.num_rows, dtype=torch.int32, device=dev), identity=True)
 
 
+def rasterize_path_masks(n, src, dst, level, endpoints, pin_xy, map_size):
+    """GPU replacement of the host preprocessing behind ``path_masks`` (critical-path back-trace,
+    verilog_parser_asap7.py:1433-1450, + bounding-box rasterisation, :1302-1369).
+
+    src, dst: every pin-graph edge in insertion order (net edges then cell edges for the synthetic
+    generator; whatever order the caller's nx.DiGraph was filled in); level: (n,) longest-path levels;
+    endpoints: (T,) pin ids; pin_xy: (n,2) integer bins.  All CUDA tensors.  Returns a ``MaskCSR``
+    on the device whose row t is bit-identical to the reference's sparse mask row."""
+    import tm_lib
+    dev = level.device
+    tm_lib.require_cuda(level, "level")
+    i32 = lambda t: t.to(device=dev, dtype=torch.int32).contiguous()      # noqa: E731
+    src, dst, level, endpoints, pin_xy = i32(src), i32(dst), i32(level), i32(endpoints), i32(pin_xy)
+    T, E = int(endpoints.numel()), int(src.numel())
+    nb = tm_lib.ws_bytes("tm_mask_ws_bytes", n, T, map_size)
+    ws = tm_lib.workspace(nb, dev)
+    counts = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+    tm_lib.call("tm_mask_count", n, E, src, dst, level, T, endpoints, pin_xy, map_size, counts, ws, nb, tm_lib.stream())
+    counts = counts[:T]
+    if T and int(counts.min().item()) < 0:
+        raise RuntimeError("rasterize_path_masks: a pin on a critical path has no predecessor one level below "
+                           "(the reference's find_critical_path would not terminate)")
+    indptr = torch.zeros(T + 1, dtype=torch.int32, device=dev)
+    indptr[1:] = torch.cumsum(counts, 0)
+    nnz = int(indptr[-1].item()) if T else 0
+    cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    tm_lib.call("tm_mask_fill", n, T, map_size, indptr, cols, ws, nb, tm_lib.stream())
+    return MaskCSR(indptr, cols[:nnz], map_size * map_size)
+
+
 class MaskRows:
     """A row selection of a MaskCSR plus its column-major transpose (built lazily on the GPU)."""
 

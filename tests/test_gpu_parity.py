@@ -285,6 +285,29 @@ def test_mask_fusion(mods):
     assert torch.equal(c2.indptr, torch.from_numpy(d.mask_indptr)) and torch.equal(c2.cols, torch.from_numpy(d.mask_cols))
 
 
+@pytest.mark.parametrize("cfg,seed", [("tiny", 0), ("c1", 1), ("c1", 7)])
+def test_mask_rasteriser_bit_exact(mods, cfg, seed):
+    """GPU critical-path trace + bounding-box rasterisation == the oracle-pinned masks (bit-exact CSR)."""
+    G = mods["graph"]
+    d = tm_synth.make_design(seed=seed, **tm_synth.CONFIGS[cfg])
+    src = np.concatenate([d.net_src, d.cell_src])
+    dst = np.concatenate([d.net_dst, d.cell_dst])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)       # noqa: E731
+    m = G.rasterize_path_masks(d.n, t(src), t(dst), t(d.level), t(d.endpoints), t(d.pin_xy), d.map_size)
+    assert np.array_equal(m.indptr.cpu().numpy(), d.mask_indptr)
+    assert np.array_equal(m.cols.cpu().numpy(), d.mask_cols)
+    # levels computed on the GPU feed it just as well
+    g = _graph(mods, d)
+    m2 = G.rasterize_path_masks(d.n, t(src), t(dst), g.schedule().level, t(d.endpoints), t(d.pin_xy), d.map_size)
+    assert torch.equal(m2.cols, m.cols) and torch.equal(m2.indptr, m.indptr)
+    # an endpoint whose only predecessors skip a level cannot be traced: reported, not a hang
+    lvl = d.level.copy()
+    e = int(d.endpoints[-1])
+    lvl[e] += 2
+    with pytest.raises(RuntimeError):
+        G.rasterize_path_masks(d.n, t(src), t(dst), t(lvl), t(d.endpoints[-1:]), t(d.pin_xy), d.map_size)
+
+
 @pytest.mark.parametrize("identity", [True, False])
 def test_mask_fusion_runs_vs_csr(mods, identity):
     """The run-length / prefix-table forward equals the per-column CSR forward and the dense oracle;
