@@ -223,6 +223,12 @@ int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, const int32_t* r
 /* loss[0] = mean((pred-y)^2); grad[i] = 2*(pred[i]-y[i])/T * grad_scale  (nn.MSELoss) */
 int tm_mse(int64_t T, const float* pred, const float* y, float* loss, float* grad,
            float grad_scale, void* stream);
+/* N4: the per-batch statistics the reference reads back one .item() at a time (train.py:513-549):
+ * out8 = [mse, R2 (torchmetrics R2Score), correct, tp, fn, tn, fp, T] with predicted critical <=>
+ * required - pred < 0 (judge_critical, train.py:391-395) against label (int64, 0 = non-critical).
+ * required / label may be NULL (regression statistics only). */
+int tm_step_metrics(int64_t T, const float* pred, const float* arrival, const float* required,
+                    const int64_t* label, float* out8, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * G4  U-Net / LayoutNet image branch, fp32 NHWC (replaces the cuDNN/ATen calls behind

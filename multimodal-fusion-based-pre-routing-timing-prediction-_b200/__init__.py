@@ -24,4 +24,4 @@ from model import MLP, PathConv, LayoutNet, PathModel  # noqa: E402,F401
 from Unet import UNet  # noqa: E402,F401
 from tm_graph import TimingGraph, MaskCSR, MaskRows, Schedule  # noqa: E402,F401
 from tm_ops import MaskedFeatureMap  # noqa: E402,F401
-from tm_engine import DesignBatch, DesignStep, build_models  # noqa: E402,F401
+from tm_engine import DesignBatch, DesignStep, HostDesign, PreparedDesign, build_models  # noqa: E402,F401

@@ -221,6 +221,43 @@ mse_kernel(int64_t T, const float* __restrict__ pred, const float* __restrict__ 
   }
 }
 
+// N4: every per-batch number the reference's loop reads back with its own .item() (train.py:513-549,
+// same in validate :220-260): MSE, torchmetrics R2Score, and the critical / non-critical confusion
+// counts of judge_critical (train.py:391-395: critical <=> required - predicted arrival < 0).
+//   out[0] mse  out[1] r2  out[2] correct  out[3] tp  out[4] fn  out[5] tn  out[6] fp  out[7] T
+__global__ void __launch_bounds__(1024)
+metrics_kernel(int64_t T, const float* __restrict__ pred, const float* __restrict__ arrival,
+               const float* __restrict__ required, const int64_t* __restrict__ label, float* __restrict__ out) {
+  __shared__ double part[32][8];
+  double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};                  // sse, sum y, sum y^2, correct, tp, fn, tn, fp
+  for (int64_t i = threadIdx.x; i < T; i += blockDim.x) {
+    const double y = arrival[i], d = (double)pred[i] - y;
+    v[0] += d * d; v[1] += y; v[2] += y * y;
+    if (required && label) {
+      const bool crit = (required[i] - pred[i]) < 0.f, lab = label[i] != 0;
+      v[3] += (crit == lab) && (label[i] == 0 || label[i] == 1);
+      v[4] += crit && lab; v[5] += !crit && lab; v[6] += !crit && !lab; v[7] += crit && !lab;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = warp_sum(v[k]);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[threadIdx.x >> 5][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = warp_sum(part[threadIdx.x][k]);
+    if (threadIdx.x == 0) {
+      const double n = (double)T, sst = v[2] - v[1] * v[1] / n;
+      out[0] = (float)(v[0] / n);
+      out[1] = (float)(1.0 - v[0] / sst);
+      out[2] = (float)v[3]; out[3] = (float)v[4]; out[4] = (float)v[5]; out[5] = (float)v[6]; out[6] = (float)v[7];
+      out[7] = (float)n;
+    }
+  }
+}
+
 __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
                             float eps, float wd, float bc1, float bc2, float gscale) {
@@ -315,6 +352,13 @@ extern "C" int tm_mse(int64_t T, const float* pred, const float* y, float* loss,
   TM_REQUIRE(T > 0, "tm_mse: empty batch");
   mse_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(T, pred, y, loss, grad, grad_scale);
   return check_launch("mse");
+}
+
+extern "C" int tm_step_metrics(int64_t T, const float* pred, const float* arrival, const float* required,
+                               const int64_t* label, float* out8, void* stream) {
+  TM_REQUIRE(T > 0, "tm_step_metrics: empty batch");
+  metrics_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(T, pred, arrival, required, label, out8);
+  return check_launch("step_metrics");
 }
 
 extern "C" int tm_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr,

@@ -294,6 +294,18 @@ class GnnPropagateFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+def step_metrics(pred, arrival, required=None, label=None):
+    """One launch, one (8,) device tensor [mse, r2, correct, tp, fn, tn, fp, T] instead of the seven
+    ``.item()`` round trips of train.py:513-549.  ``label``: int64 (0 = non-critical)."""
+    pred, arrival = _f32c(pred.detach().reshape(-1)), _f32c(arrival.detach().reshape(-1))
+    tm_lib.require_cuda(pred, "pred")
+    out = torch.empty(8, dtype=torch.float32, device=pred.device)
+    req = None if required is None else _f32c(required.detach().reshape(-1))
+    lab = None if label is None else label.detach().reshape(-1).to(torch.int64).contiguous()
+    call("tm_step_metrics", int(pred.numel()), pred, arrival, req, lab, out, stream())
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # mask fusion
 # --------------------------------------------------------------------------------------------

@@ -632,6 +632,27 @@ def test_adam_matches_torch(mods):
     assert_close(p, ref, 1e-5, 1e-6, "adam")
 
 
+def test_step_metrics(mods):
+    """N4: fused MSE / R2 / confusion counts against the reference's formulas (train.py:391-395,513-549)."""
+    ops = mods["ops"]
+    torch.manual_seed(0)
+    T = 1350
+    arrival = torch.rand(T) * 3
+    pred = arrival + 0.3 * torch.randn(T)
+    required = arrival + 0.2 * torch.randn(T)
+    label = (required - arrival < 0).long()
+    out = ops.step_metrics(pred.to(DEV), arrival.to(DEV), required.to(DEV), label.to(DEV)).cpu()
+    mse = torch.nn.functional.mse_loss(pred, arrival)
+    r2 = 1 - ((arrival - pred) ** 2).sum() / ((arrival - arrival.mean()) ** 2).sum()
+    crit = torch.ones(T); crit[(required - pred) >= 0] = 0                      # judge_critical
+    exp = [mse, r2, (crit == label).sum(), ((crit != 0) & (label != 0)).sum(), ((crit == 0) & (label != 0)).sum(),
+           ((crit == 0) & (label == 0)).sum(), ((crit != 0) & (label == 0)).sum(), T]
+    assert_close(out[:2], torch.stack([mse, r2]), 1e-5, 1e-6, "mse, r2")
+    assert [int(x) for x in out[2:]] == [int(x) for x in exp[2:]]
+    out2 = ops.step_metrics(pred.to(DEV), arrival.to(DEV)).cpu()
+    assert_close(out2[:2], out[:2], 0, 0, "regression-only call")
+
+
 def test_cpu_inputs_fail_loudly(mods):
     import model as M
     with pytest.raises(RuntimeError, match="CUDA"):
