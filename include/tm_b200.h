@@ -330,6 +330,16 @@ int tm_tc_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, 
                   const float* B, int64_t ldb, int b_is_nk, float* C, int64_t ldc,
                   const int32_t* c_rows, const float* bias, const float* mask, int64_t ldmask,
                   int flags, int precision, int* err, void* stream);
+/* Backward of the FIRST layer of an MLP whose input has 1 or 2 columns (fc_net_self.layers.0 = Linear(2,256),
+ * model.py:50), fused into the data-gradient GEMM of the second layer: with dh = (G[g_rows] @ W2) * (H > 0)
+ * (never written) it returns db1[n] = sum_m dh[m,n] and dW1[n,c] = sum_m dh[m,n] * X[x_rows[m], c].
+ * W2t: the second layer's weight transposed to [N,K] row-major (N = hidden width <= 256, K = its outputs);
+ * H: [M,N] hidden activations; 3xTF32; deterministic (fixed-order partial sums in ws). */
+size_t tm_tc_mlp1_bwd_ws(int64_t N);
+int tm_tc_mlp1_bwd_fused(int64_t M, int64_t N, int64_t K, const float* G, int64_t ldg, const int32_t* g_rows,
+                         const float* W2t, const float* H, int64_t ldh, const float* X, int64_t ldx,
+                         const int32_t* x_rows, int64_t kx, float* dW1, float* db1, void* ws, size_t ws_bytes,
+                         int* err, void* stream);
 size_t tm_tc_gemm_tn_ws(int64_t M, int64_t N, int64_t R);
 int tm_tc_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, int64_t lda, const int32_t* a_rows,
                   const float* B, int64_t ldb, const int32_t* b_rows, float* C, int64_t ldc,

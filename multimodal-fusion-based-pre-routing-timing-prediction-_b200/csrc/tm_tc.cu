@@ -47,6 +47,46 @@ extern "C" int tm_tc_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, in
   return tc::launch(al, bl, ep, M, N, K, 1, K > 0 ? cdiv(K, tc::BK) * tc::BK : tc::BK, precision, err, st);
 }
 
+namespace {
+// part [G][EPI_WARPS][3][N] -> db1[n], dW1[n][kx]  (fixed order: deterministic)
+__global__ void mlp1_reduce_kernel(const float* __restrict__ part, int slots, int64_t N, int kx,
+                                   float* __restrict__ dW1, float* __restrict__ db1) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int g = 0; g < slots; ++g)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s[k] += part[((int64_t)g * 3 + k) * N + n];
+  db1[n] = s[0];
+  dW1[n * kx] = s[1];
+  if (kx > 1) dW1[n * kx + 1] = s[2];
+}
+}  // namespace
+
+extern "C" size_t tm_tc_mlp1_bwd_ws(int64_t N) {
+  return (size_t)sm_count() * tc::EPI_WARPS * 3 * N * sizeof(float) + 256;
+}
+
+extern "C" int tm_tc_mlp1_bwd_fused(int64_t M, int64_t N, int64_t K, const float* G, int64_t ldg, const int32_t* g_rows,
+                                    const float* W2t, const float* H, int64_t ldh, const float* X, int64_t ldx,
+                                    const int32_t* x_rows, int64_t kx, float* dW1, float* db1, void* ws,
+                                    size_t ws_bytes, int* err, void* stream) {
+  TM_REQUIRE(M > 0 && N > 0 && N <= 256 && N % 4 == 0 && K > 0, "tm_tc_mlp1_bwd_fused: needs 0 < N <= 256, N % 4 == 0");
+  TM_REQUIRE(kx == 1 || kx == 2, "tm_tc_mlp1_bwd_fused: the first layer must have 1 or 2 inputs");
+  TM_REQUIRE((ldh % 4 == 0) && aligned16(H), "tm_tc_mlp1_bwd_fused: H rows must be 16-byte aligned");
+  TM_REQUIRE(ws && ws_bytes >= tm_tc_mlp1_bwd_ws(N), "tm_tc_mlp1_bwd_fused: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const int64_t tiles = cdiv(M, tc::BM) * cdiv(N, 128);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  tc::RowLoader al{G, ldg, g_rows, M, K, vec_mode(G, ldg)};
+  tc::RowLoader bl{W2t, K, nullptr, N, K, vec_mode(W2t, K)};
+  tc::ReduceEpilogue ep{H, ldh, X, ldx, x_rows, (int)kx, part};
+  TM_TRY((tc::launch_tf<tc::RowLoader, tc::RowLoader, tc::ReduceEpilogue, 128, 2>(al, bl, ep, M, N, K, 1, cdiv(K, tc::BK) * tc::BK, err, st)));
+  mlp1_reduce_kernel<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(part, grid * tc::EPI_WARPS, N, (int)kx, dW1, db1);
+  return check_launch("mlp1_reduce");
+}
+
 extern "C" size_t tm_tc_gemm_tn_ws(int64_t M, int64_t N, int64_t R) {
   size_t worst = 0;                       // the N tile depends on the precision chosen at launch
   for (int prec = 0; prec < 5; ++prec) {

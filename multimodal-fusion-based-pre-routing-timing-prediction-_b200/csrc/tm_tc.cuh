@@ -320,6 +320,26 @@ struct PartialEpilogue {
   struct Row { float* p; };
 };
 
+// Data-gradient GEMM of a first layer with <= 2 inputs (fc_net_self.layers.0: Linear(2,256)), fused
+// with everything its output is needed for: dh = (g @ W2) * (h > 0) is never written; the epilogue
+// reduces it straight into  db1[n] = sum_m dh[m,n]  and  dW1[n,c] = sum_m dh[m,n] * x[m,c].
+// Partial sums are owned per (CTA, epilogue warp) and added up in a fixed order: deterministic.
+struct ReduceEpilogue {
+  const float* mask;        // hidden activations h (ReLU mask), rows indexed like the GEMM rows
+  int64_t ldmask;
+  const float* X;           // layer inputs
+  int64_t ldx;
+  const int32_t* x_rows;    // optional gather of the input rows
+  int kx;                   // 1 or 2 input columns
+  float* part;              // [grid][EPI_WARPS][3][N]
+  struct Row { int64_t r; };
+  __device__ __forceinline__ Row row(int64_t m) const { return Row{m}; }
+  __device__ __forceinline__ void store(const Row&, int64_t, float) const {}
+};
+template <class EP> struct IsReduce { static constexpr bool value = false; };
+template <> struct IsReduce<ReduceEpilogue> { static constexpr bool value = true; };
+constexpr uint32_t REDUCE_ACC_BYTES = EPI_WARPS * 2 * 3 * 128 * 4;   // per warp [n tiles <= 2][3][BN <= 128] fp32
+
 template <class EP>
 __device__ __forceinline__ typename EP::Row epi_row(const EP& ep, int64_t m, int z) { return ep.row(m); }
 template <>
@@ -864,6 +884,7 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* scratch = reinterpret_cast<float*>(ring + (size_t)ND * SLOT);
+  float* reduce_acc = scratch + EPI_SCRATCH / 4;                 // only allocated for ReduceEpilogue launches
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
@@ -1064,6 +1085,88 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
     // ======================= epilogue =======================
     float* scr = scratch + warp * (32 * 33);
     int li = 0;
+    if constexpr (IsReduce<EP>::value) {
+      float* racc = reduce_acc + warp * (2 * 3 * BN);              // [n tile][3][BN]
+      for (int i = lane; i < 2 * 3 * BN; i += 32) racc[i] = 0.f;
+      __syncwarp();
+      for (int64_t t = blockIdx.x; t < tm.total && ok; t += G, ++li) {
+        const int buf = li & 1;
+        const uint32_t aph = (uint32_t)(li >> 1) & 1u;
+        ok = mbar_wait(&acc_full[buf], aph, abortp);
+        if (!ok) break;
+        tc_fence_after();
+        int64_t m0, nq, kb0; int zi, nkb;
+        tm.decode(t, m0, nq, zi, kb0, nkb);
+        const int64_t n0 = nq * BN;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
+        // this lane's rows of the 8 passes: input values x0, x1 (0 for rows past M)
+        float x0[8], x1[8];
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
+          x0[pass] = 0.f; x1[pass] = 0.f;
+          if (m < M) {
+            const float* xp = ep.X + (ep.x_rows ? (int64_t)ep.x_rows[m] : m) * ep.ldx;
+            x0[pass] = xp[0];
+            if (ep.kx > 1) x1[pass] = xp[1];
+          }
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= N) break;
+          float v[32];
+          tmem_ld32(trow + (uint32_t)c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+          __syncwarp();
+          const int cq = (lane & 7) * 4;
+          const int64_t n = n0 + c + cq;
+          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 mk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                                 // mask rows first (loads in flight together)
+              const int64_t m = m0 + warp * 32 + (half * 4 + q) * 4 + (lane >> 3);
+              mk[q] = (m < M && n + 4 <= N) ? ld4(ep.mask + m * ep.ldmask + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int pass = half * 4 + q, r = pass * 4 + (lane >> 3);
+              const float mq[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float d = mq[j] > 0.f ? scr[r * 33 + cq + j] : 0.f;
+                s0[j] += d;
+                s1[j] = fmaf(d, x0[pass], s1[j]);
+                s2[j] = fmaf(d, x1[pass], s2[j]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                                   // sum over the 4 row groups of the warp
+            s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], 8);  s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], 16);
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+          }
+          if (lane < 8 && nq < 2) {
+            float* a = racc + (size_t)nq * 3 * BN + c + cq;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a[j] += s0[j]; a[BN + j] += s1[j]; a[2 * BN + j] += s2[j]; }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      __syncwarp();
+      for (int i = lane; i < 2 * 3 * BN; i += 32) {                       // my partial sums -> global
+        const int nqq = i / (3 * BN), k = (i / BN) % 3, col = i % BN;
+        const int64_t n = (int64_t)nqq * BN + col;
+        if (n < N) ep.part[(((int64_t)blockIdx.x * EPI_WARPS + warp) * 3 + k) * N + n] = racc[i];
+      }
+    } else
     for (int64_t t = blockIdx.x; t < tm.total && ok; t += G, ++li) {
       const int buf = li & 1;
       const uint32_t aph = (uint32_t)(li >> 1) & 1u;
@@ -1182,7 +1285,7 @@ template <class AL, class BL, class EP, int BN, int PLANES>
 int launch_tf(const AL& al, const BL& bl, const EP& ep, int64_t M, int64_t N, int64_t K, int splits,
               int64_t k_per_split, int* err, cudaStream_t st) {
   auto kern = tf_gemm_kernel<AL, BL, EP, BN, PLANES>;
-  constexpr size_t sm = TfCfg<BN, PLANES>::SMEM;
+  constexpr size_t sm = TfCfg<BN, PLANES>::SMEM + (IsReduce<EP>::value ? REDUCE_ACC_BYTES : 0);
   static bool optin = false;
   if (!optin) {
     TM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -191,6 +191,14 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
             t.zero_()
         return dw1, db1, dw2, db2, None
     gemm_tn(nout, hid, n_rows, g, ldg, h, hid, dw2, hid, a_rows=g_rows, colsum_a=db2)
+    if kin <= 2 and hid <= 256 and hid % 4 == 0 and not need_dx and _precision() == 3:
+        # Linear(<=2, hid) first layer: its whole backward (dW1, db1) is a reduction of the hidden
+        # gradient, fused into the data-gradient GEMM's epilogue -- dh is never written or re-read
+        nb = tm_lib.ws_bytes("tm_tc_mlp1_bwd_ws", hid)
+        call("tm_tc_mlp1_bwd_fused", n_rows, hid, nout, g, ldg, g_rows, transpose(_f32c(w2)), h, hid, x, ldx, rows, kin,
+             dw1, db1, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
+        aux_join()
+        return dw1, db1, dw2, db2, None
     dh = torch.empty(n_rows, hid, dtype=torch.float32, device=dev)
     gemm_nn(n_rows, hid, nout, g, ldg, _f32c(w2), hid, dh, hid, a_rows=g_rows, mask=h, ldmask=hid)
     gemm_tn(hid, kin, n_rows, dh, hid, x, ldx, dw1, kin, b_rows=rows, colsum_a=db1)
