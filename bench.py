@@ -218,7 +218,7 @@ def main():
     step.run(batch)
     sync_all()
     launches_per_step = tm_lib.launch_count() - launches0
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     run_step = step.capture(batch) if use_graph else (lambda: step.run(batch))
     for _ in range(2):
         run_step()
@@ -396,7 +396,8 @@ def main():
                 "config": {"workload": WORKLOAD if args.config == "c2" else args.config, "pins": d.n,
                            "levels": d.num_levels, "endpoints": int(d.endpoints.size),
                            "designs_per_step": world, "parallelism": f"dp{world}",
-                           "resident_loop": "CUDA graph replay of the two-stream step" if use_graph else "eager launches",
+                           "resident_loop": ("CUDA graph replay of the two-stream step" + (" + NCCL gradient all-reduce after each replay" if world > 1 else ""))
+                           if use_graph else "eager launches",
                            "l2": "working set per step (~1.5 GB of activations) exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": world * args.steps / e2e_s, "unit": "designs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "note": e2e_note},

@@ -222,10 +222,27 @@ class DesignStep:
         """Capture ``run(b)`` (about 500 launches on two streams) into one CUDA graph.  The batch's
         tensors become the graph's static inputs: refresh them in place (``tensor.copy_``) and call
         the returned function, which replays the graph and returns the same (loss, pred) tensors;
-        ``param.grad`` tensors are rewritten in place by every replay.  Single-GPU only: the NCCL
-        all-reduce of the data-parallel path stays outside graphs."""
-        if self.world > 1:
-            raise RuntimeError("DesignStep.capture: graphs are not used on the data-parallel path")
+        ``param.grad`` tensors are rewritten in place by every replay.  On the data-parallel path the
+        graph holds the rank's compute only; the NCCL gradient all-reduce (one bucket, 11.6 MB) is
+        posted right after each replay."""
+        world, self.world = self.world, 1                  # no collectives inside the captured region
+        try:
+            replay_local = self._capture_local(b, warmup)
+        finally:
+            self.world = world
+        if world <= 1:
+            return replay_local
+        params = [p for p in list(self.model.parameters()) + list(self.cnn.parameters())]
+
+        def replay():
+            out = replay_local()
+            self._post_allreduce([p for p in params if p.grad is not None])
+            self._wait_allreduce()
+            return out
+        replay.graph = replay_local.graph
+        return replay
+
+    def _capture_local(self, b, warmup=2):
         cur = torch.cuda.current_stream()
         s = torch.cuda.Stream()
         s.wait_stream(cur)
