@@ -338,8 +338,20 @@ int tm_tc_gemm_nn(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, 
 size_t tm_tc_mlp1_bwd_ws(int64_t N);
 int tm_tc_mlp1_bwd_fused(int64_t M, int64_t N, int64_t K, const float* G, int64_t ldg, const int32_t* g_rows,
                          const float* W2t, const float* H, int64_t ldh, const float* X, int64_t ldx,
-                         const int32_t* x_rows, int64_t kx, float* dW1, float* db1, void* ws, size_t ws_bytes,
-                         int* err, void* stream);
+                         const int32_t* x_rows, int64_t kx, const float* W1, const float* b1, float* dW1,
+                         float* db1, void* ws, size_t ws_bytes, int* err, void* stream);
+/* The same MLP (first layer Linear(kx <= 2, K)) with the hidden layer GENERATED inside the operand loaders
+ * instead of stored (2 FMAs per element; H = NULL above then regenerates the ReLU mask from W1, b1):
+ *   forward:  out[out_rows[m], 0:N] = relu(X[x_rows[m]] @ W1^T + b1) @ W2^T + b2     (W2: [N,K] as stored)
+ *   wgrad2:   dW2[Mo, hid] = G[g_rows]^T @ relu(X[x_rows] @ W1^T + b1)               (ws: tm_tc_gemm_tn_ws) */
+int tm_tc_mlp2_smallk_forward(int64_t M, int64_t K, int64_t N, const float* X, int64_t ldx, const int32_t* x_rows,
+                              int64_t kx, const float* W1, const float* b1, const float* W2, const float* b2,
+                              float* out, int64_t ldo, const int32_t* out_rows, int precision, int* err,
+                              void* stream);
+int tm_tc_mlp2_smallk_wgrad2(int64_t Mo, int64_t hid, int64_t R, const float* G, int64_t ldg, const int32_t* g_rows,
+                             const float* X, int64_t ldx, const int32_t* x_rows, int64_t kx, const float* W1,
+                             const float* b1, float* dW2, int precision, void* ws, size_t ws_bytes, int* err,
+                             void* stream);
 size_t tm_tc_gemm_tn_ws(int64_t M, int64_t N, int64_t R);
 int tm_tc_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, int64_t lda, const int32_t* a_rows,
                   const float* B, int64_t ldb, const int32_t* b_rows, float* C, int64_t ldc,

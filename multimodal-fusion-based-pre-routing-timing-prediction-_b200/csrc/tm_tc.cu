@@ -69,11 +69,12 @@ extern "C" size_t tm_tc_mlp1_bwd_ws(int64_t N) {
 
 extern "C" int tm_tc_mlp1_bwd_fused(int64_t M, int64_t N, int64_t K, const float* G, int64_t ldg, const int32_t* g_rows,
                                     const float* W2t, const float* H, int64_t ldh, const float* X, int64_t ldx,
-                                    const int32_t* x_rows, int64_t kx, float* dW1, float* db1, void* ws,
-                                    size_t ws_bytes, int* err, void* stream) {
+                                    const int32_t* x_rows, int64_t kx, const float* W1, const float* b1, float* dW1,
+                                    float* db1, void* ws, size_t ws_bytes, int* err, void* stream) {
   TM_REQUIRE(M > 0 && N > 0 && N <= 256 && N % 4 == 0 && K > 0, "tm_tc_mlp1_bwd_fused: needs 0 < N <= 256, N % 4 == 0");
   TM_REQUIRE(kx == 1 || kx == 2, "tm_tc_mlp1_bwd_fused: the first layer must have 1 or 2 inputs");
-  TM_REQUIRE((ldh % 4 == 0) && aligned16(H), "tm_tc_mlp1_bwd_fused: H rows must be 16-byte aligned");
+  TM_REQUIRE(H ? ((ldh % 4 == 0) && aligned16(H)) : (W1 && b1),
+             "tm_tc_mlp1_bwd_fused: H rows must be 16-byte aligned (or pass W1, b1 to regenerate the mask)");
   TM_REQUIRE(ws && ws_bytes >= tm_tc_mlp1_bwd_ws(N), "tm_tc_mlp1_bwd_fused: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
@@ -81,10 +82,46 @@ extern "C" int tm_tc_mlp1_bwd_fused(int64_t M, int64_t N, int64_t K, const float
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   tc::RowLoader al{G, ldg, g_rows, M, K, vec_mode(G, ldg)};
   tc::RowLoader bl{W2t, K, nullptr, N, K, vec_mode(W2t, K)};
-  tc::ReduceEpilogue ep{H, ldh, X, ldx, x_rows, (int)kx, part};
+  tc::ReduceEpilogue ep{H, ldh, X, ldx, x_rows, (int)kx, part, W1, b1};
   TM_TRY((tc::launch_tf<tc::RowLoader, tc::RowLoader, tc::ReduceEpilogue, 128, 2>(al, bl, ep, M, N, K, 1, cdiv(K, tc::BK) * tc::BK, err, st)));
   mlp1_reduce_kernel<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(part, grid * tc::EPI_WARPS, N, (int)kx, dW1, db1);
   return check_launch("mlp1_reduce");
+}
+
+// out[out_rows[m], :] = relu(X[x_rows[m], 0:kx] @ W1^T + b1) @ W2^T + b2 with the hidden layer generated in
+// the A-operand loader (never stored).  W2: [N,K] row-major as nn.Linear stores it (K = hidden width).
+extern "C" int tm_tc_mlp2_smallk_forward(int64_t M, int64_t K, int64_t N, const float* X, int64_t ldx,
+                                         const int32_t* x_rows, int64_t kx, const float* W1, const float* b1,
+                                         const float* W2, const float* b2, float* out, int64_t ldo,
+                                         const int32_t* out_rows, int precision, int* err, void* stream) {
+  TM_REQUIRE(kx == 1 || kx == 2, "tm_tc_mlp2_smallk_forward: the first layer must have 1 or 2 inputs");
+  if (M <= 0 || N <= 0) return 0;
+  tc::Hidden2 h{X, ldx, x_rows, W1, b1, (int)kx};
+  tc::GenRowLoader al{h, M, K};
+  tc::RowLoader bl{W2, K, nullptr, N, K, vec_mode(W2, K)};
+  PlainEpilogue ep{out, ldo, out_rows, b2, nullptr, 0, b2 ? TM_EPI_BIAS : 0};
+  return tc::launch(al, bl, ep, M, N, K, 1, cdiv(K, tc::BK) * tc::BK, precision, err, (cudaStream_t)stream);
+}
+
+// dW2[M_out, hid] = G[g_rows]^T @ hidden, hidden generated in the B-operand loader (R = samples)
+extern "C" int tm_tc_mlp2_smallk_wgrad2(int64_t Mo, int64_t hid, int64_t R, const float* G, int64_t ldg,
+                                        const int32_t* g_rows, const float* X, int64_t ldx, const int32_t* x_rows,
+                                        int64_t kx, const float* W1, const float* b1, float* dW2, int precision,
+                                        void* ws, size_t ws_bytes, int* err, void* stream) {
+  TM_REQUIRE(kx == 1 || kx == 2, "tm_tc_mlp2_smallk_wgrad2: the first layer must have 1 or 2 inputs");
+  if (Mo <= 0 || hid <= 0) return 0;
+  TM_REQUIRE(ws_bytes >= tm_tc_gemm_tn_ws(Mo, hid, R), "tm_tc_mlp2_smallk_wgrad2: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int splits;
+  int64_t kps;
+  tn_split(Mo, hid, R, tc::pick_bn(hid, precision), &splits, &kps);
+  tc::Hidden2 h{X, ldx, x_rows, W1, b1, (int)kx};
+  tc::ColLoader al{G, ldg, g_rows, Mo, R, vec_mode(G, ldg)};
+  tc::GenColLoader bl{h, hid, R};
+  tc::PartialEpilogue ep{(float*)ws, Mo, hid};
+  TM_TRY(tc::launch(al, bl, ep, Mo, hid, R, splits, kps, precision, err, st));
+  split_reduce_kernel<<<(unsigned)cdiv(Mo * hid, 256), 256, 0, st>>>((const float*)ws, Mo * hid, splits, dW2, hid, hid, 0);
+  return check_launch("split_reduce(smallk wgrad2)");
 }
 
 extern "C" size_t tm_tc_gemm_tn_ws(int64_t M, int64_t N, int64_t R) {

@@ -29,6 +29,14 @@
 
 #include "tm_gemm.cuh"
 
+// Bottleneck-bisection switches (TM_TC_DEBUG bits) and the clock64 timeline (TM_TC_TRACE) are compiled
+// in only with -DTM_TC_INSTRUMENT=1 (make INSTRUMENT=1); production kernels carry none of it.
+#ifndef TM_TC_INSTRUMENT
+#define TM_TC_INSTRUMENT 0
+#endif
+#define TM_DBGBITS (TM_TC_INSTRUMENT ? tm.dbg : 0)
+#define TM_TRACEPTR (TM_TC_INSTRUMENT ? tm.trace : (long long*)nullptr)
+
 namespace tmk {
 namespace tc {
 
@@ -188,6 +196,78 @@ struct ColLoader {      // element(row, k) = A[krows ? krows[k] : k][row]   (row
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// GENERATED operands: the hidden layer of an MLP whose input has 1 or 2 columns
+// (fc_net_self: Linear(2,256) -> ReLU -> Linear(256,128), model.py:50) costs 2 FMAs per element to
+// recompute, so it is never stored: the loaders below synthesise  hid(r, j) = relu(w1[j,:] . x[r,:] + b1[j])
+// straight into the shared-memory stage (plain st.shared instead of cp.async), in the forward GEMM
+// (K-major A operand) and in the weight-gradient GEMM (MN-major B operand); the fused first-layer
+// backward regenerates the ReLU mask the same way.  One expression everywhere: bit-identical values.
+// ---------------------------------------------------------------------------------------------
+struct Hidden2 {
+  const float* X;           // layer inputs [*, ldx]
+  int64_t ldx;
+  const int32_t* x_rows;    // optional gather
+  const float* W1;          // [hid][kx] row-major (nn.Linear weight)
+  const float* b1;          // [hid]
+  int kx;                   // 1 or 2
+  __device__ __forceinline__ float2 x_of(int64_t r) const {
+    const float* p = X + (x_rows ? (int64_t)x_rows[r] : r) * ldx;
+    return make_float2(p[0], kx > 1 ? p[1] : 0.f);
+  }
+  __device__ __forceinline__ float pre(float2 x, int64_t j) const {     // pre-activation of hidden unit j
+    const float w0 = __ldg(W1 + j * kx), w1 = kx > 1 ? __ldg(W1 + j * kx + 1) : 0.f;
+    return fmaf(w0, x.x, fmaf(w1, x.y, __ldg(b1 + j)));
+  }
+  __device__ __forceinline__ float act(float2 x, int64_t j) const { return fmaxf(pre(x, j), 0.f); }
+};
+__device__ __forceinline__ void st_shared4(uint32_t dst, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct GenRowLoader {   // element(row, k) = hid(row, k)          (k = hidden unit, contiguous in the stage)
+  static constexpr bool kTransposed = false;
+  Hidden2 h;
+  int64_t nrows, K;
+  struct St { float2 x; bool ok; };
+  __device__ __forceinline__ St begin(int64_t row) const {
+    St s;
+    s.ok = row < nrows;
+    s.x = s.ok ? h.x_of(row) : make_float2(0.f, 0.f);
+    return s;
+  }
+  __device__ __forceinline__ void copy4(uint32_t dst, const St& s, int64_t k) const {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (s.ok && k + i < K) ? h.act(s.x, k + i) : 0.f;
+    st_shared4(dst, v[0], v[1], v[2], v[3]);
+  }
+};
+
+struct GenColLoader {   // element(row, k) = hid(k, row)          (row = hidden unit: 4 consecutive units per chunk)
+  static constexpr bool kTransposed = true;
+  Hidden2 h;
+  int64_t nrows, K;     // nrows = hidden width, K = number of samples
+  struct St { int64_t row4; int nr; };
+  __device__ __forceinline__ St begin(int64_t row4) const {
+    St s;
+    s.row4 = row4;
+    const int64_t nr = nrows - row4;
+    s.nr = nr >= 4 ? 4 : (nr > 0 ? (int)nr : 0);
+    return s;
+  }
+  __device__ __forceinline__ void copy4(uint32_t dst, const St& s, int64_t k) const {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k < K && s.nr > 0) {
+      const float2 x = h.x_of(k);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < s.nr) v[i] = h.act(x, s.row4 + i);
+    }
+    st_shared4(dst, v[0], v[1], v[2], v[3]);
+  }
+};
+
 // im2col view of an NHWC tensor: row = output pixel, k = tap * Cin + ci (stride 1, pad ks/2)
 struct Im2colLoader8 {
   static constexpr bool kTransposed = false;
@@ -325,13 +405,15 @@ struct PartialEpilogue {
 // reduces it straight into  db1[n] = sum_m dh[m,n]  and  dW1[n,c] = sum_m dh[m,n] * x[m,c].
 // Partial sums are owned per (CTA, epilogue warp) and added up in a fixed order: deterministic.
 struct ReduceEpilogue {
-  const float* mask;        // hidden activations h (ReLU mask), rows indexed like the GEMM rows
-  int64_t ldmask;
+  const float* mask;        // hidden activations h (ReLU mask), rows indexed like the GEMM rows;
+  int64_t ldmask;           //   NULL: the mask is regenerated from (X, W1, b1) below
   const float* X;           // layer inputs
   int64_t ldx;
   const int32_t* x_rows;    // optional gather of the input rows
   int kx;                   // 1 or 2 input columns
   float* part;              // [grid][EPI_WARPS][3][N]
+  const float* W1;          // [N][kx], b1 [N]: only read when mask == NULL
+  const float* b1;
   struct Row { int64_t r; };
   __device__ __forceinline__ Row row(int64_t m) const { return Row{m}; }
   __device__ __forceinline__ void store(const Row&, int64_t, float) const {}
@@ -594,7 +676,7 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
     };
     uint32_t ls = 0;                                               // raw slot of the next k-block to load
     auto issue = [&]() {                                           // always commits exactly one group
-      if (lvalid && !(tm.dbg & 2)) {
+      if (lvalid && !(TM_DBGBITS & 2)) {
         const uint32_t ra = smem_u32(rawring + (size_t)ls * RAW), rb = ra + RAW_A;
         if (AL::kTransposed) {
 #pragma unroll
@@ -648,21 +730,21 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
 
     uint32_t s = 0, ph = 0, rs = 0;
     uint32_t tr_n = 0;
-    const bool tr_on = tm.trace && blockIdx.x == 0 && pw == 0 && lane == 0;
+    const bool tr_on = TM_TRACEPTR && blockIdx.x == 0 && pw == 0 && lane == 0;
 #pragma unroll 1
     for (uint32_t g = 0; g < total; ++g) {
-      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 0] = clock64();
+      if (tr_on && tr_n < 64) TM_TRACEPTR[tr_n * 4 + 0] = clock64();
       cp_async_wait<ND - 1>();                                         // my copies of k-block g have landed
       if (!mbar_wait(&empty_bar[s], ph ^ 1u, abortp)) abort_s = 1;    // MMAs that read this stage are done
       if (COOP) asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory");   // everybody's copies landed
       else __syncwarp();
       if (*abortp) { ok = false; break; }                              // (uniform across the barrier)
-      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 1] = clock64();
+      if (tr_on && tr_n < 64) TM_TRACEPTR[tr_n * 4 + 1] = clock64();
       const uint8_t* raw_a = rawring + (size_t)rs * RAW;
       const uint8_t* raw_b = raw_a + RAW_A;
       uint8_t* a_base = ring + (size_t)s * STAGE;
       uint8_t* b_base = a_base + A_BYTES * PARTS;
-      if (!(tm.dbg & 4)) {
+      if (!(TM_DBGBITS & 4)) {
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) {
           float v[8];
@@ -678,14 +760,14 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
           }
         }
       }
-      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 2] = clock64();
+      if (tr_on && tr_n < 64) TM_TRACEPTR[tr_n * 4 + 2] = clock64();
       fence_async_smem();                                              // generic-proxy stores -> async proxy (UMMA)
       if (COOP) asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory");   // everyone is done reading raw slot rs
       else __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);                        // one arrival per producer warp
       if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
       if (++rs == (uint32_t)ND) rs = 0;
-      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 3] = clock64();
+      if (tr_on && tr_n < 64) TM_TRACEPTR[tr_n * 4 + 3] = clock64();
       ++tr_n;
       issue();                                                         // refill the slot just freed (k-block g + ND)
     }
@@ -706,14 +788,14 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
         tm.decode(t, m0, nq, zi, kb0, nkb);
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < nkb; ++kb) {
-          const bool tr_on = tm.trace && blockIdx.x == 0 && li == 0 + (kb >> 6) && kb < 64;
-          if (tr_on) tm.trace[256 + kb * 4 + 0] = clock64();
+          const bool tr_on = TM_TRACEPTR && blockIdx.x == 0 && li == 0 + (kb >> 6) && kb < 64;
+          if (tr_on) TM_TRACEPTR[256 + kb * 4 + 0] = clock64();
           ok = mbar_wait(&full_bar[s], ph, abortp);
           if (!ok) break;
           tc_fence_after();
-          if (tr_on) tm.trace[256 + kb * 4 + 1] = clock64();
+          if (tr_on) TM_TRACEPTR[256 + kb * 4 + 1] = clock64();
           const uint32_t sa = smem_u32(ring + (size_t)s * STAGE), sb = sa + A_BYTES * PARTS;
-          if (!(tm.dbg & 8))
+          if (!(TM_DBGBITS & 8))
 #pragma unroll
           for (int ks = 0; ks < BK / 16; ++ks) {
             const uint32_t koff = (uint32_t)ks * 256u;                   // two 128-byte core matrices per K = 16
@@ -733,7 +815,7 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
             }
           }
           umma_commit(&empty_bar[s]);                                    // stage reusable once these MMAs retire
-          if (tr_on) tm.trace[256 + kb * 4 + 2] = clock64();
+          if (tr_on) TM_TRACEPTR[256 + kb * 4 + 2] = clock64();
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
         }
         if (!ok) break;
@@ -748,12 +830,12 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
     for (int64_t t = blockIdx.x; t < tm.total && ok; t += G, ++li) {
       const int buf = li & 1;
       const uint32_t aph = (uint32_t)(li >> 1) & 1u;
-      const bool tr_on = tm.trace && blockIdx.x == 0 && warp == 0 && lane == 0 && li < 16;
-      if (tr_on) tm.trace[512 + li * 4 + 0] = clock64();
+      const bool tr_on = TM_TRACEPTR && blockIdx.x == 0 && warp == 0 && lane == 0 && li < 16;
+      if (tr_on) TM_TRACEPTR[512 + li * 4 + 0] = clock64();
       ok = mbar_wait(&acc_full[buf], aph, abortp);
       if (!ok) break;
       tc_fence_after();
-      if (tr_on) tm.trace[512 + li * 4 + 1] = clock64();
+      if (tr_on) TM_TRACEPTR[512 + li * 4 + 1] = clock64();
       int64_t m0, nq, kb0; int zi, nkb;
       tm.decode(t, m0, nq, zi, kb0, nkb);
       const int64_t n0 = nq * BN;
@@ -789,7 +871,7 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
             const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
             const int64_t m = m0 + warp * 32 + r;
             const int64_t n = n0 + c + cq;
-            if (m < M && n < N && !(tm.dbg & 1)) {
+            if (m < M && n < N && !(TM_DBGBITS & 1)) {
               const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
               store4<EP>(ep, rws[pass], n, N, o, b4, aux[q]);
             }
@@ -800,7 +882,7 @@ tc_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      if (tr_on) tm.trace[512 + li * 4 + 2] = clock64();
+      if (tr_on) TM_TRACEPTR[512 + li * 4 + 2] = clock64();
     }
   }
   if (!ok) {
@@ -969,7 +1051,7 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
     auto issue = [&]() -> bool {                                     // always commits exactly one group
       if (lvalid) {
         if (!mbar_wait(&empty_bar[ls], lph ^ 1u, abortp)) return false;   // MMAs that read this slot are done
-        if (!(tm.dbg & 2)) {
+        if (!(TM_DBGBITS & 2)) {
           const uint32_t base = smem_u32(ring + (size_t)ls * SLOT);
 #pragma unroll
           for (int j = 0; j < A_CH; ++j) {
@@ -998,13 +1080,13 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
 
     uint32_t s = 0;
     uint32_t tr_n = 0;
-    const bool tr_on = tm.trace && blockIdx.x == 0 && warp == PROD_WARP0 && lane == 0;
+    const bool tr_on = TM_TRACEPTR && blockIdx.x == 0 && warp == PROD_WARP0 && lane == 0;
 #pragma unroll 1
     for (uint32_t g = 0; g < total && ok; ++g) {
-      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 0] = clock64();
+      if (tr_on && tr_n < 64) TM_TRACEPTR[tr_n * 4 + 0] = clock64();
       cp_async_wait<D - 1>();                                          // my chunks of k-block g have landed
-      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 1] = clock64();
-      if (PLANES == 2 && !(tm.dbg & 4)) {
+      if (tr_on && tr_n < 64) TM_TRACEPTR[tr_n * 4 + 1] = clock64();
+      if (PLANES == 2 && !(TM_DBGBITS & 4)) {
         uint8_t* base = ring + (size_t)s * SLOT;
         auto residual = [&](uint32_t hi_off, uint32_t lo_off) {
           const float4 x = *reinterpret_cast<const float4*>(base + hi_off);
@@ -1021,12 +1103,12 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
         for (int j = 0; j < B_CH; ++j)
           if (b_on[j]) residual(OFF_BHI + b_o[j], OFF_BLO + b_o[j]);
       }
-      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 2] = clock64();
+      if (tr_on && tr_n < 64) TM_TRACEPTR[tr_n * 4 + 2] = clock64();
       fence_async_smem();                                              // cp.async + generic stores -> async proxy (UMMA)
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);                        // one arrival per producer warp
       if (++s == (uint32_t)ND) s = 0;
-      if (tr_on && tr_n < 64) tm.trace[tr_n * 4 + 3] = clock64();
+      if (tr_on && tr_n < 64) TM_TRACEPTR[tr_n * 4 + 3] = clock64();
       ++tr_n;
       ok = issue();                                                    // k-block g + D
     }
@@ -1052,14 +1134,14 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
         tm.decode(t, m0, nq, zi, kb0, nkb);
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < nkb; ++kb) {
-          const bool tr_on = tm.trace && blockIdx.x == 0 && li == 0 && kb < 64;
-          if (tr_on) tm.trace[256 + kb * 4 + 0] = clock64();
+          const bool tr_on = TM_TRACEPTR && blockIdx.x == 0 && li == 0 && kb < 64;
+          if (tr_on) TM_TRACEPTR[256 + kb * 4 + 0] = clock64();
           ok = mbar_wait(&full_bar[s], ph, abortp);
           if (!ok) break;
           tc_fence_after();
-          if (tr_on) tm.trace[256 + kb * 4 + 1] = clock64();
+          if (tr_on) TM_TRACEPTR[256 + kb * 4 + 1] = clock64();
           const uint32_t base = smem_u32(ring + (size_t)s * SLOT);
-          if (!(tm.dbg & 8))
+          if (!(TM_DBGBITS & 8))
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             const uint64_t ah = make_desc_sw128(base + OFF_AHI + ks * A_KSTEP, A_LBO, A_SBO, A_TY);
@@ -1073,7 +1155,7 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
             }
           }
           umma_commit(&empty_bar[s]);                                    // slot reusable once these MMAs retire
-          if (tr_on) tm.trace[256 + kb * 4 + 2] = clock64();
+          if (tr_on) TM_TRACEPTR[256 + kb * 4 + 2] = clock64();
           if (++s == (uint32_t)ND) { s = 0; ph ^= 1u; }
         }
         if (!ok) break;
@@ -1125,10 +1207,31 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float4 mk[4];
+            if (ep.mask) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {                                 // mask rows first (loads in flight together)
-              const int64_t m = m0 + warp * 32 + (half * 4 + q) * 4 + (lane >> 3);
-              mk[q] = (m < M && n + 4 <= N) ? ld4(ep.mask + m * ep.ldmask + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int q = 0; q < 4; ++q) {                               // mask rows first (loads in flight together)
+                const int64_t m = m0 + warp * 32 + (half * 4 + q) * 4 + (lane >> 3);
+                mk[q] = (m < M && n + 4 <= N) ? ld4(ep.mask + m * ep.ldmask + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            } else {                                                      // regenerate the pre-activations (Hidden2::pre)
+              float w0[4], w1[4], bb[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool on = n + j < N;
+                w0[j] = on ? __ldg(ep.W1 + (n + j) * ep.kx) : 0.f;
+                w1[j] = (on && ep.kx > 1) ? __ldg(ep.W1 + (n + j) * ep.kx + 1) : 0.f;
+                bb[j] = on ? __ldg(ep.b1 + n + j) : -1.f;
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int pass = half * 4 + q;
+                const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
+                const bool on = m < M;
+                mk[q].x = on ? fmaf(w0[0], x0[pass], fmaf(w1[0], x1[pass], bb[0])) : 0.f;
+                mk[q].y = on ? fmaf(w0[1], x0[pass], fmaf(w1[1], x1[pass], bb[1])) : 0.f;
+                mk[q].z = on ? fmaf(w0[2], x0[pass], fmaf(w1[2], x1[pass], bb[2])) : 0.f;
+                mk[q].w = on ? fmaf(w0[3], x0[pass], fmaf(w1[3], x1[pass], bb[3])) : 0.f;
+              }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -1208,7 +1311,7 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
             const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
             const int64_t m = m0 + warp * 32 + r;
             const int64_t n = n0 + c + cq;
-            if (m < M && n < N && !(tm.dbg & 1)) {
+            if (m < M && n < N && !(TM_DBGBITS & 1)) {
               const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
               store4<EP>(ep, rws[pass], n, N, o, b4, aux[q]);
             }

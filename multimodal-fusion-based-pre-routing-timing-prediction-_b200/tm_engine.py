@@ -193,7 +193,7 @@ class DesignStep:
                                                       hs["hf"], gpred, 1, need_dx=True)
         a0, a2 = m.mlp_alpha.layers[0], m.mlp_alpha.layers[2]
         da1, dab1, da2, dab2, _ = tm_ops.mlp2_backward(hs["lv"], 1, None, T, a0.weight.detach(), a2.weight.detach(),
-                                                       hs["ha"], dX[:, 2 * D:], width)
+                                                       hs["ha"], dX[:, 2 * D:], width, b1=a0.bias.detach())
         dF, dfw, dfb = tm_ops.fusion_backward(b.mask_rows, feat, hs["wt"], dX[:, D:], width)
         head = [(f0.weight, dw1), (f0.bias, db1), (f2.weight, dw2), (f2.bias, db2), (a0.weight, da1),
                 (a0.bias, dab1), (a2.weight, da2), (a2.bias, dab2), (m.fcn.weight, dfw), (m.fcn.bias, dfb)]

@@ -32,6 +32,7 @@ BIAS, RELU, MASK, ACCUM = 1, 2, 4, 8
 #   "bf16" tcgen05 with plain bf16 operands (rtol 2e-2 class);
 #   "fp32" the CUDA-core FFMA kernels (tm_gemm_nn / tm_gemm_tn).
 MATH = os.environ.get("TM_MATH", "tf32x3")
+GEN_HIDDEN = os.environ.get("TM_GEN_HIDDEN", "1") != "0"  # generate Linear(<=2, hid) hidden layers instead of storing them
 FUSE_RUNS = os.environ.get("TM_FUSE_RUNS", "1") != "0"    # run-length / prefix-table mask fusion forward
 TC_MIN_K = 16          # contractions shorter than this stay on the CUDA-core kernel (K = 1, 2: pure bandwidth)
 
@@ -170,18 +171,27 @@ def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, 
     Returns the hidden activations (n_rows, hid) needed by ``mlp2_backward``."""
     hid, kin = w1.shape
     nout = w2.shape[0]
+    prec = _precision(math)
+    if GEN_HIDDEN and kin <= 2 and prec is not None and n_rows > 0 and hid >= TC_MIN_K:
+        # Linear(<=2, hid) first layer: the hidden activations cost 2 FMAs each to recompute, so they are
+        # generated inside the GEMM's operand loader and never stored (returns None; mlp2_backward
+        # regenerates them the same way)
+        call("tm_tc_mlp2_smallk_forward", n_rows, hid, nout, x, ldx, rows, kin, _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2),
+             out, ldo, out_rows, prec, tm_lib.err_flag(out.device), stream())
+        return None
     h = torch.empty(n_rows, hid, dtype=torch.float32, device=out.device)
     gemm_nn(n_rows, hid, kin, x, ldx, _f32c(w1), kin, h, hid, a_rows=rows, bias=b1, flags=RELU, b_is_nk=True, math=math)
     gemm_nn(n_rows, nout, hid, h, hid, _f32c(w2), hid, out, ldo, c_rows=out_rows, bias=b2, b_is_nk=True, math=math)
     return h
 
 
-def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=False):
+def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=False, b1=None):
     """Gradients of a two-layer MLP.  ``g``: dLoss/d(out) rows (optionally gathered by ``g_rows``).
-    Returns (dw1, db1, dw2, db2, dx or None)."""
+    ``h``: the hidden activations mlp2_forward returned, or None when they were generated on the fly
+    (then ``b1`` is required).  Returns (dw1, db1, dw2, db2, dx or None)."""
     hid, kin = w1.shape
     nout = w2.shape[0]
-    dev = h.device
+    dev = g.device
     dw2 = torch.empty(nout, hid, dtype=torch.float32, device=dev)
     db2 = torch.empty(nout, dtype=torch.float32, device=dev)
     dw1 = torch.empty(hid, kin, dtype=torch.float32, device=dev)
@@ -190,13 +200,27 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
         for t in (dw1, db1, dw2, db2):
             t.zero_()
         return dw1, db1, dw2, db2, None
+    if h is None:                                            # generated hidden layer (kin <= 2)
+        if b1 is None or need_dx:
+            raise RuntimeError("mlp2_backward: generated hidden activations need b1 (and have no dx path)")
+        prec = _precision()
+        prec = 3 if prec is None else prec
+        _Aux.run(lambda: _colsum(n_rows, nout, g, ldg, g_rows, db2, 0), g, db2, g_rows)
+        nb = tm_lib.ws_bytes("tm_tc_gemm_tn_ws", nout, hid, n_rows)
+        call("tm_tc_mlp2_smallk_wgrad2", nout, hid, n_rows, g, ldg, g_rows, x, ldx, rows, kin, _f32c(w1), _f32c(b1), dw2,
+             prec, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
+        nb = tm_lib.ws_bytes("tm_tc_mlp1_bwd_ws", hid)
+        call("tm_tc_mlp1_bwd_fused", n_rows, hid, nout, g, ldg, g_rows, transpose(_f32c(w2)), None, 0, x, ldx, rows, kin,
+             _f32c(w1), _f32c(b1), dw1, db1, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
+        aux_join()
+        return dw1, db1, dw2, db2, None
     gemm_tn(nout, hid, n_rows, g, ldg, h, hid, dw2, hid, a_rows=g_rows, colsum_a=db2)
     if kin <= 2 and hid <= 256 and hid % 4 == 0 and not need_dx and _precision() == 3:
         # Linear(<=2, hid) first layer: its whole backward (dW1, db1) is a reduction of the hidden
         # gradient, fused into the data-gradient GEMM's epilogue -- dh is never written or re-read
         nb = tm_lib.ws_bytes("tm_tc_mlp1_bwd_ws", hid)
         call("tm_tc_mlp1_bwd_fused", n_rows, hid, nout, g, ldg, g_rows, transpose(_f32c(w2)), h, hid, x, ldx, rows, kin,
-             dw1, db1, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
+             None, None, dw1, db1, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
         aux_join()
         return dw1, db1, dw2, db2, None
     dh = torch.empty(n_rows, hid, dtype=torch.float32, device=dev)
@@ -281,7 +305,7 @@ def gnn_backward(sched, saved, params, G):
     dcs1w, dcs1b, dcs2w, dcs2b, _ = mlp2_backward(cf, cf.stride(0), sched.cell_class, nc, cs1w, cs2w,
                                                   saved["hc"], G, D, g_rows=sched.cell_class)
     dns1w, dns1b, dns2w, dns2b, _ = mlp2_backward(nf, nf.stride(0), sched.net_class, nn_, ns1w, ns2w,
-                                                  saved["hn"], G, D, g_rows=sched.net_class)
+                                                  saved["hn"], G, D, g_rows=sched.net_class, b1=ns1b)
     return (dcs1w, dcs1b, dcs2w, dcs2b, dns1w, dns1b, dns2w, dns2b, dcn1w, dcn1b, dcn2w, dcn2b)
 
 
