@@ -365,6 +365,32 @@ int tm_tc_conv2d_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_
                             int precision, void* ws, size_t ws_bytes, int* err, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * A6 (bf16 mode)  TMA-fed tcgen05 3x3 convolutions on bf16 NHWC activations
+ * Replaces nn.Conv2d(k=3, padding=1, bias=False) of DoubleConv (src/Unet.py:15-22) and its
+ * autograd (data + weight gradients) when the image branch runs with bf16 tensor-core operands
+ * (BASELINE config 4).  Activations are compact bf16 [B][H][W][C], C a multiple of 16; H and W
+ * powers of two.  One cp.async.bulk.tensor box per (128-pixel tile, tap): the box shifted by the
+ * tap offset, out-of-bounds zero fill = the convolution's padding.  fp32 accumulate in TMEM,
+ * fp32 outputs (they feed the batch-norm statistics).
+ * ---------------------------------------------------------------------------------- */
+int tm_conv3x3_bf16_supported(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
+/* fp32 rows (stride ldx, C channels) -> compact bf16 rows of Cp >= C channels (zero padded) */
+int tm_to_bf16_rows(int64_t npix, int64_t C, const float* x, int64_t ldx, void* out, int64_t Cp, void* stream);
+/* nn.Conv2d weight [Cout][Cin][3][3] fp32 -> wf bf16 [9][Cout][CinP] (forward operand) and, if wd != NULL,
+ * wd bf16 [9][Cin][CoutP] with reversed taps (data-gradient operand) */
+int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, void* wf, int64_t CinP, void* wd,
+                         int64_t CoutP, void* stream);
+/* y[pix, 0:N] (fp32, row stride ldy) = sum_{tap,c} xb[pix + tap, c] * wq[tap][n][c]; bias optional,
+ * flags: TM_EPI_RELU.  The data gradient is the same call on bf16(dy) with wd. */
+int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, const void* xb, const void* wq,
+                    const float* bias, float* y, int64_t ldy, int flags, int* err, void* stream);
+/* dw[co][ci][ky][kx] (torch layout, ci < Cin_real) = sum_pix dyb[pix, co] * xb[pix + (ky-1,kx-1), ci] */
+size_t tm_conv3x3_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
+int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cin_real, int64_t Cout,
+                          const void* xb, const void* dyb, float* dw, void* ws, size_t ws_bytes, int* err,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------
  * N4  fused Adam (torch.optim.Adam defaults, src/train.py:431-435,555)
  * ---------------------------------------------------------------------------------- */
 int tm_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr, float beta1,

@@ -1,0 +1,605 @@
+// TMA-fed tcgen05 3x3 convolutions on bf16 NHWC activations (U-Net bf16 mode, Unet.py:8-22).
+//
+// The activation is a compact bf16 tensor [B][H][W][C] (C a multiple of 16).  A 4-D tensor map
+// (C, W, H, B) lets ONE cp.async.bulk.tensor per (tile, tap) fetch the 128 input pixels a tile of
+// 128 output pixels needs for that tap -- the box is simply shifted by (tap_x-1, tap_y-1) and TMA's
+// out-of-bounds zero fill IS the convolution's zero padding (and the tail of the batch).  The box
+// lands in shared memory in exactly the swizzled K-major layout tcgen05.mma reads (32/64/128-byte
+// swizzle for 16/32/64 channels per step), so no thread ever touches an operand:
+//
+//   warp 0   one thread: TMA producer (activation box + weight box per k-step, mbarrier expect_tx)
+//   warp 1   one thread: tcgen05.mma issuer, fp32 accumulator double-buffered in tensor memory
+//   warps 2-5 epilogue: tcgen05.ld -> (+bias, ReLU) -> 128-bit fp32 stores (NHWC, strided rows)
+//
+//   fprop / dgrad (conv3x3_tma_kernel):  Y[pix, n] = sum_{tap, c} X[pix + tap, c] * Wq[tap][n][c]
+//       (the data gradient is the same kernel on dY with the tap-reversed, transposed weights)
+//   wgrad (conv3x3_wgrad_tma_kernel):    dW[tap][co][ci] = sum_pix dY[pix, co] * X[pix + tap, ci]
+//       both operands are MN-major (channels contiguous, pixels = K): the same activation boxes,
+//       no transposition anywhere; split over pixel blocks x kernel rows, fp32 partials reduced in
+//       a fixed order (deterministic).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "tm_tc.cuh"
+
+using namespace tmk;
+using namespace tmk::tc;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps (the encoder lives in libcuda; resolved at run time so the library links without it)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+inline CUtensorMapSwizzle swizzle_for(int inner_bytes) {
+  return inner_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                            : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// bf16 [B][H][W][C] with a box of (boxC channels, TW, TH, TB)
+int encode_act(CUtensorMap* m, const void* ptr, int64_t C, int64_t W, int64_t H, int64_t B, int boxC, int TW,
+               int TH, int TB) {
+  EncodeTiledFn enc = encoder();
+  if (!enc) return fail(TM_EINVAL, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(boxC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TM_EINVAL, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+  return 0;
+}
+
+// bf16 [rows][C] with a box of (boxC, boxRows)
+int encode_2d(CUtensorMap* m, const void* ptr, int64_t C, int64_t rows, int boxC, int boxRows) {
+  EncodeTiledFn enc = encoder();
+  if (!enc) return fail(TM_EINVAL, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {(cuuint32_t)boxC, (cuuint32_t)boxRows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(boxC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TM_EINVAL, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// shared-memory matrix descriptor, version 1.  type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t type) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46) | ((uint64_t)type << 61);
+}
+__host__ __device__ constexpr uint32_t sw_type(int inner_bytes) { return inner_bytes >= 128 ? 2u : inner_bytes == 64 ? 4u : 6u; }
+// kind::f16, D = f32, A = B = bf16, M = 128; a_mn / b_mn: operand is MN-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct Geom {
+  int B, H, W, TW, TH, TB, tiles_x, tiles_y;
+  int64_t ntiles;
+  __host__ __device__ void origin(int64_t t, int& x0, int& y0, int& b0) const {
+    x0 = (int)(t % tiles_x) * TW;
+    y0 = (int)((t / tiles_x) % tiles_y) * TH;
+    b0 = (int)(t / ((int64_t)tiles_x * tiles_y)) * TB;
+  }
+};
+
+inline bool pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+inline Geom make_geom(int64_t B, int64_t H, int64_t W) {
+  Geom g;
+  g.B = (int)B; g.H = (int)H; g.W = (int)W;
+  g.TW = (int)(W < 128 ? W : 128);
+  g.TH = (int)(H < 128 / g.TW ? H : 128 / g.TW);
+  g.TB = 128 / (g.TW * g.TH);
+  g.tiles_x = (int)(W / g.TW);
+  g.tiles_y = (int)(H / g.TH);
+  g.ntiles = (int64_t)g.tiles_x * g.tiles_y * cdiv(B, g.TB);
+  return g;
+}
+
+constexpr int CONV_THREADS = 192;
+constexpr int CONV_MAX_STAGES = 8;
+constexpr uint32_t CONV_SMEM_BUDGET = 200 * 1024;
+
+struct ConvArgs {
+  Geom g;
+  int Cin, N, stages;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  float* y;
+  int64_t ldy;
+  const float* bias;
+  int flags;
+  int* err;
+};
+
+// ------------------------------------------------------------------------------------------------
+// fprop / dgrad
+// ------------------------------------------------------------------------------------------------
+template <int CK>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int abort_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = a.stages, N = a.N;
+  const uint32_t tmem_cols = 2 * N < 32 ? 32u : (uint32_t)(2 * N);
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+    abort_s = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_map(&tmx);
+    prefetch_map(&tmw);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  volatile int* abortp = &abort_s;
+  bool ok = true;
+  const int64_t G = gridDim.x;
+  const int csteps = a.Cin / CK;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int64_t t = blockIdx.x; t < a.g.ntiles && ok; t += G) {
+        int x0, y0, b0;
+        a.g.origin(t, x0, y0, b0);
+        for (int tap = 0; tap < 9 && ok; ++tap) {
+          const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+          for (int cs = 0; cs < csteps; ++cs) {
+            ok = mbar_wait(&empty_bar[s], ph ^ 1u, abortp);
+            if (!ok) break;
+            const uint32_t base = smem_u32(ring + (size_t)s * a.stage_bytes);
+            mbar_expect_tx(&full_bar[s], a.a_bytes + a.b_bytes);
+            tma_load_4d(base, &tmx, cs * CK, x0 + dx, y0 + dy, b0, &full_bar[s]);
+            tma_load_2d(base + a.a_bytes, &tmw, cs * CK, tap * N, &full_bar[s]);
+            if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(N, false, false);
+      constexpr uint32_t TY = sw_type(CK * 2), SBO = 8u * CK * 2u;
+      uint32_t s = 0, ph = 0;
+      int li = 0;
+      for (int64_t t = blockIdx.x; t < a.g.ntiles && ok; t += G, ++li) {
+        const int buf = li & 1;
+        ok = mbar_wait(&acc_empty[buf], (((uint32_t)(li >> 1)) & 1u) ^ 1u, abortp);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * N);
+        const int ksteps = 9 * csteps;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          ok = mbar_wait(&full_bar[s], ph, abortp);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t base = smem_u32(ring + (size_t)s * a.stage_bytes);
+#pragma unroll
+          for (int j = 0; j < CK / 16; ++j) {
+            const uint64_t da = make_desc_sw(base + j * 32, 16, SBO, TY);
+            const uint64_t db = make_desc_sw(base + a.a_bytes + j * 32, 16, SBO, TY);
+            umma(tmem_d, da, db, idesc, (ks > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue =======================
+    const int q = warp & 3;                               // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int tw = m % a.g.TW, th = (m / a.g.TW) % a.g.TH, tb = m / (a.g.TW * a.g.TH);
+    int li = 0;
+    for (int64_t t = blockIdx.x; t < a.g.ntiles && ok; t += G, ++li) {
+      const int buf = li & 1;
+      ok = mbar_wait(&acc_full[buf], ((uint32_t)(li >> 1)) & 1u, abortp);
+      if (!ok) break;
+      tc_fence_after();
+      int x0, y0, b0;
+      a.g.origin(t, x0, y0, b0);
+      const bool valid = b0 + tb < a.g.B;
+      float* yp = a.y + (((int64_t)(b0 + tb) * a.g.H + (y0 + th)) * a.g.W + (x0 + tw)) * a.ldy;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N);
+      for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        if (a.flags & TM_EPI_BIAS) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + c + i);
+        }
+        if (a.flags & TM_EPI_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) st4(yp + c + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  if (!ok) {
+    abort_s = 1;
+    if (a.err) atomicExch(a.err, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: grid (pixel splits, 3 kernel rows); CTA (z, r) accumulates taps (r, 0..2) over its pixel blocks
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  Geom g;
+  int Cin, Cout, stages;
+  int cbx, nbx, cby, nby;            // channels per TMA box / boxes per tile, x and dy
+  uint32_t x_bytes, dy_bytes, stage_bytes;
+  float* part;                       // [splits][9][Cout][Cin]
+  int* err;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmdy, WgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int abort_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = a.stages, Cin = a.Cin, Cout = a.Cout;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(3 * Cin)) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_full, 1);
+    abort_s = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_map(&tmx);
+    prefetch_map(&tmdy);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  volatile int* abortp = &abort_s;
+  bool ok = true;
+  const int64_t G = gridDim.x;
+  const int r = blockIdx.y;                               // kernel row: taps r*3 .. r*3+2
+  constexpr int STEPS = 3 / NT;                           // stages per pixel block
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int64_t t = blockIdx.x; t < a.g.ntiles && ok; t += G) {
+        int x0, y0, b0;
+        a.g.origin(t, x0, y0, b0);
+        for (int st = 0; st < STEPS && ok; ++st) {
+          ok = mbar_wait(&empty_bar[s], ph ^ 1u, abortp);
+          if (!ok) break;
+          const uint32_t base = smem_u32(ring + (size_t)s * a.stage_bytes);
+          mbar_expect_tx(&full_bar[s], a.dy_bytes + NT * a.x_bytes);
+          for (int j = 0; j < a.nby; ++j)
+            tma_load_4d(base + j * (a.dy_bytes / a.nby), &tmdy, j * a.cby, x0, y0, b0, &full_bar[s]);
+#pragma unroll
+          for (int u = 0; u < NT; ++u) {
+            const int dx = (NT == 3 ? u : st) - 1;
+            for (int j = 0; j < a.nbx; ++j)
+              tma_load_4d(base + a.dy_bytes + u * a.x_bytes + j * (a.x_bytes / a.nbx), &tmx, j * a.cbx, x0 + dx,
+                          y0 + r - 1, b0, &full_bar[s]);
+          }
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(Cin, true, true);
+      // MN-major operand tiles: pixel row k at k * (cb*2) bytes; 8-pixel groups at SBO; the next 64-channel box at LBO
+      const uint32_t a_ty = sw_type(a.cby * 2), b_ty = sw_type(a.cbx * 2);
+      const uint32_t a_sbo = 8u * a.cby * 2u, b_sbo = 8u * a.cbx * 2u;
+      const uint32_t a_lbo = a.nby > 1 ? a.dy_bytes / a.nby : 0u, b_lbo = a.nbx > 1 ? a.x_bytes / a.nbx : 0u;
+      const uint32_t a_kstep = 16u * a.cby * 2u, b_kstep = 16u * a.cbx * 2u;   // 16 pixels per MMA
+      uint32_t s = 0, ph = 0;
+      bool first = true;
+      for (int64_t t = blockIdx.x; t < a.g.ntiles && ok; t += G) {
+        for (int st = 0; st < STEPS && ok; ++st) {
+          ok = mbar_wait(&full_bar[s], ph, abortp);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t base = smem_u32(ring + (size_t)s * a.stage_bytes);
+#pragma unroll
+          for (int u = 0; u < NT; ++u) {
+            const int tl = NT == 3 ? u : st;              // tap inside the kernel row
+            const uint32_t tmem_d = tmem_base + (uint32_t)(tl * Cin);
+            const uint32_t xb = base + a.dy_bytes + u * a.x_bytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t da = make_desc_sw(base + j * a_kstep, a_lbo, a_sbo, a_ty);
+              const uint64_t db = make_desc_sw(xb + j * b_kstep, b_lbo, b_sbo, b_ty);
+              umma(tmem_d, da, db, idesc, (!first || j > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+          if (NT == 3 || st == STEPS - 1) first = false;
+        }
+      }
+      if (ok) umma_commit(&acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int co = q * 32 + lane;
+    ok = mbar_wait(&acc_full, 0, abortp);
+    if (ok) {
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int tl = 0; tl < 3; ++tl) {
+        float* pp = a.part + (((int64_t)blockIdx.x * 9 + r * 3 + tl) * Cout + co) * Cin;
+        for (int c = 0; c < Cin; c += 16) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)(tl * Cin + c), v);
+          if (co < Cout) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) st4(pp + c + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          }
+        }
+      }
+    }
+  }
+  if (!ok) {
+    abort_s = 1;
+    if (a.err) atomicExch(a.err, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// part [splits][9][Cout][CinP] -> dw [Cout][Cin][3][3] (torch layout), fixed summation order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Cout, int CinP, int Cin,
+                                    float* __restrict__ dw) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)9 * Cout * CinP) return;
+  const int ci = (int)(i % CinP), co = (int)((i / CinP) % Cout), tap = (int)(i / ((int64_t)CinP * Cout));
+  if (ci >= Cin) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * 9 * Cout * CinP + i];
+  dw[((int64_t)co * Cin + ci) * 9 + tap] = s;
+}
+
+// fp32 rows (stride ld) -> compact bf16 rows of Cp >= C channels (zero padded); 8 channels per thread
+__global__ void to_bf16_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ld, __nv_bfloat16* __restrict__ out,
+                               int Cp, int vec) {
+  const int groups = Cp / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * groups) return;
+  const int64_t p = i / groups;
+  const int c0 = (int)(i % groups) * 8;
+  float v[8];
+  const float* xp = x + p * ld + c0;
+  if (vec && c0 + 8 <= C) {
+    const float4 a = ld4_stream(xp), b = ld4_stream(xp + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c0 + j < C ? xp[j] : 0.f;
+  }
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + p * Cp + c0) = o;
+}
+
+// w [Cout][Cin][3][3] fp32 -> wf [9][Cout][CinP] (fprop) and wd [9][Cin][CoutP] with reversed taps (dgrad)
+__global__ void pack_w_bf16_kernel(int Cout, int Cin, const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int CinP,
+                                   __nv_bfloat16* __restrict__ wd, int CoutP) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nf = (int64_t)9 * Cout * CinP, nd = wd ? (int64_t)9 * Cin * CoutP : 0;
+  if (i < nf) {
+    const int ci = (int)(i % CinP), co = (int)((i / CinP) % Cout), tap = (int)(i / ((int64_t)CinP * Cout));
+    wf[i] = __float2bfloat16(ci < Cin ? w[((int64_t)co * Cin + ci) * 9 + tap] : 0.f);
+  } else if (i < nf + nd) {
+    const int64_t k = i - nf;
+    const int co = (int)(k % CoutP), ci = (int)((k / CoutP) % Cin), tap = (int)(k / ((int64_t)CoutP * Cin));
+    wd[k] = __float2bfloat16(co < Cout ? w[((int64_t)co * Cin + ci) * 9 + (8 - tap)] : 0.f);
+  }
+}
+
+inline bool conv_shape_ok(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N) {
+  return B > 0 && pow2(H) && pow2(W) && H * W >= 1 && Cin % 16 == 0 && Cin >= 16 && Cin <= 256 &&
+         (Cin <= 64 ? pow2(Cin) : Cin % 64 == 0) && N % 16 == 0 && N >= 16 && N <= 256 && W <= 65536 && H <= 65536;
+}
+
+}  // namespace
+
+extern "C" int tm_conv3x3_bf16_supported(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout) {
+  return conv_shape_ok(B, H, W, Cin, Cout) ? 1 : 0;
+}
+
+extern "C" int tm_to_bf16_rows(int64_t npix, int64_t C, const float* x, int64_t ldx, void* out, int64_t Cp, void* stream) {
+  TM_REQUIRE(Cp % 8 == 0 && Cp >= C, "tm_to_bf16_rows: padded width must be a multiple of 8 and >= C");
+  if (npix <= 0) return 0;
+  const int vec = (ldx % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
+  const int64_t n = npix * (Cp / 8);
+  to_bf16_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(npix, (int)C, x, ldx, (__nv_bfloat16*)out, (int)Cp, vec);
+  return check_launch("to_bf16");
+}
+
+extern "C" int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, void* wf, int64_t CinP, void* wd,
+                                    int64_t CoutP, void* stream) {
+  const int64_t n = 9 * Cout * CinP + (wd ? 9 * Cin * CoutP : 0);
+  pack_w_bf16_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((int)Cout, (int)Cin, w, (__nv_bfloat16*)wf,
+                                                                             (int)CinP, (__nv_bfloat16*)wd, (int)CoutP);
+  return check_launch("pack_w_bf16");
+}
+
+// Y[pix, 0:N] = sum_{tap,c} X[pix+tap, c] * Wq[tap][n][c]  (3x3, stride 1, zero padding 1)
+// xb: bf16 [B][H][W][Cin] compact; wq: bf16 [9][N][Cin]; y: fp32 rows of stride ldy.
+extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, const void* xb, const void* wq,
+                               const float* bias, float* y, int64_t ldy, int flags, int* err, void* stream) {
+  TM_REQUIRE(conv_shape_ok(B, H, W, Cin, N), "tm_conv3x3_bf16: unsupported shape (H, W powers of two; channels multiples of 16)");
+  TM_REQUIRE(ldy % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0, "tm_conv3x3_bf16: output rows must be 16-byte aligned");
+  TM_REQUIRE(reinterpret_cast<uintptr_t>(xb) % 16 == 0 && reinterpret_cast<uintptr_t>(wq) % 16 == 0, "tm_conv3x3_bf16: operands must be 16-byte aligned");
+  const int CK = Cin >= 64 ? 64 : (int)Cin;
+  ConvArgs a;
+  a.g = make_geom(B, H, W);
+  a.Cin = (int)Cin; a.N = (int)N;
+  a.a_bytes = 128u * CK * 2u;
+  a.b_bytes = (uint32_t)N * CK * 2u;
+  a.stage_bytes = a.a_bytes + (uint32_t)align_up(a.b_bytes, 1024);
+  int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
+  a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
+  a.y = y; a.ldy = ldy; a.bias = bias;
+  a.flags = (flags & TM_EPI_RELU) | (bias ? TM_EPI_BIAS : 0);
+  a.err = err;
+  CUtensorMap tmx, tmw;
+  TM_TRY(encode_act(&tmx, xb, Cin, W, H, B, CK, a.g.TW, a.g.TH, a.g.TB));
+  TM_TRY(encode_2d(&tmw, wq, Cin, 9 * N, CK, (int)N));
+  const size_t smem = (size_t)a.stages * a.stage_bytes + 1024;
+  const int grid = (int)(a.g.ntiles < sm_count() ? a.g.ntiles : sm_count());
+  cudaStream_t st = (cudaStream_t)stream;
+#define TM_LAUNCH_CONV(CK_)                                                                                   \
+  do {                                                                                                        \
+    static bool optin = false;                                                                                \
+    if (!optin) {                                                                                             \
+      TM_CUDA(cudaFuncSetAttribute(conv3x3_tma_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                   (int)CONV_SMEM_BUDGET + 1024));                                            \
+      optin = true;                                                                                           \
+    }                                                                                                         \
+    conv3x3_tma_kernel<CK_><<<grid, CONV_THREADS, smem, st>>>(tmx, tmw, a);                                   \
+  } while (0)
+  if (CK == 64) TM_LAUNCH_CONV(64);
+  else if (CK == 32) TM_LAUNCH_CONV(32);
+  else TM_LAUNCH_CONV(16);
+#undef TM_LAUNCH_CONV
+  return check_launch("conv3x3_tma");
+}
+
+namespace {
+inline int wgrad_splits(const Geom& g) {
+  const int want = sm_count() / 3 > 0 ? sm_count() / 3 : 1;
+  return (int)(g.ntiles < want ? g.ntiles : want);
+}
+}  // namespace
+
+extern "C" size_t tm_conv3x3_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout) {
+  const Geom g = make_geom(B, H, W);
+  return (size_t)wgrad_splits(g) * 9 * Cout * Cin * sizeof(float) + 256;
+}
+
+// dw[co][ci][ky][kx] (ci < Cin_real) = sum_pix dY[pix, co] * X[pix + (ky-1, kx-1), ci]
+// xb: bf16 [B][H][W][Cin]; dyb: bf16 [B][H][W][Cout]; both compact, channels multiples of 16.
+extern "C" int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cin_real, int64_t Cout,
+                                     const void* xb, const void* dyb, float* dw, void* ws, size_t ws_bytes, int* err,
+                                     void* stream) {
+  TM_REQUIRE(conv_shape_ok(B, H, W, Cin, Cout) && Cin <= 128 && Cout <= 128 && pow2(Cout) && pow2(Cin),
+             "tm_conv3x3_bf16_wgrad: unsupported shape");
+  TM_REQUIRE(ws && ws_bytes >= tm_conv3x3_bf16_wgrad_ws(B, H, W, Cin, Cout), "tm_conv3x3_bf16_wgrad: workspace too small");
+  WgradArgs a;
+  a.g = make_geom(B, H, W);
+  a.Cin = (int)Cin; a.Cout = (int)Cout;
+  a.cbx = Cin > 64 ? 64 : (int)Cin; a.nbx = (int)Cin / a.cbx;
+  a.cby = Cout > 64 ? 64 : (int)Cout; a.nby = (int)Cout / a.cby;
+  a.x_bytes = 128u * (uint32_t)Cin * 2u;
+  a.dy_bytes = 128u * (uint32_t)Cout * 2u;
+  const int NT = Cin <= 64 ? 3 : 1;
+  a.stage_bytes = (uint32_t)align_up(a.dy_bytes + NT * a.x_bytes, 1024);
+  int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
+  a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
+  TM_REQUIRE(a.stages >= 2, "tm_conv3x3_bf16_wgrad: tile does not fit shared memory");
+  a.part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  a.err = err;
+  CUtensorMap tmx, tmdy;
+  TM_TRY(encode_act(&tmx, xb, Cin, W, H, B, a.cbx, a.g.TW, a.g.TH, a.g.TB));
+  TM_TRY(encode_act(&tmdy, dyb, Cout, W, H, B, a.cby, a.g.TW, a.g.TH, a.g.TB));
+  const int splits = wgrad_splits(a.g);
+  const size_t smem = (size_t)a.stages * a.stage_bytes + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)splits, 3);
+  static bool optin = false;
+  if (!optin) {
+    TM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BUDGET + 1024));
+    TM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BUDGET + 1024));
+    optin = true;
+  }
+  if (NT == 3) conv3x3_wgrad_tma_kernel<3><<<grid, CONV_THREADS, smem, st>>>(tmx, tmdy, a);
+  else conv3x3_wgrad_tma_kernel<1><<<grid, CONV_THREADS, smem, st>>>(tmx, tmdy, a);
+  TM_TRY(check_launch("conv3x3_wgrad_tma"));
+  const int64_t n = 9 * Cout * Cin;
+  wgrad_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a.part, splits, (int)Cout, (int)Cin, (int)Cin_real, dw);
+  return check_launch("wgrad_reduce");
+}

@@ -1,0 +1,74 @@
+"""TMA-fed tcgen05 3x3 convolutions on bf16 NHWC activations (tm_conv3x3_bf16*, csrc/tm_tma.cu) against an
+fp64 PyTorch reference evaluated on the SAME bf16-rounded operands: what is left is the fp32 accumulation
+order, so the bar is far tighter than the bf16 2e-2 (rtol 1e-4, atol 1e-5 x max|ref|)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+SHAPES = [(1, 16, 16, 16, 16), (2, 8, 8, 32, 32), (3, 32, 32, 64, 64), (1, 16, 32, 128, 64), (2, 128, 128, 16, 32),
+          (1, 64, 256, 32, 16), (5, 4, 4, 128, 128), (1, 2, 2, 16, 16), (2, 16, 16, 3, 16), (1, 256, 256, 16, 16),
+          (2, 32, 64, 64, 128), (33, 2, 4, 32, 64)]
+
+
+@pytest.fixture(scope="module")
+def lib(pkg):
+    import tm_lib
+    return tm_lib
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def _to_bf16(lib, t_nhwc, C, Cp):
+    npix = t_nhwc.numel() // C
+    out = torch.empty(npix, Cp, dtype=torch.bfloat16, device=DEV)
+    lib.call("tm_to_bf16_rows", npix, C, t_nhwc, C, out, Cp, lib.stream())
+    return out
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", SHAPES)
+def test_conv3x3_bf16_tma(lib, B, H, W, Cin, Cout):
+    torch.manual_seed(B * 7 + H + W + Cin + Cout)
+    CinP = max(16, (Cin + 15) // 16 * 16)
+    assert lib.ws_bytes("tm_conv3x3_bf16_supported", B, H, W, CinP, Cout) == 1
+    x = _bf(torch.randn(B, Cin, H, W, device=DEV)).requires_grad_(True)
+    w = _bf(torch.randn(Cout, Cin, 3, 3, device=DEV) * 0.1).requires_grad_(True)
+    g = _bf(torch.randn(B, Cout, H, W, device=DEV))
+    bias = torch.randn(Cout, device=DEV)
+    ref = F.conv2d(x.double(), w.double(), None, padding=1)
+    gx, gw = torch.autograd.grad(ref, (x, w), g.double())
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous()            # noqa: E731
+    xb = _to_bf16(lib, nhwc(x), Cin, CinP)
+    assert torch.equal(xb[:, :Cin].float().reshape(B, H, W, Cin), nhwc(x)) and bool((xb[:, Cin:] == 0).all())
+    gb = _to_bf16(lib, nhwc(g), Cout, Cout)
+    wf = torch.empty(9, Cout, CinP, dtype=torch.bfloat16, device=DEV)
+    wd = torch.empty(9, Cin, Cout, dtype=torch.bfloat16, device=DEV)
+    lib.call("tm_conv3x3_pack_bf16", Cout, Cin, w.detach().contiguous(), wf, CinP, wd, Cout, lib.stream())
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    # ---- forward, written into the second half of a wider (concat-style) buffer, with bias + ReLU
+    ybuf = torch.full((B * H * W, 2 * Cout), 7.0, device=DEV)
+    lib.call("tm_conv3x3_bf16", B, H, W, CinP, Cout, xb, wf, bias, ybuf[:, Cout:], 2 * Cout, 2, err, lib.stream())
+    want = torch.relu(ref + bias.double().view(1, -1, 1, 1)).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    assert int(err.item()) == 0
+    assert_close(ybuf[:, Cout:], want, 1e-4, 1e-5, "tma fprop")
+    assert bool((ybuf[:, :Cout] == 7.0).all())
+    # ---- data gradient: the same kernel on dy with the reversed-tap weights
+    if Cin % 16 == 0:
+        dx = torch.empty(B * H * W, Cin, device=DEV)
+        lib.call("tm_conv3x3_bf16", B, H, W, Cout, Cin, gb, wd, None, dx, Cin, 0, err, lib.stream())
+        assert_close(dx, gx.permute(0, 2, 3, 1).reshape(B * H * W, Cin), 1e-4, 1e-5, "tma dgrad")
+    # ---- weight gradient
+    nb = lib.ws_bytes("tm_conv3x3_bf16_wgrad_ws", B, H, W, CinP, Cout)
+    dw = torch.empty(Cout, Cin, 3, 3, device=DEV)
+    lib.call("tm_conv3x3_bf16_wgrad", B, H, W, CinP, Cin, Cout, xb, gb, dw, lib.workspace(nb, DEV), nb, err, lib.stream())
+    assert int(err.item()) == 0
+    assert_close(dw, gw, 1e-4, 1e-5, "tma wgrad")
+    dw2 = torch.empty_like(dw)
+    lib.call("tm_conv3x3_bf16_wgrad", B, H, W, CinP, Cin, Cout, xb, gb, dw2, lib.workspace(nb, DEV), nb, err, lib.stream())
+    assert torch.equal(dw, dw2), "weight gradient is not bit-deterministic"
