@@ -376,13 +376,18 @@ int tm_tc_conv2d_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_
 int tm_conv3x3_bf16_supported(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
 /* fp32 rows (stride ldx, C channels) -> compact bf16 rows of Cp >= C channels (zero padded) */
 int tm_to_bf16_rows(int64_t npix, int64_t C, const float* x, int64_t ldx, void* out, int64_t Cp, void* stream);
-/* nn.Conv2d weight [Cout][Cin][3][3] fp32 -> wf bf16 [9][Cout][CinP] (forward operand) and, if wd != NULL,
- * wd bf16 [9][Cin][CoutP] with reversed taps (data-gradient operand) */
-int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, void* wf, int64_t CinP, void* wd,
-                         int64_t CoutP, void* stream);
-/* y[pix, 0:N] (fp32, row stride ldy) = sum_{tap,c} xb[pix + tap, c] * wq[tap][n][c]; bias optional,
- * flags: TM_EPI_RELU.  The data gradient is the same call on bf16(dy) with wd. */
-int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, const void* xb, const void* wq,
+/* Narrow layers run as 64-channel layers over rows of P horizontally adjacent pixels (every TMA row a full
+ * 128-byte line; the packed weights are block sparse).  P for a convolution reading Cin and producing Cout
+ * channels per pixel on images W wide: */
+int tm_conv3x3_bf16_pack(int64_t W, int64_t Cin, int64_t Cout);
+/* nn.Conv2d weight w [Cout][Cin][3][3] fp32 -> bf16 operand q [9][P*Nc][P*KcP] of tm_conv3x3_bf16:
+ * dgrad = 0: forward (Nc = Cout, K = Cin padded to KcP); dgrad = 1: data gradient (Nc = Cin, K = Cout padded
+ * to KcP, taps reversed).  P = tm_conv3x3_bf16_pack(W, K padded, Nc). */
+int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, void* q, int64_t P, int64_t KcP, int dgrad,
+                         void* stream);
+/* y[pix, 0:N] (fp32, row stride ldy) = sum_{tap,c} xb[pix + tap, c] * W[tap][n][c]; bias optional,
+ * flags: TM_EPI_RELU.  The data gradient is the same call on bf16(dy) with the dgrad operand. */
+int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, int64_t P, const void* xb, const void* wq,
                     const float* bias, float* y, int64_t ldy, int flags, int* err, void* stream);
 /* dw[co][ci][ky][kx] (torch layout, ci < Cin_real) = sum_pix dyb[pix, co] * xb[pix + (ky-1,kx-1), ci] */
 size_t tm_conv3x3_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);

@@ -145,8 +145,9 @@ constexpr int CONV_MAX_STAGES = 8;
 constexpr uint32_t CONV_SMEM_BUDGET = 200 * 1024;
 
 struct ConvArgs {
-  Geom g;
-  int Cin, N, stages;
+  Geom g;                            // geometry in PACKED pixels (rows of P pixels)
+  int Cin, N, stages;                // channels per packed row: Cin = P * cin, N = P * cout
+  int P, cpx;                        // pixels per row, output channels per pixel
   uint32_t a_bytes, b_bytes, stage_bytes;
   float* y;
   int64_t ldy;
@@ -258,22 +259,24 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       int x0, y0, b0;
       a.g.origin(t, x0, y0, b0);
       const bool valid = b0 + tb < a.g.B;
-      float* yp = a.y + (((int64_t)(b0 + tb) * a.g.H + (y0 + th)) * a.g.W + (x0 + tw)) * a.ldy;
+      float* yp = a.y + (((int64_t)(b0 + tb) * a.g.H + (y0 + th)) * a.g.W + (x0 + tw)) * a.P * a.ldy;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N);
       for (int c = 0; c < N; c += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
+        const int po = c / a.cpx, co = c - po * a.cpx;     // pixel inside the packed row, its first channel
         if (a.flags & TM_EPI_BIAS) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + c + i);
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + co + i);
         }
         if (a.flags & TM_EPI_RELU) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (valid) {
+          float* o = yp + (int64_t)po * a.ldy + co;
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) st4(yp + c + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          for (int i = 0; i < 16; i += 4) st4(o + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         }
       }
       tc_fence_before();
@@ -430,16 +433,24 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
   }
 }
 
-// part [splits][9][Cout][CinP] -> dw [Cout][Cin][3][3] (torch layout), fixed summation order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Cout, int CinP, int Cin,
+// part [splits][(r,S)][po*Cout+co][pi*CinP+ci] (packed rows of P pixels) -> dw [Cout][Cin][3][3] (torch layout):
+// tap (r, s) collects every (S, po, pi) with S*P + pi - po + 1 == s.  Fixed summation order.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int P, int Cout, int CinP, int Cin,
                                     float* __restrict__ dw) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)9 * Cout * CinP) return;
-  const int ci = (int)(i % CinP), co = (int)((i / CinP) % Cout), tap = (int)(i / ((int64_t)CinP * Cout));
-  if (ci >= Cin) return;
+  if (i >= (int64_t)9 * Cout * Cin) return;
+  const int tap = (int)(i % 9), ci = (int)((i / 9) % Cin), co = (int)(i / ((int64_t)9 * Cin));
+  const int r = tap / 3, sx = tap % 3;
+  const int64_t ldn = (int64_t)P * CinP, per_tap = (int64_t)P * Cout * ldn;
   float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * 9 * Cout * CinP + i];
-  dw[((int64_t)co * Cin + ci) * 9 + tap] = s;
+  for (int z = 0; z < splits; ++z)
+    for (int S = -1; S <= 1; ++S)
+      for (int po = 0; po < P; ++po) {
+        const int pi = sx - 1 + po - S * P;
+        if (pi < 0 || pi >= P) continue;
+        s += part[((int64_t)z * 9 + r * 3 + S + 1) * per_tap + ((int64_t)po * Cout + co) * ldn + (int64_t)pi * CinP + ci];
+      }
+  dw[i] = s;
 }
 
 // fp32 rows (stride ld) -> compact bf16 rows of Cp >= C channels (zero padded); 8 channels per thread
@@ -464,19 +475,28 @@ __global__ void to_bf16_kernel(int64_t npix, int C, const float* __restrict__ x,
   *reinterpret_cast<uint4*>(out + p * Cp + c0) = o;
 }
 
-// w [Cout][Cin][3][3] fp32 -> wf [9][Cout][CinP] (fprop) and wd [9][Cin][CoutP] with reversed taps (dgrad)
-__global__ void pack_w_bf16_kernel(int Cout, int Cin, const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int CinP,
-                                   __nv_bfloat16* __restrict__ wd, int CoutP) {
+// w [Cout][Cin][3][3] fp32 -> operand of the convolution over rows of P packed pixels:
+//   q[(r,S)][n = po*Nc + nc][k = pi*KcP + kc],  S in {-1,0,1} = neighbouring packed row, po / pi = pixel inside
+//   the output / input row; the entry is the tap s = S*P + pi - po + 1 of kernel row r when 0 <= s <= 2, else 0.
+//   dgrad == 0: n = output channel co, k = input channel ci            (forward operand)
+//   dgrad == 1: n = ci, k = co, taps reversed (r, s) -> (2-r, 2-s)     (data-gradient operand)
+__global__ void pack_w_bf16_kernel(int Cout, int Cin, const float* __restrict__ w, __nv_bfloat16* __restrict__ q, int P,
+                                   int KcP, int dgrad) {
+  const int Nc = dgrad ? Cin : Cout, Kc = dgrad ? Cout : Cin;
+  const int64_t ldk = (int64_t)P * KcP, rows = (int64_t)P * Nc;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nf = (int64_t)9 * Cout * CinP, nd = wd ? (int64_t)9 * Cin * CoutP : 0;
-  if (i < nf) {
-    const int ci = (int)(i % CinP), co = (int)((i / CinP) % Cout), tap = (int)(i / ((int64_t)CinP * Cout));
-    wf[i] = __float2bfloat16(ci < Cin ? w[((int64_t)co * Cin + ci) * 9 + tap] : 0.f);
-  } else if (i < nf + nd) {
-    const int64_t k = i - nf;
-    const int co = (int)(k % CoutP), ci = (int)((k / CoutP) % Cin), tap = (int)(k / ((int64_t)CoutP * Cin));
-    wd[k] = __float2bfloat16(co < Cout ? w[((int64_t)co * Cin + ci) * 9 + (8 - tap)] : 0.f);
+  if (i >= 9 * rows * ldk) return;
+  const int k = (int)(i % ldk), n = (int)((i / ldk) % rows), t = (int)(i / (ldk * rows));
+  const int r = t / 3, S = t % 3 - 1;
+  const int pi = k / KcP, kc = k % KcP, po = n / Nc, nc = n % Nc;
+  const int sx = S * P + pi - po + 1;
+  float v = 0.f;
+  if (sx >= 0 && sx <= 2 && kc < Kc) {
+    const int co = dgrad ? kc : nc, ci = dgrad ? nc : kc;
+    const int tap = dgrad ? (2 - r) * 3 + (2 - sx) : r * 3 + sx;
+    v = w[((int64_t)co * Cin + ci) * 9 + tap];
   }
+  q[i] = __float2bfloat16(v);
 }
 
 inline bool conv_shape_ok(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N) {
@@ -484,11 +504,29 @@ inline bool conv_shape_ok(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t 
          (Cin <= 64 ? pow2(Cin) : Cin % 64 == 0) && N % 16 == 0 && N >= 16 && N <= 256 && W <= 65536 && H <= 65536;
 }
 
+// pixels packed into one operand row: narrow layers (16 / 32 channels) are run as 64-channel layers over rows of
+// 4 / 2 horizontally adjacent pixels (block-sparse packed weights), so that every TMA row is a full 128-byte line
+inline int conv_pack(int64_t W, int64_t cin, int64_t cout) {
+  int P = 1;
+  while (P * cin < 64 && 2 * P <= W && 2 * P * cout <= 256) P *= 2;
+  return P;
+}
+inline int wgrad_pack(int64_t W, int64_t cin, int64_t cout) {
+  const int64_t lo = cin < cout ? cin : cout, hi = cin < cout ? cout : cin;
+  int P = 1;
+  while (P * lo < 64 && 2 * P <= W && 2 * P * hi <= 128) P *= 2;
+  return P;
+}
 }  // namespace
 
 extern "C" int tm_conv3x3_bf16_supported(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout) {
-  return conv_shape_ok(B, H, W, Cin, Cout) ? 1 : 0;
+  if (W <= 0 || Cin <= 0 || Cout <= 0 || Cin % 16 || Cout % 16) return 0;
+  const int P = conv_pack(W, Cin, Cout), Pw = wgrad_pack(W, Cin, Cout);
+  return conv_shape_ok(B, H, W / P, P * Cin, P * Cout) && conv_shape_ok(B, H, W / Pw, Pw * Cin, Pw * Cout) &&
+         Pw * Cin <= 128 && Pw * Cout <= 128 && pow2(Cin) && pow2(Cout) ? 1 : 0;
 }
+
+extern "C" int tm_conv3x3_bf16_pack(int64_t W, int64_t Cin, int64_t Cout) { return conv_pack(W, Cin, Cout); }
 
 extern "C" int tm_to_bf16_rows(int64_t npix, int64_t C, const float* x, int64_t ldx, void* out, int64_t Cp, void* stream) {
   TM_REQUIRE(Cp % 8 == 0 && Cp >= C, "tm_to_bf16_rows: padded width must be a multiple of 8 and >= C");
@@ -499,27 +537,32 @@ extern "C" int tm_to_bf16_rows(int64_t npix, int64_t C, const float* x, int64_t 
   return check_launch("to_bf16");
 }
 
-extern "C" int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, void* wf, int64_t CinP, void* wd,
-                                    int64_t CoutP, void* stream) {
-  const int64_t n = 9 * Cout * CinP + (wd ? 9 * Cin * CoutP : 0);
-  pack_w_bf16_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((int)Cout, (int)Cin, w, (__nv_bfloat16*)wf,
-                                                                             (int)CinP, (__nv_bfloat16*)wd, (int)CoutP);
+// q: bf16 [9][P*Nc][P*KcP]; dgrad = 0: Nc = Cout, Kc = Cin (padded to KcP); dgrad = 1: Nc = Cin, Kc = Cout
+extern "C" int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, void* q, int64_t P, int64_t KcP, int dgrad,
+                                    void* stream) {
+  TM_REQUIRE(P >= 1 && KcP >= (dgrad ? Cout : Cin), "tm_conv3x3_pack_bf16: bad packing");
+  const int64_t n = 9 * P * (dgrad ? Cin : Cout) * P * KcP;
+  pack_w_bf16_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((int)Cout, (int)Cin, w, (__nv_bfloat16*)q, (int)P,
+                                                                             (int)KcP, dgrad);
   return check_launch("pack_w_bf16");
 }
 
-// Y[pix, 0:N] = sum_{tap,c} X[pix+tap, c] * Wq[tap][n][c]  (3x3, stride 1, zero padding 1)
-// xb: bf16 [B][H][W][Cin] compact; wq: bf16 [9][N][Cin]; y: fp32 rows of stride ldy.
-extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, const void* xb, const void* wq,
-                               const float* bias, float* y, int64_t ldy, int flags, int* err, void* stream) {
-  TM_REQUIRE(conv_shape_ok(B, H, W, Cin, N), "tm_conv3x3_bf16: unsupported shape (H, W powers of two; channels multiples of 16)");
+// Y[pix, 0:N] = sum_{tap,c} X[pix+tap, c] * W[tap][n][c]  (3x3, stride 1, zero padding 1)
+// xb: bf16 [B][H][W][Cin] compact; wq: tm_conv3x3_pack_bf16 operand for P = tm_conv3x3_bf16_pack(W, Cin, N);
+// y: fp32 rows of stride ldy.
+extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, int64_t P, const void* xb,
+                               const void* wq, const float* bias, float* y, int64_t ldy, int flags, int* err, void* stream) {
+  TM_REQUIRE(P >= 1 && W % P == 0 && conv_shape_ok(B, H, W / P, P * Cin, P * N) && N % 16 == 0,
+             "tm_conv3x3_bf16: unsupported shape (H, W powers of two; channels multiples of 16)");
   TM_REQUIRE(ldy % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0, "tm_conv3x3_bf16: output rows must be 16-byte aligned");
   TM_REQUIRE(reinterpret_cast<uintptr_t>(xb) % 16 == 0 && reinterpret_cast<uintptr_t>(wq) % 16 == 0, "tm_conv3x3_bf16: operands must be 16-byte aligned");
-  const int CK = Cin >= 64 ? 64 : (int)Cin;
+  const int64_t Wp = W / P, Cp = P * Cin, Np = P * N;
+  const int CK = Cp >= 64 ? 64 : (int)Cp;
   ConvArgs a;
-  a.g = make_geom(B, H, W);
-  a.Cin = (int)Cin; a.N = (int)N;
+  a.g = make_geom(B, H, Wp);
+  a.Cin = (int)Cp; a.N = (int)Np; a.P = (int)P; a.cpx = (int)N;
   a.a_bytes = 128u * CK * 2u;
-  a.b_bytes = (uint32_t)N * CK * 2u;
+  a.b_bytes = (uint32_t)Np * CK * 2u;
   a.stage_bytes = a.a_bytes + (uint32_t)align_up(a.b_bytes, 1024);
   int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
   a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
@@ -527,8 +570,8 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   a.flags = (flags & TM_EPI_RELU) | (bias ? TM_EPI_BIAS : 0);
   a.err = err;
   CUtensorMap tmx, tmw;
-  TM_TRY(encode_act(&tmx, xb, Cin, W, H, B, CK, a.g.TW, a.g.TH, a.g.TB));
-  TM_TRY(encode_2d(&tmw, wq, Cin, 9 * N, CK, (int)N));
+  TM_TRY(encode_act(&tmx, xb, Cp, Wp, H, B, CK, a.g.TW, a.g.TH, a.g.TB));
+  TM_TRY(encode_2d(&tmw, wq, Cp, 9 * Np, CK, (int)Np));
   const size_t smem = (size_t)a.stages * a.stage_bytes + 1024;
   const int grid = (int)(a.g.ntiles < sm_count() ? a.g.ntiles : sm_count());
   cudaStream_t st = (cudaStream_t)stream;
@@ -557,8 +600,9 @@ inline int wgrad_splits(const Geom& g) {
 }  // namespace
 
 extern "C" size_t tm_conv3x3_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout) {
-  const Geom g = make_geom(B, H, W);
-  return (size_t)wgrad_splits(g) * 9 * Cout * Cin * sizeof(float) + 256;
+  const int P = wgrad_pack(W, Cin, Cout);
+  const Geom g = make_geom(B, H, W / P);
+  return (size_t)wgrad_splits(g) * 9 * (P * Cout) * (P * Cin) * sizeof(float) + 256;
 }
 
 // dw[co][ci][ky][kx] (ci < Cin_real) = sum_pix dY[pix, co] * X[pix + (ky-1, kx-1), ci]
@@ -566,17 +610,20 @@ extern "C" size_t tm_conv3x3_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int6
 extern "C" int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cin_real, int64_t Cout,
                                      const void* xb, const void* dyb, float* dw, void* ws, size_t ws_bytes, int* err,
                                      void* stream) {
-  TM_REQUIRE(conv_shape_ok(B, H, W, Cin, Cout) && Cin <= 128 && Cout <= 128 && pow2(Cout) && pow2(Cin),
+  TM_REQUIRE(W > 0 && Cin > 0 && Cout > 0, "tm_conv3x3_bf16_wgrad: bad sizes");
+  const int P = wgrad_pack(W, Cin, Cout);
+  const int64_t Wp = W / P, Cp = P * Cin, Np = P * Cout;
+  TM_REQUIRE(conv_shape_ok(B, H, Wp, Cp, Np) && Cp <= 128 && Np <= 128 && pow2(Cp) && pow2(Np),
              "tm_conv3x3_bf16_wgrad: unsupported shape");
   TM_REQUIRE(ws && ws_bytes >= tm_conv3x3_bf16_wgrad_ws(B, H, W, Cin, Cout), "tm_conv3x3_bf16_wgrad: workspace too small");
   WgradArgs a;
-  a.g = make_geom(B, H, W);
-  a.Cin = (int)Cin; a.Cout = (int)Cout;
-  a.cbx = Cin > 64 ? 64 : (int)Cin; a.nbx = (int)Cin / a.cbx;
-  a.cby = Cout > 64 ? 64 : (int)Cout; a.nby = (int)Cout / a.cby;
-  a.x_bytes = 128u * (uint32_t)Cin * 2u;
-  a.dy_bytes = 128u * (uint32_t)Cout * 2u;
-  const int NT = Cin <= 64 ? 3 : 1;
+  a.g = make_geom(B, H, Wp);
+  a.Cin = (int)Cp; a.Cout = (int)Np;
+  a.cbx = Cp > 64 ? 64 : (int)Cp; a.nbx = (int)Cp / a.cbx;
+  a.cby = Np > 64 ? 64 : (int)Np; a.nby = (int)Np / a.cby;
+  a.x_bytes = 128u * (uint32_t)Cp * 2u;
+  a.dy_bytes = 128u * (uint32_t)Np * 2u;
+  const int NT = Cp <= 64 ? 3 : 1;
   a.stage_bytes = (uint32_t)align_up(a.dy_bytes + NT * a.x_bytes, 1024);
   int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
   a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
@@ -584,8 +631,8 @@ extern "C" int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Ci
   a.part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   a.err = err;
   CUtensorMap tmx, tmdy;
-  TM_TRY(encode_act(&tmx, xb, Cin, W, H, B, a.cbx, a.g.TW, a.g.TH, a.g.TB));
-  TM_TRY(encode_act(&tmdy, dyb, Cout, W, H, B, a.cby, a.g.TW, a.g.TH, a.g.TB));
+  TM_TRY(encode_act(&tmx, xb, Cp, Wp, H, B, a.cbx, a.g.TW, a.g.TH, a.g.TB));
+  TM_TRY(encode_act(&tmdy, dyb, Np, Wp, H, B, a.cby, a.g.TW, a.g.TH, a.g.TB));
   const int splits = wgrad_splits(a.g);
   const size_t smem = (size_t)a.stages * a.stage_bytes + 1024;
   cudaStream_t st = (cudaStream_t)stream;
@@ -599,7 +646,7 @@ extern "C" int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Ci
   if (NT == 3) conv3x3_wgrad_tma_kernel<3><<<grid, CONV_THREADS, smem, st>>>(tmx, tmdy, a);
   else conv3x3_wgrad_tma_kernel<1><<<grid, CONV_THREADS, smem, st>>>(tmx, tmdy, a);
   TM_TRY(check_launch("conv3x3_wgrad_tma"));
-  const int64_t n = 9 * Cout * Cin;
-  wgrad_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a.part, splits, (int)Cout, (int)Cin, (int)Cin_real, dw);
+  const int64_t n = 9 * Cout * Cin_real;
+  wgrad_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a.part, splits, P, (int)Cout, (int)Cin, (int)Cin_real, dw);
   return check_launch("wgrad_reduce");
 }

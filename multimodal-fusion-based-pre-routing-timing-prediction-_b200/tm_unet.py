@@ -7,6 +7,8 @@ nothing).  BatchNorm always uses batch statistics -- the reference never calls `
 (momentum 0.1, unbiased variance).  Every contraction is a ``tm_conv2d_nhwc`` /
 ``tm_convt2x2_nhwc`` implicit GEMM; nothing here calls cuDNN or ATen convolution.
 """
+import os
+
 import torch
 
 import tm_lib
@@ -45,6 +47,55 @@ def _prec(math):
 def _enter(net):
     global _CUR
     _CUR = getattr(net, "math", None)
+
+
+USE_TMA = os.environ.get("TM_CONV_TMA", "1") != "0"   # bf16 mode: TMA-fed 3x3 convolutions on bf16 activations
+
+
+def _cpad(c):
+    return max(16, (c + 15) // 16 * 16)
+
+
+def _tma_ok(B, H, W, cin, cout):
+    """bf16 mode and a shape the TMA kernels take (H, W powers of two; channels multiples of 16)."""
+    return (USE_TMA and _prec(None) == 0 and cout <= 128 and _cpad(cin) <= 128
+            and tm_lib.ws_bytes("tm_conv3x3_bf16_supported", B, H, W, _cpad(cin), cout) == 1
+            and (cin % 16 != 0 or tm_lib.ws_bytes("tm_conv3x3_bf16_supported", B, H, W, cout, cin) == 1))
+
+
+def _to_bf16(x, ldx, npix, C):
+    """fp32 rows (stride ldx) -> compact bf16 [npix][pad16(C)]: the TMA operand of the next convolution."""
+    out = torch.empty(npix, _cpad(C), dtype=torch.bfloat16, device=x.device)
+    call("tm_to_bf16_rows", npix, C, x, ldx, out, _cpad(C), stream())
+    return out
+
+
+def _pack_bf16(w, W, need_dgrad):
+    """-> ((forward operand, P), (data-gradient operand, P) or None) for images W wide."""
+    cout, cin = w.shape[0], w.shape[1]
+    dev = w.device
+    wc = w.detach().float().contiguous()
+
+    def one(nc, kc, dgrad):
+        kp = _cpad(kc)
+        P = tm_lib.ws_bytes("tm_conv3x3_bf16_pack", W, kp, nc)
+        q = torch.empty(9, P * nc, P * kp, dtype=torch.bfloat16, device=dev)
+        call("tm_conv3x3_pack_bf16", cout, cin, wc, q, P, kp, dgrad, stream())
+        return q, P
+    return one(cout, cin, 0), (one(cin, cout, 1) if need_dgrad else None)
+
+
+def _conv_tma(xb, B, H, W, cinp, cout, wq, y, ldy):
+    q, P = wq
+    call("tm_conv3x3_bf16", B, H, W, cinp, cout, P, xb, q, None, y, ldy, 0, tm_lib.err_flag(y.device), stream())
+
+
+def _wgrad_tma(ws, xb, dyb, B, H, W, cin, cout):
+    dev = dyb.device
+    dw = _empty(cout, cin, 3, 3, dev=dev)
+    nb = tm_lib.ws_bytes("tm_conv3x3_bf16_wgrad_ws", B, H, W, _cpad(cin), cout)
+    call("tm_conv3x3_bf16_wgrad", B, H, W, _cpad(cin), cin, cout, xb, dyb, dw, ws.get(nb), nb, tm_lib.err_flag(dev), stream())
+    return dw
 
 
 def _conv(x, ldx, B, H, W, cin, cout, k, wf, bias, y, ldy, flags=0, math=None):
@@ -117,9 +168,23 @@ def _double_conv_fwd(ws, st, name, mods, x, ldx, B, H, W, cin, cout, out, ldo, u
     dev = x.device
     npix = B * H * W
     cmid = conv1.weight.shape[0]
+    r1, a1, r2 = _empty(npix, cmid, dev=dev), _empty(npix, cmid, dev=dev), _empty(npix, cout, dev=dev)
+    if _tma_ok(B, H, W, cin, cmid) and _tma_ok(B, H, W, cmid, cout):
+        # bf16 mode: TMA-fed tcgen05 convolutions on compact bf16 copies of the activations (kept for wgrad)
+        xb = _to_bf16(x, ldx, npix, cin)
+        wq1, wd1 = _pack_bf16(conv1.weight, W, need_bwd and cin % 16 == 0)
+        wq2, wd2 = _pack_bf16(conv2.weight, W, need_bwd)
+        _conv_tma(xb, B, H, W, _cpad(cin), cmid, wq1, r1, cmid)
+        m1, i1 = _bn_relu_fwd(ws, r1, cmid, npix, cmid, bn1, a1, cmid, update_stats)
+        a1b = _to_bf16(a1, cmid, npix, cmid)
+        _conv_tma(a1b, B, H, W, cmid, cout, wq2, r2, cout)
+        m2, i2 = _bn_relu_fwd(ws, r2, cout, npix, cout, bn2, out, ldo, update_stats)
+        st[name] = dict(tma=True, xb=xb if need_bwd else None, a1b=a1b if need_bwd else None, wd1=wd1, wd2=wd2,
+                        x=x, ldx=ldx, B=B, H=H, W=W, cin=cin, cmid=cmid, cout=cout, r1=r1, a1=a1, r2=r2, out=out,
+                        ldo=ldo, m1=m1, i1=i1, m2=m2, i2=i2, g1=bn1.weight.detach(), g2=bn2.weight.detach())
+        return
     wf1, wb1 = _pack(conv1.weight, need_bwd)
     wf2, wb2 = _pack(conv2.weight, need_bwd)
-    r1, a1, r2 = _empty(npix, cmid, dev=dev), _empty(npix, cmid, dev=dev), _empty(npix, cout, dev=dev)
     _conv(x, ldx, B, H, W, cin, cmid, 3, wf1, None, r1, cmid)
     m1, i1 = _bn_relu_fwd(ws, r1, cmid, npix, cmid, bn1, a1, cmid, update_stats)
     _conv(a1, cmid, B, H, W, cmid, cout, 3, wf2, None, r2, cout)
@@ -137,15 +202,26 @@ def _double_conv_bwd(ws, s, dout, lddo, grads, prefix, dx, lddx):
     dr2 = _empty(npix, cout, dev=dev)
     dg2, db2 = _bn_relu_bwd(ws, s["r2"], cout, s["out"], s["ldo"], dout, lddo, npix, cout, s["g2"], s["m2"],
                             s["i2"], dr2, cout)
-    dw2, _ = _conv_wgrad(ws, s["a1"], cmid, dr2, cout, B, H, W, cmid, cout, 3, False)
     da1 = _empty(npix, cmid, dev=dev)
-    _conv(dr2, cout, B, H, W, cout, cmid, 3, s["wb2"], None, da1, cmid)
     dr1 = _empty(npix, cmid, dev=dev)
-    dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, s["a1"], cmid, da1, cmid, npix, cmid, s["g1"], s["m1"], s["i1"],
-                            dr1, cmid)
-    dw1, _ = _conv_wgrad(ws, s["x"], s["ldx"], dr1, cmid, B, H, W, cin, cmid, 3, False)
-    if dx is not None:
-        _conv(dr1, cmid, B, H, W, cmid, cin, 3, s["wb1"], None, dx, lddx)
+    if s.get("tma"):
+        dr2b = _to_bf16(dr2, cout, npix, cout)                 # shared by the weight and the data gradient
+        dw2 = _wgrad_tma(ws, s["a1b"], dr2b, B, H, W, cmid, cout)
+        _conv_tma(dr2b, B, H, W, cout, cmid, s["wd2"], da1, cmid)
+        dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, s["a1"], cmid, da1, cmid, npix, cmid, s["g1"], s["m1"], s["i1"],
+                                dr1, cmid)
+        dr1b = _to_bf16(dr1, cmid, npix, cmid)
+        dw1 = _wgrad_tma(ws, s["xb"], dr1b, B, H, W, cin, cmid)
+        if dx is not None:
+            _conv_tma(dr1b, B, H, W, cmid, cin, s["wd1"], dx, lddx)
+    else:
+        dw2, _ = _conv_wgrad(ws, s["a1"], cmid, dr2, cout, B, H, W, cmid, cout, 3, False)
+        _conv(dr2, cout, B, H, W, cout, cmid, 3, s["wb2"], None, da1, cmid)
+        dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, s["a1"], cmid, da1, cmid, npix, cmid, s["g1"], s["m1"], s["i1"],
+                                dr1, cmid)
+        dw1, _ = _conv_wgrad(ws, s["x"], s["ldx"], dr1, cmid, B, H, W, cin, cmid, 3, False)
+        if dx is not None:
+            _conv(dr1, cmid, B, H, W, cmid, cin, 3, s["wb1"], None, dx, lddx)
     grads[prefix + ".0.weight"] = dw1
     grads[prefix + ".1.weight"], grads[prefix + ".1.bias"] = dg1, db1
     grads[prefix + ".3.weight"] = dw2

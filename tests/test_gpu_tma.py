@@ -47,21 +47,24 @@ def test_conv3x3_bf16_tma(lib, B, H, W, Cin, Cout):
     xb = _to_bf16(lib, nhwc(x), Cin, CinP)
     assert torch.equal(xb[:, :Cin].float().reshape(B, H, W, Cin), nhwc(x)) and bool((xb[:, Cin:] == 0).all())
     gb = _to_bf16(lib, nhwc(g), Cout, Cout)
-    wf = torch.empty(9, Cout, CinP, dtype=torch.bfloat16, device=DEV)
-    wd = torch.empty(9, Cin, Cout, dtype=torch.bfloat16, device=DEV)
-    lib.call("tm_conv3x3_pack_bf16", Cout, Cin, w.detach().contiguous(), wf, CinP, wd, Cout, lib.stream())
+    Pf = lib.ws_bytes("tm_conv3x3_bf16_pack", W, CinP, Cout)
+    wf = torch.empty(9, Pf * Cout, Pf * CinP, dtype=torch.bfloat16, device=DEV)
+    lib.call("tm_conv3x3_pack_bf16", Cout, Cin, w.detach().contiguous(), wf, Pf, CinP, 0, lib.stream())
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
     # ---- forward, written into the second half of a wider (concat-style) buffer, with bias + ReLU
     ybuf = torch.full((B * H * W, 2 * Cout), 7.0, device=DEV)
-    lib.call("tm_conv3x3_bf16", B, H, W, CinP, Cout, xb, wf, bias, ybuf[:, Cout:], 2 * Cout, 2, err, lib.stream())
+    lib.call("tm_conv3x3_bf16", B, H, W, CinP, Cout, Pf, xb, wf, bias, ybuf[:, Cout:], 2 * Cout, 2, err, lib.stream())
     want = torch.relu(ref + bias.double().view(1, -1, 1, 1)).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
     assert int(err.item()) == 0
     assert_close(ybuf[:, Cout:], want, 1e-4, 1e-5, "tma fprop")
     assert bool((ybuf[:, :Cout] == 7.0).all())
     # ---- data gradient: the same kernel on dy with the reversed-tap weights
     if Cin % 16 == 0:
+        Pd = lib.ws_bytes("tm_conv3x3_bf16_pack", W, Cout, Cin)
+        wd = torch.empty(9, Pd * Cin, Pd * Cout, dtype=torch.bfloat16, device=DEV)
+        lib.call("tm_conv3x3_pack_bf16", Cout, Cin, w.detach().contiguous(), wd, Pd, Cout, 1, lib.stream())
         dx = torch.empty(B * H * W, Cin, device=DEV)
-        lib.call("tm_conv3x3_bf16", B, H, W, Cout, Cin, gb, wd, None, dx, Cin, 0, err, lib.stream())
+        lib.call("tm_conv3x3_bf16", B, H, W, Cout, Cin, Pd, gb, wd, None, dx, Cin, 0, err, lib.stream())
         assert_close(dx, gx.permute(0, 2, 3, 1).reshape(B * H * W, Cin), 1e-4, 1e-5, "tma dgrad")
     # ---- weight gradient
     nb = lib.ws_bytes("tm_conv3x3_bf16_wgrad_ws", B, H, W, CinP, Cout)
