@@ -282,17 +282,28 @@ int tm_convt2x2_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t
 size_t tm_bn_ws(int64_t npix, int64_t C);
 /* Train-mode BatchNorm2d + ReLU (Unet.py:17-18,20-21): batch statistics over B*H*W,
  * y = relu(gamma*(x-mean)*invstd+beta); running stats updated with `momentum`, unbiased var.
- * save_mean/save_invstd [C] kept for backward. */
+ * save_mean/save_invstd [C] kept for backward.  y_bf16 (optional): compact bf16 copy [npix][C] of y written by
+ * the same pass (the TMA operand of the next convolution in bf16 mode); dx_bf16 likewise for the backward. */
 int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* gamma,
                        const float* beta, float* running_mean, float* running_var, float momentum,
                        float eps, float* y, int64_t ldy, float* save_mean, float* save_invstd,
-                       void* ws, size_t ws_bytes, void* stream);
+                       void* y_bf16, void* ws, size_t ws_bytes, void* stream);
 /* Backward of the pair: dy is the gradient w.r.t. the ReLU output y.
- * dx = BN'( dy * (y>0) ), dgamma, dbeta [C]. */
+ * dx = BN'( dy * (y>0) ), dgamma, dbeta [C].  dx may be NULL when only dx_bf16 is wanted. */
 int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* y,
                         int64_t ldy, const float* dy, int64_t lddy, const float* gamma,
                         const float* save_mean, const float* save_invstd, float* dx, int64_t lddx,
-                        float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+                        float* dgamma, float* dbeta, void* dx_bf16, void* ws, size_t ws_bytes, void* stream);
+
+/* OutConv (Unet.py:74-75): nn.Conv2d(C, 1, kernel_size=1) as streaming kernels, exact fp32.
+ * forward y[p] = x[p,:] . w + bias; dgrad dx[p,c] = dy[p] * w[c]; wgrad dw[c] = sum_p x[p,c] dy[p], dbias = sum_p dy[p]. */
+int tm_conv1x1_c1_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* w, const float* bias,
+                          float* y, int64_t ldy, void* stream);
+int tm_conv1x1_c1_dgrad(int64_t npix, int64_t C, const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx,
+                        void* stream);
+size_t tm_conv1x1_c1_wgrad_ws(int64_t C);
+int tm_conv1x1_c1_wgrad(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* dy, int64_t lddy, float* dw,
+                        float* dbias, void* ws, size_t ws_bytes, void* stream);
 
 /* 2x2 stride-2 pooling (Unet.py:89-91, model.py:222-224). mode 0 = max (idx: uint8 argmax
  * saved for backward, first maximum in row-major window order), 1 = avg (idx unused).

@@ -6,6 +6,10 @@
 // fp32 GEMM core (tm_gemm.cuh) with im2col performed by the operand loader; every activation
 // carries an explicit pixel stride so torch.cat (Unet.py:67) is free: producers write straight
 // into the halves of the concat buffer.  The bf16 tcgen05 path lives in tm_conv_tc.cu.
+#include <cuda_bf16.h>
+#include <initializer_list>
+#include <utility>
+
 #include "tm_gemm.cuh"
 
 using namespace tmk;
@@ -64,29 +68,75 @@ __global__ void fold4_kernel(int64_t Cout, const float* __restrict__ cs, float* 
 }
 
 // ------------------------------------------------------------------------------ batch norm
-// block = 32 channels x 8 pixel lanes; grid.x = pixel chunks, grid.y = channel groups of 32
-constexpr int BN_PIX_PER_BLOCK = 128;
+// Statistics: a fixed number of blocks (BN_BLOCKS, independent of the image size) each sweep a contiguous
+// pixel range; a thread owns VEC consecutive channels (128-bit loads when the layout allows) of every
+// (256 / groups)-th pixel, accumulates in fp64 and the block folds its pixel lanes in shared memory:
+// part[block][C][2].  The finalize kernels add the <= BN_BLOCKS partials per channel in a fixed order.
+constexpr int BN_BLOCKS = 592;           // 4 per SM
+constexpr int BN_THREADS = 256;
 
-__global__ void __launch_bounds__(256)
-bn_stats_kernel(int64_t npix, int64_t C, const float* __restrict__ x, int64_t ldx, double* __restrict__ part) {
-  __shared__ double s1[8][32], s2[8][32];
-  const int c = blockIdx.y * 32 + threadIdx.x;
-  const int64_t p0 = (int64_t)blockIdx.x * BN_PIX_PER_BLOCK;
-  const int64_t p1 = (p0 + BN_PIX_PER_BLOCK < npix) ? p0 + BN_PIX_PER_BLOCK : npix;
-  double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int64_t p = p0 + threadIdx.y; p < p1; p += 8) {
-      const double v = (double)x[p * ldx + c];
-      a += v;
-      b += v * v;
+__device__ __forceinline__ uint32_t bn_pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int VEC, bool BWD>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_stats_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx, const float* __restrict__ y, int64_t ldy,
+                const float* __restrict__ dy, int64_t lddy, const float* __restrict__ mean,
+                const float* __restrict__ invstd, double* __restrict__ part) {
+  extern __shared__ double sh[];                       // [lanes][C][2]
+  const int groups = (C + VEC - 1) / VEC;              // channel groups per pixel
+  const int lanes = BN_THREADS / groups;               // pixel lanes (groups <= 256)
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int c0 = g * VEC;
+  const int64_t per = (npix + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = (int64_t)blockIdx.x * per, p1 = p0 + per < npix ? p0 + per : npix;
+  double a[VEC], b[VEC];
+  float mu[VEC], is[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    a[j] = 0.0; b[j] = 0.0;
+    mu[j] = (BWD && c0 + j < C) ? mean[c0 + j] : 0.f;
+    is[j] = (BWD && c0 + j < C) ? invstd[c0 + j] : 0.f;
+  }
+  if (pl < lanes) {
+    for (int64_t p = p0 + pl; p < p1; p += lanes) {
+      float xv[VEC], yv[VEC], gv[VEC];
+      if (VEC == 4) {
+        const float4 t = ld4_stream(x + p * ldx + c0);
+        xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+        if (BWD) {
+          const float4 u = ld4_stream(y + p * ldy + c0), w = ld4_stream(dy + p * lddy + c0);
+          yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+          gv[0] = w.x; gv[1] = w.y; gv[2] = w.z; gv[3] = w.w;
+        }
+      } else {
+        xv[0] = c0 < C ? x[p * ldx + c0] : 0.f;
+        if (BWD) { yv[0] = c0 < C ? y[p * ldy + c0] : 0.f; gv[0] = c0 < C ? dy[p * lddy + c0] : 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (BWD) {
+          const float gg = yv[j] > 0.f ? gv[j] : 0.f;
+          a[j] += (double)gg;
+          b[j] += (double)gg * (double)((xv[j] - mu[j]) * is[j]);
+        } else {
+          const double v = (double)xv[j];
+          a[j] += v;
+          b[j] += v * v;
+        }
+      }
     }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = b;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      if (c0 + j < C) { sh[((int64_t)pl * C + c0 + j) * 2] = a[j]; sh[((int64_t)pl * C + c0 + j) * 2 + 1] = b[j]; }
+  }
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-    part[((int64_t)blockIdx.x * C + c) * 2 + 0] = a;
-    part[((int64_t)blockIdx.x * C + c) * 2 + 1] = b;
+  for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) {
+    double s = 0.0;
+    for (int l = 0; l < lanes; ++l) s += sh[(int64_t)l * C * 2 + i];
+    part[(int64_t)blockIdx.x * C * 2 + i] = s;
   }
 }
 
@@ -114,42 +164,34 @@ __global__ void bn_finalize_kernel(int64_t npix, int64_t C, int nblk, const doub
   }
 }
 
-__global__ void bn_relu_apply_kernel(int64_t npix, int64_t C, const float* __restrict__ x, int64_t ldx,
+// y = relu((x - mean) * invstd * gamma + beta); optionally also a compact bf16 copy yb [npix][C] (the TMA
+// operand of the next convolution).  VEC == 4: one thread per 4 channels, 128-bit loads and stores.
+template <int VEC>
+__global__ void bn_relu_apply_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     float* __restrict__ y, int64_t ldy) {
+                                     float* __restrict__ y, int64_t ldy, __nv_bfloat16* __restrict__ yb) {
+  const int groups = C / VEC;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix * C) return;
-  const int64_t p = i / C, c = i - p * C;
-  const float v = (x[p * ldx + c] - mean[c]) * invstd[c] * gamma[c] + beta[c];
-  y[p * ldy + c] = fmaxf(v, 0.f);
-}
-
-__global__ void __launch_bounds__(256)
-bn_bwd_stats_kernel(int64_t npix, int64_t C, const float* __restrict__ x, int64_t ldx,
-                    const float* __restrict__ y, int64_t ldy, const float* __restrict__ dy, int64_t lddy,
-                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                    double* __restrict__ part) {
-  __shared__ double s1[8][32], s2[8][32];
-  const int c = blockIdx.y * 32 + threadIdx.x;
-  const int64_t p0 = (int64_t)blockIdx.x * BN_PIX_PER_BLOCK;
-  const int64_t p1 = (p0 + BN_PIX_PER_BLOCK < npix) ? p0 + BN_PIX_PER_BLOCK : npix;
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    const float mu = mean[c], is = invstd[c];
-    for (int64_t p = p0 + threadIdx.y; p < p1; p += 8) {
-      const float g = (y[p * ldy + c] > 0.f) ? dy[p * lddy + c] : 0.f;
-      a += (double)g;
-      b += (double)g * (double)((x[p * ldx + c] - mu) * is);
-    }
+  if (i >= npix * groups) return;
+  const int64_t p = i / groups;
+  const int c = (int)(i - p * groups) * VEC;
+  float v[VEC];
+  if (VEC == 4) {
+    const float4 t = ld4_stream(x + p * ldx + c);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = x[p * ldx + c];
   }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-    part[((int64_t)blockIdx.x * C + c) * 2 + 0] = a;
-    part[((int64_t)blockIdx.x * C + c) * 2 + 1] = b;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    v[j] = fmaxf((v[j] - __ldg(mean + c + j)) * __ldg(invstd + c + j) * __ldg(gamma + c + j) + __ldg(beta + c + j), 0.f);
+  if (VEC == 4) {
+    st4(y + p * ldy + c, make_float4(v[0], v[1], v[2], v[3]));
+    if (yb) *reinterpret_cast<uint2*>(yb + p * C + c) = make_uint2(bn_pack_bf16(v[0], v[1]), bn_pack_bf16(v[2], v[3]));
+  } else {
+    y[p * ldy + c] = v[0];
+    if (yb) yb[p * C + c] = __float2bfloat16(v[0]);
   }
 }
 
@@ -165,19 +207,111 @@ __global__ void bn_bwd_finalize_kernel(int64_t C, int nblk, const double* __rest
   if (lane == 0) { dbeta[c] = (float)a; dgamma[c] = (float)b; }
 }
 
-__global__ void bn_bwd_apply_kernel(int64_t npix, int64_t C, const float* __restrict__ x, int64_t ldx,
+template <int VEC>
+__global__ void bn_bwd_apply_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx,
                                     const float* __restrict__ y, int64_t ldy, const float* __restrict__ dy,
                                     int64_t lddy, const float* __restrict__ gamma,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                    float* __restrict__ dx, int64_t lddx) {
+                                    float* __restrict__ dx, int64_t lddx, __nv_bfloat16* __restrict__ dxb) {
+  const int groups = C / VEC;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * groups) return;
+  const int64_t p = i / groups;
+  const int c = (int)(i - p * groups) * VEC;
+  float xv[VEC], yv[VEC], gv[VEC], o[VEC];
+  if (VEC == 4) {
+    const float4 t = ld4_stream(x + p * ldx + c), u = ld4_stream(y + p * ldy + c), w = ld4_stream(dy + p * lddy + c);
+    xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+    yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+    gv[0] = w.x; gv[1] = w.y; gv[2] = w.z; gv[3] = w.w;
+  } else {
+    xv[0] = x[p * ldx + c]; yv[0] = y[p * ldy + c]; gv[0] = dy[p * lddy + c];
+  }
+  const float inv_n = 1.f / (float)npix;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float g = (yv[j] > 0.f) ? gv[j] : 0.f;
+    const float is = __ldg(invstd + c + j);
+    const float xh = (xv[j] - __ldg(mean + c + j)) * is;
+    o[j] = __ldg(gamma + c + j) * is * (g - __ldg(dbeta + c + j) * inv_n - xh * __ldg(dgamma + c + j) * inv_n);
+  }
+  if (VEC == 4) {
+    if (dx) st4(dx + p * lddx + c, make_float4(o[0], o[1], o[2], o[3]));
+    if (dxb) *reinterpret_cast<uint2*>(dxb + p * C + c) = make_uint2(bn_pack_bf16(o[0], o[1]), bn_pack_bf16(o[2], o[3]));
+  } else {
+    if (dx) dx[p * lddx + c] = o[0];
+    if (dxb) dxb[p * C + c] = __float2bfloat16(o[0]);
+  }
+}
+
+// ------------------------------------------------------------------------------ OutConv (1x1, one output channel)
+// Unet.py:74-75: nn.Conv2d(16, 1, kernel_size=1).  Three streaming kernels (exact fp32): a 1x1 convolution with a
+// single output channel is a dot product per pixel, its data gradient an outer product, its weight gradient a
+// column reduction -- none of them is a GEMM worth a tensor-core launch.
+template <int VEC>
+__global__ void conv1x1_c1_fwd_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx,
+                                      const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                                      int64_t ldy) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float s = bias ? __ldg(bias) : 0.f;
+  const float* xp = x + p * ldx;
+  if (VEC == 4) {
+    for (int c = 0; c < C; c += 4) {
+      const float4 t = ld4_stream(xp + c);
+      s += t.x * __ldg(w + c) + t.y * __ldg(w + c + 1) + t.z * __ldg(w + c + 2) + t.w * __ldg(w + c + 3);
+    }
+  } else {
+    for (int c = 0; c < C; ++c) s += xp[c] * __ldg(w + c);
+  }
+  y[p * ldy] = s;
+}
+__global__ void conv1x1_c1_dgrad_kernel(int64_t npix, int C, const float* __restrict__ dy, int64_t lddy,
+                                        const float* __restrict__ w, float* __restrict__ dx, int64_t lddx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * C) return;
-  const int64_t p = i / C, c = i - p * C;
-  const float g = (y[p * ldy + c] > 0.f) ? dy[p * lddy + c] : 0.f;
-  const float xh = (x[p * ldx + c] - mean[c]) * invstd[c];
-  const float inv_n = 1.f / (float)npix;
-  dx[p * lddx + c] = gamma[c] * invstd[c] * (g - dbeta[c] * inv_n - xh * dgamma[c] * inv_n);
+  const int64_t p = i / C;
+  const int c = (int)(i - p * C);
+  dx[p * lddx + c] = dy[p * lddy] * __ldg(w + c);
+}
+// part[block][C + 1]: sum_p x[p][c] * dy[p] for c < C, sum_p dy[p] at index C
+__global__ void __launch_bounds__(BN_THREADS)
+conv1x1_c1_wgrad_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy,
+                        int64_t lddy, double* __restrict__ part) {
+  extern __shared__ double sh[];                       // [lanes][C + 1]
+  const int lanes = BN_THREADS / C;
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  const int64_t per = (npix + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = (int64_t)blockIdx.x * per, p1 = p0 + per < npix ? p0 + per : npix;
+  double a = 0.0, b = 0.0;
+  if (pl < lanes) {
+    for (int64_t p = p0 + pl; p < p1; p += lanes) {
+      const float g = dy[p * lddy];
+      a += (double)x[p * ldx + c] * (double)g;
+      if (c == 0) b += (double)g;
+    }
+    sh[pl * (C + 1) + c] = a;
+    if (c == 0) sh[pl * (C + 1) + C] = b;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= C; i += BN_THREADS) {
+    double s2 = 0.0;
+    for (int l = 0; l < lanes; ++l) s2 += sh[l * (C + 1) + i];
+    part[(int64_t)blockIdx.x * (C + 1) + i] = s2;
+  }
+}
+__global__ void conv1x1_c1_wgrad_final_kernel(int C, int nblk, const double* __restrict__ part, float* __restrict__ dw,
+                                              float* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c > C) return;
+  double a = 0.0;
+  for (int i = lane; i < nblk; i += 32) a += part[(int64_t)i * (C + 1) + c];
+  a = warp_sum(a);
+  if (lane != 0) return;
+  if (c < C) dw[c] = (float)a;
+  else if (dbias) dbias[0] = (float)a;
 }
 
 // ------------------------------------------------------------------------------ pooling etc.
@@ -346,46 +480,92 @@ extern "C" int tm_convt2x2_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t C
   return 0;
 }
 
+namespace {
+inline int bn_blocks(int64_t npix) { return (int)(npix < BN_BLOCKS ? npix : BN_BLOCKS); }
+inline bool bn_vec4(int64_t C, std::initializer_list<std::pair<const void*, int64_t>> ts) {
+  if (C % 4 != 0 || C > 1024) return false;
+  for (auto& t : ts)
+    if (t.first && ((reinterpret_cast<uintptr_t>(t.first) % 16 != 0) || (t.second % 4 != 0))) return false;
+  return true;
+}
+}  // namespace
+
 extern "C" size_t tm_bn_ws(int64_t npix, int64_t C) {
-  return (size_t)cdiv(npix, BN_PIX_PER_BLOCK) * C * 2 * sizeof(double) + 256;
+  return (size_t)BN_BLOCKS * C * 2 * sizeof(double) + 256;
 }
 
+/* y_bf16 (optional): compact bf16 copy [npix][C] of y, written by the same pass */
 extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* gamma,
                                   const float* beta, float* running_mean, float* running_var,
                                   float momentum, float eps, float* y, int64_t ldy, float* save_mean,
-                                  float* save_invstd, void* ws, size_t ws_bytes, void* stream) {
-  TM_REQUIRE(npix > 0 && C > 0, "tm_bn_relu_forward: bad sizes");
+                                  float* save_invstd, void* y_bf16, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(npix > 0 && C > 0 && C <= 256, "tm_bn_relu_forward: bad sizes (C <= 256)");
   TM_REQUIRE(ws_bytes >= tm_bn_ws(npix, C), "tm_bn_relu_forward: workspace too small");
-  const int nblk = (int)cdiv(npix, BN_PIX_PER_BLOCK);
+  const int nblk = bn_blocks(npix);
   double* part = (double*)ws;
-  bn_stats_kernel<<<dim3(nblk, (unsigned)cdiv(C, 32)), dim3(32, 8), 0, ST>>>(npix, C, x, ldx, part);
+  const bool v4 = bn_vec4(C, {{x, ldx}, {y, ldy}});
+  const int groups = v4 ? (int)C / 4 : (int)C;
+  const size_t sh = (size_t)(BN_THREADS / groups) * C * 2 * sizeof(double);
+  if (v4) bn_stats_kernel<4, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, part);
+  else bn_stats_kernel<1, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, part);
   TM_TRY(check_launch("bn_stats"));
   bn_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(npix, C, nblk, part, running_mean, running_var,
                                                              momentum, eps, save_mean, save_invstd);
   TM_TRY(check_launch("bn_finalize"));
-  bn_relu_apply_kernel<<<blocks_for(npix * C), 256, 0, ST>>>(npix, C, x, ldx, gamma, beta, save_mean,
-                                                             save_invstd, y, ldy);
+  if (v4) bn_relu_apply_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, x, ldx, gamma, beta, save_mean, save_invstd, y, ldy, (__nv_bfloat16*)y_bf16);
+  else bn_relu_apply_kernel<1><<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, x, ldx, gamma, beta, save_mean, save_invstd, y, ldy, (__nv_bfloat16*)y_bf16);
   return check_launch("bn_relu_apply");
 }
 
+/* dx_bf16 (optional): compact bf16 copy [npix][C] of dx, written by the same pass */
 extern "C" int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* y,
                                    int64_t ldy, const float* dy, int64_t lddy, const float* gamma,
                                    const float* save_mean, const float* save_invstd, float* dx,
-                                   int64_t lddx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                                   int64_t lddx, float* dgamma, float* dbeta, void* dx_bf16, void* ws, size_t ws_bytes,
                                    void* stream) {
-  TM_REQUIRE(npix > 0 && C > 0, "tm_bn_relu_backward: bad sizes");
+  TM_REQUIRE(npix > 0 && C > 0 && C <= 256, "tm_bn_relu_backward: bad sizes (C <= 256)");
+  TM_REQUIRE(dx || dx_bf16, "tm_bn_relu_backward: neither dx nor dx_bf16 given");
   TM_REQUIRE(ws_bytes >= tm_bn_ws(npix, C), "tm_bn_relu_backward: workspace too small");
-  const int nblk = (int)cdiv(npix, BN_PIX_PER_BLOCK);
+  const int nblk = bn_blocks(npix);
   double* part = (double*)ws;
-  bn_bwd_stats_kernel<<<dim3(nblk, (unsigned)cdiv(C, 32)), dim3(32, 8), 0, ST>>>(npix, C, x, ldx, y, ldy, dy,
-                                                                                 lddy, save_mean, save_invstd,
-                                                                                 part);
+  const bool v4 = bn_vec4(C, {{x, ldx}, {y, ldy}, {dy, lddy}, {dx, lddx}});
+  const int groups = v4 ? (int)C / 4 : (int)C;
+  const size_t sh = (size_t)(BN_THREADS / groups) * C * 2 * sizeof(double);
+  if (v4) bn_stats_kernel<4, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, part);
+  else bn_stats_kernel<1, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, part);
   TM_TRY(check_launch("bn_bwd_stats"));
   bn_bwd_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(C, nblk, part, dgamma, dbeta);
   TM_TRY(check_launch("bn_bwd_finalize"));
-  bn_bwd_apply_kernel<<<blocks_for(npix * C), 256, 0, ST>>>(npix, C, x, ldx, y, ldy, dy, lddy, gamma, save_mean,
-                                                            save_invstd, dgamma, dbeta, dx, lddx);
+  if (v4) bn_bwd_apply_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, gamma, save_mean, save_invstd, dgamma, dbeta, dx, lddx, (__nv_bfloat16*)dx_bf16);
+  else bn_bwd_apply_kernel<1><<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, gamma, save_mean, save_invstd, dgamma, dbeta, dx, lddx, (__nv_bfloat16*)dx_bf16);
   return check_launch("bn_bwd_apply");
+}
+
+extern "C" int tm_conv1x1_c1_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* w,
+                                     const float* bias, float* y, int64_t ldy, void* stream) {
+  if (npix <= 0) return 0;
+  const bool v4 = (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x);
+  if (v4) conv1x1_c1_fwd_kernel<4><<<blocks_for(npix), 256, 0, ST>>>(npix, (int)C, x, ldx, w, bias, y, ldy);
+  else conv1x1_c1_fwd_kernel<1><<<blocks_for(npix), 256, 0, ST>>>(npix, (int)C, x, ldx, w, bias, y, ldy);
+  return check_launch("conv1x1_c1_fwd");
+}
+extern "C" int tm_conv1x1_c1_dgrad(int64_t npix, int64_t C, const float* dy, int64_t lddy, const float* w, float* dx,
+                                   int64_t lddx, void* stream) {
+  if (npix <= 0) return 0;
+  conv1x1_c1_dgrad_kernel<<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, dy, lddy, w, dx, lddx);
+  return check_launch("conv1x1_c1_dgrad");
+}
+extern "C" size_t tm_conv1x1_c1_wgrad_ws(int64_t C) { return (size_t)BN_BLOCKS * (C + 1) * sizeof(double) + 256; }
+extern "C" int tm_conv1x1_c1_wgrad(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* dy, int64_t lddy,
+                                   float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(npix > 0 && C > 0 && C <= BN_THREADS, "tm_conv1x1_c1_wgrad: bad sizes");
+  TM_REQUIRE(ws_bytes >= tm_conv1x1_c1_wgrad_ws(C), "tm_conv1x1_c1_wgrad: workspace too small");
+  const int nblk = bn_blocks(npix);
+  const size_t sh = (size_t)(BN_THREADS / C) * (C + 1) * sizeof(double);
+  conv1x1_c1_wgrad_kernel<<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, dy, lddy, (double*)ws);
+  TM_TRY(check_launch("conv1x1_c1_wgrad"));
+  conv1x1_c1_wgrad_final_kernel<<<(unsigned)cdiv((C + 1) * 32, 128), 128, 0, ST>>>((int)C, nblk, (const double*)ws, dw, dbias);
+  return check_launch("conv1x1_c1_wgrad_final");
 }
 
 extern "C" int tm_pool2x2_forward(int64_t B, int64_t H, int64_t W, int64_t C, int mode, const float* x,

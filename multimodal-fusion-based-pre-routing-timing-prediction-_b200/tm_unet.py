@@ -137,24 +137,25 @@ def _pack(w, need_bwd=True):
     return wf, wb
 
 
-def _bn_relu_fwd(ws, x, ldx, npix, C, bn, y, ldy, update_stats):
+def _bn_relu_fwd(ws, x, ldx, npix, C, bn, y, ldy, update_stats, yb=None):
     dev = x.device
     mean, invstd = _empty(C, dev=dev), _empty(C, dev=dev)
     nb = tm_lib.ws_bytes("tm_bn_ws", npix, C)
     rm = bn.running_mean if update_stats else None
     rv = bn.running_var if update_stats else None
     call("tm_bn_relu_forward", npix, C, x, ldx, bn.weight.detach(), bn.bias.detach(), rm, rv,
-         float(bn.momentum), float(bn.eps), y, ldy, mean, invstd, ws.get(nb), nb, stream())
+         float(bn.momentum), float(bn.eps), y, ldy, mean, invstd, yb, ws.get(nb), nb, stream())
     if update_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return mean, invstd
 
 
-def _bn_relu_bwd(ws, x, ldx, y, ldy, dy, lddy, npix, C, gamma, mean, invstd, dx, lddx):
+def _bn_relu_bwd(ws, x, ldx, y, ldy, dy, lddy, npix, C, gamma, mean, invstd, dx, lddx, dxb=None):
+    """dx (fp32, may be None) and / or dxb (compact bf16) receive the gradient w.r.t. the BN input."""
     dev = x.device
     dg, db = _empty(C, dev=dev), _empty(C, dev=dev)
     nb = tm_lib.ws_bytes("tm_bn_ws", npix, C)
-    call("tm_bn_relu_backward", npix, C, x, ldx, y, ldy, dy, lddy, gamma, mean, invstd, dx, lddx, dg, db,
+    call("tm_bn_relu_backward", npix, C, x, ldx, y, ldy, dy, lddy, gamma, mean, invstd, dx, lddx, dg, db, dxb,
          ws.get(nb), nb, stream())
     return dg, db
 
@@ -175,8 +176,8 @@ def _double_conv_fwd(ws, st, name, mods, x, ldx, B, H, W, cin, cout, out, ldo, u
         wq1, wd1 = _pack_bf16(conv1.weight, W, need_bwd and cin % 16 == 0)
         wq2, wd2 = _pack_bf16(conv2.weight, W, need_bwd)
         _conv_tma(xb, B, H, W, _cpad(cin), cmid, wq1, r1, cmid)
-        m1, i1 = _bn_relu_fwd(ws, r1, cmid, npix, cmid, bn1, a1, cmid, update_stats)
-        a1b = _to_bf16(a1, cmid, npix, cmid)
+        a1b = torch.empty(npix, cmid, dtype=torch.bfloat16, device=dev)
+        m1, i1 = _bn_relu_fwd(ws, r1, cmid, npix, cmid, bn1, a1, cmid, update_stats, yb=a1b)
         _conv_tma(a1b, B, H, W, cmid, cout, wq2, r2, cout)
         m2, i2 = _bn_relu_fwd(ws, r2, cout, npix, cout, bn2, out, ldo, update_stats)
         st[name] = dict(tma=True, xb=xb if need_bwd else None, a1b=a1b if need_bwd else None, wd1=wd1, wd2=wd2,
@@ -199,22 +200,26 @@ def _double_conv_bwd(ws, s, dout, lddo, grads, prefix, dx, lddx):
     B, H, W, cin, cmid, cout = s["B"], s["H"], s["W"], s["cin"], s["cmid"], s["cout"]
     npix = B * H * W
     dev = dout.device
-    dr2 = _empty(npix, cout, dev=dev)
-    dg2, db2 = _bn_relu_bwd(ws, s["r2"], cout, s["out"], s["ldo"], dout, lddo, npix, cout, s["g2"], s["m2"],
-                            s["i2"], dr2, cout)
     da1 = _empty(npix, cmid, dev=dev)
-    dr1 = _empty(npix, cmid, dev=dev)
     if s.get("tma"):
-        dr2b = _to_bf16(dr2, cout, npix, cout)                 # shared by the weight and the data gradient
+        # the batch-norm backward emits its result directly as the bf16 operand shared by the weight and the
+        # data gradient; the fp32 copy is never needed
+        dr2b = torch.empty(npix, cout, dtype=torch.bfloat16, device=dev)
+        dg2, db2 = _bn_relu_bwd(ws, s["r2"], cout, s["out"], s["ldo"], dout, lddo, npix, cout, s["g2"], s["m2"],
+                                s["i2"], None, 0, dxb=dr2b)
         dw2 = _wgrad_tma(ws, s["a1b"], dr2b, B, H, W, cmid, cout)
         _conv_tma(dr2b, B, H, W, cout, cmid, s["wd2"], da1, cmid)
+        dr1b = torch.empty(npix, cmid, dtype=torch.bfloat16, device=dev)
         dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, s["a1"], cmid, da1, cmid, npix, cmid, s["g1"], s["m1"], s["i1"],
-                                dr1, cmid)
-        dr1b = _to_bf16(dr1, cmid, npix, cmid)
+                                None, 0, dxb=dr1b)
         dw1 = _wgrad_tma(ws, s["xb"], dr1b, B, H, W, cin, cmid)
         if dx is not None:
             _conv_tma(dr1b, B, H, W, cmid, cin, s["wd1"], dx, lddx)
     else:
+        dr2 = _empty(npix, cout, dev=dev)
+        dg2, db2 = _bn_relu_bwd(ws, s["r2"], cout, s["out"], s["ldo"], dout, lddo, npix, cout, s["g2"], s["m2"],
+                                s["i2"], dr2, cout)
+        dr1 = _empty(npix, cmid, dev=dev)
         dw2, _ = _conv_wgrad(ws, s["a1"], cmid, dr2, cout, B, H, W, cmid, cout, 3, False)
         _conv(dr2, cout, B, H, W, cout, cmid, 3, s["wb2"], None, da1, cmid)
         dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, s["a1"], cmid, da1, cmid, npix, cmid, s["g1"], s["m1"], s["i1"],
@@ -288,13 +293,13 @@ def unet_forward(net, x, need_bwd=True, update_stats=True):
         y, ldy, cy = out, chans[i], chans[i]
     # OutConv: 1x1 conv (bias) -> pool -> ReLU (Unet.py:74-78)
     oc = net.outc.conv[0]
-    wfo, wbo = _pack(oc.weight, need_bwd)
+    wo = oc.weight.detach().float().reshape(-1).contiguous()         # (1,16,1,1) -> [16]
     o_raw = _empty(B * H * W, 1, dev=dev)
-    _conv(y, ldy, B, H, W, 16, 1, 1, wfo, oc.bias.detach(), o_raw, 1)
+    call("tm_conv1x1_c1_forward", B * H * W, 16, y, ldy, wo, oc.bias.detach(), o_raw, 1, stream())
     out = _empty(B, 1, H // 2, W // 2, dev=dev)
     oidx = torch.empty(B * (H // 2) * (W // 2), dtype=torch.uint8, device=dev) if mode == 0 else None
     call("tm_pool2x2_forward", B, H, W, 1, mode, o_raw, 1, out, 1, oidx, RELU, stream())
-    st.update(y3=y, wbo=wbo, out=out, oidx=oidx, cat=cat, chans=chans, Hs=Hs, Ws=Ws_)
+    st.update(y3=y, ld3=ldy, wo=wo, out=out, oidx=oidx, cat=cat, chans=chans, Hs=Hs, Ws=Ws_)
     return out, st
 
 
@@ -308,10 +313,12 @@ def unet_backward(net, st, gout):
     grads = {}
     d_oraw = _empty(B * H * W, 1, dev=dev)
     call("tm_pool2x2_backward", B, H, W, 1, mode, gout, 1, st["out"], 1, st["oidx"], d_oraw, 1, RELU, stream())
-    dw, db = _conv_wgrad(ws, st["y3"], 16, d_oraw, 1, B, H, W, 16, 1, 1, True)
+    dw, db = _empty(1, 16, 1, 1, dev=dev), _empty(1, dev=dev)
+    nb = tm_lib.ws_bytes("tm_conv1x1_c1_wgrad_ws", 16)
+    call("tm_conv1x1_c1_wgrad", B * H * W, 16, st["y3"], st["ld3"], d_oraw, 1, dw, db, ws.get(nb), nb, stream())
     grads["outc.conv.0.weight"], grads["outc.conv.0.bias"] = dw, db
     dy = _empty(B * H * W, 16, dev=dev)
-    _conv(d_oraw, 1, B, H, W, 1, 16, 1, st["wbo"], None, dy, 16)
+    call("tm_conv1x1_c1_dgrad", B * H * W, 16, d_oraw, 1, st["wo"], dy, 16, stream())
     lddy = 16
     dskip = [None, None, None]
     names = ["up1", "up2", "up3"]
