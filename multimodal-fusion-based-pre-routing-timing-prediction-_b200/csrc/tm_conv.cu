@@ -363,6 +363,43 @@ __global__ void pool_bwd_kernel(int64_t B, int64_t H, int64_t W, int64_t C, int 
   dx[((b * H + yi) * W + xi) * lddx + c] = g;
 }
 
+// 128-bit variant: one thread per (output pixel, 4 channels) writes the 2x2 input window (H, W even, C % 4 == 0)
+__global__ void pool_bwd_vec_kernel(int B, int H, int W, int C, int mode, const float* __restrict__ dy, int64_t lddy,
+                                    const float* __restrict__ y, int64_t ldy, const uint8_t* __restrict__ idx,
+                                    float* __restrict__ dx, int64_t lddx, int relu) {
+  const int Ho = H / 2, Wo = W / 2, cg = C / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * Ho * Wo * cg) return;
+  const int c = (int)(i % cg) * 4;
+  const int64_t o = i / cg;                              // output pixel (b, yo, xo)
+  const int xo = (int)(o % Wo);
+  const int64_t t = o / Wo;
+  const int yo = (int)(t % Ho), b = (int)(t / Ho);
+  float4 g = ld4_stream(dy + o * lddy + c);
+  if (relu) {
+    const float4 yy = ld4(y + o * ldy + c);
+    if (!(yy.x > 0.f)) g.x = 0.f;
+    if (!(yy.y > 0.f)) g.y = 0.f;
+    if (!(yy.z > 0.f)) g.z = 0.f;
+    if (!(yy.w > 0.f)) g.w = 0.f;
+  }
+  uint32_t am = 0;
+  if (mode == 0) am = *reinterpret_cast<const uint32_t*>(idx + o * C + c);
+  else { g.x *= 0.25f; g.y *= 0.25f; g.z *= 0.25f; g.w *= 0.25f; }
+  float* base = dx + (((int64_t)b * H + 2 * yo) * W + 2 * xo) * lddx + c;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 v = g;
+    if (mode == 0) {
+      if ((am & 0xFF) != (uint32_t)q) v.x = 0.f;
+      if (((am >> 8) & 0xFF) != (uint32_t)q) v.y = 0.f;
+      if (((am >> 16) & 0xFF) != (uint32_t)q) v.z = 0.f;
+      if (((am >> 24) & 0xFF) != (uint32_t)q) v.w = 0.f;
+    }
+    st4(base + ((int64_t)(q >> 1) * W + (q & 1)) * lddx, v);
+  }
+}
+
 __global__ void lrelu_fwd_kernel(int64_t n, const float* __restrict__ x, float slope, float* __restrict__ y) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const float v = x[i]; y[i] = v > 0.f ? v : v * slope; }
@@ -583,8 +620,15 @@ extern "C" int tm_pool2x2_backward(int64_t B, int64_t H, int64_t W, int64_t C, i
   TM_REQUIRE(mode == 1 || idx, "tm_pool2x2_backward: max pooling needs idx");
   const int64_t n = B * H * W * C;
   if (n <= 0) return 0;
-  pool_bwd_kernel<<<blocks_for(n), 256, 0, ST>>>(B, H, W, C, mode, dy, lddy, y, ldy, idx, dx, lddx,
-                                                 (flags & TM_EPI_RELU) != 0);
+  const bool relu = (flags & TM_EPI_RELU) != 0;
+  if (C % 4 == 0 && H % 2 == 0 && W % 2 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && aligned16(dy) && aligned16(dx) &&
+      (!relu || (ldy % 4 == 0 && aligned16(y))) && (mode != 0 || reinterpret_cast<uintptr_t>(idx) % 4 == 0) &&
+      B * H * W < (1ll << 31)) {
+    pool_bwd_vec_kernel<<<blocks_for(n / 16), 256, 0, ST>>>((int)B, (int)H, (int)W, (int)C, mode, dy, lddy, y, ldy, idx,
+                                                          dx, lddx, relu);
+    return check_launch("pool_bwd_vec");
+  }
+  pool_bwd_kernel<<<blocks_for(n), 256, 0, ST>>>(B, H, W, C, mode, dy, lddy, y, ldy, idx, dx, lddx, relu);
   return check_launch("pool_bwd");
 }
 extern "C" int tm_leaky_relu_forward(int64_t n, const float* x, float slope, float* y, void* stream) {

@@ -439,7 +439,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
                                     float* __restrict__ dw) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)9 * Cout * Cin) return;
-  const int tap = (int)(i % 9), ci = (int)((i / 9) % Cin), co = (int)(i / ((int64_t)9 * Cin));
+  // ci fastest: neighbouring threads read neighbouring partials
+  const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), tap = (int)(i / ((int64_t)Cin * Cout));
   const int r = tap / 3, sx = tap % 3;
   const int64_t ldn = (int64_t)P * CinP, per_tap = (int64_t)P * Cout * ldn;
   float s = 0.f;
@@ -450,7 +451,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
         if (pi < 0 || pi >= P) continue;
         s += part[((int64_t)z * 9 + r * 3 + S + 1) * per_tap + ((int64_t)po * Cout + co) * ldn + (int64_t)pi * CinP + ci];
       }
-  dw[i] = s;
+  dw[((int64_t)co * Cin + ci) * 9 + tap] = s;
 }
 
 // fp32 rows (stride ld) -> compact bf16 rows of Cp >= C channels (zero padded); 8 channels per thread
