@@ -19,6 +19,7 @@
 //       a fixed order (deterministic).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "tm_tc.cuh"
 
@@ -274,6 +275,158 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (valid) {
+          float* o = yp + (int64_t)po * a.ldy + co;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) st4(o + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  if (!ok) {
+    abort_s = 1;
+    if (a.err) atomicExch(a.err, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fprop / dgrad, row-reuse variant for layers whose whole packed weight (9 taps x N x 64 channels, N <= 64)
+// stays resident in shared memory and whose rows are >= 128 packed pixels wide.
+// A tile is 128 packed pixels x ROWS image rows.  Every input row y0-1 .. y0+ROWS is fetched ONCE per horizontal
+// shift (3 boxes) and feeds the three output rows it touches (kernel rows r = 0..2 -> accumulators j = iy+1-r):
+// shared-memory fill per output row drops from 9 activation boxes + 9 weight boxes to 3 (ROWS+2)/ROWS boxes.
+// ------------------------------------------------------------------------------------------------
+constexpr int V2_ROWS = 4;
+
+template <int ROWS>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int N = a.N;
+  const uint32_t w_tap = (uint32_t)N * 128u;                       // one tap: N rows x 64 channels bf16
+  uint8_t* ring = wsm + 9 * (size_t)w_tap;                          // 9 * N * 128 is a multiple of 1024 (N % 16 == 0 -> check on host)
+  __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full[2], acc_empty[2], w_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int abort_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = a.stages;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * ROWS * N)) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+    mbar_init(&w_full, 1);
+    abort_s = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_map(&tmx);
+    prefetch_map(&tmw);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  volatile int* abortp = &abort_s;
+  bool ok = true;
+  const int64_t G = gridDim.x;
+  // tiles: (x block of 128 packed pixels, group of ROWS image rows, image)
+  const int tiles_x = a.g.W / 128, tiles_y = a.g.H / ROWS;
+  const int64_t ntiles = (int64_t)tiles_x * tiles_y * a.g.B;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, 9u * w_tap);
+      for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(wsm + (size_t)t * w_tap), &tmw, 0, t * N, &w_full);
+      uint32_t s = 0, ph = 0;
+      for (int64_t t = blockIdx.x; t < ntiles && ok; t += G) {
+        const int x0 = (int)(t % tiles_x) * 128, y0 = (int)((t / tiles_x) % tiles_y) * ROWS;
+        const int b = (int)(t / ((int64_t)tiles_x * tiles_y));
+        for (int iy = -1; iy <= ROWS && ok; ++iy) {
+          for (int S = 0; S < 3; ++S) {
+            ok = mbar_wait(&empty_bar[s], ph ^ 1u, abortp);
+            if (!ok) break;
+            mbar_expect_tx(&full_bar[s], a.a_bytes);
+            tma_load_4d(smem_u32(ring + (size_t)s * a.a_bytes), &tmx, 0, x0 + S - 1, y0 + iy, b, &full_bar[s]);
+            if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(N, false, false);
+      ok = mbar_wait(&w_full, 0, abortp);
+      uint32_t s = 0, ph = 0;
+      int li = 0;
+      for (int64_t t = blockIdx.x; t < ntiles && ok; t += G, ++li) {
+        const int buf = li & 1;
+        ok = mbar_wait(&acc_empty[buf], (((uint32_t)(li >> 1)) & 1u) ^ 1u, abortp);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * ROWS * N);
+        for (int iy = -1; iy <= ROWS && ok; ++iy) {
+          for (int S = 0; S < 3; ++S) {
+            ok = mbar_wait(&full_bar[s], ph, abortp);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t abase = smem_u32(ring + (size_t)s * a.a_bytes);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const int j = iy + 1 - r;                    // output row fed by input row iy through kernel row r
+              if (j < 0 || j >= ROWS) continue;
+              const uint32_t wbase = smem_u32(wsm + (size_t)(r * 3 + S) * w_tap);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma(acc0 + (uint32_t)(j * N), make_desc_sw(abase + k * 32, 16, 1024, 2), make_desc_sw(wbase + k * 32, 16, 1024, 2),
+                     idesc, (r == 0 && S == 0 && k == 0) ? 0u : 1u);
+            }
+            umma_commit(&empty_bar[s]);
+            if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
+          }
+        }
+        if (!ok) break;
+        umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int li = 0;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += G, ++li) {
+      const int buf = li & 1;
+      ok = mbar_wait(&acc_full[buf], ((uint32_t)(li >> 1)) & 1u, abortp);
+      if (!ok) break;
+      tc_fence_after();
+      const int x0 = (int)(t % tiles_x) * 128, y0 = (int)((t / tiles_x) % tiles_y) * ROWS;
+      const int b = (int)(t / ((int64_t)tiles_x * tiles_y));
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ROWS * N);
+      for (int j = 0; j < ROWS; ++j) {
+        float* yp = a.y + (((int64_t)b * a.g.H + (y0 + j)) * a.g.W + (x0 + m)) * a.P * a.ldy;
+        for (int c = 0; c < N; c += 16) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)(j * N + c), v);
+          const int po = c / a.cpx, co = c - po * a.cpx;
+          if (a.flags & TM_EPI_BIAS) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + co + i);
+          }
+          if (a.flags & TM_EPI_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
           float* o = yp + (int64_t)po * a.ldy + co;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) st4(o + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
@@ -571,11 +724,31 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   a.flags = (flags & TM_EPI_RELU) | (bias ? TM_EPI_BIAS : 0);
   a.err = err;
   CUtensorMap tmx, tmw;
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool rows_on = !(getenv("TM_CONV_ROWS") && atoi(getenv("TM_CONV_ROWS")) == 0);
+  if (rows_on && Cp == 64 && Np <= 64 && Wp >= 128 && H % V2_ROWS == 0) {
+    // whole packed weight resident in shared memory, every input row fetched once per horizontal shift
+    const size_t wbytes = (size_t)9 * Np * 128;
+    int ns2 = (int)((CONV_SMEM_BUDGET - wbytes) / a.a_bytes);
+    a.stages = ns2 > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns2;
+    TM_TRY(encode_act(&tmx, xb, Cp, Wp, H, B, 64, 128, 1, 1));
+    TM_TRY(encode_2d(&tmw, wq, Cp, 9 * Np, 64, (int)Np));
+    const int64_t nt = (Wp / 128) * (H / V2_ROWS) * B;
+    const int grid2 = (int)(nt < sm_count() ? nt : sm_count());
+    const size_t smem2 = wbytes + (size_t)a.stages * a.a_bytes + 1024;
+    static bool optin2 = false;
+    if (!optin2) {
+      TM_CUDA(cudaFuncSetAttribute(conv3x3_tma_rows_kernel<V2_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)CONV_SMEM_BUDGET + 1024));
+      optin2 = true;
+    }
+    conv3x3_tma_rows_kernel<V2_ROWS><<<grid2, CONV_THREADS, smem2, st>>>(tmx, tmw, a);
+    return check_launch("conv3x3_tma_rows");
+  }
   TM_TRY(encode_act(&tmx, xb, Cp, Wp, H, B, CK, a.g.TW, a.g.TH, a.g.TB));
   TM_TRY(encode_2d(&tmw, wq, Cp, 9 * Np, CK, (int)Np));
   const size_t smem = (size_t)a.stages * a.stage_bytes + 1024;
   const int grid = (int)(a.g.ntiles < sm_count() ? a.g.ntiles : sm_count());
-  cudaStream_t st = (cudaStream_t)stream;
 #define TM_LAUNCH_CONV(CK_)                                                                                   \
   do {                                                                                                        \
     static bool optin = false;                                                                                \

@@ -12,7 +12,9 @@ DEV = "cuda"
 
 SHAPES = [(1, 16, 16, 16, 16), (2, 8, 8, 32, 32), (3, 32, 32, 64, 64), (1, 16, 32, 128, 64), (2, 128, 128, 16, 32),
           (1, 64, 256, 32, 16), (5, 4, 4, 128, 128), (1, 2, 2, 16, 16), (2, 16, 16, 3, 16), (1, 256, 256, 16, 16),
-          (2, 32, 64, 64, 128), (33, 2, 4, 32, 64)]
+          (2, 32, 64, 64, 128), (33, 2, 4, 32, 64),
+          # rows wide enough for the row-reuse kernel (>= 128 packed pixels, resident weights)
+          (1, 8, 512, 16, 16), (2, 4, 128, 64, 64), (1, 16, 256, 32, 32), (3, 8, 256, 64, 32), (1, 12 // 3 * 4, 1024, 3, 16)]
 
 
 @pytest.fixture(scope="module")
