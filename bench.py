@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", help="tm_synth.CONFIGS key (c2 = the headline workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config-3 / config-4 device timings")
     ap.add_argument("--no-graph", action="store_true", help="time the resident loop eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit "
@@ -359,23 +360,54 @@ def main():
                              "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": bytes_f,
                              "ms": t_prop}
-        # the largest dense contraction of the step (second layer of the hoisted net-pin MLP) on the tcgen05 path
+        # tensor-pipe family: the TMA-fed tcgen05 3x3 convolution of the U-Net's bf16 mode on its tensor-bound layer
+        # (down3.conv2 of BASELINE config 4: 128 -> 128 channels, batch 32 of 64x64 maps; SURVEY 8a layer table)
+        pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        tpeak = float(json.load(open(pj))["bf16_tflops"]) if os.path.isfile(pj) else 1590.0
+        cb, ch, cw, cc = 32, 64, 64, 128
+        npx = cb * ch * cw
+        xb16 = torch.randn(npx, cc, device=dev).bfloat16()
+        w16 = torch.randn(cc, cc, 3, 3, device=dev) * 0.05
+        pk = tm_lib.ws_bytes("tm_conv3x3_bf16_pack", cw, cc, cc)
+        wq16 = torch.empty(9, pk * cc, pk * cc, dtype=torch.bfloat16, device=dev)
+        tm_lib.call("tm_conv3x3_pack_bf16", cc, cc, w16, wq16, pk, cc, 0, tm_lib.stream())
+        y16 = torch.empty(npx, cc, device=dev)
+        t_conv = timed(lambda: tm_lib.call("tm_conv3x3_bf16", cb, ch, cw, cc, cc, pk, xb16, wq16, None, y16, cc, 0,
+                                           tm_lib.err_flag(dev), tm_lib.stream()), reps=20)
+        cflop = 2.0 * 9 * cc * cc * npx
+        extra["roofline_tensor"] = {"kernel": "conv3x3_tma_kernel<64> (bf16 operands by TMA, fp32 accumulate in TMEM; 128->128 channels, "
+                                              "32 x 64x64 maps = U-Net down3.conv2 of config 4)",
+                                    "bound": "tensor", "achieved": cflop / (t_conv * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                    "frac": cflop / (t_conv * 1e-3) / 1e12 / tpeak, "ms": t_conv, "algorithmic_flops": cflop,
+                                    "hbm_GBps": npx * (2 * cc + 4 * cc) / (t_conv * 1e-3) / 1e9,
+                                    "peak_source": "measured burst (MEASURED_PEAKS.json)" if os.path.isfile(pj) else "fallback"}
+        del xb16, w16, wq16, y16
+        # the largest dense contraction of the design step itself (second layer of the hoisted net-pin MLP, 3xTF32)
         Mg, Ng, Kg = int(sched.net_class.numel()), 128, 256
         Ag = torch.randn(Mg, Kg, device=dev); Wg = torch.randn(Ng, Kg, device=dev); Cg = torch.empty(Mg, Ng, device=dev)
         t_gemm = timed(lambda: tm_ops.gemm_nn(Mg, Ng, Kg, Ag, Kg, Wg, Kg, Cg, Ng, b_is_nk=True))
-        pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        tpeak = float(json.load(open(pj))["bf16_tflops"]) if os.path.isfile(pj) else 1639.0
         tf = 2.0 * Mg * Ng * Kg / (t_gemm * 1e-3) / 1e12
-        extra["roofline_tensor"] = {"kernel": f"tf_gemm_kernel 3xTF32 (M={Mg}, N={Ng}, K={Kg}; 3 tcgen05 MMAs per product)",
-                                    "bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
-                                    "frac": tf / tpeak, "ms": t_gemm, "algorithmic_flops": 2.0 * Mg * Ng * Kg,
-                                    "hbm_GBps": (Mg * Kg + Mg * Ng) * 4 / (t_gemm * 1e-3) / 1e9,
-                                    "note": "operands are fp32 in HBM: this GEMM is bounded by HBM (353 MB), not the tensor pipe"}
+        extra["hoisted_gemm"] = {"kernel": f"tf_gemm_kernel 3xTF32 (M={Mg}, N={Ng}, K={Kg}; 3 tcgen05 MMAs per product)",
+                                 "TFLOPs": tf, "ms": t_gemm, "hbm_GBps": (Mg * Kg + Mg * Ng) * 4 / (t_gemm * 1e-3) / 1e9,
+                                 "note": "operands are fp32 in HBM: this GEMM is bounded by HBM (353 MB), not the tensor pipe"}
         del Ag, Wg, Cg
         extra["kernels_ms"] = {"gnn_propagate_fwd": t_prop, "gnn_propagate_bwd": t_bwd,
                                "gnn_fwd_total(with hoisted MLPs)": t_gnn_f, "gnn_bwd_total(with weight grads)": t_gnn_b,
                                "unet_fwd": t_unet_f, "unet_bwd": t_unet_b,
                                "gnn_bwd_GBps": sched.algorithmic_bytes_bwd() / (t_bwd * 1e-3) / 1e9}
+        if world == 1 and not args.no_configs and args.config == "c2":
+            # BASELINE configs 3 (GNN only, ~1M pins) and 4 (U-Net alone, 32 x 512x512, bf16): device timings next to
+            # the headline (profiles/bench_configs.py; parity for both lives in tests/test_gpu_configs.py)
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("bench_configs", os.path.join(ROOT, "profiles", "bench_configs.py"))
+            bc = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(bc)
+            del H, saved, S, G, GA, GH, GZ
+            torch.cuda.empty_cache()
+            try:
+                extra["other_configs"] = {"config3": bc.config3(), "config4": bc.config4()[0]}
+            except Exception as e:                                   # noqa: BLE001  (report, do not lose the headline line)
+                extra["other_configs"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             total, gnn_only, n_sample = cpu_step(CPU_SAMPLE_SCALE, threads=threads)

@@ -117,6 +117,23 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int n, bool a_mn, bool b_mn) {
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// Store one 16-column chunk of a 32-row accumulator slab.  After tcgen05.ld lane = row; writing from that layout
+// would touch 32 different lines with 16 bytes each per instruction.  The chunk is transposed through a padded
+// per-warp scratch instead, so that four neighbouring lanes write the 64 contiguous bytes of one row (8 rows per
+// instruction, only full 32-byte sectors).  rowp[pass]: output row pass * 8 + lane / 4 (nullptr = outside the batch).
+__device__ __forceinline__ void store_chunk16(float* scr, int lane, const float (&v)[16], float* const (&rowp)[4], int64_t coff) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) scr[lane * 17 + i] = v[i];
+  __syncwarp();
+  const int c4 = (lane & 3) * 4;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const float* sp = scr + (pass * 8 + (lane >> 2)) * 17 + c4;
+    if (rowp[pass]) st4(rowp[pass] + coff + c4, make_float4(sp[0], sp[1], sp[2], sp[3]));
+  }
+  __syncwarp();
+}
+
 struct Geom {
   int B, H, W, TW, TH, TB, tiles_x, tiles_y;
   int64_t ntiles;
@@ -166,6 +183,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full[2], acc_empty[2];
+  __shared__ float epi_scr[4][32 * 17];
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -249,8 +267,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   } else {
     // ======================= epilogue =======================
     const int q = warp & 3;                               // TMEM lane quarter this warp may read
-    const int m = q * 32 + lane;
-    const int tw = m % a.g.TW, th = (m / a.g.TW) % a.g.TH, tb = m / (a.g.TW * a.g.TH);
+    float* scr = epi_scr[q];
     int li = 0;
     for (int64_t t = blockIdx.x; t < a.g.ntiles && ok; t += G, ++li) {
       const int buf = li & 1;
@@ -259,8 +276,15 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       tc_fence_after();
       int x0, y0, b0;
       a.g.origin(t, x0, y0, b0);
-      const bool valid = b0 + tb < a.g.B;
-      float* yp = a.y + (((int64_t)(b0 + tb) * a.g.H + (y0 + th)) * a.g.W + (x0 + tw)) * a.P * a.ldy;
+      float* rowp[4];
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {                // the rows this lane stores after the transposition
+        const int m = q * 32 + pass * 8 + (lane >> 2);
+        const int tw = m % a.g.TW, th = (m / a.g.TW) % a.g.TH, tb = m / (a.g.TW * a.g.TH);
+        rowp[pass] = b0 + tb < a.g.B
+                         ? a.y + (((int64_t)(b0 + tb) * a.g.H + (y0 + th)) * a.g.W + (x0 + tw)) * a.P * a.ldy
+                         : nullptr;
+      }
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N);
       for (int c = 0; c < N; c += 16) {
         float v[16];
@@ -274,11 +298,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (valid) {
-          float* o = yp + (int64_t)po * a.ldy + co;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) st4(o + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-        }
+        store_chunk16(scr, lane, v, rowp, (int64_t)po * a.ldy + co);
       }
       tc_fence_before();
       __syncwarp();
@@ -315,6 +335,7 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
   const uint32_t w_tap = (uint32_t)N * 128u;                       // one tap: N rows x 64 channels bf16
   uint8_t* ring = wsm + 9 * (size_t)w_tap;                          // 9 * N * 128 is a multiple of 1024 (N % 16 == 0 -> check on host)
   __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full[2], acc_empty[2], w_full;
+  __shared__ float epi_scr[4][32 * 17];
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -403,7 +424,7 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int m = q * 32 + lane;
+    float* scr = epi_scr[q];
     int li = 0;
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += G, ++li) {
       const int buf = li & 1;
@@ -414,7 +435,10 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
       const int b = (int)(t / ((int64_t)tiles_x * tiles_y));
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ROWS * N);
       for (int j = 0; j < ROWS; ++j) {
-        float* yp = a.y + (((int64_t)b * a.g.H + (y0 + j)) * a.g.W + (x0 + m)) * a.P * a.ldy;
+        float* rowp[4];
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass)
+          rowp[pass] = a.y + (((int64_t)b * a.g.H + (y0 + j)) * a.g.W + (x0 + q * 32 + pass * 8 + (lane >> 2))) * a.P * a.ldy;
         for (int c = 0; c < N; c += 16) {
           float v[16];
           tmem_ld16(trow + (uint32_t)(j * N + c), v);
@@ -427,9 +451,7 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          float* o = yp + (int64_t)po * a.ldy + co;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) st4(o + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          store_chunk16(scr, lane, v, rowp, (int64_t)po * a.ldy + co);
         }
       }
       tc_fence_before();
