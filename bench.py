@@ -21,6 +21,7 @@ excluded).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import importlib
+import importlib.util
 import json
 import os
 import subprocess
@@ -398,7 +399,6 @@ def main():
         if world == 1 and not args.no_configs and args.config == "c2":
             # BASELINE configs 3 (GNN only, ~1M pins) and 4 (U-Net alone, 32 x 512x512, bf16): device timings next to
             # the headline (profiles/bench_configs.py; parity for both lives in tests/test_gpu_configs.py)
-            import importlib.util
             spec = importlib.util.spec_from_file_location("bench_configs", os.path.join(ROOT, "profiles", "bench_configs.py"))
             bc = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(bc)

@@ -110,7 +110,7 @@ def config4(batch=32, size=512, modes=("bf16",)):
 
             def fwd():
                 st["o"], st["s"] = tm_unet.unet_forward(net, x, need_bwd=True, update_stats=False)
-            t_f = timed(fwd, reps=3, warm=2)
+            t_f = timed(fwd, reps=3, warm=3)
             g = torch.ones_like(st["o"])
 
             def both():
