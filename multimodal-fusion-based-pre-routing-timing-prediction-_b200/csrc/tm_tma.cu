@@ -368,7 +368,10 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(&w_full, 9u * w_tap);
-      for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(wsm + (size_t)t * w_tap), &tmw, 0, t * N, &w_full);
+      // resident order: for every horizontal shift S the kernel rows r = 2, 1, 0 are stacked, so that the taps that
+      // read the same input row write NEIGHBOURING accumulators and fuse into one MMA of up to 3N columns
+      for (int t = 0; t < 9; ++t)
+        tma_load_2d(smem_u32(wsm + (size_t)((t % 3) * 3 + (2 - t / 3)) * w_tap), &tmw, 0, t * N, &w_full);
       uint32_t s = 0, ph = 0;
       for (int64_t t = blockIdx.x; t < ntiles && ok; t += G) {
         const int x0 = (int)(t % tiles_x) * 128, y0 = (int)((t / tiles_x) % tiles_y) * ROWS;
@@ -377,8 +380,11 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
           for (int S = 0; S < 3; ++S) {
             ok = mbar_wait(&empty_bar[s], ph ^ 1u, abortp);
             if (!ok) break;
+            if (a.flags & 0x400) { mbar_arrive(&full_bar[s]); }
+            else {
             mbar_expect_tx(&full_bar[s], a.a_bytes);
             tma_load_4d(smem_u32(ring + (size_t)s * a.a_bytes), &tmx, 0, x0 + S - 1, y0 + iy, b, &full_bar[s]);
+            }
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
           }
         }
@@ -403,15 +409,29 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
             if (!ok) break;
             tc_fence_after();
             const uint32_t abase = smem_u32(ring + (size_t)s * a.a_bytes);
+            // input row iy feeds output rows j = iy + 1 - r through kernel row r; valid r: 0 <= j < ROWS
+            const int r_lo = iy + 1 - (ROWS - 1) > 0 ? iy + 1 - (ROWS - 1) : 0;
+            const int r_hi = iy + 1 < 2 ? iy + 1 : 2;
+            if (!(a.flags & 0x200)) {
+              const uint32_t wS = smem_u32(wsm + (size_t)(S * 3) * w_tap);       // stacked [r=2; r=1; r=0] for this shift
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const int j = iy + 1 - r;                    // output row fed by input row iy through kernel row r
-              if (j < 0 || j >= ROWS) continue;
-              const uint32_t wbase = smem_u32(wsm + (size_t)(r * 3 + S) * w_tap);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma(acc0 + (uint32_t)(j * N), make_desc_sw(abase + k * 32, 16, 1024, 2), make_desc_sw(wbase + k * 32, 16, 1024, 2),
-                     idesc, (r == 0 && S == 0 && k == 0) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = make_desc_sw(abase + k * 32, 16, 1024, 2);
+                int hi = r_hi;
+                if (S == 0 && k == 0 && r_lo == 0) {
+                  // first touch of accumulator j = iy + 1 (kernel row 0): overwrite instead of accumulate
+                  umma(acc0 + (uint32_t)((iy + 1) * N), da, make_desc_sw(wS + 2 * w_tap + k * 32, 16, 1024, 2), idesc, 0u);
+                  if (r_hi == 0) continue;
+                  // the remaining rows r = 1 .. r_hi accumulate: handled below with r_lo' = 1
+                  const int nr = r_hi;                                             // rows 1 .. r_hi
+                  umma(acc0 + (uint32_t)((iy + 1 - r_hi) * N), da, make_desc_sw(wS + (uint32_t)(2 - r_hi) * w_tap + k * 32, 16, 1024, 2),
+                       idesc_bf16(nr * N, false, false), 1u);
+                  continue;
+                }
+                const int nr = hi - r_lo + 1;
+                umma(acc0 + (uint32_t)((iy + 1 - hi) * N), da, make_desc_sw(wS + (uint32_t)(2 - hi) * w_tap + k * 32, 16, 1024, 2),
+                     idesc_bf16(nr * N, false, false), 1u);
+              }
             }
             umma_commit(&empty_bar[s]);
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
@@ -451,7 +471,7 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          store_chunk16(scr, lane, v, rowp, (int64_t)po * a.ldy + co);
+          if (!(a.flags & 0x100)) store_chunk16(scr, lane, v, rowp, (int64_t)po * a.ldy + co);
         }
       }
       tc_fence_before();
@@ -556,11 +576,19 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
           if (!ok) break;
           tc_fence_after();
           const uint32_t base = smem_u32(ring + (size_t)s * a.stage_bytes);
+          if (NT == 3) {
+            // the three shifted x tiles are one MN-major operand of 3 * Cin columns (tile stride = leading byte
+            // offset), their accumulators neighbours in TMEM: ONE MMA per 16 pixels instead of three
+            const uint32_t idesc3 = idesc_bf16(3 * Cin, true, true);
 #pragma unroll
-          for (int u = 0; u < NT; ++u) {
-            const int tl = NT == 3 ? u : st;              // tap inside the kernel row
-            const uint32_t tmem_d = tmem_base + (uint32_t)(tl * Cin);
-            const uint32_t xb = base + a.dy_bytes + u * a.x_bytes;
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t da = make_desc_sw(base + j * a_kstep, a_lbo, a_sbo, a_ty);
+              const uint64_t db = make_desc_sw(base + a.dy_bytes + j * b_kstep, a.x_bytes, b_sbo, b_ty);
+              umma(tmem_base, da, db, idesc3, (!first || j > 0) ? 1u : 0u);
+            }
+          } else {
+            const uint32_t tmem_d = tmem_base + (uint32_t)(st * Cin);       // tap inside the kernel row
+            const uint32_t xb = base + a.dy_bytes;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint64_t da = make_desc_sw(base + j * a_kstep, a_lbo, a_sbo, a_ty);
@@ -744,6 +772,7 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
   a.y = y; a.ldy = ldy; a.bias = bias;
   a.flags = (flags & TM_EPI_RELU) | (bias ? TM_EPI_BIAS : 0);
+  if (getenv("TM_CONV_DEBUG")) a.flags |= atoi(getenv("TM_CONV_DEBUG")) & 0x700;   // bottleneck bisection (rows kernel)
   a.err = err;
   CUtensorMap tmx, tmw;
   cudaStream_t st = (cudaStream_t)stream;

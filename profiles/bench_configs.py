@@ -8,6 +8,8 @@
   config 5: 64 config-2 designs (seeds 0..63) stepped one after the other on ONE GPU (the
             denominator of the data-parallel scaling runs): designs/s.
 
+  config 1: the reference's CPU-runnable inference case (~5k cells, 64x64 image): GPU vs the CPU oracle.
+
 Prints one JSON object per config.  CUDA events on the launching stream, 3 warm-ups.
 Usage: python profiles/bench_configs.py [c3] [c4] [c5] [--c5-designs N]
 """
@@ -50,6 +52,45 @@ def timed(fn, reps=5, warm=3):
     b.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
+
+
+def config1(cpu=True):
+    """BASELINE config 1 (the reference's own CPU-runnable case): inference on a ~5k-cell design with a 64x64 image.
+    GPU: DesignStep.forward (schedule cached), CUDA events.  CPU: the oracle port, no_grad, all host threads."""
+    import numpy as np
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["c1"])
+    model, cnn = tm_engine.build_models(d.map_size, seed=0, device=DEV)
+    batch = tm_engine.DesignBatch.from_synth(d, DEV)
+    step = tm_engine.DesignStep(model, cnn)
+    with torch.no_grad():
+        t_gpu = timed(lambda: step.forward(batch), reps=10)
+        pred = step.forward(batch).cpu()
+    out = {"config": "c1: inference, %d pins, %d levels, %dx%d image, %d endpoints" % (d.n, d.num_levels, 2 * d.map_size, 2 * d.map_size, d.endpoints.size),
+           "gpu_ms": t_gpu, "gpu_designs_per_s": 1e3 / t_gpu}
+    if cpu:
+        from oracle import levelize, restate
+        torch.set_num_threads(os.cpu_count() or 1)
+        t = torch.from_numpy
+        ni, ns = levelize.in_csr(d.n, d.net_src, d.net_dst)
+        ci, cs = levelize.in_csr(d.n, d.cell_src, d.cell_dst)
+        od = dict(n=d.n, levels=[t(x.astype(np.int64)) for x in d.level_lists()],
+                  net_csr=(t(ni).long(), t(ns).long()), cell_csr=(t(ci).long(), t(cs).long()),
+                  cell_feat=t(d.cell_feat), net_feat=t(d.net_feat), image=t(d.image), endpoints=t(d.endpoints),
+                  endpoint_level=t(d.level[d.endpoints].astype(np.int64)), mask_indptr=t(d.mask_indptr).long(),
+                  mask_cols=t(d.mask_cols).long(), arrival_time=t(d.arrival_time))
+        sd_m = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        sd_c = {k: v.detach().cpu() for k, v in cnn.state_dict().items()}
+        with torch.no_grad():
+            ref = restate.design_step(sd_m, sd_c, od, with_grad=False)
+            best = 1e9
+            for _ in range(3):
+                t0 = time.perf_counter()
+                restate.design_step(sd_m, sd_c, od, with_grad=False)
+                best = min(best, time.perf_counter() - t0)
+        err = float((pred - ref["pred"]).abs().max() / ref["pred"].abs().max())
+        out.update({"cpu_oracle_ms(best of 3, %d threads)" % (os.cpu_count() or 1): best * 1e3,
+                    "max_rel_err_vs_oracle": err})
+    return out
 
 
 def config3():
@@ -176,7 +217,9 @@ if __name__ == "__main__":
     if "--profile-c4" in sys.argv:
         profile_c4(mode=os.environ.get("TM_C4_MODE", "bf16"))
         sys.exit(0)
-    want = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3", "c4", "c5"]
+    want = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c3", "c4", "c5"]
+    if "c1" in want:
+        print(json.dumps(config1()), flush=True)
     if "c3" in want:
         print(json.dumps(config3()), flush=True)
     if "c4" in want:
