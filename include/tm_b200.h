@@ -289,9 +289,11 @@ int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, con
                        float eps, float* y, int64_t ldy, float* save_mean, float* save_invstd,
                        void* y_bf16, void* ws, size_t ws_bytes, void* stream);
 /* Backward of the pair: dy is the gradient w.r.t. the ReLU output y.
- * dx = BN'( dy * (y>0) ), dgamma, dbeta [C].  dx may be NULL when only dx_bf16 is wanted. */
+ * dx = BN'( dy * (y>0) ), dgamma, dbeta [C].  dx may be NULL when only dx_bf16 is wanted; y may be NULL:
+ * the ReLU mask is then rebuilt bit-for-bit from x, the saved statistics, gamma and beta (one tensor less to
+ * read, and the forward need not store y: tm_bn_relu_forward accepts y = NULL when y_bf16 is given). */
 int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* y,
-                        int64_t ldy, const float* dy, int64_t lddy, const float* gamma,
+                        int64_t ldy, const float* dy, int64_t lddy, const float* gamma, const float* beta,
                         const float* save_mean, const float* save_invstd, float* dx, int64_t lddx,
                         float* dgamma, float* dbeta, void* dx_bf16, void* ws, size_t ws_bytes, void* stream);
 

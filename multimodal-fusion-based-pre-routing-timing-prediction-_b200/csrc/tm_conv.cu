@@ -80,11 +80,18 @@ __device__ __forceinline__ uint32_t bn_pack_bf16(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// The normalised pre-activation, with every rounding pinned (no FMA contraction): the backward pass re-evaluates it
+// to rebuild the ReLU mask bit-for-bit instead of reading the stored activation.
+__device__ __forceinline__ float bn_affine(float x, float mu, float is, float ga, float be) {
+  return __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x, mu), is), ga), be);
+}
+
 template <int VEC, bool BWD>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_stats_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx, const float* __restrict__ y, int64_t ldy,
                 const float* __restrict__ dy, int64_t lddy, const float* __restrict__ mean,
-                const float* __restrict__ invstd, double* __restrict__ part) {
+                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                double* __restrict__ part) {
   extern __shared__ double sh[];                       // [lanes][C][2]
   const int groups = (C + VEC - 1) / VEC;              // channel groups per pixel
   const int lanes = BN_THREADS / groups;               // pixel lanes (groups <= 256)
@@ -93,12 +100,14 @@ bn_stats_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx, c
   const int64_t per = (npix + gridDim.x - 1) / gridDim.x;
   const int64_t p0 = (int64_t)blockIdx.x * per, p1 = p0 + per < npix ? p0 + per : npix;
   double a[VEC], b[VEC];
-  float mu[VEC], is[VEC];
+  float mu[VEC], is[VEC], ga[VEC], be[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     a[j] = 0.0; b[j] = 0.0;
     mu[j] = (BWD && c0 + j < C) ? mean[c0 + j] : 0.f;
     is[j] = (BWD && c0 + j < C) ? invstd[c0 + j] : 0.f;
+    ga[j] = (BWD && !y && c0 + j < C) ? gamma[c0 + j] : 0.f;
+    be[j] = (BWD && !y && c0 + j < C) ? beta[c0 + j] : 0.f;
   }
   if (pl < lanes) {
     for (int64_t p = p0 + pl; p < p1; p += lanes) {
@@ -107,13 +116,22 @@ bn_stats_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx, c
         const float4 t = ld4_stream(x + p * ldx + c0);
         xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
         if (BWD) {
-          const float4 u = ld4_stream(y + p * ldy + c0), w = ld4_stream(dy + p * lddy + c0);
-          yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+          const float4 w = ld4_stream(dy + p * lddy + c0);
           gv[0] = w.x; gv[1] = w.y; gv[2] = w.z; gv[3] = w.w;
+          if (y) {
+            const float4 u = ld4_stream(y + p * ldy + c0);
+            yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yv[j] = bn_affine(xv[j], mu[j], is[j], ga[j], be[j]);
+          }
         }
       } else {
         xv[0] = c0 < C ? x[p * ldx + c0] : 0.f;
-        if (BWD) { yv[0] = c0 < C ? y[p * ldy + c0] : 0.f; gv[0] = c0 < C ? dy[p * lddy + c0] : 0.f; }
+        if (BWD) {
+          gv[0] = c0 < C ? dy[p * lddy + c0] : 0.f;
+          yv[0] = c0 >= C ? 0.f : y ? y[p * ldy + c0] : bn_affine(xv[0], mu[0], is[0], ga[0], be[0]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
@@ -185,12 +203,12 @@ __global__ void bn_relu_apply_kernel(int64_t npix, int C, const float* __restric
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j)
-    v[j] = fmaxf((v[j] - __ldg(mean + c + j)) * __ldg(invstd + c + j) * __ldg(gamma + c + j) + __ldg(beta + c + j), 0.f);
+    v[j] = fmaxf(bn_affine(v[j], __ldg(mean + c + j), __ldg(invstd + c + j), __ldg(gamma + c + j), __ldg(beta + c + j)), 0.f);
   if (VEC == 4) {
-    st4(y + p * ldy + c, make_float4(v[0], v[1], v[2], v[3]));
+    if (y) st4(y + p * ldy + c, make_float4(v[0], v[1], v[2], v[3]));
     if (yb) *reinterpret_cast<uint2*>(yb + p * C + c) = make_uint2(bn_pack_bf16(v[0], v[1]), bn_pack_bf16(v[2], v[3]));
   } else {
-    y[p * ldy + c] = v[0];
+    if (y) y[p * ldy + c] = v[0];
     if (yb) yb[p * C + c] = __float2bfloat16(v[0]);
   }
 }
@@ -211,9 +229,10 @@ template <int VEC>
 __global__ void bn_bwd_apply_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx,
                                     const float* __restrict__ y, int64_t ldy, const float* __restrict__ dy,
                                     int64_t lddy, const float* __restrict__ gamma,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                    float* __restrict__ dx, int64_t lddx, __nv_bfloat16* __restrict__ dxb) {
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta, float* __restrict__ dx, int64_t lddx,
+                                    __nv_bfloat16* __restrict__ dxb) {
   const int groups = C / VEC;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * groups) return;
@@ -221,12 +240,21 @@ __global__ void bn_bwd_apply_kernel(int64_t npix, int C, const float* __restrict
   const int c = (int)(i - p * groups) * VEC;
   float xv[VEC], yv[VEC], gv[VEC], o[VEC];
   if (VEC == 4) {
-    const float4 t = ld4_stream(x + p * ldx + c), u = ld4_stream(y + p * ldy + c), w = ld4_stream(dy + p * lddy + c);
+    const float4 t = ld4_stream(x + p * ldx + c), w = ld4_stream(dy + p * lddy + c);
     xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-    yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
     gv[0] = w.x; gv[1] = w.y; gv[2] = w.z; gv[3] = w.w;
+    if (y) {
+      const float4 u = ld4_stream(y + p * ldy + c);
+      yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+    }
   } else {
-    xv[0] = x[p * ldx + c]; yv[0] = y[p * ldy + c]; gv[0] = dy[p * lddy + c];
+    xv[0] = x[p * ldx + c]; gv[0] = dy[p * lddy + c];
+    if (y) yv[0] = y[p * ldy + c];
+  }
+  if (!y) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      yv[j] = bn_affine(xv[j], __ldg(mean + c + j), __ldg(invstd + c + j), __ldg(gamma + c + j), __ldg(beta + c + j));
   }
   const float inv_n = 1.f / (float)npix;
 #pragma unroll
@@ -543,8 +571,9 @@ extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64
   const bool v4 = bn_vec4(C, {{x, ldx}, {y, ldy}});
   const int groups = v4 ? (int)C / 4 : (int)C;
   const size_t sh = (size_t)(BN_THREADS / groups) * C * 2 * sizeof(double);
-  if (v4) bn_stats_kernel<4, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, part);
-  else bn_stats_kernel<1, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, part);
+  TM_REQUIRE(y || y_bf16, "tm_bn_relu_forward: neither y nor y_bf16 given");
+  if (v4) bn_stats_kernel<4, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, part);
+  else bn_stats_kernel<1, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, part);
   TM_TRY(check_launch("bn_stats"));
   bn_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(npix, C, nblk, part, running_mean, running_var,
                                                              momentum, eps, save_mean, save_invstd);
@@ -556,25 +585,26 @@ extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64
 
 /* dx_bf16 (optional): compact bf16 copy [npix][C] of dx, written by the same pass */
 extern "C" int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* y,
-                                   int64_t ldy, const float* dy, int64_t lddy, const float* gamma,
+                                   int64_t ldy, const float* dy, int64_t lddy, const float* gamma, const float* beta,
                                    const float* save_mean, const float* save_invstd, float* dx,
                                    int64_t lddx, float* dgamma, float* dbeta, void* dx_bf16, void* ws, size_t ws_bytes,
                                    void* stream) {
   TM_REQUIRE(npix > 0 && C > 0 && C <= 256, "tm_bn_relu_backward: bad sizes (C <= 256)");
   TM_REQUIRE(dx || dx_bf16, "tm_bn_relu_backward: neither dx nor dx_bf16 given");
+  TM_REQUIRE(y || beta, "tm_bn_relu_backward: without the stored activation y the mask is rebuilt from beta");
   TM_REQUIRE(ws_bytes >= tm_bn_ws(npix, C), "tm_bn_relu_backward: workspace too small");
   const int nblk = bn_blocks(npix);
   double* part = (double*)ws;
   const bool v4 = bn_vec4(C, {{x, ldx}, {y, ldy}, {dy, lddy}, {dx, lddx}});
   const int groups = v4 ? (int)C / 4 : (int)C;
   const size_t sh = (size_t)(BN_THREADS / groups) * C * 2 * sizeof(double);
-  if (v4) bn_stats_kernel<4, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, part);
-  else bn_stats_kernel<1, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, part);
+  if (v4) bn_stats_kernel<4, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, gamma, beta, part);
+  else bn_stats_kernel<1, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, gamma, beta, part);
   TM_TRY(check_launch("bn_bwd_stats"));
   bn_bwd_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(C, nblk, part, dgamma, dbeta);
   TM_TRY(check_launch("bn_bwd_finalize"));
-  if (v4) bn_bwd_apply_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, gamma, save_mean, save_invstd, dgamma, dbeta, dx, lddx, (__nv_bfloat16*)dx_bf16);
-  else bn_bwd_apply_kernel<1><<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, gamma, save_mean, save_invstd, dgamma, dbeta, dx, lddx, (__nv_bfloat16*)dx_bf16);
+  if (v4) bn_bwd_apply_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dx, lddx, (__nv_bfloat16*)dx_bf16);
+  else bn_bwd_apply_kernel<1><<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dx, lddx, (__nv_bfloat16*)dx_bf16);
   return check_launch("bn_bwd_apply");
 }
 

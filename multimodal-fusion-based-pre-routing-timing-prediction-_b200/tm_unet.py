@@ -150,12 +150,13 @@ def _bn_relu_fwd(ws, x, ldx, npix, C, bn, y, ldy, update_stats, yb=None):
     return mean, invstd
 
 
-def _bn_relu_bwd(ws, x, ldx, y, ldy, dy, lddy, npix, C, gamma, mean, invstd, dx, lddx, dxb=None):
-    """dx (fp32, may be None) and / or dxb (compact bf16) receive the gradient w.r.t. the BN input."""
+def _bn_relu_bwd(ws, x, ldx, dy, lddy, npix, C, gamma, beta, mean, invstd, dx, lddx, dxb=None):
+    """dx (fp32, may be None) and / or dxb (compact bf16) receive the gradient w.r.t. the BN input.  The ReLU mask
+    is rebuilt from x and the saved statistics (bit-identical to the forward), so the activation is not read."""
     dev = x.device
     dg, db = _empty(C, dev=dev), _empty(C, dev=dev)
     nb = tm_lib.ws_bytes("tm_bn_ws", npix, C)
-    call("tm_bn_relu_backward", npix, C, x, ldx, y, ldy, dy, lddy, gamma, mean, invstd, dx, lddx, dg, db, dxb,
+    call("tm_bn_relu_backward", npix, C, x, ldx, None, 0, dy, lddy, gamma, beta, mean, invstd, dx, lddx, dg, db, dxb,
          ws.get(nb), nb, stream())
     return dg, db
 
@@ -169,7 +170,7 @@ def _double_conv_fwd(ws, st, name, mods, x, ldx, B, H, W, cin, cout, out, ldo, u
     dev = x.device
     npix = B * H * W
     cmid = conv1.weight.shape[0]
-    r1, a1, r2 = _empty(npix, cmid, dev=dev), _empty(npix, cmid, dev=dev), _empty(npix, cout, dev=dev)
+    r1, r2 = _empty(npix, cmid, dev=dev), _empty(npix, cout, dev=dev)
     if _tma_ok(B, H, W, cin, cmid) and _tma_ok(B, H, W, cmid, cout):
         # bf16 mode: TMA-fed tcgen05 convolutions on compact bf16 copies of the activations (kept for wgrad)
         xb = _to_bf16(x, ldx, npix, cin)
@@ -177,13 +178,16 @@ def _double_conv_fwd(ws, st, name, mods, x, ldx, B, H, W, cin, cout, out, ldo, u
         wq2, wd2 = _pack_bf16(conv2.weight, W, need_bwd)
         _conv_tma(xb, B, H, W, _cpad(cin), cmid, wq1, r1, cmid)
         a1b = torch.empty(npix, cmid, dtype=torch.bfloat16, device=dev)
-        m1, i1 = _bn_relu_fwd(ws, r1, cmid, npix, cmid, bn1, a1, cmid, update_stats, yb=a1b)
+        # the mid activation exists only as the bf16 operand of conv2 (the backward rebuilds its ReLU mask from r1)
+        m1, i1 = _bn_relu_fwd(ws, r1, cmid, npix, cmid, bn1, None, 0, update_stats, yb=a1b)
         _conv_tma(a1b, B, H, W, cmid, cout, wq2, r2, cout)
         m2, i2 = _bn_relu_fwd(ws, r2, cout, npix, cout, bn2, out, ldo, update_stats)
         st[name] = dict(tma=True, xb=xb if need_bwd else None, a1b=a1b if need_bwd else None, wd1=wd1, wd2=wd2,
-                        x=x, ldx=ldx, B=B, H=H, W=W, cin=cin, cmid=cmid, cout=cout, r1=r1, a1=a1, r2=r2, out=out,
-                        ldo=ldo, m1=m1, i1=i1, m2=m2, i2=i2, g1=bn1.weight.detach(), g2=bn2.weight.detach())
+                        x=x, ldx=ldx, B=B, H=H, W=W, cin=cin, cmid=cmid, cout=cout, r1=r1, r2=r2, out=out,
+                        ldo=ldo, m1=m1, i1=i1, m2=m2, i2=i2, g1=bn1.weight.detach(), g2=bn2.weight.detach(),
+                        be1=bn1.bias.detach(), be2=bn2.bias.detach())
         return
+    a1 = _empty(npix, cmid, dev=dev)
     wf1, wb1 = _pack(conv1.weight, need_bwd)
     wf2, wb2 = _pack(conv2.weight, need_bwd)
     _conv(x, ldx, B, H, W, cin, cmid, 3, wf1, None, r1, cmid)
@@ -192,7 +196,7 @@ def _double_conv_fwd(ws, st, name, mods, x, ldx, B, H, W, cin, cout, out, ldo, u
     m2, i2 = _bn_relu_fwd(ws, r2, cout, npix, cout, bn2, out, ldo, update_stats)
     st[name] = dict(x=x, ldx=ldx, B=B, H=H, W=W, cin=cin, cmid=cmid, cout=cout, r1=r1, a1=a1, r2=r2, out=out,
                     ldo=ldo, m1=m1, i1=i1, m2=m2, i2=i2, wb1=wb1, wb2=wb2, g1=bn1.weight.detach(),
-                    g2=bn2.weight.detach())
+                    g2=bn2.weight.detach(), be1=bn1.bias.detach(), be2=bn2.bias.detach())
 
 
 def _double_conv_bwd(ws, s, dout, lddo, grads, prefix, dx, lddx):
@@ -205,24 +209,24 @@ def _double_conv_bwd(ws, s, dout, lddo, grads, prefix, dx, lddx):
         # the batch-norm backward emits its result directly as the bf16 operand shared by the weight and the
         # data gradient; the fp32 copy is never needed
         dr2b = torch.empty(npix, cout, dtype=torch.bfloat16, device=dev)
-        dg2, db2 = _bn_relu_bwd(ws, s["r2"], cout, s["out"], s["ldo"], dout, lddo, npix, cout, s["g2"], s["m2"],
-                                s["i2"], None, 0, dxb=dr2b)
+        dg2, db2 = _bn_relu_bwd(ws, s["r2"], cout, dout, lddo, npix, cout, s["g2"], s["be2"], s["m2"], s["i2"],
+                                None, 0, dxb=dr2b)
         dw2 = _wgrad_tma(ws, s["a1b"], dr2b, B, H, W, cmid, cout)
         _conv_tma(dr2b, B, H, W, cout, cmid, s["wd2"], da1, cmid)
         dr1b = torch.empty(npix, cmid, dtype=torch.bfloat16, device=dev)
-        dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, s["a1"], cmid, da1, cmid, npix, cmid, s["g1"], s["m1"], s["i1"],
+        dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, da1, cmid, npix, cmid, s["g1"], s["be1"], s["m1"], s["i1"],
                                 None, 0, dxb=dr1b)
         dw1 = _wgrad_tma(ws, s["xb"], dr1b, B, H, W, cin, cmid)
         if dx is not None:
             _conv_tma(dr1b, B, H, W, cmid, cin, s["wd1"], dx, lddx)
     else:
         dr2 = _empty(npix, cout, dev=dev)
-        dg2, db2 = _bn_relu_bwd(ws, s["r2"], cout, s["out"], s["ldo"], dout, lddo, npix, cout, s["g2"], s["m2"],
-                                s["i2"], dr2, cout)
+        dg2, db2 = _bn_relu_bwd(ws, s["r2"], cout, dout, lddo, npix, cout, s["g2"], s["be2"], s["m2"], s["i2"],
+                                dr2, cout)
         dr1 = _empty(npix, cmid, dev=dev)
         dw2, _ = _conv_wgrad(ws, s["a1"], cmid, dr2, cout, B, H, W, cmid, cout, 3, False)
         _conv(dr2, cout, B, H, W, cout, cmid, 3, s["wb2"], None, da1, cmid)
-        dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, s["a1"], cmid, da1, cmid, npix, cmid, s["g1"], s["m1"], s["i1"],
+        dg1, db1 = _bn_relu_bwd(ws, s["r1"], cmid, da1, cmid, npix, cmid, s["g1"], s["be1"], s["m1"], s["i1"],
                                 dr1, cmid)
         dw1, _ = _conv_wgrad(ws, s["x"], s["ldx"], dr1, cmid, B, H, W, cin, cmid, 3, False)
         if dx is not None:
