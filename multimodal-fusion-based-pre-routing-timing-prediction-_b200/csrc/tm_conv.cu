@@ -110,40 +110,65 @@ bn_stats_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx, c
     be[j] = (BWD && !y && c0 + j < C) ? beta[c0 + j] : 0.f;
   }
   if (pl < lanes) {
-    for (int64_t p = p0 + pl; p < p1; p += lanes) {
-      float xv[VEC], yv[VEC], gv[VEC];
-      if (VEC == 4) {
-        const float4 t = ld4_stream(x + p * ldx + c0);
-        xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-        if (BWD) {
-          const float4 w = ld4_stream(dy + p * lddy + c0);
-          gv[0] = w.x; gv[1] = w.y; gv[2] = w.z; gv[3] = w.w;
-          if (y) {
-            const float4 u = ld4_stream(y + p * ldy + c0);
-            yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
-          } else {
+    // short runs (<= 8 pixels) are summed in fp32 and folded into the fp64 accumulators: the conversions and
+    // fp64 adds, not the loads, bound this kernel when every element went through fp64
+    float sa[VEC], sb[VEC];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) yv[j] = bn_affine(xv[j], mu[j], is[j], ga[j], be[j]);
-          }
-        }
-      } else {
-        xv[0] = c0 < C ? x[p * ldx + c0] : 0.f;
-        if (BWD) {
-          gv[0] = c0 < C ? dy[p * lddy + c0] : 0.f;
-          yv[0] = c0 >= C ? 0.f : y ? y[p * ldy + c0] : bn_affine(xv[0], mu[0], is[0], ga[0], be[0]);
-        }
-      }
+    for (int j = 0; j < VEC; ++j) { sa[j] = 0.f; sb[j] = 0.f; }
+    auto fold = [&]() {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { a[j] += (double)sa[j]; b[j] += (double)sb[j]; sa[j] = 0.f; sb[j] = 0.f; }
+    };
+    auto accumulate = [&](const float (&xv)[VEC], const float (&yv)[VEC], const float (&gv)[VEC]) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         if (BWD) {
           const float gg = yv[j] > 0.f ? gv[j] : 0.f;
-          a[j] += (double)gg;
-          b[j] += (double)gg * (double)((xv[j] - mu[j]) * is[j]);
+          sa[j] += gg;
+          sb[j] = fmaf(gg, (xv[j] - mu[j]) * is[j], sb[j]);
         } else {
-          const double v = (double)xv[j];
-          a[j] += v;
-          b[j] += v * v;
+          sa[j] += xv[j];
+          sb[j] = fmaf(xv[j], xv[j], sb[j]);
         }
+      }
+    };
+    if constexpr (VEC == 4) {
+      // four pixels per iteration, every load issued before the first use: all loads of an iteration in flight together
+      constexpr int U = 2;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      int it = 0;
+      for (int64_t p = p0 + pl; p < p1; p += (int64_t)U * lanes) {
+        float4 tx[U], tg[U], ty[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t pu = p + (int64_t)u * lanes;
+          const bool on = pu < p1;                       // a skipped pixel contributes exact zeros
+          tx[u] = on ? ld4_stream(x + pu * ldx + c0) : z4;
+          tg[u] = (BWD && on) ? ld4_stream(dy + pu * lddy + c0) : z4;
+          ty[u] = (BWD && y && on) ? ld4_stream(y + pu * ldy + c0) : z4;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float xv[VEC] = {tx[u].x, tx[u].y, tx[u].z, tx[u].w};
+          const float gv[VEC] = {tg[u].x, tg[u].y, tg[u].z, tg[u].w};
+          float yv[VEC] = {ty[u].x, ty[u].y, ty[u].z, ty[u].w};
+          if (BWD && !y) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) yv[j] = bn_affine(xv[j], mu[j], is[j], ga[j], be[j]);
+          }
+          accumulate(xv, yv, gv);
+        }
+        if ((++it & 3) == 0) fold();
+      }
+      fold();
+    } else {
+      for (int64_t p = p0 + pl; p < p1; p += lanes) {
+        float xv[VEC], yv[VEC], gv[VEC];
+        xv[0] = c0 < C ? x[p * ldx + c0] : 0.f;
+        gv[0] = (BWD && c0 < C) ? dy[p * lddy + c0] : 0.f;
+        yv[0] = (!BWD || c0 >= C) ? 0.f : y ? y[p * ldy + c0] : bn_affine(xv[0], mu[0], is[0], ga[0], be[0]);
+        accumulate(xv, yv, gv);
+        fold();
       }
     }
 #pragma unroll
