@@ -402,6 +402,18 @@ int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, void* q, int
  * flags: TM_EPI_RELU.  The data gradient is the same call on bf16(dy) with the dgrad operand. */
 int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, int64_t P, const void* xb, const void* wq,
                     const float* bias, float* y, int64_t ldy, int flags, int* err, void* stream);
+/* nn.ConvTranspose2d(k=2, s=2) (Unet.py:53) on the same TMA path.  Weight w [Cin][Cout][2][2] fp32 ->
+ * wf bf16 [4*Cout][Cin] (forward operand) and wd bf16 [4][Cin][Cout] (data-gradient operand; either may be NULL).
+ * forward: y[b,2y+dy,2x+dx,co] = bias[co] + sum_ci xb[b,y,x,ci] w[ci][co][dy][dx]: ONE tap, the accumulator row of
+ *   an input pixel is its 2x2 output window, scattered by the epilogue into (B,2H,2W,*) rows of stride ldy;
+ * dgrad: dx[b,y,x,ci] = sum dyb[b,2y+dy,2x+dx,co] w[ci][co][dy][dx]: four taps, each reading every other pixel of
+ *   the compact bf16 gradient [B][2H][2W][Cout] through a tensor map with element strides (1,2,2,1). */
+int tm_convt2x2_bf16_supported(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
+int tm_convt2x2_pack_bf16(int64_t Cin, int64_t Cout, const float* w, void* wf, void* wd, void* stream);
+int tm_convt2x2_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, const void* xb, const void* wf,
+                     const float* bias, float* y, int64_t ldy, int* err, void* stream);
+int tm_convt2x2_bf16_dgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, const void* dyb, const void* wd,
+                           float* dx, int64_t lddx, int* err, void* stream);
 /* dw[co][ci][ky][kx] (torch layout, ci < Cin_real) = sum_pix dyb[pix, co] * xb[pix + (ky-1,kx-1), ci] */
 size_t tm_conv3x3_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
 int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cin_real, int64_t Cout,

@@ -54,13 +54,13 @@ inline CUtensorMapSwizzle swizzle_for(int inner_bytes) {
 
 // bf16 [B][H][W][C] with a box of (boxC channels, TW, TH, TB)
 int encode_act(CUtensorMap* m, const void* ptr, int64_t C, int64_t W, int64_t H, int64_t B, int boxC, int TW,
-               int TH, int TB) {
+               int TH, int TB, int step = 1) {   // step 2: every other pixel in W and H (transposed-conv gradients)
   EncodeTiledFn enc = encoder();
   if (!enc) return fail(TM_EINVAL, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)(TW * step), (cuuint32_t)(TH * step), (cuuint32_t)TB};
+  cuuint32_t es[4] = {1, (cuuint32_t)step, (cuuint32_t)step, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(boxC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -166,6 +166,8 @@ struct ConvArgs {
   Geom g;                            // geometry in PACKED pixels (rows of P pixels)
   int Cin, N, stages;                // channels per packed row: Cin = P * cin, N = P * cout
   int P, cpx;                        // pixels per row, output channels per pixel
+  int ntaps, cscale, convt;          // taps (9 / 4 / 1), coordinate scale of the input map, transposed-conv scatter epilogue
+  signed char tdx[9], tdy[9];        // input offset of every tap
   uint32_t a_bytes, b_bytes, stage_bytes;
   float* y;
   int64_t ldy;
@@ -216,14 +218,14 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       for (int64_t t = blockIdx.x; t < a.g.ntiles && ok; t += G) {
         int x0, y0, b0;
         a.g.origin(t, x0, y0, b0);
-        for (int tap = 0; tap < 9 && ok; ++tap) {
-          const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+        for (int tap = 0; tap < a.ntaps && ok; ++tap) {
+          const int dx = a.tdx[tap], dy = a.tdy[tap];
           for (int cs = 0; cs < csteps; ++cs) {
             ok = mbar_wait(&empty_bar[s], ph ^ 1u, abortp);
             if (!ok) break;
             const uint32_t base = smem_u32(ring + (size_t)s * a.stage_bytes);
             mbar_expect_tx(&full_bar[s], a.a_bytes + a.b_bytes);
-            tma_load_4d(base, &tmx, cs * CK, x0 + dx, y0 + dy, b0, &full_bar[s]);
+            tma_load_4d(base, &tmx, cs * CK, x0 * a.cscale + dx, y0 * a.cscale + dy, b0, &full_bar[s]);
             tma_load_2d(base + a.a_bytes, &tmw, cs * CK, tap * N, &full_bar[s]);
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
           }
@@ -244,7 +246,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         if (!ok) break;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * N);
-        const int ksteps = 9 * csteps;
+        const int ksteps = a.ntaps * csteps;
         for (int ks = 0; ks < ksteps; ++ks) {
           ok = mbar_wait(&full_bar[s], ph, abortp);
           if (!ok) break;
@@ -281,9 +283,14 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       for (int pass = 0; pass < 4; ++pass) {                // the rows this lane stores after the transposition
         const int m = q * 32 + pass * 8 + (lane >> 2);
         const int tw = m % a.g.TW, th = (m / a.g.TW) % a.g.TH, tb = m / (a.g.TW * a.g.TH);
-        rowp[pass] = b0 + tb < a.g.B
-                         ? a.y + (((int64_t)(b0 + tb) * a.g.H + (y0 + th)) * a.g.W + (x0 + tw)) * a.P * a.ldy
-                         : nullptr;
+        if (a.convt)       // transposed conv k2 s2: the row is the 2x2 output window of input pixel (y0+th, x0+tw)
+          rowp[pass] = b0 + tb < a.g.B
+                           ? a.y + (((int64_t)(b0 + tb) * 2 * a.g.H + 2 * (y0 + th)) * 2 * a.g.W + 2 * (x0 + tw)) * a.ldy
+                           : nullptr;
+        else
+          rowp[pass] = b0 + tb < a.g.B
+                           ? a.y + (((int64_t)(b0 + tb) * a.g.H + (y0 + th)) * a.g.W + (x0 + tw)) * a.P * a.ldy
+                           : nullptr;
       }
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N);
       for (int c = 0; c < N; c += 16) {
@@ -298,7 +305,9 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        store_chunk16(scr, lane, v, rowp, (int64_t)po * a.ldy + co);
+        // po: pixel inside the packed row -- or, for the transposed conv, the quadrant (dy, dx) of the 2x2 window
+        const int64_t coff = a.convt ? ((int64_t)(po >> 1) * 2 * a.g.W + (po & 1)) * a.ldy + co : (int64_t)po * a.ldy + co;
+        store_chunk16(scr, lane, v, rowp, coff);
       }
       tc_fence_before();
       __syncwarp();
@@ -732,6 +741,10 @@ extern "C" int tm_conv3x3_bf16_supported(int64_t B, int64_t H, int64_t W, int64_
 
 extern "C" int tm_conv3x3_bf16_pack(int64_t W, int64_t Cin, int64_t Cout) { return conv_pack(W, Cin, Cout); }
 
+namespace {
+int launch_taps(const ConvArgs& a, const CUtensorMap& tmx, const CUtensorMap& tmw, int CK, cudaStream_t st);
+}
+
 extern "C" int tm_to_bf16_rows(int64_t npix, int64_t C, const float* x, int64_t ldx, void* out, int64_t Cp, void* stream) {
   TM_REQUIRE(Cp % 8 == 0 && Cp >= C, "tm_to_bf16_rows: padded width must be a multiple of 8 and >= C");
   if (npix <= 0) return 0;
@@ -771,6 +784,8 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
   a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
   a.y = y; a.ldy = ldy; a.bias = bias;
+  a.ntaps = 9; a.cscale = 1; a.convt = 0;
+  for (int t = 0; t < 9; ++t) { a.tdx[t] = (signed char)(t % 3 - 1); a.tdy[t] = (signed char)(t / 3 - 1); }
   a.flags = (flags & TM_EPI_RELU) | (bias ? TM_EPI_BIAS : 0);
   if (getenv("TM_CONV_DEBUG")) a.flags |= atoi(getenv("TM_CONV_DEBUG")) & 0x700;   // bottleneck bisection (rows kernel)
   a.err = err;
@@ -798,6 +813,11 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   }
   TM_TRY(encode_act(&tmx, xb, Cp, Wp, H, B, CK, a.g.TW, a.g.TH, a.g.TB));
   TM_TRY(encode_2d(&tmw, wq, Cp, 9 * Np, CK, (int)Np));
+  return launch_taps(a, tmx, tmw, CK, st);
+}
+
+namespace {
+int launch_taps(const ConvArgs& a, const CUtensorMap& tmx, const CUtensorMap& tmw, int CK, cudaStream_t st) {
   const size_t smem = (size_t)a.stages * a.stage_bytes + 1024;
   const int grid = (int)(a.g.ntiles < sm_count() ? a.g.ntiles : sm_count());
 #define TM_LAUNCH_CONV(CK_)                                                                                   \
@@ -814,7 +834,83 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   else if (CK == 32) TM_LAUNCH_CONV(32);
   else TM_LAUNCH_CONV(16);
 #undef TM_LAUNCH_CONV
-  return check_launch("conv3x3_tma");
+  return check_launch("conv_tma");
+}
+
+__global__ void pack_convt_bf16_kernel(int Cin, int Cout, const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                       __nv_bfloat16* __restrict__ wd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)Cin * Cout * 4) return;
+  const int q = (int)(i % 4), co = (int)((i / 4) % Cout), ci = (int)(i / (4 * Cout));   // w[ci][co][dy][dx], q = dy*2+dx
+  const __nv_bfloat16 v = __float2bfloat16(w[i]);
+  if (wf) wf[((int64_t)q * Cout + co) * Cin + ci] = v;         // forward operand  [(q,co)][ci]
+  if (wd) wd[((int64_t)q * Cin + ci) * Cout + co] = v;         // data-gradient operand, tap q: [ci][co]
+}
+}  // namespace
+
+// nn.ConvTranspose2d(k=2, s=2) weight w [Cin][Cout][2][2] fp32 -> wf bf16 [4*Cout][Cin], wd bf16 [4][Cin][Cout]
+extern "C" int tm_convt2x2_pack_bf16(int64_t Cin, int64_t Cout, const float* w, void* wf, void* wd, void* stream) {
+  pack_convt_bf16_kernel<<<(unsigned)cdiv(Cin * Cout * 4, 256), 256, 0, (cudaStream_t)stream>>>((int)Cin, (int)Cout, w,
+                                                                                              (__nv_bfloat16*)wf, (__nv_bfloat16*)wd);
+  return check_launch("pack_convt_bf16");
+}
+
+namespace {
+inline bool convt_shape_ok(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout) {
+  return conv_shape_ok(B, H, W, Cin, 4 * Cout) && conv_shape_ok(B, H, W, Cout, Cin);
+}
+void fill_common(ConvArgs& a, int64_t B, int64_t H, int64_t W, int64_t K, int64_t N, int CK, float* y, int64_t ldy,
+                 const float* bias, int* err) {
+  a.g = make_geom(B, H, W);
+  a.Cin = (int)K; a.N = (int)N; a.P = 1;
+  a.a_bytes = 128u * CK * 2u;
+  a.b_bytes = (uint32_t)N * CK * 2u;
+  a.stage_bytes = a.a_bytes + (uint32_t)align_up(a.b_bytes, 1024);
+  const int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
+  a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
+  a.y = y; a.ldy = ldy; a.bias = bias;
+  a.flags = bias ? TM_EPI_BIAS : 0;
+  a.err = err;
+}
+}  // namespace
+
+extern "C" int tm_convt2x2_bf16_supported(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout) {
+  return convt_shape_ok(B, H, W, Cin, Cout) ? 1 : 0;
+}
+
+// y[b, 2y+dy, 2x+dx, co] (fp32, pixel stride ldy, (B,2H,2W,*)) = bias[co] + sum_ci xb[b,y,x,ci] * w[ci][co][dy][dx]
+// One tap; the accumulator row of an input pixel is its 2x2 output window (4*Cout columns), scattered by the epilogue.
+extern "C" int tm_convt2x2_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, const void* xb, const void* wf,
+                                const float* bias, float* y, int64_t ldy, int* err, void* stream) {
+  TM_REQUIRE(convt_shape_ok(B, H, W, Cin, Cout), "tm_convt2x2_bf16: unsupported shape");
+  TM_REQUIRE(ldy % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0, "tm_convt2x2_bf16: output rows must be 16-byte aligned");
+  const int CK = Cin >= 64 ? 64 : (int)Cin;
+  ConvArgs a;
+  fill_common(a, B, H, W, Cin, 4 * Cout, CK, y, ldy, bias, err);
+  a.cpx = (int)Cout; a.ntaps = 1; a.cscale = 1; a.convt = 1;
+  a.tdx[0] = 0; a.tdy[0] = 0;
+  CUtensorMap tmx, tmw;
+  TM_TRY(encode_act(&tmx, xb, Cin, W, H, B, CK, a.g.TW, a.g.TH, a.g.TB));
+  TM_TRY(encode_2d(&tmw, wf, Cin, 4 * Cout, CK, (int)(4 * Cout)));
+  return launch_taps(a, tmx, tmw, CK, (cudaStream_t)stream);
+}
+
+// dx[b,y,x,ci] (fp32, stride lddx) = sum_{dy,dx,co} dyb[b, 2y+dy, 2x+dx, co] * w[ci][co][dy][dx]
+// Four taps; tap (dy,dx) reads every other pixel of the compact bf16 gradient [B][2H][2W][Cout] through a tensor
+// map with element strides (1, 2, 2, 1).
+extern "C" int tm_convt2x2_bf16_dgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, const void* dyb,
+                                      const void* wd, float* dx, int64_t lddx, int* err, void* stream) {
+  TM_REQUIRE(convt_shape_ok(B, H, W, Cin, Cout), "tm_convt2x2_bf16_dgrad: unsupported shape");
+  TM_REQUIRE(lddx % 4 == 0 && reinterpret_cast<uintptr_t>(dx) % 16 == 0, "tm_convt2x2_bf16_dgrad: output rows must be 16-byte aligned");
+  const int CK = Cout >= 64 ? 64 : (int)Cout;
+  ConvArgs a;
+  fill_common(a, B, H, W, Cout, Cin, CK, dx, lddx, nullptr, err);
+  a.cpx = (int)Cin; a.ntaps = 4; a.cscale = 2; a.convt = 0;
+  for (int q = 0; q < 4; ++q) { a.tdx[q] = (signed char)(q & 1); a.tdy[q] = (signed char)(q >> 1); }
+  CUtensorMap tmx, tmw;
+  TM_TRY(encode_act(&tmx, dyb, Cout, 2 * W, 2 * H, B, CK, a.g.TW, a.g.TH, a.g.TB, 2));
+  TM_TRY(encode_2d(&tmw, wd, Cout, 4 * Cin, CK, (int)Cin));
+  return launch_taps(a, tmx, tmw, CK, (cudaStream_t)stream);
 }
 
 namespace {

@@ -285,12 +285,24 @@ def unet_forward(net, x, need_bwd=True, update_stats=True):
     for j, up in enumerate(ups):
         i = 2 - j                                      # resolution index of the skip
         cout_t = cy // 2
-        wt, wtT = _empty(cy, 4 * cout_t, dev=dev), _empty(4 * cout_t, cy, dev=dev)
-        call("tm_convt_pack_weight", cy, cout_t, up.up.weight.detach().float().contiguous(), wt, wtT, stream())
         half = cat[i][:, chans[i]:]                    # second half of the concat buffer
-        call("tm_convt2x2_nhwc", B, Hs[i + 1], Ws_[i + 1], cy, cout_t, y, ldy, wt, up.up.bias.detach(), half,
-             2 * chans[i], Hs[i], Ws_[i], 0, 0, stream())
-        st[f"up{j}"] = dict(x=y, ldx=ldy, cin=cy, cout=cout_t, wtT=wtT, i=i)
+        wup = up.up.weight.detach().float().contiguous()
+        if (USE_TMA and _prec(None) == 0
+                and tm_lib.ws_bytes("tm_convt2x2_bf16_supported", B, Hs[i + 1], Ws_[i + 1], cy, cout_t) == 1):
+            # bf16 mode: one-tap TMA convolution whose epilogue scatters the 2x2 output windows
+            yb = _to_bf16(y, ldy, B * Hs[i + 1] * Ws_[i + 1], cy)
+            wfq = torch.empty(4 * cout_t, cy, dtype=torch.bfloat16, device=dev)
+            wdq = torch.empty(4, cy, cout_t, dtype=torch.bfloat16, device=dev) if need_bwd else None
+            call("tm_convt2x2_pack_bf16", cy, cout_t, wup, wfq, wdq, stream())
+            call("tm_convt2x2_bf16", B, Hs[i + 1], Ws_[i + 1], cy, cout_t, yb, wfq, up.up.bias.detach(), half,
+                 2 * chans[i], tm_lib.err_flag(dev), stream())
+            st[f"up{j}"] = dict(x=y, ldx=ldy, cin=cy, cout=cout_t, wdq=wdq, i=i)
+        else:
+            wt, wtT = _empty(cy, 4 * cout_t, dev=dev), _empty(4 * cout_t, cy, dev=dev)
+            call("tm_convt_pack_weight", cy, cout_t, wup, wt, wtT, stream())
+            call("tm_convt2x2_nhwc", B, Hs[i + 1], Ws_[i + 1], cy, cout_t, y, ldy, wt, up.up.bias.detach(), half,
+                 2 * chans[i], Hs[i], Ws_[i], 0, 0, stream())
+            st[f"up{j}"] = dict(x=y, ldx=ldy, cin=cy, cout=cout_t, wtT=wtT, i=i)
         out = _empty(B * Hs[i] * Ws_[i], chans[i], dev=dev)
         _double_conv_fwd(ws, st, f"dec{j}", _dc_mods(up.conv), cat[i], 2 * chans[i], B, Hs[i], Ws_[i], 2 * chans[i],
                          chans[i], out, chans[i], update_stats, need_bwd)
@@ -341,8 +353,13 @@ def unet_backward(net, st, gout):
         call("tm_convt_unpack_wgrad", u["cin"], u["cout"], dwt, dwu, stream())
         grads[f"{names[j]}.up.weight"], grads[f"{names[j]}.up.bias"] = dwu, dbt
         dy = _empty(B * Hs[i + 1] * Ws_[i + 1], u["cin"], dev=dev)
-        call("tm_convt2x2_dgrad_nhwc", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"], half, 2 * chans[i], Hs[i],
-             Ws_[i], 0, 0, u["wtT"], dy, u["cin"], stream())
+        if u.get("wdq") is not None:
+            halfb = _to_bf16(half, 2 * chans[i], B * Hs[i] * Ws_[i], u["cout"])
+            call("tm_convt2x2_bf16_dgrad", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"], halfb, u["wdq"], dy, u["cin"],
+                 tm_lib.err_flag(dev), stream())
+        else:
+            call("tm_convt2x2_dgrad_nhwc", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"], half, 2 * chans[i], Hs[i],
+                 Ws_[i], 0, 0, u["wtT"], dy, u["cin"], stream())
         lddy = u["cin"]
     # encoder, deepest first; dy is the gradient of x4
     enc_names = ["inc.double_conv", "down1.maxpool_conv.1.double_conv", "down2.maxpool_conv.1.double_conv",

@@ -77,3 +77,33 @@ def test_conv3x3_bf16_tma(lib, B, H, W, Cin, Cout):
     dw2 = torch.empty_like(dw)
     lib.call("tm_conv3x3_bf16_wgrad", B, H, W, CinP, Cin, Cout, xb, gb, dw2, lib.workspace(nb, DEV), nb, err, lib.stream())
     assert torch.equal(dw, dw2), "weight gradient is not bit-deterministic"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 8, 32, 16), (2, 16, 32, 64, 32), (3, 4, 4, 128, 64), (1, 64, 128, 32, 16),
+                                            (5, 2, 2, 128, 64), (2, 32, 32, 64, 32)])
+def test_convt2x2_bf16_tma(lib, B, H, W, Cin, Cout):
+    """ConvTranspose2d(k=2, s=2) forward (scatter epilogue into a concat half) and data gradient (strided tensor map)."""
+    torch.manual_seed(B + H + W + Cin + Cout)
+    assert lib.ws_bytes("tm_convt2x2_bf16_supported", B, H, W, Cin, Cout) == 1
+    x = _bf(torch.randn(B, Cin, H, W, device=DEV)).requires_grad_(True)
+    w = _bf(torch.randn(Cin, Cout, 2, 2, device=DEV) * 0.1)
+    bias = torch.randn(Cout, device=DEV)
+    g = _bf(torch.randn(B, Cout, 2 * H, 2 * W, device=DEV))
+    ref = F.conv_transpose2d(x.double(), w.double(), bias.double(), stride=2)
+    gx, = torch.autograd.grad(ref, (x,), g.double())
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous()            # noqa: E731
+    xb = _to_bf16(lib, nhwc(x), Cin, Cin)
+    gb = _to_bf16(lib, nhwc(g), Cout, Cout)
+    wf = torch.empty(4 * Cout, Cin, dtype=torch.bfloat16, device=DEV)
+    wd = torch.empty(4, Cin, Cout, dtype=torch.bfloat16, device=DEV)
+    lib.call("tm_convt2x2_pack_bf16", Cin, Cout, w.contiguous(), wf, wd, lib.stream())
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ybuf = torch.full((B * 4 * H * W, 2 * Cout), 7.0, device=DEV)           # [skip | up] concat buffer
+    lib.call("tm_convt2x2_bf16", B, H, W, Cin, Cout, xb, wf, bias, ybuf[:, Cout:], 2 * Cout, err, lib.stream())
+    assert int(err.item()) == 0
+    assert_close(ybuf[:, Cout:], ref.permute(0, 2, 3, 1).reshape(-1, Cout), 1e-4, 1e-5, "tma convT fwd")
+    assert bool((ybuf[:, :Cout] == 7.0).all())
+    dx = torch.empty(B * H * W, Cin, device=DEV)
+    lib.call("tm_convt2x2_bf16_dgrad", B, H, W, Cin, Cout, gb, wd, dx, Cin, err, lib.stream())
+    assert int(err.item()) == 0
+    assert_close(dx, gx.permute(0, 2, 3, 1).reshape(-1, Cin), 1e-4, 1e-5, "tma convT dgrad")
