@@ -414,6 +414,10 @@ int tm_convt2x2_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                      const float* bias, float* y, int64_t ldy, int* err, void* stream);
 int tm_convt2x2_bf16_dgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, const void* dyb, const void* wd,
                            float* dx, int64_t lddx, int* err, void* stream);
+/* dw[ci][co][dy][dx] (torch layout) = sum xb[b,y,x,ci] * dyb[b,2y+dy,2x+dx,co]; the bias gradient is tm_colsum of dy */
+size_t tm_convt2x2_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
+int tm_convt2x2_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, const void* xb, const void* dyb,
+                           float* dw, void* ws, size_t ws_bytes, int* err, void* stream);
 /* dw[co][ci][ky][kx] (torch layout, ci < Cin_real) = sum_pix dyb[pix, co] * xb[pix + (ky-1,kx-1), ci] */
 size_t tm_conv3x3_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout);
 int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cin_real, int64_t Cout,

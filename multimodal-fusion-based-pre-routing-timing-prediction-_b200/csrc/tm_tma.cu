@@ -508,8 +508,10 @@ struct WgradArgs {
   int Cin, Cout, stages;
   int cbx, nbx, cby, nby;            // channels per TMA box / boxes per tile, x and dy
   uint32_t x_bytes, dy_bytes, stage_bytes;
-  float* part;                       // [splits][9][Cout][Cin]
+  float* part;                       // [splits][taps][Cout][Cin]
   int* err;
+  int cscale;                        // coordinate scale of the tapped map (2: transposed-conv gradient, every other pixel)
+  signed char tdx[4], tdy[4];        // NT == 4: offsets of the four taps (transposed conv); NT == 3 / 1 use (u - 1, r - 1)
 };
 
 template <int NT>
@@ -522,8 +524,10 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
   __shared__ int abort_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NS = a.stages, Cin = a.Cin, Cout = a.Cout;
+  constexpr int NTOT = NT == 4 ? 4 : 3;                  // taps accumulated by one CTA
+  const int TT = NT == 4 ? 4 : 9;                         // taps in the whole gradient
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(3 * Cin)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(NTOT * Cin)) tmem_cols <<= 1;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -542,7 +546,7 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
   bool ok = true;
   const int64_t G = gridDim.x;
   const int r = blockIdx.y;                               // kernel row: taps r*3 .. r*3+2
-  constexpr int STEPS = 3 / NT;                           // stages per pixel block
+  constexpr int STEPS = NT == 1 ? 3 : 1;                  // stages per pixel block
 
   if (warp == 0) {
     if (lane == 0) {
@@ -559,10 +563,11 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
             tma_load_4d(base + j * (a.dy_bytes / a.nby), &tmdy, j * a.cby, x0, y0, b0, &full_bar[s]);
 #pragma unroll
           for (int u = 0; u < NT; ++u) {
-            const int dx = (NT == 3 ? u : st) - 1;
+            const int cx = NT == 4 ? x0 * a.cscale + a.tdx[u] : x0 + (NT == 3 ? u : st) - 1;
+            const int cy = NT == 4 ? y0 * a.cscale + a.tdy[u] : y0 + r - 1;
             for (int j = 0; j < a.nbx; ++j)
-              tma_load_4d(base + a.dy_bytes + u * a.x_bytes + j * (a.x_bytes / a.nbx), &tmx, j * a.cbx, x0 + dx,
-                          y0 + r - 1, b0, &full_bar[s]);
+              tma_load_4d(base + a.dy_bytes + u * a.x_bytes + j * (a.x_bytes / a.nbx), &tmx, j * a.cbx, cx, cy, b0,
+                          &full_bar[s]);
           }
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
         }
@@ -585,10 +590,10 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
           if (!ok) break;
           tc_fence_after();
           const uint32_t base = smem_u32(ring + (size_t)s * a.stage_bytes);
-          if (NT == 3) {
-            // the three shifted x tiles are one MN-major operand of 3 * Cin columns (tile stride = leading byte
-            // offset), their accumulators neighbours in TMEM: ONE MMA per 16 pixels instead of three
-            const uint32_t idesc3 = idesc_bf16(3 * Cin, true, true);
+          if (NT >= 3) {
+            // the NT tapped tiles are one MN-major operand of NT * Cin columns (tile stride = leading byte
+            // offset), their accumulators neighbours in TMEM: ONE MMA per 16 pixels instead of NT
+            const uint32_t idesc3 = idesc_bf16(NT * Cin, true, true);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint64_t da = make_desc_sw(base + j * a_kstep, a_lbo, a_sbo, a_ty);
@@ -607,7 +612,7 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
           }
           umma_commit(&empty_bar[s]);
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1u; }
-          if (NT == 3 || st == STEPS - 1) first = false;
+          if (NT >= 3 || st == STEPS - 1) first = false;
         }
       }
       if (ok) umma_commit(&acc_full);
@@ -620,8 +625,8 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
     if (ok) {
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int tl = 0; tl < 3; ++tl) {
-        float* pp = a.part + (((int64_t)blockIdx.x * 9 + r * 3 + tl) * Cout + co) * Cin;
+      for (int tl = 0; tl < NTOT; ++tl) {
+        float* pp = a.part + (((int64_t)blockIdx.x * TT + r * NTOT + tl) * Cout + co) * Cin;
         for (int c = 0; c < Cin; c += 16) {
           float v[16];
           tmem_ld16(trow + (uint32_t)(tl * Cin + c), v);
@@ -924,6 +929,65 @@ extern "C" size_t tm_conv3x3_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int6
   const int P = wgrad_pack(W, Cin, Cout);
   const Geom g = make_geom(B, H, W / P);
   return (size_t)wgrad_splits(g) * 9 * (P * Cout) * (P * Cin) * sizeof(float) + 256;
+}
+
+namespace {
+// part [splits][q][ci][co] -> dw [Cin][Cout][2][2] (torch ConvTranspose2d layout), fixed order
+__global__ void convt_wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Cin, int Cout, float* __restrict__ dw) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)4 * Cin * Cout) return;
+  const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), q = (int)(i / ((int64_t)Cout * Cin));
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * 4 * Cin * Cout + i];
+  dw[((int64_t)ci * Cout + co) * 4 + q] = s;
+}
+inline int convt_wgrad_splits(const Geom& g) { return (int)(g.ntiles < sm_count() ? g.ntiles : sm_count()); }
+}  // namespace
+
+extern "C" size_t tm_convt2x2_bf16_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout) {
+  const Geom g = make_geom(B, H, W);
+  return (size_t)convt_wgrad_splits(g) * 4 * Cin * Cout * sizeof(float) + 256;
+}
+
+// dw[ci][co][dy][dx] = sum_{b,y,x} xb[b,y,x,ci] * dyb[b, 2y+dy, 2x+dx, co]   (the bias gradient is a column sum of dy)
+// xb: bf16 [B][H][W][Cin]; dyb: bf16 compact [B][2H][2W][Cout].  A = x (M = Cin), B = the four strided taps of dy
+// fused into one MN-major operand of 4*Cout columns.
+extern "C" int tm_convt2x2_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, const void* xb,
+                                      const void* dyb, float* dw, void* ws, size_t ws_bytes, int* err, void* stream) {
+  TM_REQUIRE(convt_shape_ok(B, H, W, Cin, Cout) && Cin <= 128 && Cout <= 64 && pow2(Cin) && pow2(Cout),
+             "tm_convt2x2_bf16_wgrad: unsupported shape");
+  TM_REQUIRE(ws && ws_bytes >= tm_convt2x2_bf16_wgrad_ws(B, H, W, Cin, Cout), "tm_convt2x2_bf16_wgrad: workspace too small");
+  WgradArgs a;
+  a.g = make_geom(B, H, W);
+  // kernel roles: "dy" slot = the untapped M-side operand (here x), "x" slot = the tapped N-side operand (here dy)
+  a.Cin = (int)Cout; a.Cout = (int)Cin;
+  a.cbx = (int)Cout; a.nbx = 1;
+  a.cby = Cin > 64 ? 64 : (int)Cin; a.nby = (int)Cin / a.cby;
+  a.x_bytes = 128u * (uint32_t)Cout * 2u;
+  a.dy_bytes = 128u * (uint32_t)Cin * 2u;
+  a.stage_bytes = (uint32_t)align_up(a.dy_bytes + 4 * a.x_bytes, 1024);
+  const int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
+  a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
+  TM_REQUIRE(a.stages >= 2, "tm_convt2x2_bf16_wgrad: tile does not fit shared memory");
+  a.part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  a.err = err;
+  a.cscale = 2;
+  for (int q = 0; q < 4; ++q) { a.tdx[q] = (signed char)(q & 1); a.tdy[q] = (signed char)(q >> 1); }
+  CUtensorMap tm_tap, tm_m;
+  TM_TRY(encode_act(&tm_tap, dyb, Cout, 2 * W, 2 * H, B, a.cbx, a.g.TW, a.g.TH, a.g.TB, 2));
+  TM_TRY(encode_act(&tm_m, xb, Cin, W, H, B, a.cby, a.g.TW, a.g.TH, a.g.TB));
+  const int splits = convt_wgrad_splits(a.g);
+  const size_t smem = (size_t)a.stages * a.stage_bytes + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool optin = false;
+  if (!optin) {
+    TM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BUDGET + 1024));
+    optin = true;
+  }
+  conv3x3_wgrad_tma_kernel<4><<<dim3((unsigned)splits, 1), CONV_THREADS, smem, st>>>(tm_tap, tm_m, a);
+  TM_TRY(check_launch("convt_wgrad_tma"));
+  convt_wgrad_reduce_kernel<<<(unsigned)cdiv(4 * Cin * Cout, 256), 256, 0, st>>>(a.part, splits, (int)Cin, (int)Cout, dw);
+  return check_launch("convt_wgrad_reduce");
 }
 
 // dw[co][ci][ky][kx] (ci < Cin_real) = sum_pix dY[pix, co] * X[pix + (ky-1, kx-1), ci]

@@ -296,7 +296,7 @@ def unet_forward(net, x, need_bwd=True, update_stats=True):
             call("tm_convt2x2_pack_bf16", cy, cout_t, wup, wfq, wdq, stream())
             call("tm_convt2x2_bf16", B, Hs[i + 1], Ws_[i + 1], cy, cout_t, yb, wfq, up.up.bias.detach(), half,
                  2 * chans[i], tm_lib.err_flag(dev), stream())
-            st[f"up{j}"] = dict(x=y, ldx=ldy, cin=cy, cout=cout_t, wdq=wdq, i=i)
+            st[f"up{j}"] = dict(x=y, ldx=ldy, cin=cy, cout=cout_t, wdq=wdq, xb=yb if need_bwd else None, i=i)
         else:
             wt, wtT = _empty(cy, 4 * cout_t, dev=dev), _empty(4 * cout_t, cy, dev=dev)
             call("tm_convt_pack_weight", cy, cout_t, wup, wt, wtT, stream())
@@ -345,21 +345,29 @@ def unet_backward(net, st, gout):
         dskip[i] = dcat                                  # first half = gradient of the skip tensor
         u = st[f"up{j}"]
         half = dcat[:, chans[i]:]
-        nb = tm_lib.ws_bytes("tm_convt2x2_wgrad_ws", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"])
-        dwt, dbt = _empty(u["cin"], 4 * u["cout"], dev=dev), _empty(u["cout"], dev=dev)
-        call("tm_convt2x2_wgrad_nhwc", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"], u["x"], u["ldx"], half,
-             2 * chans[i], Hs[i], Ws_[i], 0, 0, dwt, dbt, ws.get(nb), nb, stream())
-        dwu = _empty(u["cin"], u["cout"], 2, 2, dev=dev)
-        call("tm_convt_unpack_wgrad", u["cin"], u["cout"], dwt, dwu, stream())
-        grads[f"{names[j]}.up.weight"], grads[f"{names[j]}.up.bias"] = dwu, dbt
         dy = _empty(B * Hs[i + 1] * Ws_[i + 1], u["cin"], dev=dev)
         if u.get("wdq") is not None:
-            halfb = _to_bf16(half, 2 * chans[i], B * Hs[i] * Ws_[i], u["cout"])
+            # bf16 mode: weight and data gradient on the TMA path, both from one bf16 copy of the gradient half
+            npo = B * Hs[i] * Ws_[i]
+            halfb = _to_bf16(half, 2 * chans[i], npo, u["cout"])
+            dwu, dbt = _empty(u["cin"], u["cout"], 2, 2, dev=dev), _empty(u["cout"], dev=dev)
+            nb = tm_lib.ws_bytes("tm_convt2x2_bf16_wgrad_ws", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"])
+            call("tm_convt2x2_bf16_wgrad", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"], u["xb"], halfb, dwu, ws.get(nb), nb,
+                 tm_lib.err_flag(dev), stream())
+            nbc = tm_lib.ws_bytes("tm_colsum_ws", npo, u["cout"])
+            call("tm_colsum", npo, u["cout"], half, 2 * chans[i], None, dbt, 0, tm_lib.workspace(nbc, dev), nbc, stream())
             call("tm_convt2x2_bf16_dgrad", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"], halfb, u["wdq"], dy, u["cin"],
                  tm_lib.err_flag(dev), stream())
         else:
+            nb = tm_lib.ws_bytes("tm_convt2x2_wgrad_ws", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"])
+            dwt, dbt = _empty(u["cin"], 4 * u["cout"], dev=dev), _empty(u["cout"], dev=dev)
+            call("tm_convt2x2_wgrad_nhwc", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"], u["x"], u["ldx"], half,
+                 2 * chans[i], Hs[i], Ws_[i], 0, 0, dwt, dbt, ws.get(nb), nb, stream())
+            dwu = _empty(u["cin"], u["cout"], 2, 2, dev=dev)
+            call("tm_convt_unpack_wgrad", u["cin"], u["cout"], dwt, dwu, stream())
             call("tm_convt2x2_dgrad_nhwc", B, Hs[i + 1], Ws_[i + 1], u["cin"], u["cout"], half, 2 * chans[i], Hs[i],
                  Ws_[i], 0, 0, u["wtT"], dy, u["cin"], stream())
+        grads[f"{names[j]}.up.weight"], grads[f"{names[j]}.up.bias"] = dwu, dbt
         lddy = u["cin"]
     # encoder, deepest first; dy is the gradient of x4
     enc_names = ["inc.double_conv", "down1.maxpool_conv.1.double_conv", "down2.maxpool_conv.1.double_conv",

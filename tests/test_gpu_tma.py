@@ -107,3 +107,10 @@ def test_convt2x2_bf16_tma(lib, B, H, W, Cin, Cout):
     lib.call("tm_convt2x2_bf16_dgrad", B, H, W, Cin, Cout, gb, wd, dx, Cin, err, lib.stream())
     assert int(err.item()) == 0
     assert_close(dx, gx.permute(0, 2, 3, 1).reshape(-1, Cin), 1e-4, 1e-5, "tma convT dgrad")
+    wr = w.clone().requires_grad_(True)
+    gw, = torch.autograd.grad(F.conv_transpose2d(x.detach().double(), wr.double(), None, stride=2), (wr,), g.double())
+    nb = lib.ws_bytes("tm_convt2x2_bf16_wgrad_ws", B, H, W, Cin, Cout)
+    dw = torch.empty(Cin, Cout, 2, 2, device=DEV)
+    lib.call("tm_convt2x2_bf16_wgrad", B, H, W, Cin, Cout, xb, gb, dw, lib.workspace(nb, DEV), nb, err, lib.stream())
+    assert int(err.item()) == 0
+    assert_close(dw, gw, 1e-4, 1e-5, "tma convT wgrad")
