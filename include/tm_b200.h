@@ -313,10 +313,11 @@ int tm_conv1x1_c1_wgrad(int64_t npix, int64_t C, const float* x, int64_t ldx, co
 int tm_pool2x2_forward(int64_t B, int64_t H, int64_t W, int64_t C, int mode, const float* x,
                        int64_t ldx, float* y, int64_t ldy, uint8_t* idx, int flags, void* stream);
 /* dx (B,H,W,C) fully written (zeros where no gradient flows; odd trailing row/col get 0).
- * With TM_EPI_RELU, dy is first masked by (y>0). */
+ * With TM_EPI_RELU, dy is first masked by (y>0).  add (optional, pixel stride ldadd): a second gradient of the
+ * pooled tensor's source (the U-Net skip connection, Unet.py:67) summed into dx by the same pass. */
 int tm_pool2x2_backward(int64_t B, int64_t H, int64_t W, int64_t C, int mode, const float* dy,
                         int64_t lddy, const float* y, int64_t ldy, const uint8_t* idx, float* dx,
-                        int64_t lddx, int flags, void* stream);
+                        int64_t lddx, int flags, const float* add, int64_t ldadd, void* stream);
 /* dx = dy * (y > 0) * (slope where y <= 0)   elementwise helper for bare ReLU / LeakyReLU layers
  * (LayoutNet, model.py:219-220).  y is the activation OUTPUT. n elements, contiguous. */
 int tm_leaky_relu_backward(int64_t n, const float* y, const float* dy, float slope, float* dx,

@@ -320,13 +320,17 @@ __global__ void conv1x1_c1_fwd_kernel(int64_t npix, int C, const float* __restri
   }
   y[p * ldy] = s;
 }
+template <int VEC>
 __global__ void conv1x1_c1_dgrad_kernel(int64_t npix, int C, const float* __restrict__ dy, int64_t lddy,
                                         const float* __restrict__ w, float* __restrict__ dx, int64_t lddx) {
+  const int groups = C / VEC;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix * C) return;
-  const int64_t p = i / C;
-  const int c = (int)(i - p * C);
-  dx[p * lddx + c] = dy[p * lddy] * __ldg(w + c);
+  if (i >= npix * groups) return;
+  const int64_t p = i / groups;
+  const int c = (int)(i - p * groups) * VEC;
+  const float g = dy[p * lddy];
+  if (VEC == 4) st4(dx + p * lddx + c, make_float4(g * __ldg(w + c), g * __ldg(w + c + 1), g * __ldg(w + c + 2), g * __ldg(w + c + 3)));
+  else dx[p * lddx + c] = g * __ldg(w + c);
 }
 // part[block][C + 1]: sum_p x[p][c] * dy[p] for c < C, sum_p dy[p] at index C
 __global__ void __launch_bounds__(BN_THREADS)
@@ -392,6 +396,42 @@ __global__ void pool_fwd_kernel(int64_t B, int64_t H, int64_t W, int64_t C, int 
   y[((b * Ho + yo) * Wo + xo) * ldy + c] = out;
 }
 
+// 128-bit variant: one thread per (output pixel, 4 channels); same first-maximum / NaN rule per channel
+__global__ void pool_fwd_vec_kernel(int B, int H, int W, int C, int mode, const float* __restrict__ x, int64_t ldx,
+                                    float* __restrict__ y, int64_t ldy, uint8_t* __restrict__ idx, int relu) {
+  const int Ho = H / 2, Wo = W / 2, cg = C / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * Ho * Wo * cg) return;
+  const int c = (int)(i % cg) * 4;
+  const int64_t o = i / cg;
+  const int xo = (int)(o % Wo);
+  const int64_t t = o / Wo;
+  const int yo = (int)(t % Ho), b = (int)(t / Ho);
+  const float* base = x + (((int64_t)b * H + 2 * yo) * W + 2 * xo) * ldx + c;
+  const float4 q0 = ld4_stream(base), q1 = ld4_stream(base + ldx), q2 = ld4_stream(base + (int64_t)W * ldx),
+               q3 = ld4_stream(base + (int64_t)W * ldx + ldx);
+  const float v[4][4] = {{q0.x, q0.y, q0.z, q0.w}, {q1.x, q1.y, q1.z, q1.w}, {q2.x, q2.y, q2.z, q2.w}, {q3.x, q3.y, q3.z, q3.w}};
+  float out[4];
+  uint32_t am = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (mode == 0) {
+      int a = 0;
+      float m = v[0][j];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q][j] > m || v[q][j] != v[q][j]) { m = v[q][j]; a = q; }
+      out[j] = m;
+      am |= (uint32_t)a << (8 * j);
+    } else {
+      out[j] = 0.25f * (v[0][j] + v[1][j] + v[2][j] + v[3][j]);
+    }
+    if (relu) out[j] = fmaxf(out[j], 0.f);
+  }
+  if (mode == 0 && idx) *reinterpret_cast<uint32_t*>(idx + o * C + c) = am;
+  st4(y + o * ldy + c, make_float4(out[0], out[1], out[2], out[3]));
+}
+
 __global__ void pool_bwd_kernel(int64_t B, int64_t H, int64_t W, int64_t C, int mode,
                                 const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y,
                                 int64_t ldy, const uint8_t* __restrict__ idx, float* __restrict__ dx,
@@ -419,7 +459,8 @@ __global__ void pool_bwd_kernel(int64_t B, int64_t H, int64_t W, int64_t C, int 
 // 128-bit variant: one thread per (output pixel, 4 channels) writes the 2x2 input window (H, W even, C % 4 == 0)
 __global__ void pool_bwd_vec_kernel(int B, int H, int W, int C, int mode, const float* __restrict__ dy, int64_t lddy,
                                     const float* __restrict__ y, int64_t ldy, const uint8_t* __restrict__ idx,
-                                    float* __restrict__ dx, int64_t lddx, int relu) {
+                                    float* __restrict__ dx, int64_t lddx, int relu, const float* __restrict__ add,
+                                    int64_t ldadd) {
   const int Ho = H / 2, Wo = W / 2, cg = C / 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * Ho * Wo * cg) return;
@@ -449,7 +490,12 @@ __global__ void pool_bwd_vec_kernel(int B, int H, int W, int C, int mode, const 
       if (((am >> 16) & 0xFF) != (uint32_t)q) v.z = 0.f;
       if (((am >> 24) & 0xFF) != (uint32_t)q) v.w = 0.f;
     }
-    st4(base + ((int64_t)(q >> 1) * W + (q & 1)) * lddx, v);
+    const int64_t off = (int64_t)(q >> 1) * W + (q & 1);
+    if (add) {                                           // + gradient arriving through the skip connection
+      const float4 s4 = ld4_stream(add + ((((int64_t)b * H + 2 * yo) * W + 2 * xo) + off) * ldadd + c);
+      v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
+    }
+    st4(base + off * lddx, v);
   }
 }
 
@@ -644,7 +690,10 @@ extern "C" int tm_conv1x1_c1_forward(int64_t npix, int64_t C, const float* x, in
 extern "C" int tm_conv1x1_c1_dgrad(int64_t npix, int64_t C, const float* dy, int64_t lddy, const float* w, float* dx,
                                    int64_t lddx, void* stream) {
   if (npix <= 0) return 0;
-  conv1x1_c1_dgrad_kernel<<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, dy, lddy, w, dx, lddx);
+  if ((C % 4 == 0) && (lddx % 4 == 0) && aligned16(dx))
+    conv1x1_c1_dgrad_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, dy, lddy, w, dx, lddx);
+  else
+    conv1x1_c1_dgrad_kernel<1><<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, dy, lddy, w, dx, lddx);
   return check_launch("conv1x1_c1_dgrad");
 }
 extern "C" size_t tm_conv1x1_c1_wgrad_ws(int64_t C) { return (size_t)BN_BLOCKS * (C + 1) * sizeof(double) + 256; }
@@ -665,12 +714,18 @@ extern "C" int tm_pool2x2_forward(int64_t B, int64_t H, int64_t W, int64_t C, in
   TM_REQUIRE(mode == 0 || mode == 1, "tm_pool2x2: mode must be 0 (max) or 1 (avg)");
   const int64_t n = B * (H / 2) * (W / 2) * C;
   if (n <= 0) return 0;
+  if (C % 4 == 0 && H % 2 == 0 && W % 2 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned16(x) && aligned16(y) &&
+      (!idx || reinterpret_cast<uintptr_t>(idx) % 4 == 0) && B * H * W < (1ll << 31)) {
+    pool_fwd_vec_kernel<<<blocks_for(n / 4), 256, 0, ST>>>((int)B, (int)H, (int)W, (int)C, mode, x, ldx, y, ldy, idx,
+                                                         (flags & TM_EPI_RELU) != 0);
+    return check_launch("pool_fwd_vec");
+  }
   pool_fwd_kernel<<<blocks_for(n), 256, 0, ST>>>(B, H, W, C, mode, x, ldx, y, ldy, idx, (flags & TM_EPI_RELU) != 0);
   return check_launch("pool_fwd");
 }
 extern "C" int tm_pool2x2_backward(int64_t B, int64_t H, int64_t W, int64_t C, int mode, const float* dy,
                                    int64_t lddy, const float* y, int64_t ldy, const uint8_t* idx, float* dx,
-                                   int64_t lddx, int flags, void* stream) {
+                                   int64_t lddx, int flags, const float* add, int64_t ldadd, void* stream) {
   TM_REQUIRE(mode == 0 || mode == 1, "tm_pool2x2: mode must be 0 (max) or 1 (avg)");
   TM_REQUIRE(mode == 1 || idx, "tm_pool2x2_backward: max pooling needs idx");
   const int64_t n = B * H * W * C;
@@ -678,12 +733,16 @@ extern "C" int tm_pool2x2_backward(int64_t B, int64_t H, int64_t W, int64_t C, i
   const bool relu = (flags & TM_EPI_RELU) != 0;
   if (C % 4 == 0 && H % 2 == 0 && W % 2 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && aligned16(dy) && aligned16(dx) &&
       (!relu || (ldy % 4 == 0 && aligned16(y))) && (mode != 0 || reinterpret_cast<uintptr_t>(idx) % 4 == 0) &&
-      B * H * W < (1ll << 31)) {
+      (!add || (ldadd % 4 == 0 && aligned16(add))) && B * H * W < (1ll << 31)) {
     pool_bwd_vec_kernel<<<blocks_for(n / 16), 256, 0, ST>>>((int)B, (int)H, (int)W, (int)C, mode, dy, lddy, y, ldy, idx,
-                                                          dx, lddx, relu);
+                                                          dx, lddx, relu, add, ldadd);
     return check_launch("pool_bwd_vec");
   }
   pool_bwd_kernel<<<blocks_for(n), 256, 0, ST>>>(B, H, W, C, mode, dy, lddy, y, ldy, idx, dx, lddx, relu);
+  if (add) {
+    TM_TRY(check_launch("pool_bwd"));
+    add_strided_kernel<<<blocks_for(B * H * W * C), 256, 0, ST>>>(B * H * W, C, add, ldadd, dx, lddx);
+  }
   return check_launch("pool_bwd");
 }
 extern "C" int tm_leaky_relu_forward(int64_t n, const float* x, float slope, float* y, void* stream) {

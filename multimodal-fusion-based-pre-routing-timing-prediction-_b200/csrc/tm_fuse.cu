@@ -192,13 +192,16 @@ colsum_partial_kernel(int64_t R, int64_t C, const float* __restrict__ X, int64_t
     part[(int64_t)blockIdx.y * C + c] = s;
   }
 }
+// one warp per column: lane l adds chunks l, l+32, ...; the lanes are folded by a fixed shuffle tree
 __global__ void colsum_final_kernel(int64_t C, int nchunk, const float* __restrict__ part, float* __restrict__ out,
                                     int accumulate) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
   float s = 0.f;
-  for (int i = 0; i < nchunk; ++i) s += part[(int64_t)i * C + c];
-  out[c] = accumulate ? out[c] + s : s;
+  for (int i = lane; i < nchunk; i += 32) s += part[(int64_t)i * C + c];
+  s = warp_sum(s);
+  if (lane == 0) out[c] = accumulate ? out[c] + s : s;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -343,7 +346,7 @@ extern "C" int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, const
   const int nchunk = (int)cdiv(R > 0 ? R : 1, CS_ROWS);
   colsum_partial_kernel<<<dim3((unsigned)cdiv(C, 32), (unsigned)nchunk), dim3(32, 8), 0, st>>>(R, C, X, ld, rows, (float*)ws);
   TM_TRY(check_launch("colsum_partial"));
-  colsum_final_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(C, nchunk, (const float*)ws, out, accumulate);
+  colsum_final_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, st>>>(C, nchunk, (const float*)ws, out, accumulate);
   return check_launch("colsum_final");
 }
 

@@ -651,24 +651,27 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_c
 }
 
 // part [splits][(r,S)][po*Cout+co][pi*CinP+ci] (packed rows of P pixels) -> dw [Cout][Cin][3][3] (torch layout):
-// tap (r, s) collects every (S, po, pi) with S*P + pi - po + 1 == s.  Fixed summation order.
+// tap (r, s) collects every (S, po, pi) with S*P + pi - po + 1 == s.  One warp per output element: lane z owns the
+// splits z, z+32, ..., the lanes are folded by a fixed shuffle tree (deterministic).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int P, int Cout, int CinP, int Cin,
                                     float* __restrict__ dw) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= (int64_t)9 * Cout * Cin) return;
-  // ci fastest: neighbouring threads read neighbouring partials
+  // ci fastest: neighbouring warps read neighbouring partials
   const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), tap = (int)(i / ((int64_t)Cin * Cout));
   const int r = tap / 3, sx = tap % 3;
   const int64_t ldn = (int64_t)P * CinP, per_tap = (int64_t)P * Cout * ldn;
   float s = 0.f;
-  for (int z = 0; z < splits; ++z)
+  for (int z = lane; z < splits; z += 32)
     for (int S = -1; S <= 1; ++S)
       for (int po = 0; po < P; ++po) {
         const int pi = sx - 1 + po - S * P;
         if (pi < 0 || pi >= P) continue;
         s += part[((int64_t)z * 9 + r * 3 + S + 1) * per_tap + ((int64_t)po * Cout + co) * ldn + (int64_t)pi * CinP + ci];
       }
-  dw[((int64_t)co * Cin + ci) * 9 + tap] = s;
+  s = warp_sum(s);
+  if (lane == 0) dw[((int64_t)co * Cin + ci) * 9 + tap] = s;
 }
 
 // fp32 rows (stride ld) -> compact bf16 rows of Cp >= C channels (zero padded); 8 channels per thread
@@ -1032,6 +1035,6 @@ extern "C" int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Ci
   else conv3x3_wgrad_tma_kernel<1><<<grid, CONV_THREADS, smem, st>>>(tmx, tmdy, a);
   TM_TRY(check_launch("conv3x3_wgrad_tma"));
   const int64_t n = 9 * Cout * Cin_real;
-  wgrad_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a.part, splits, P, (int)Cout, (int)Cin, (int)Cin_real, dw);
+  wgrad_reduce_kernel<<<(unsigned)cdiv(n * 32, 256), 256, 0, st>>>(a.part, splits, P, (int)Cout, (int)Cin, (int)Cin_real, dw);
   return check_launch("wgrad_reduce");
 }

@@ -328,7 +328,7 @@ def unet_backward(net, st, gout):
     gout = gout.detach().float().contiguous()
     grads = {}
     d_oraw = _empty(B * H * W, 1, dev=dev)
-    call("tm_pool2x2_backward", B, H, W, 1, mode, gout, 1, st["out"], 1, st["oidx"], d_oraw, 1, RELU, stream())
+    call("tm_pool2x2_backward", B, H, W, 1, mode, gout, 1, st["out"], 1, st["oidx"], d_oraw, 1, RELU, None, 0, stream())
     dw, db = _empty(1, 16, 1, 1, dev=dev), _empty(1, dev=dev)
     nb = tm_lib.ws_bytes("tm_conv1x1_c1_wgrad_ws", 16)
     call("tm_conv1x1_c1_wgrad", B * H * W, 16, st["y3"], st["ld3"], d_oraw, 1, dw, db, ws.get(nb), nb, stream())
@@ -379,10 +379,9 @@ def unet_backward(net, st, gout):
             _double_conv_bwd(ws, s, dy, lddy, grads, enc_names[i], dpool, chans[i - 1])
             p = st["pool"][i - 1]
             dprev = _empty(B * Hs[i - 1] * Ws_[i - 1], chans[i - 1], dev=dev)
+            # pooling backward and the gradient arriving through the skip connection (first half of dcat) in one pass
             call("tm_pool2x2_backward", B, Hs[i - 1], Ws_[i - 1], chans[i - 1], mode, dpool, chans[i - 1], None, 0,
-                 p["idx"], dprev, chans[i - 1], 0, stream())
-            call("tm_add_strided", B * Hs[i - 1] * Ws_[i - 1], chans[i - 1], dskip[i - 1], 2 * chans[i - 1], dprev,
-                 chans[i - 1], stream())
+                 p["idx"], dprev, chans[i - 1], 0, dskip[i - 1], 2 * chans[i - 1], stream())
             dy, lddy = dprev, chans[i - 1]
         else:
             _double_conv_bwd(ws, s, dy, lddy, grads, enc_names[0], None, 0)
@@ -477,7 +476,7 @@ def layoutnet_backward(net, st, gout):
             if r["pool"] is not None:
                 dyp = _empty(npix, cout, dev=dev)
                 call("tm_pool2x2_backward", B, h, w, cout, mode, g, cout, None, 0,
-                     r["pool"] if mode == 0 else None, dyp, cout, 0, stream())
+                     r["pool"] if mode == 0 else None, dyp, cout, 0, None, 0, stream())
                 g = dyp
             dy = _empty(npix, cout, dev=dev)
             call("tm_leaky_relu_backward", npix * cout, r["y"], g, 0.0, dy, stream())   # ReLU
