@@ -29,6 +29,12 @@ import sys
 import threading
 import time
 
+# NCCL's own log lines ("NCCL version ...") must not land on stdout next to the ONE JSON line: route them to stderr
+# (read when NCCL first initialises its logging, so it is set before torch is imported)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # the one level NCCL_DEBUG_FILE does not apply to
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np
 import torch
 
@@ -187,7 +193,6 @@ def main():
     pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's own log lines ("NCCL version ...") off stdout: one JSON line only
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
         pg = dist.group.WORLD
 
