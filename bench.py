@@ -402,6 +402,29 @@ def main():
                                "gnn_fwd_total(with hoisted MLPs)": t_gnn_f, "gnn_bwd_total(with weight grads)": t_gnn_b,
                                "unet_fwd": t_unet_f, "unet_bwd": t_unet_b,
                                "gnn_bwd_GBps": sched.algorithmic_bytes_bwd() / (t_bwd * 1e-3) / 1e9}
+        if world == 1 and use_graph:
+            # the same step with the image branch in its bf16 mode (TMA-fed tcgen05 convolutions, north_star (b)):
+            # reported NEXT to the fp32-class headline, never instead of it (predictions then carry the bf16 bar, rtol 2e-2)
+            try:
+                cnn.math = "bf16"
+                run_mixed = step.capture(batch)
+                for _ in range(3):
+                    run_mixed()
+                torch.cuda.synchronize()
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                m0.record()
+                for _ in range(args.steps):
+                    loss_m, _ = run_mixed()
+                m1.record()
+                torch.cuda.synchronize()
+                ms_m = m0.elapsed_time(m1) / args.steps
+                extra["mixed_precision_step"] = {"value": 1e3 / ms_m, "unit": "designs/s", "ms_per_step": ms_m,
+                                                 "loss": float(loss_m.item()), "dtype": "f32 (netlist branch, 3xTF32) + bf16 operands / fp32 accumulate (U-Net)",
+                                                 "note": "not the headline: same design step with cnn.math = 'bf16'"}
+            except Exception as e:                                   # noqa: BLE001
+                extra["mixed_precision_step"] = {"error": repr(e)}
+            finally:
+                cnn.math = None
         if world == 1 and not args.no_configs and args.config == "c2":
             # BASELINE configs 3 (GNN only, ~1M pins) and 4 (U-Net alone, 32 x 512x512, bf16): device timings next to
             # the headline (profiles/bench_configs.py; parity for both lives in tests/test_gpu_configs.py)

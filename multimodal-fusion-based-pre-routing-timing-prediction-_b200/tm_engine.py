@@ -12,6 +12,8 @@ and the only exchange is one gradient all-reduce per step.  ``DesignStep`` posts
 buckets on a side stream as soon as each group of gradients exists (head+fusion -> GNN ->
 U-Net), so the NCCL transfers over NVLink overlap the remaining backward kernels.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -34,6 +36,8 @@ def build_models(map_size, pooling="max", seed=0, device="cuda"):
     torch.nn.init.xavier_uniform_(fcn.weight, gain=torch.nn.init.calculate_gain("relu"))
     mdl = M.PathModel(gnn, None, fcn, None, None, M.MLP(128 + 128 + 32, 2 * (128 + 128 + 32), 1))
     cnn = U.UNet(pooling)
+    if os.environ.get("TM_UNET_MATH"):                 # e.g. "bf16": image branch on the TMA-fed bf16 tensor-core path
+        cnn.math = os.environ["TM_UNET_MATH"]
     return mdl.to(device).train(), cnn.to(device).train()
 
 

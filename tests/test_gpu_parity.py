@@ -506,6 +506,36 @@ def test_design_step_vs_golden(mods, math_mode):
     _check_step_against_golden(z, model, cnn, pred, loss)
 
 
+def test_design_step_mixed_precision_vs_golden(mods):
+    """The fused step with the image branch in its bf16 mode (TMA-fed tcgen05 convolutions; `cnn.math = "bf16"`)
+    against the fixture of the unmodified reference at the bf16 bar: predictions and loss per element at rtol 2e-2
+    (atol 2e-2 x max|ref|); the gradients of the netlist branch / head / fusion at 2e-2 relative L2 error per tensor
+    (their error is the image branch's bf16 rounding spread over a whole tensor: a few of 166k elements of the
+    widest head layer sit at 5 % of the tensor's scale); the U-Net's own parameter gradients by direction
+    (cosine >= 0.85), as in tests/test_gpu_configs.py."""
+    eng = mods["engine"]
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["tiny"])
+    z, sd_m, sd_c = load_golden_step("tiny")
+    model, cnn = _load_models(sd_m, sd_c, d.map_size)
+    cnn.math = "bf16"
+    batch = eng.DesignBatch.from_synth(d, DEV)
+    loss, pred = eng.DesignStep(model, cnn).run(batch)
+    assert_close(pred, z["pred"], 2e-2, 2e-2, "pred (bf16 image branch)")
+    assert_close(loss.reshape(()), z["loss"], 2e-2, 2e-2, "loss (bf16 image branch)")
+    for k, p in model.named_parameters():
+        ref = z["grad.model." + k]
+        if ref.size:
+            a, b = p.grad.double().cpu().reshape(-1), torch.from_numpy(ref).double().reshape(-1)
+            rel = float((a - b).norm() / (b.norm() + 1e-300))
+            assert rel <= 2e-2, f"model.{k}: relative L2 error {rel:.3e}"
+    for k, p in cnn.named_parameters():
+        if p.numel() == 1:
+            continue
+        a, b = p.grad.double().cpu().reshape(-1), torch.from_numpy(z["grad.cnn." + k]).double().reshape(-1)
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-300))
+        assert cos >= 0.85, f"cnn.{k}: cosine {cos:.3f}"
+
+
 def test_prepared_design_graph_replay(mods):
     """DesignStep.prepare(): the captured CUDA-graph step, fed new per-step VALUES from host memory,
     reproduces the eager two-stream step bit for bit (loss, predictions, every gradient), also when two
