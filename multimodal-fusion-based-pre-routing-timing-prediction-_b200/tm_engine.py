@@ -248,7 +248,7 @@ class DesignStep:
 
     def _capture_local(self, b, warmup=2):
         cur = torch.cuda.current_stream()
-        s = torch.cuda.Stream()
+        s = torch.cuda.Stream(priority=int(os.environ.get("TM_MAIN_PRIORITY", "0")))   # (a higher priority for the netlist branch was measured: no effect)
         s.wait_stream(cur)
         with torch.cuda.stream(s):
             for _ in range(warmup):
