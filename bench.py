@@ -387,6 +387,8 @@ def main():
                                     "bound": "tensor", "achieved": cflop / (t_conv * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                                     "frac": cflop / (t_conv * 1e-3) / 1e12 / tpeak, "ms": t_conv, "algorithmic_flops": cflop,
                                     "hbm_GBps": npx * (2 * cc + 4 * cc) / (t_conv * 1e-3) / 1e9,
+                                    "traffic": (json.load(open(tj)).get("conv3x3_tma_128x128_32x64x64_dram_bytes")
+                                                if os.path.isfile(tj) else None),
                                     "peak_source": "measured burst (MEASURED_PEAKS.json)" if os.path.isfile(pj) else "fallback"}
         del xb16, w16, wq16, y16
         # the largest dense contraction of the design step itself (second layer of the hoisted net-pin MLP, 3xTF32)
