@@ -380,7 +380,7 @@ def main():
         tm_lib.call("tm_conv3x3_pack_bf16", cc, cc, w16, wq16, pk, cc, 0, tm_lib.stream())
         y16 = torch.empty(npx, cc, device=dev)
         t_conv = timed(lambda: tm_lib.call("tm_conv3x3_bf16", cb, ch, cw, cc, cc, pk, xb16, wq16, None, y16, cc, 0,
-                                           tm_lib.err_flag(dev), tm_lib.stream()), reps=20)
+                                           None, tm_lib.err_flag(dev), tm_lib.stream()), reps=20)
         cflop = 2.0 * 9 * cc * cc * npx
         extra["roofline_tensor"] = {"kernel": "conv3x3_tma_kernel<64> (bf16 operands by TMA, fp32 accumulate in TMEM; 128->128 channels, "
                                               "32 x 64x64 maps = U-Net down3.conv2 of config 4)",

@@ -283,11 +283,13 @@ size_t tm_bn_ws(int64_t npix, int64_t C);
 /* Train-mode BatchNorm2d + ReLU (Unet.py:17-18,20-21): batch statistics over B*H*W,
  * y = relu(gamma*(x-mean)*invstd+beta); running stats updated with `momentum`, unbiased var.
  * save_mean/save_invstd [C] kept for backward.  y_bf16 (optional): compact bf16 copy [npix][C] of y written by
- * the same pass (the TMA operand of the next convolution in bf16 mode); dx_bf16 likewise for the backward. */
+ * the same pass (the TMA operand of the next convolution in bf16 mode); dx_bf16 likewise for the backward.
+ * stats_part (optional): nparts fp64 partials [nparts][C][2] (sum, sum of squares) already produced by the
+ * convolution's epilogue (tm_conv3x3_bf16 stats): the statistics pass over x is skipped. */
 int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* gamma,
                        const float* beta, float* running_mean, float* running_var, float momentum,
                        float eps, float* y, int64_t ldy, float* save_mean, float* save_invstd,
-                       void* y_bf16, void* ws, size_t ws_bytes, void* stream);
+                       void* y_bf16, const void* stats_part, int64_t nparts, void* ws, size_t ws_bytes, void* stream);
 /* Backward of the pair: dy is the gradient w.r.t. the ReLU output y.
  * dx = BN'( dy * (y>0) ), dgamma, dbeta [C].  dx may be NULL when only dx_bf16 is wanted; y may be NULL:
  * the ReLU mask is then rebuilt bit-for-bit from x, the saved statistics, gamma and beta (one tensor less to
@@ -401,8 +403,12 @@ int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, void* q, int
                          void* stream);
 /* y[pix, 0:N] (fp32, row stride ldy) = sum_{tap,c} xb[pix + tap, c] * W[tap][n][c]; bias optional,
  * flags: TM_EPI_RELU.  The data gradient is the same call on bf16(dy) with the dgrad operand. */
+/* stats (optional; tm_conv3x3_bf16_stats_bytes(N, P) bytes; bias must be NULL, P * N <= 128): the batch-norm
+ * statistics of the output, taken from the fp32 accumulators by the epilogue -- fp64 partial sums / sums of squares,
+ * layout [slots = SMs * 4][P][N][2], consumed by tm_bn_relu_forward(stats_part, nparts = slots * P). */
+size_t tm_conv3x3_bf16_stats_bytes(int64_t N, int64_t P);
 int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, int64_t P, const void* xb, const void* wq,
-                    const float* bias, float* y, int64_t ldy, int flags, int* err, void* stream);
+                    const float* bias, float* y, int64_t ldy, int flags, void* stats, int* err, void* stream);
 /* nn.ConvTranspose2d(k=2, s=2) (Unet.py:53) on the same TMA path.  Weight w [Cin][Cout][2][2] fp32 ->
  * wf bf16 [4*Cout][Cin] (forward operand) and wd bf16 [4][Cin][Cout] (data-gradient operand; either may be NULL).
  * forward: y[b,2y+dy,2x+dx,co] = bias[co] + sum_ci xb[b,y,x,ci] w[ci][co][dy][dx]: ONE tap, the accumulator row of

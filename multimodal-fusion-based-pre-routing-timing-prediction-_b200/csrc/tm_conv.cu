@@ -634,7 +634,8 @@ extern "C" size_t tm_bn_ws(int64_t npix, int64_t C) {
 extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* gamma,
                                   const float* beta, float* running_mean, float* running_var,
                                   float momentum, float eps, float* y, int64_t ldy, float* save_mean,
-                                  float* save_invstd, void* y_bf16, void* ws, size_t ws_bytes, void* stream) {
+                                  float* save_invstd, void* y_bf16, const void* stats_part, int64_t nparts, void* ws,
+                                  size_t ws_bytes, void* stream) {
   TM_REQUIRE(npix > 0 && C > 0 && C <= 256, "tm_bn_relu_forward: bad sizes (C <= 256)");
   TM_REQUIRE(ws_bytes >= tm_bn_ws(npix, C), "tm_bn_relu_forward: workspace too small");
   const int nblk = bn_blocks(npix);
@@ -643,10 +644,16 @@ extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64
   const int groups = v4 ? (int)C / 4 : (int)C;
   const size_t sh = (size_t)(BN_THREADS / groups) * C * 2 * sizeof(double);
   TM_REQUIRE(y || y_bf16, "tm_bn_relu_forward: neither y nor y_bf16 given");
-  if (v4) bn_stats_kernel<4, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, part);
-  else bn_stats_kernel<1, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, part);
-  TM_TRY(check_launch("bn_stats"));
-  bn_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(npix, C, nblk, part, running_mean, running_var,
+  int nfin = nblk;
+  if (stats_part) {                      // statistics already taken by the producing convolution's epilogue
+    part = (double*)stats_part;
+    nfin = (int)nparts;
+  } else {
+    if (v4) bn_stats_kernel<4, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, part);
+    else bn_stats_kernel<1, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, part);
+    TM_TRY(check_launch("bn_stats"));
+  }
+  bn_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(npix, C, nfin, part, running_mean, running_var,
                                                              momentum, eps, save_mean, save_invstd);
   TM_TRY(check_launch("bn_finalize"));
   if (v4) bn_relu_apply_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, x, ldx, gamma, beta, save_mean, save_invstd, y, ldy, (__nv_bfloat16*)y_bf16);

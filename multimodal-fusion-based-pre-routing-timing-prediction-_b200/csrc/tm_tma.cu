@@ -121,15 +121,38 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int n, bool a_mn, bool b_mn) {
 // would touch 32 different lines with 16 bytes each per instruction.  The chunk is transposed through a padded
 // per-warp scratch instead, so that four neighbouring lanes write the 64 contiguous bytes of one row (8 rows per
 // instruction, only full 32-byte sectors).  rowp[pass]: output row pass * 8 + lane / 4 (nullptr = outside the batch).
-__device__ __forceinline__ void store_chunk16(float* scr, int lane, const float (&v)[16], float* const (&rowp)[4], int64_t coff) {
+__device__ __forceinline__ void store_chunk16(float* scr, int lane, const float (&v)[16], float* const (&rowp)[4], int64_t coff,
+                                              double* stat = nullptr) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) scr[lane * 17 + i] = v[i];
   __syncwarp();
   const int c4 = (lane & 3) * 4;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
     const float* sp = scr + (pass * 8 + (lane >> 2)) * 17 + c4;
-    if (rowp[pass]) st4(rowp[pass] + coff + c4, make_float4(sp[0], sp[1], sp[2], sp[3]));
+    const float4 o = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    if (rowp[pass]) st4(rowp[pass] + coff + c4, o);
+    if (stat) {          // rows outside the batch are exact zeros (zero-filled input, no bias): they add nothing
+      s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+      s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
+    }
+  }
+  if (stat) {
+    // batch-norm statistics of the convolution's output, from the fp32 accumulators: fold the 8 lanes that own
+    // the same 4 columns (fixed shuffle tree), then lanes 0..3 add the chunk's 32-row sums into the warp's fp64 slots
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+      }
+    }
+    if (lane < 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { stat[(c4 + j) * 2] += (double)s1[j]; stat[(c4 + j) * 2 + 1] += (double)s2[j]; }
+    }
   }
   __syncwarp();
 }
@@ -159,6 +182,7 @@ inline Geom make_geom(int64_t B, int64_t H, int64_t W) {
 }
 
 constexpr int CONV_THREADS = 192;
+constexpr int STAT_MAX_N = 128;          // widest accumulator row the fused batch-norm statistics support
 constexpr int CONV_MAX_STAGES = 8;
 constexpr uint32_t CONV_SMEM_BUDGET = 200 * 1024;
 
@@ -174,6 +198,7 @@ struct ConvArgs {
   const float* bias;
   int flags;
   int* err;
+  double* stats;                     // optional [gridDim.x * 4][N][2]: per epilogue warp sum / sum of squares per column
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -186,6 +211,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ float epi_scr[4][32 * 17];
+  __shared__ double epi_stat[4][STAT_MAX_N * 2];       // per epilogue warp: column sums / sums of squares (a.stats)
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -270,6 +296,11 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     // ======================= epilogue =======================
     const int q = warp & 3;                               // TMEM lane quarter this warp may read
     float* scr = epi_scr[q];
+    double* wstat = epi_stat[q];
+    if (a.stats) {
+      for (int i = lane; i < 2 * N; i += 32) wstat[i] = 0.0;
+      __syncwarp();
+    }
     int li = 0;
     for (int64_t t = blockIdx.x; t < a.g.ntiles && ok; t += G, ++li) {
       const int buf = li & 1;
@@ -307,11 +338,15 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         }
         // po: pixel inside the packed row -- or, for the transposed conv, the quadrant (dy, dx) of the 2x2 window
         const int64_t coff = a.convt ? ((int64_t)(po >> 1) * 2 * a.g.W + (po & 1)) * a.ldy + co : (int64_t)po * a.ldy + co;
-        store_chunk16(scr, lane, v, rowp, coff);
+        store_chunk16(scr, lane, v, rowp, coff, a.stats ? wstat + c * 2 : nullptr);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (a.stats && ok) {
+      __syncwarp();
+      for (int i = lane; i < 2 * N; i += 32) a.stats[((int64_t)blockIdx.x * 4 + q) * 2 * N + i] = wstat[i];
     }
   }
   if (!ok) {
@@ -345,6 +380,7 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
   uint8_t* ring = wsm + 9 * (size_t)w_tap;                          // 9 * N * 128 is a multiple of 1024 (N % 16 == 0 -> check on host)
   __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full[2], acc_empty[2], w_full;
   __shared__ float epi_scr[4][32 * 17];
+  __shared__ double epi_stat[4][STAT_MAX_N * 2];       // per epilogue warp: column sums / sums of squares (a.stats)
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -454,6 +490,11 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
   } else {
     const int q = warp & 3;
     float* scr = epi_scr[q];
+    double* wstat = epi_stat[q];
+    if (a.stats) {
+      for (int i = lane; i < 2 * N; i += 32) wstat[i] = 0.0;
+      __syncwarp();
+    }
     int li = 0;
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += G, ++li) {
       const int buf = li & 1;
@@ -480,12 +521,17 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (!(a.flags & 0x100)) store_chunk16(scr, lane, v, rowp, (int64_t)po * a.ldy + co);
+          if (!(a.flags & 0x100))
+            store_chunk16(scr, lane, v, rowp, (int64_t)po * a.ldy + co, a.stats ? wstat + (c) * 2 : nullptr);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (a.stats && ok) {
+      __syncwarp();
+      for (int i = lane; i < 2 * N; i += 32) a.stats[((int64_t)blockIdx.x * 4 + q) * 2 * N + i] = wstat[i];
     }
   }
   if (!ok) {
@@ -775,8 +821,16 @@ extern "C" int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, v
 // Y[pix, 0:N] = sum_{tap,c} X[pix+tap, c] * W[tap][n][c]  (3x3, stride 1, zero padding 1)
 // xb: bf16 [B][H][W][Cin] compact; wq: tm_conv3x3_pack_bf16 operand for P = tm_conv3x3_bf16_pack(W, Cin, N);
 // y: fp32 rows of stride ldy.
+extern "C" size_t tm_conv3x3_bf16_stats_bytes(int64_t N, int64_t P) {
+  return (size_t)sm_count() * 4 * 2 * (size_t)(N * P) * sizeof(double);
+}
+
+// stats (optional, tm_conv3x3_bf16_stats_bytes(N, P) bytes, no bias): per-column sum / sum of squares of the output,
+// [sm_count * 4 slots][P * N][2] fp64 -- the batch-norm statistics pass fused into the epilogue (slot s, pixel po,
+// channel c at ((s * P + po) * N + c) * 2: tm_bn_relu_forward reads it as sm_count * 4 * P partials of N channels).
 extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t N, int64_t P, const void* xb,
-                               const void* wq, const float* bias, float* y, int64_t ldy, int flags, int* err, void* stream) {
+                               const void* wq, const float* bias, float* y, int64_t ldy, int flags, void* stats, int* err,
+                               void* stream) {
   TM_REQUIRE(P >= 1 && W % P == 0 && conv_shape_ok(B, H, W / P, P * Cin, P * N) && N % 16 == 0,
              "tm_conv3x3_bf16: unsupported shape (H, W powers of two; channels multiples of 16)");
   TM_REQUIRE(ldy % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0, "tm_conv3x3_bf16: output rows must be 16-byte aligned");
@@ -792,6 +846,11 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
   a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
   a.y = y; a.ldy = ldy; a.bias = bias;
+  a.stats = (double*)stats;
+  if (stats) {
+    TM_REQUIRE(!bias && Np <= STAT_MAX_N, "tm_conv3x3_bf16: fused statistics need no bias and P * N <= 128");
+    TM_CUDA(cudaMemsetAsync(stats, 0, tm_conv3x3_bf16_stats_bytes(N, P), (cudaStream_t)stream));   // slots of idle CTAs
+  }
   a.ntaps = 9; a.cscale = 1; a.convt = 0;
   for (int t = 0; t < 9; ++t) { a.tdx[t] = (signed char)(t % 3 - 1); a.tdy[t] = (signed char)(t / 3 - 1); }
   a.flags = (flags & TM_EPI_RELU) | (bias ? TM_EPI_BIAS : 0);
@@ -879,6 +938,7 @@ void fill_common(ConvArgs& a, int64_t B, int64_t H, int64_t W, int64_t K, int64_
   a.y = y; a.ldy = ldy; a.bias = bias;
   a.flags = bias ? TM_EPI_BIAS : 0;
   a.err = err;
+  a.stats = nullptr;
 }
 }  // namespace
 

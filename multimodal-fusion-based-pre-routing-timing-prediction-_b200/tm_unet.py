@@ -85,9 +85,19 @@ def _pack_bf16(w, W, need_dgrad):
     return one(cout, cin, 0), (one(cin, cout, 1) if need_dgrad else None)
 
 
-def _conv_tma(xb, B, H, W, cinp, cout, wq, y, ldy):
+FUSE_BN_STATS = os.environ.get("TM_FUSE_BN_STATS", "1") != "0"   # BN statistics in the convolution's epilogue
+
+
+def _conv_tma(xb, B, H, W, cinp, cout, wq, y, ldy, want_stats=False):
+    """-> (stats buffer, number of partials) when the epilogue also took the batch-norm statistics, else None."""
     q, P = wq
-    call("tm_conv3x3_bf16", B, H, W, cinp, cout, P, xb, q, None, y, ldy, 0, tm_lib.err_flag(y.device), stream())
+    stats = None
+    if want_stats and FUSE_BN_STATS and P * cout <= 128:
+        nb = tm_lib.ws_bytes("tm_conv3x3_bf16_stats_bytes", cout, P)
+        stats = (torch.empty(nb, dtype=torch.uint8, device=y.device), nb // (16 * cout))
+    call("tm_conv3x3_bf16", B, H, W, cinp, cout, P, xb, q, None, y, ldy, 0, stats[0] if stats else None,
+         tm_lib.err_flag(y.device), stream())
+    return stats
 
 
 def _wgrad_tma(ws, xb, dyb, B, H, W, cin, cout):
@@ -137,14 +147,15 @@ def _pack(w, need_bwd=True):
     return wf, wb
 
 
-def _bn_relu_fwd(ws, x, ldx, npix, C, bn, y, ldy, update_stats, yb=None):
+def _bn_relu_fwd(ws, x, ldx, npix, C, bn, y, ldy, update_stats, yb=None, stats=None):
     dev = x.device
     mean, invstd = _empty(C, dev=dev), _empty(C, dev=dev)
     nb = tm_lib.ws_bytes("tm_bn_ws", npix, C)
     rm = bn.running_mean if update_stats else None
     rv = bn.running_var if update_stats else None
     call("tm_bn_relu_forward", npix, C, x, ldx, bn.weight.detach(), bn.bias.detach(), rm, rv,
-         float(bn.momentum), float(bn.eps), y, ldy, mean, invstd, yb, ws.get(nb), nb, stream())
+         float(bn.momentum), float(bn.eps), y, ldy, mean, invstd, yb, stats[0] if stats else None,
+         stats[1] if stats else 0, ws.get(nb), nb, stream())
     if update_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return mean, invstd
@@ -176,12 +187,12 @@ def _double_conv_fwd(ws, st, name, mods, x, ldx, B, H, W, cin, cout, out, ldo, u
         xb = _to_bf16(x, ldx, npix, cin)
         wq1, wd1 = _pack_bf16(conv1.weight, W, need_bwd and cin % 16 == 0)
         wq2, wd2 = _pack_bf16(conv2.weight, W, need_bwd)
-        _conv_tma(xb, B, H, W, _cpad(cin), cmid, wq1, r1, cmid)
+        s1 = _conv_tma(xb, B, H, W, _cpad(cin), cmid, wq1, r1, cmid, want_stats=True)
         a1b = torch.empty(npix, cmid, dtype=torch.bfloat16, device=dev)
         # the mid activation exists only as the bf16 operand of conv2 (the backward rebuilds its ReLU mask from r1)
-        m1, i1 = _bn_relu_fwd(ws, r1, cmid, npix, cmid, bn1, None, 0, update_stats, yb=a1b)
-        _conv_tma(a1b, B, H, W, cmid, cout, wq2, r2, cout)
-        m2, i2 = _bn_relu_fwd(ws, r2, cout, npix, cout, bn2, out, ldo, update_stats)
+        m1, i1 = _bn_relu_fwd(ws, r1, cmid, npix, cmid, bn1, None, 0, update_stats, yb=a1b, stats=s1)
+        s2 = _conv_tma(a1b, B, H, W, cmid, cout, wq2, r2, cout, want_stats=True)
+        m2, i2 = _bn_relu_fwd(ws, r2, cout, npix, cout, bn2, out, ldo, update_stats, stats=s2)
         st[name] = dict(tma=True, xb=xb if need_bwd else None, a1b=a1b if need_bwd else None, wd1=wd1, wd2=wd2,
                         x=x, ldx=ldx, B=B, H=H, W=W, cin=cin, cmid=cmid, cout=cout, r1=r1, r2=r2, out=out,
                         ldo=ldo, m1=m1, i1=i1, m2=m2, i2=i2, g1=bn1.weight.detach(), g2=bn2.weight.detach(),

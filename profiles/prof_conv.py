@@ -27,7 +27,7 @@ err = L.err_flag(dev)
 
 
 def fprop():
-    L.call("tm_conv3x3_bf16", B, H, W, Cin, Cout, P, xb, wq, None, y, Cout, 0, err, L.stream())
+    L.call("tm_conv3x3_bf16", B, H, W, Cin, Cout, P, xb, wq, None, y, Cout, 0, None, err, L.stream())
 
 
 def wgrad():

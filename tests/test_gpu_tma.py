@@ -55,18 +55,29 @@ def test_conv3x3_bf16_tma(lib, B, H, W, Cin, Cout):
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
     # ---- forward, written into the second half of a wider (concat-style) buffer, with bias + ReLU
     ybuf = torch.full((B * H * W, 2 * Cout), 7.0, device=DEV)
-    lib.call("tm_conv3x3_bf16", B, H, W, CinP, Cout, Pf, xb, wf, bias, ybuf[:, Cout:], 2 * Cout, 2, err, lib.stream())
+    lib.call("tm_conv3x3_bf16", B, H, W, CinP, Cout, Pf, xb, wf, bias, ybuf[:, Cout:], 2 * Cout, 2, None, err, lib.stream())
     want = torch.relu(ref + bias.double().view(1, -1, 1, 1)).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
     assert int(err.item()) == 0
     assert_close(ybuf[:, Cout:], want, 1e-4, 1e-5, "tma fprop")
     assert bool((ybuf[:, :Cout] == 7.0).all())
+    # ---- batch-norm statistics fused into the epilogue (no bias): per-channel sum and sum of squares of the output
+    if Pf * Cout <= 128:
+        nb = lib.ws_bytes("tm_conv3x3_bf16_stats_bytes", Cout, Pf)
+        stats = torch.empty(nb // 8, dtype=torch.float64, device=DEV)
+        y2 = torch.empty(B * H * W, Cout, device=DEV)
+        lib.call("tm_conv3x3_bf16", B, H, W, CinP, Cout, Pf, xb, wf, None, y2, Cout, 0, stats, err, lib.stream())
+        got = stats.reshape(-1, Cout, 2).sum(0)
+        refn = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+        assert_close(y2, refn, 1e-4, 1e-5, "tma fprop (stats launch)")
+        assert_close(got[:, 0], refn.sum(0), 1e-4, 1e-4, "fused BN sum")
+        assert_close(got[:, 1], (refn * refn).sum(0), 1e-4, 1e-5, "fused BN sum of squares")
     # ---- data gradient: the same kernel on dy with the reversed-tap weights
     if Cin % 16 == 0:
         Pd = lib.ws_bytes("tm_conv3x3_bf16_pack", W, Cout, Cin)
         wd = torch.empty(9, Pd * Cin, Pd * Cout, dtype=torch.bfloat16, device=DEV)
         lib.call("tm_conv3x3_pack_bf16", Cout, Cin, w.detach().contiguous(), wd, Pd, Cout, 1, lib.stream())
         dx = torch.empty(B * H * W, Cin, device=DEV)
-        lib.call("tm_conv3x3_bf16", B, H, W, Cout, Cin, Pd, gb, wd, None, dx, Cin, 0, err, lib.stream())
+        lib.call("tm_conv3x3_bf16", B, H, W, Cout, Cin, Pd, gb, wd, None, dx, Cin, 0, None, err, lib.stream())
         assert_close(dx, gx.permute(0, 2, 3, 1).reshape(B * H * W, Cin), 1e-4, 1e-5, "tma dgrad")
     # ---- weight gradient
     nb = lib.ws_bytes("tm_conv3x3_bf16_wgrad_ws", B, H, W, CinP, Cout)
