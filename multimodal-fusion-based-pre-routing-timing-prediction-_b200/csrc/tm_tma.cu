@@ -9,7 +9,7 @@
 //
 //   warp 0   one thread: TMA producer (activation box + weight box per k-step, mbarrier expect_tx)
 //   warp 1   one thread: tcgen05.mma issuer, fp32 accumulator double-buffered in tensor memory
-//   warps 2-5 epilogue: tcgen05.ld -> (+bias, ReLU) -> 128-bit fp32 stores (NHWC, strided rows)
+//   warps 2-9 epilogue (two per TMEM lane quarter): tcgen05.ld -> (+bias, ReLU, BN statistics) -> transposed 128-bit stores
 //
 //   fprop / dgrad (conv3x3_tma_kernel):  Y[pix, n] = sum_{tap, c} X[pix + tap, c] * Wq[tap][n][c]
 //       (the data gradient is the same kernel on dY with the tap-reversed, transposed weights)
@@ -185,6 +185,11 @@ constexpr int CONV_THREADS = 192;
 constexpr int STAT_MAX_N = 128;          // widest accumulator row the fused batch-norm statistics support
 constexpr int CONV_MAX_STAGES = 8;
 constexpr uint32_t CONV_SMEM_BUDGET = 200 * 1024;
+// forward / data-gradient kernels: 8 epilogue warps (two per TMEM lane quarter, splitting the columns / rows of a
+// tile) -- the epilogue, not TMA, is what the MMA stream waits for
+constexpr int FWD_EPI_WARPS = 8;
+constexpr int FWD_THREADS = (2 + FWD_EPI_WARPS) * 32;
+constexpr uint32_t FWD_SMEM_BUDGET = 184 * 1024;
 
 struct ConvArgs {
   Geom g;                            // geometry in PACKED pixels (rows of P pixels)
@@ -205,13 +210,13 @@ struct ConvArgs {
 // fprop / dgrad
 // ------------------------------------------------------------------------------------------------
 template <int CK>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full[2], acc_empty[2];
-  __shared__ float epi_scr[4][32 * 17];
-  __shared__ double epi_stat[4][STAT_MAX_N * 2];       // per epilogue warp: column sums / sums of squares (a.stats)
+  __shared__ float epi_scr[FWD_EPI_WARPS][32 * 17];
+  __shared__ double epi_stat[FWD_EPI_WARPS][STAT_MAX_N * 2];       // per epilogue warp: column sums / sums of squares (a.stats)
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -221,7 +226,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+    mbar_init(&acc_empty[0], FWD_EPI_WARPS); mbar_init(&acc_empty[1], FWD_EPI_WARPS);
     abort_s = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_map(&tmx);
@@ -295,8 +300,9 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   } else {
     // ======================= epilogue =======================
     const int q = warp & 3;                               // TMEM lane quarter this warp may read
-    float* scr = epi_scr[q];
-    double* wstat = epi_stat[q];
+    const int e = warp - 2, half = e >> 2;                // two warps per quarter: even / odd 16-column chunks
+    float* scr = epi_scr[e];
+    double* wstat = epi_stat[e];
     if (a.stats) {
       for (int i = lane; i < 2 * N; i += 32) wstat[i] = 0.0;
       __syncwarp();
@@ -324,7 +330,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                            : nullptr;
       }
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N);
-      for (int c = 0; c < N; c += 16) {
+      for (int c = half * 16; c < N; c += 32) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
         const int po = c / a.cpx, co = c - po * a.cpx;     // pixel inside the packed row, its first channel
@@ -346,7 +352,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     }
     if (a.stats && ok) {
       __syncwarp();
-      for (int i = lane; i < 2 * N; i += 32) a.stats[((int64_t)blockIdx.x * 4 + q) * 2 * N + i] = wstat[i];
+      for (int i = lane; i < 2 * N; i += 32) a.stats[((int64_t)blockIdx.x * FWD_EPI_WARPS + e) * 2 * N + i] = wstat[i];
     }
   }
   if (!ok) {
@@ -371,7 +377,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
 constexpr int V2_ROWS = 4;
 
 template <int ROWS>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -379,8 +385,8 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
   const uint32_t w_tap = (uint32_t)N * 128u;                       // one tap: N rows x 64 channels bf16
   uint8_t* ring = wsm + 9 * (size_t)w_tap;                          // 9 * N * 128 is a multiple of 1024 (N % 16 == 0 -> check on host)
   __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES], empty_bar[CONV_MAX_STAGES], acc_full[2], acc_empty[2], w_full;
-  __shared__ float epi_scr[4][32 * 17];
-  __shared__ double epi_stat[4][STAT_MAX_N * 2];       // per epilogue warp: column sums / sums of squares (a.stats)
+  __shared__ float epi_scr[FWD_EPI_WARPS][32 * 17];
+  __shared__ double epi_stat[FWD_EPI_WARPS][STAT_MAX_N * 2];       // per epilogue warp: column sums / sums of squares (a.stats)
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -391,7 +397,7 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+    mbar_init(&acc_empty[0], FWD_EPI_WARPS); mbar_init(&acc_empty[1], FWD_EPI_WARPS);
     mbar_init(&w_full, 1);
     abort_s = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -489,8 +495,9 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
     __syncwarp();
   } else {
     const int q = warp & 3;
-    float* scr = epi_scr[q];
-    double* wstat = epi_stat[q];
+    const int e = warp - 2, half = e >> 2;                // two warps per quarter: even / odd image rows of the tile
+    float* scr = epi_scr[e];
+    double* wstat = epi_stat[e];
     if (a.stats) {
       for (int i = lane; i < 2 * N; i += 32) wstat[i] = 0.0;
       __syncwarp();
@@ -504,7 +511,7 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
       const int x0 = (int)(t % tiles_x) * 128, y0 = (int)((t / tiles_x) % tiles_y) * ROWS;
       const int b = (int)(t / ((int64_t)tiles_x * tiles_y));
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ROWS * N);
-      for (int j = 0; j < ROWS; ++j) {
+      for (int j = half; j < ROWS; j += 2) {
         float* rowp[4];
 #pragma unroll
         for (int pass = 0; pass < 4; ++pass)
@@ -531,7 +538,7 @@ conv3x3_tma_rows_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_co
     }
     if (a.stats && ok) {
       __syncwarp();
-      for (int i = lane; i < 2 * N; i += 32) a.stats[((int64_t)blockIdx.x * 4 + q) * 2 * N + i] = wstat[i];
+      for (int i = lane; i < 2 * N; i += 32) a.stats[((int64_t)blockIdx.x * FWD_EPI_WARPS + e) * 2 * N + i] = wstat[i];
     }
   }
   if (!ok) {
@@ -822,7 +829,7 @@ extern "C" int tm_conv3x3_pack_bf16(int64_t Cout, int64_t Cin, const float* w, v
 // xb: bf16 [B][H][W][Cin] compact; wq: tm_conv3x3_pack_bf16 operand for P = tm_conv3x3_bf16_pack(W, Cin, N);
 // y: fp32 rows of stride ldy.
 extern "C" size_t tm_conv3x3_bf16_stats_bytes(int64_t N, int64_t P) {
-  return (size_t)sm_count() * 4 * 2 * (size_t)(N * P) * sizeof(double);
+  return (size_t)sm_count() * FWD_EPI_WARPS * 2 * (size_t)(N * P) * sizeof(double);
 }
 
 // stats (optional, tm_conv3x3_bf16_stats_bytes(N, P) bytes, no bias): per-column sum / sum of squares of the output,
@@ -843,7 +850,7 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   a.a_bytes = 128u * CK * 2u;
   a.b_bytes = (uint32_t)Np * CK * 2u;
   a.stage_bytes = a.a_bytes + (uint32_t)align_up(a.b_bytes, 1024);
-  int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
+  int ns = (int)(FWD_SMEM_BUDGET / a.stage_bytes);
   a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
   a.y = y; a.ldy = ldy; a.bias = bias;
   a.stats = (double*)stats;
@@ -862,7 +869,7 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
   if (rows_on && Cp == 64 && Np <= 64 && Wp >= 128 && H % V2_ROWS == 0) {
     // whole packed weight resident in shared memory, every input row fetched once per horizontal shift
     const size_t wbytes = (size_t)9 * Np * 128;
-    int ns2 = (int)((CONV_SMEM_BUDGET - wbytes) / a.a_bytes);
+    int ns2 = (int)((FWD_SMEM_BUDGET - wbytes) / a.a_bytes);
     a.stages = ns2 > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns2;
     TM_TRY(encode_act(&tmx, xb, Cp, Wp, H, B, 64, 128, 1, 1));
     TM_TRY(encode_2d(&tmw, wq, Cp, 9 * Np, 64, (int)Np));
@@ -872,10 +879,10 @@ extern "C" int tm_conv3x3_bf16(int64_t B, int64_t H, int64_t W, int64_t Cin, int
     static bool optin2 = false;
     if (!optin2) {
       TM_CUDA(cudaFuncSetAttribute(conv3x3_tma_rows_kernel<V2_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)CONV_SMEM_BUDGET + 1024));
+                                   (int)FWD_SMEM_BUDGET + 1024));
       optin2 = true;
     }
-    conv3x3_tma_rows_kernel<V2_ROWS><<<grid2, CONV_THREADS, smem2, st>>>(tmx, tmw, a);
+    conv3x3_tma_rows_kernel<V2_ROWS><<<grid2, FWD_THREADS, smem2, st>>>(tmx, tmw, a);
     return check_launch("conv3x3_tma_rows");
   }
   TM_TRY(encode_act(&tmx, xb, Cp, Wp, H, B, CK, a.g.TW, a.g.TH, a.g.TB));
@@ -892,10 +899,10 @@ int launch_taps(const ConvArgs& a, const CUtensorMap& tmx, const CUtensorMap& tm
     static bool optin = false;                                                                                \
     if (!optin) {                                                                                             \
       TM_CUDA(cudaFuncSetAttribute(conv3x3_tma_kernel<CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                   (int)CONV_SMEM_BUDGET + 1024));                                            \
+                                   (int)FWD_SMEM_BUDGET + 1024));                                             \
       optin = true;                                                                                           \
     }                                                                                                         \
-    conv3x3_tma_kernel<CK_><<<grid, CONV_THREADS, smem, st>>>(tmx, tmw, a);                                   \
+    conv3x3_tma_kernel<CK_><<<grid, FWD_THREADS, smem, st>>>(tmx, tmw, a);                                    \
   } while (0)
   if (CK == 64) TM_LAUNCH_CONV(64);
   else if (CK == 32) TM_LAUNCH_CONV(32);
@@ -933,7 +940,7 @@ void fill_common(ConvArgs& a, int64_t B, int64_t H, int64_t W, int64_t K, int64_
   a.a_bytes = 128u * CK * 2u;
   a.b_bytes = (uint32_t)N * CK * 2u;
   a.stage_bytes = a.a_bytes + (uint32_t)align_up(a.b_bytes, 1024);
-  const int ns = (int)(CONV_SMEM_BUDGET / a.stage_bytes);
+  const int ns = (int)(FWD_SMEM_BUDGET / a.stage_bytes);
   a.stages = ns > CONV_MAX_STAGES ? CONV_MAX_STAGES : ns;
   a.y = y; a.ldy = ldy; a.bias = bias;
   a.flags = bias ? TM_EPI_BIAS : 0;
