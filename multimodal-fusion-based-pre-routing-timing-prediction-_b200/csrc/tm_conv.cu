@@ -183,18 +183,29 @@ bn_stats_kernel(int64_t npix, int C, const float* __restrict__ x, int64_t ldx, c
   }
 }
 
-__global__ void bn_finalize_kernel(int64_t npix, int64_t C, int nblk, const double* __restrict__ part,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float momentum, float eps, float* __restrict__ save_mean,
-                                   float* __restrict__ save_invstd) {
-  const int lane = threadIdx.x & 31;
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
-  if (c >= C) return;
-  double a = 0.0, b = 0.0;
-  for (int i = lane; i < nblk; i += 32) { a += part[((int64_t)i * C + c) * 2]; b += part[((int64_t)i * C + c) * 2 + 1]; }
+// one block of 256 threads per channel: thread t adds partials t, t+256, ...; warps and then the 8 warp sums are
+// folded in a fixed order (deterministic).  (One warp per channel was latency-bound once the fused convolution
+// statistics brought thousands of partials per channel.)
+__device__ __forceinline__ void bn_block_sum2(double& a, double& b) {
+  __shared__ double sa[8], sb[8];
   a = warp_sum(a);
   b = warp_sum(b);
-  if (lane != 0) return;
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  a = 0.0; b = 0.0;
+  for (int i = 0; i < 8; ++i) { a += sa[i]; b += sb[i]; }
+}
+
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(int64_t npix, int64_t C, int nblk, const double* __restrict__ part,
+                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                   float momentum, float eps, float* __restrict__ save_mean,
+                   float* __restrict__ save_invstd) {
+  const int c = blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 256) { a += part[((int64_t)i * C + c) * 2]; b += part[((int64_t)i * C + c) * 2 + 1]; }
+  bn_block_sum2(a, b);
+  if (threadIdx.x != 0) return;
   const double mean = a / (double)npix;
   double var = b / (double)npix - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -238,16 +249,14 @@ __global__ void bn_relu_apply_kernel(int64_t npix, int C, const float* __restric
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(int64_t C, int nblk, const double* __restrict__ part,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int lane = threadIdx.x & 31;
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
-  if (c >= C) return;
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(int64_t C, int nblk, const double* __restrict__ part, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
+  const int c = blockIdx.x;
   double a = 0.0, b = 0.0;
-  for (int i = lane; i < nblk; i += 32) { a += part[((int64_t)i * C + c) * 2]; b += part[((int64_t)i * C + c) * 2 + 1]; }
-  a = warp_sum(a);
-  b = warp_sum(b);
-  if (lane == 0) { dbeta[c] = (float)a; dgamma[c] = (float)b; }
+  for (int i = threadIdx.x; i < nblk; i += 256) { a += part[((int64_t)i * C + c) * 2]; b += part[((int64_t)i * C + c) * 2 + 1]; }
+  bn_block_sum2(a, b);
+  if (threadIdx.x == 0) { dbeta[c] = (float)a; dgamma[c] = (float)b; }
 }
 
 template <int VEC>
@@ -653,7 +662,7 @@ extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64
     else bn_stats_kernel<1, false><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, part);
     TM_TRY(check_launch("bn_stats"));
   }
-  bn_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(npix, C, nfin, part, running_mean, running_var,
+  bn_finalize_kernel<<<(unsigned)C, 256, 0, ST>>>(npix, C, nfin, part, running_mean, running_var,
                                                              momentum, eps, save_mean, save_invstd);
   TM_TRY(check_launch("bn_finalize"));
   if (v4) bn_relu_apply_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, x, ldx, gamma, beta, save_mean, save_invstd, y, ldy, (__nv_bfloat16*)y_bf16);
@@ -679,7 +688,7 @@ extern "C" int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int6
   if (v4) bn_stats_kernel<4, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, gamma, beta, part);
   else bn_stats_kernel<1, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, gamma, beta, part);
   TM_TRY(check_launch("bn_bwd_stats"));
-  bn_bwd_finalize_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, ST>>>(C, nblk, part, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(unsigned)C, 256, 0, ST>>>(C, nblk, part, dgamma, dbeta);
   TM_TRY(check_launch("bn_bwd_finalize"));
   if (v4) bn_bwd_apply_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dx, lddx, (__nv_bfloat16*)dx_bf16);
   else bn_bwd_apply_kernel<1><<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dx, lddx, (__nv_bfloat16*)dx_bf16);
