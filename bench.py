@@ -262,17 +262,33 @@ def main():
         preps = [step.prepare(host, dev, graph=graph) for _ in range(2)]
         e2e_h2d = preps[0].nbytes()
         e2e_note = ("DesignStep.prepare(): netlist / endpoint / mask structure resident, step replayed as a CUDA graph; "
-                    "per step: features + image + labels uploaded (prefetched on a copy stream), loss read back")
+                    "per step: features + image + labels uploaded (prefetched on a copy stream), loss copied to pinned memory and "
+                    "read by the host one step later")
+
+        loss_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
 
         def e2e_loop(n):
+            # software pipeline of a training loop: while step i computes, step i+1's inputs are uploaded on the copy
+            # stream and step i-1's loss (copied to pinned memory right behind its step) is read on the host
             ev = [torch.cuda.Event(), torch.cuda.Event()]
+            done = [torch.cuda.Event(), torch.cuda.Event()]
             preps[0].upload(host, copy_stream); ev[0].record(copy_stream)
             out = 0.0
             for i in range(n):
                 if i + 1 < n:
+                    # (the copy stream must not overwrite the inputs of the prepared copy still in flight two steps back)
+                    if i >= 1:
+                        copy_stream.wait_event(done[(i + 1) & 1])
                     preps[(i + 1) & 1].upload(host, copy_stream); ev[(i + 1) & 1].record(copy_stream)
                 torch.cuda.current_stream().wait_event(ev[i & 1])
-                out = float(preps[i & 1].step()[0].item())           # D2H read of the step's loss
+                loss_d = preps[i & 1].step()[0]
+                loss_host[i & 1].copy_(loss_d, non_blocking=True)     # D2H of this step's loss
+                done[i & 1].record()
+                if i >= 1:
+                    done[(i - 1) & 1].synchronize()
+                    out = float(loss_host[(i - 1) & 1])               # host reads the previous step's loss
+            done[(n - 1) & 1].synchronize()
+            out = float(loss_host[(n - 1) & 1])
             return out
     else:
         e2e_h2d = host.nbytes(per_step_only=True)
