@@ -196,6 +196,49 @@ def config5(n_designs=64, distinct=8):
             "ms_total": ms, "designs_per_s": n_designs / (ms * 1e-3)}
 
 
+def cpu_baselines():
+    """the CPU side of configs 3 and 4 (the oracle port on all host threads): config 3 GNN-only
+    forward+backward on the full ~1M-pin graph; config 4 on a reduced batch (2 images), scaled linearly to 32."""
+    import numpy as np
+    from oracle import levelize, restate
+    import model as M
+    import Unet as U
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    out = []
+    d = tm_synth.make_design(seed=0, n_endpoints=64, **tm_synth.CONFIGS["c3"])
+    torch.manual_seed(3)
+    gnn = M.PathConv(out_feat_dim=128, hidden_feat_dim=128, cell_feat_dim=36, net_feat_dim=2)
+    t = torch.from_numpy
+    ni, ns = levelize.in_csr(d.n, d.net_src, d.net_dst)
+    ci, cs = levelize.in_csr(d.n, d.cell_src, d.cell_dst)
+    levels = [t(x.astype(np.int64)) for x in d.level_lists()]
+    P = {"gnn." + k: v.detach().clone().requires_grad_(True) for k, v in gnn.state_dict().items() if "drive" not in k and "attn" not in k}
+    best = 1e9
+    for _ in range(2):
+        t0 = time.perf_counter()
+        H = restate.gnn_propagate(P, "gnn", d.n, levels, (t(ni).long(), t(ns).long()), (t(ci).long(), t(cs).long()),
+                                  t(d.cell_feat), t(d.net_feat))
+        H[t(d.endpoints).long()].square().sum().backward()
+        best = min(best, time.perf_counter() - t0)
+    out.append({"config": "c3 CPU: GNN-only forward+backward, %d pins" % d.n, "cpu_s": best, "threads": threads,
+                "pins_per_s": d.n / best})
+    torch.manual_seed(4)
+    net = U.UNet("max").train()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.rand(2, 3, 512, 512)
+    best = 1e9
+    for _ in range(2):
+        Pc = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+        t0 = time.perf_counter()
+        o, _ = restate.unet_forward(Pc, x, "max")
+        o.sum().backward()
+        best = min(best, time.perf_counter() - t0)
+    out.append({"config": "c4 CPU: U-Net forward+backward, batch 2 x 512x512 fp32 (reduced batch)", "cpu_s": best, "threads": threads,
+                "images_per_s": 2 / best, "batch32_s(scaled x16)": best * 16})
+    return out
+
+
 def profile_c4(mode="bf16", batch=32, size=512):
     """One forward+backward between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)."""
     import Unet as U
@@ -227,3 +270,6 @@ if __name__ == "__main__":
             print(json.dumps(r), flush=True)
     if "c5" in want:
         print(json.dumps(config5()), flush=True)
+    if "cpu" in want:
+        for r in cpu_baselines():
+            print(json.dumps(r), flush=True)
