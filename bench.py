@@ -475,7 +475,9 @@ def main():
                 "config": {"workload": WORKLOAD if args.config == "c2" else args.config, "pins": d.n,
                            "levels": d.num_levels, "endpoints": int(d.endpoints.size),
                            "designs_per_step": world, "parallelism": f"dp{world}",
-                           "resident_loop": ("CUDA graph replay of the two-stream step" + (" + NCCL gradient all-reduce after each replay" if world > 1 else ""))
+                           "resident_loop": ("CUDA graph replay of the two-stream step" + (
+                               "" if world <= 1 else " with the bucketed NCCL all-reduces captured inside (TM_DP_GRAPH=1)"
+                               if os.environ.get("TM_DP_GRAPH", "0") == "1" else " + NCCL gradient all-reduce after each replay"))
                            if use_graph else "eager launches",
                            "l2": "working set per step (~1.5 GB of activations) exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": world * args.steps / e2e_s, "unit": "designs/s", "h2d_bytes_per_step": h2d,
@@ -484,6 +486,12 @@ def main():
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if os.environ.get("TM_DP_GRAPH", "0") == "1":
+            # experimental NCCL-in-graph mode: communicator teardown with captured collectives alive was seen to hang;
+            # everything is measured and printed, so leave without running destructors
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         dist.barrier()
         dist.destroy_process_group()
 

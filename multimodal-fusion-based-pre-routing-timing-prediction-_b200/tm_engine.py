@@ -229,6 +229,9 @@ class DesignStep:
         ``param.grad`` tensors are rewritten in place by every replay.  On the data-parallel path the
         graph holds the rank's compute only; the NCCL gradient all-reduce (one bucket, 11.6 MB) is
         posted right after each replay."""
+        if self.world > 1 and os.environ.get("TM_DP_GRAPH", "0") == "1":
+            # experimental: capture the three bucketed NCCL all-reduces (overlapping the backward) inside the graph
+            return self._capture_local(b, warmup)
         world, self.world = self.world, 1                  # no collectives inside the captured region
         try:
             replay_local = self._capture_local(b, warmup)
