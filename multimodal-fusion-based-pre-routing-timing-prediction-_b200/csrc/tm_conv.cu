@@ -5,7 +5,8 @@
 // src/model.py:227-243 (LayoutNet 9x9 / 7x7 convs).  Convolutions are implicit GEMMs on the shared
 // fp32 GEMM core (tm_gemm.cuh) with im2col performed by the operand loader; every activation
 // carries an explicit pixel stride so torch.cat (Unet.py:67) is free: producers write straight
-// into the halves of the concat buffer.  The bf16 tcgen05 path lives in tm_conv_tc.cu.
+// into the halves of the concat buffer.  The tensor-core paths live in tm_tc.cu (cp.async-fed, every precision) and
+// tm_tma.cu (TMA-fed, bf16 activations); the batch-norm / pooling / OutConv kernels below serve all of them.
 #include <cuda_bf16.h>
 #include <initializer_list>
 #include <utility>
