@@ -53,6 +53,11 @@ typedef struct {
   const int32_t* f_ptr;  const int32_t* f_src;         /* forward gather sources           */
   const int32_t* bn_ptr; const int32_t* bn_dst; const float* bn_w;   /* backward, net edges */
   const int32_t* bc_ptr; const int32_t* bc_row;        /* backward, cell edges (compact row) */
+  /* device copies the persistent propagation kernels read (one launch loops over all levels) */
+  const int32_t* level_ptr;  /* [num_levels+1] first schedule position of each level       */
+  const int32_t* cell_base;  /* [num_levels+1] first compact cell row of each level        */
+  int32_t* sync_flags;       /* [n + n_cell_rows] scratch: per-pin / per-cell-row ready flags of the
+                              * dataflow-synchronised persistent kernels (zeroed by every call)   */
 } tm_schedule;
 
 /* ------------------------------------------------------------------------------------
@@ -147,8 +152,26 @@ int tm_transpose(int64_t rows, int64_t cols, const float* in, float* out, void* 
  *   W1t[128,256], b1[256], W2t[256,128], b2[128]: fc_cell_neigh, weights TRANSPOSED;
  *   A[n_cell_rows,128], LSE[n_cell_rows,128], HID[n_cell_rows,256]: saved for backward
  *              (may be NULL for inference). */
-size_t tm_gnn_ws_bytes(void);   /* workspace of tm_gnn_forward / tm_gnn_backward: the weights re-packed
-                                 * (padded rows, 3xTF32 hi/lo pre-split) for the tile MLP */
+size_t tm_gnn_ws_bytes(void);   /* workspace of tm_gnn_forward / tm_gnn_backward: the grid-barrier counter of the
+                                 * persistent kernels (default) / the re-packed weights of the per-level kernels */
+/* Implementation selector (process-wide; also env TM_GNN_IMPL=<bits>|persist|levels).  Bit 0 selects the forward
+ * pass, bit 1 the backward pass (default 1: persistent forward, per-level backward -- what measures fastest):
+ *   bit set   = ONE persistent kernel for the whole pass: 2-CTA clusters, fc_cell_neigh resident in shared memory,
+ *               the tile MLP transposed on tcgen05 (fp16 two-term split, fp32 accumulate in TMEM), one grid-wide
+ *               barrier per level (or, with TM_GNN_SYNC=flow, per-pin ready flags and no barrier);
+ *   bit clear = one launch per level (mma.sync 3xTF32 tile MLP, weights streamed per level, PDL-chained).
+ * Returns the previous value; impl < 0 only queries. */
+int tm_gnn_set_impl(int impl);
+/* Level ordering inside the persistent kernels: 0 = grid barrier per level (default), 1 = per-pin ready flags
+ * (dataflow; also env TM_GNN_SYNC=flow).  Returns the previous value; flow < 0 only queries. */
+int tm_gnn_set_sync(int flow);
+/* Grid-wide barriers inside the last tm_gnn_forward / tm_gnn_backward call of this thread (persistent kernel:
+ * one per non-empty level; per-level kernels: 0, they synchronise by kernel boundaries). */
+int tm_gnn_last_barriers(void);
+/* Diagnostics: with clocks != NULL (device int64 [grid CTAs <= 148][slots], zero-filled by the caller) thread 0 of
+ * every CTA of the persistent kernels adds the SM cycles it spent per phase (setup, barrier wait, gather, MMA 1,
+ * epilogue 1, MMA 2, exchange, tail; net-level wait / body / tail; slots = 16).  NULL disables. */
+int tm_gnn_set_profile(void* clocks);
 int tm_gnn_forward(const tm_schedule* s, int32_t level_begin, int32_t level_end, float* H,
                    const float* S, const float* W1t, const float* b1, const float* W2t,
                    const float* b2, float* A, float* LSE, float* HID, void* ws, size_t ws_bytes,

@@ -186,6 +186,7 @@ class Schedule:
                     s.cell_iptr, s.cell_isrc, s.crow, cell_base, viol, st)
         host = torch.cat([level_ptr, cell_base, viol]).cpu().numpy()          # the one sync
         s.level_ptr = level_ptr
+        s.cell_base = cell_base
         s.h_level_ptr = np.ascontiguousarray(host[:L + 1], dtype=np.int32)
         s.h_cell_base = np.ascontiguousarray(host[L + 1:2 * L + 2], dtype=np.int32)
         s.n_sched = int(s.h_level_ptr[L])
@@ -206,7 +207,10 @@ class Schedule:
             net_iptr=s.net_iptr.data_ptr(), net_isrc=s.net_isrc.data_ptr(),
             cell_iptr=s.cell_iptr.data_ptr(), cell_isrc=s.cell_isrc.data_ptr(),
             net_optr=s.net_optr.data_ptr(), net_odst=s.net_odst.data_ptr(),
-            cell_optr=s.cell_optr.data_ptr(), cell_odst=s.cell_odst.data_ptr())
+            cell_optr=s.cell_optr.data_ptr(), cell_odst=s.cell_odst.data_ptr(),
+            level_ptr=s.level_ptr.data_ptr(), cell_base=s.cell_base.data_ptr())
+        s.sync_flags = torch.zeros(n + s.n_cell_rows + 64, dtype=torch.int32, device=dev)
+        s.struct.sync_flags = s.sync_flags.data_ptr()
         # level-ordered edge lists: what the propagation kernels actually walk
         e_net, e_cell = int(s.net_isrc.numel()), int(s.cell_isrc.numel())
         ns1 = s.n_sched + 1

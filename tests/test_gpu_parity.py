@@ -687,3 +687,41 @@ def test_cpu_inputs_fail_loudly(mods):
     import model as M
     with pytest.raises(RuntimeError, match="CUDA"):
         M.MLP(4, 8, 2)(torch.randn(3, 4))
+
+
+@pytest.mark.parametrize("impl,flow", [(0, 0), (3, 0), (3, 1)])
+@pytest.mark.parametrize("cfg,seed", [("tiny", 2), ("c1", 3)])
+def test_gnn_kernel_variants_vs_oracle(mods, impl, flow, cfg, seed):
+    """The three propagation back ends -- per-level launches (0), persistent cluster kernels with a grid
+    barrier per level (3, flow 0) and with per-pin ready flags (3, flow 1) -- against the oracle, forward
+    (no allowance) and backward, and bit-deterministic from run to run."""
+    ops, lib = mods["ops"], mods["lib"].lib()
+    d = tm_synth.make_design(seed=seed, **tm_synth.CONFIGS[cfg])
+    gnn = _gnn_params(seed)
+    sd = {"gnn." + k: v.detach().clone().requires_grad_(True) for k, v in gnn.state_dict().items()}
+    od = design_to_oracle(d)
+    Href = restate.gnn_propagate(sd, "gnn", d.n, od["levels"], od["net_csr"], od["cell_csr"], od["cell_feat"], od["net_feat"])
+    torch.manual_seed(seed)
+    Gout = 0.01 * torch.randn(d.n, 128)
+    Gout[torch.from_numpy(d.endpoints)] += torch.randn(len(d.endpoints), 128)
+    names = ["gnn." + k for k in ops.GNN_PARAM_NAMES]
+    gref = torch.autograd.grad(Href, [sd[k] for k in names], Gout)
+    old_impl, old_flow = lib.tm_gnn_set_impl(impl), lib.tm_gnn_set_sync(flow)
+    try:
+        gnn = gnn.to(DEV)
+        g = _graph(mods, d)
+        runs = []
+        for _ in range(2):
+            gnn.zero_grad()
+            H = gnn.propagate(g)
+            H.backward(Gout.to(DEV))
+            runs.append((H.detach().clone(), {k: p.grad.clone() for k, p in gnn.named_parameters() if p.grad is not None}))
+        assert_close(runs[0][0], Href, 1e-3, 1e-4, "H")
+        for k, r in zip(ops.GNN_PARAM_NAMES, gref):
+            assert_close(runs[0][1][k], r, 1e-3, 1e-4, k, flip_frac=5e-3)
+        assert torch.equal(runs[0][0], runs[1][0])
+        for k in runs[0][1]:
+            assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+    finally:
+        lib.tm_gnn_set_impl(old_impl)
+        lib.tm_gnn_set_sync(old_flow)
