@@ -12,12 +12,16 @@ over every level, mask fusion + head, MSE, backward to every parameter gradient 
 excluded).  Prints ONE JSON line on rank 0.
 
 * value  : designs/s with the batch resident in HBM (CUDA events, max over ranks);
-* e2e    : the same through the public API from pinned HOST buffers: per step the H2D copy of
-           features / image / masks / labels / endpoints and a D2H read of the loss are inside the
-           timed region (graph structure + level schedule cached per design, as DGL's graph is);
+* e2e    : the same through the public API from pinned HOST buffers.  The design's STRUCTURE (netlist edges,
+           level schedule, the endpoint batch and its path masks) is resident, like the reference's prebuilt DGL
+           graph and mask tensor; per step the H2D copy of that step's VALUES -- cell / net features, image,
+           labels (51.2 MB) -- and a D2H read of the loss are inside the timed region;
 * roofline: the level-wise propagation forward (the HBM-bound kernel family), algorithmic bytes of
            SURVEY.md 8d / its CUDA-event time, against MEASURED_PEAKS.json;
 * cpu_baseline: the oracle (a port of the reference arithmetic) on the host cores.
+Under torchrun the three bucketed NCCL gradient all-reduces are captured inside each rank's CUDA graph and
+overlap the backward; `allreduce` reports their stand-alone time, the exposed part and the overlap fraction,
+`config5` the 64-design run of SURVEY.md 8d (seeds 0..63 sharded round-robin over the ranks).
 """
 import argparse
 import importlib
@@ -152,8 +156,18 @@ def reference_arm(args, rank, world):
             "config": {"workload": WORKLOAD, "sample": sample},
             "cpu_baseline": {"value": 1.0 / sec, "unit": "designs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": 1.0 / sec, "unit": "designs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "note": "kind 'port': the unmodified reference needs DGL (absent, not installable offline) and cannot travel to "
+                    "the GPU box; the port is the same arithmetic without DGL's per-level scheduling and the reference's "
+                    "per-level full-column index_copy, and is ~8x FASTER than the reference measured through a fake-DGL "
+                    "graph during the survey (35 s/design on 8 cores, SURVEY.md section 6): ratios against this arm are "
+                    "conservative"}
     print(json.dumps(line), flush=True)
+
+
+def _make_c2(seed):
+    import tm_synth
+    return tm_synth.make_design(seed=seed, **tm_synth.CONFIGS["c2"])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -169,6 +183,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the config-3 / config-4 device timings")
     ap.add_argument("--no-graph", action="store_true", help="time the resident loop eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained repeat of the resident loop")
+    ap.add_argument("--config5", type=int, default=64, help="designs of the config-5 run (0 = skip)")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit "
                          "(for `ncu --profile-from-start off`); prints no bench line")
@@ -178,6 +194,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return reference_arm(args, rank, world)
+
+    # config 5's designs are generated first, by forked workers, while this process has no CUDA context / NCCL threads
+    c5_seeds, c5_designs = None, None
+    if args.config5 > 0 and args.config == "c2" and not args.no_graph and not args.profile_step:
+        import multiprocessing as mp
+        import tm_dp
+        c5_seeds = tm_dp.shard_designs(list(range(args.config5)), rank, world)
+        with mp.get_context("fork").Pool(min(len(c5_seeds), max(1, (os.cpu_count() or 8) // max(world, 1)))) as pool:
+            c5_designs = pool.map(_make_c2, c5_seeds)
 
     import torch.distributed as dist
     importlib.import_module(PKG_NAME)
@@ -321,7 +346,96 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+
+    # ---- the same resident loop for >= 3 s: does the number survive sustained clocks?
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(3.2e3 / (ms_total / args.steps)))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        s0.record()
+        for _ in range(n_sus):
+            run_step()
+        s1.record()
+        sync_all()
+        ms_sus = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_sus, op=dist.ReduceOp.MAX)
+        sustained = {"steps": n_sus, "seconds": float(ms_sus.item()) * 1e-3, "ms_per_step": float(ms_sus.item()) / n_sus,
+                     "value": world * n_sus / (float(ms_sus.item()) * 1e-3), "unit": "designs/s"}
     clocks = sampler.finish() if rank == 0 else None
+
+    # ---- data parallel: what the gradient exchange costs and how much of it the backward hides
+    allreduce = None
+    if world > 1 and use_graph:
+        bks = list(step._buckets.values())
+        cs = step.comm_stream
+
+        def ar_only():
+            for b in bks:
+                with torch.cuda.stream(cs):
+                    dist.all_reduce(b.flat, op=dist.ReduceOp.SUM)
+                    b.flat.mul_(1.0 / world)
+            torch.cuda.current_stream().wait_stream(cs)
+        for _ in range(3):
+            ar_only()
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            ar_only()
+        a1.record()
+        sync_all()
+        # the rank's compute alone: the same step captured without the collectives
+        w_, step.world = step.world, 1
+        try:
+            local_replay = step._capture_local(batch)
+        finally:
+            step.world = w_
+        for _ in range(2):
+            local_replay()
+        sync_all()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(args.steps):
+            local_replay()
+        l1.record()
+        sync_all()
+        t3 = torch.tensor([a0.elapsed_time(a1) / args.steps, l0.elapsed_time(l1) / args.steps], device=dev)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        ar_ms, local_ms = float(t3[0]), float(t3[1])
+        exposed = max(ms_total / args.steps - local_ms, 0.0)
+        allreduce = {"buckets": {k: int(b.flat.numel()) * 4 for k, b in step._buckets.items()},
+                     "ms_standalone": ar_ms, "step_ms_without_exchange": local_ms, "exposed_ms": exposed,
+                     "overlap_frac": max(0.0, min(1.0, 1.0 - exposed / ar_ms)) if ar_ms > 0 else None,
+                     "where": "three bucketed ncclAllReduce (head+fusion, GNN, U-Net) on a side stream INSIDE the captured graph"}
+
+    # ---- BASELINE config 5: 64 designs of config-2 shape, seeds 0..63, round-robin over the ranks
+    config5 = None
+    if c5_designs is not None and use_graph:
+        seeds, ds = c5_seeds, c5_designs
+        pool5 = torch.cuda.graph_pool_handle()
+        t_prep = time.perf_counter()
+        preps5 = [step.prepare(tm_engine.HostDesign(dd, pin=False), dev, pool=pool5) for dd in ds]
+        t_prep = time.perf_counter() - t_prep
+        for pr in preps5[:2]:
+            pr.step()
+        sync_all()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for pr in preps5:
+            loss5, _ = pr.step()
+        c1.record()
+        sync_all()
+        ms5 = torch.tensor([c0.elapsed_time(c1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms5, op=dist.ReduceOp.MAX)
+        config5 = {"designs": args.config5, "seeds": f"0..{args.config5 - 1}", "per_rank": len(seeds), "ms_total": float(ms5.item()),
+                   "value": args.config5 / (float(ms5.item()) * 1e-3), "unit": "designs/s", "prepare_s_per_rank": t_prep,
+                   "note": "distinct designs, sharded round-robin (tm_dp.shard_designs); one DP step = every rank's next design + the "
+                           "in-graph gradient all-reduce; strong-scaling efficiency = T1 / (n * Tn) over the ms_total of the N = 1 run"}
+        del preps5, ds
+        torch.cuda.empty_cache()
 
     # ---- per-family device times on rank 0 (CUDA events on the launching stream)
     def timed(fn, reps=5):
@@ -353,7 +467,15 @@ def main():
 
         S.copy_(torch.rand_like(S))
         t_zero = timed(lambda: H.zero_())
-        t_prop = timed(prop_only) - t_zero
+        # both back ends of the propagation, each timed alone: bit 0 of tm_gnn_set_impl = forward as ONE persistent
+        # cluster kernel (the library default), 0 = one launch per level (what DesignStep uses next to the image stream)
+        variants = {}
+        for nm, impl in (("persistent (1 launch, grid barrier per level)", 1), ("per-level launches (PDL-chained)", 0)):
+            old_impl = tm_lib.lib().tm_gnn_set_impl(impl)
+            variants[nm] = {"ms": timed(prop_only) - t_zero, "grid_barriers": int(tm_lib.lib().tm_gnn_last_barriers())}
+            tm_lib.lib().tm_gnn_set_impl(old_impl)
+        best = min(variants, key=lambda k: variants[k]["ms"])
+        t_prop = variants[best]["ms"]
         G = torch.zeros(sched.n, 128, device=dev)
         GA = torch.empty_like(saved["A"]); GH = torch.empty_like(saved["HID"]); GZ = torch.empty_like(saved["A"])
 
@@ -376,13 +498,18 @@ def main():
         ach = bytes_f / (t_prop * 1e-3) / 1e9
         # DRAM bytes of the same 101 launches from an ncu capture (profiles/<round>_traffic.json), if one was committed
         traffic = None
-        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tj = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if not os.path.isfile(tj):
+            tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.isfile(tj) and args.config == "c2":
             traffic = json.load(open(tj)).get("gnn_propagate_fwd_dram_bytes")
-        extra["roofline"] = {"kernel": "tm_gnn_forward (level-wise propagation, %d level launches)" % sched.num_levels,
+        for v in variants.values():
+            v["GBps"] = bytes_f / (v["ms"] * 1e-3) / 1e9
+            v["frac"] = v["GBps"] / peak
+        extra["roofline"] = {"kernel": "tm_gnn_forward (level-wise propagation over %d levels), %s" % (sched.num_levels, best),
                              "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": bytes_f,
-                             "ms": t_prop}
+                             "ms": t_prop, "variants": variants}
         # tensor-pipe family: the TMA-fed tcgen05 3x3 convolution of the U-Net's bf16 mode on its tensor-bound layer
         # (down3.conv2 of BASELINE config 4: 128 -> 128 channels, batch 32 of 64x64 maps; SURVEY 8a layer table)
         pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -476,23 +603,23 @@ def main():
                            "levels": d.num_levels, "endpoints": int(d.endpoints.size),
                            "designs_per_step": world, "parallelism": f"dp{world}",
                            "resident_loop": ("CUDA graph replay of the two-stream step" + (
-                               "" if world <= 1 else " with the bucketed NCCL all-reduces captured inside (TM_DP_GRAPH=1)"
-                               if os.environ.get("TM_DP_GRAPH", "0") == "1" else " + NCCL gradient all-reduce after each replay"))
+                               "" if world <= 1 else " with the bucketed NCCL all-reduces captured inside"
+                               if os.environ.get("TM_DP_GRAPH", "1") != "0" else " + NCCL gradient all-reduce after each replay (TM_DP_GRAPH=0)"))
                            if use_graph else "eager launches",
                            "l2": "working set per step (~1.5 GB of activations) exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": world * args.steps / e2e_s, "unit": "designs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "note": e2e_note},
-                "gpu_launches": launches, "clocks": clocks, "loss": lv}
+                "gpu_launches": launches, "clocks": clocks, "loss": lv, "sustained": sustained, "allreduce": allreduce,
+                "config5": config5}
         line.update(extra)
+        tm_lib.check_err_flags()                 # no tensor-core barrier timed out anywhere in this run
         print(json.dumps(line), flush=True)
     if world > 1:
-        if os.environ.get("TM_DP_GRAPH", "0") == "1":
-            # experimental NCCL-in-graph mode: communicator teardown with captured collectives alive was seen to hang;
-            # everything is measured and printed, so leave without running destructors
-            torch.cuda.synchronize()
-            sys.stdout.flush()
-            os._exit(0)
+        # captured graphs hold NCCL kernels of this communicator: release them before tearing it down
+        del run_step
+        step.close()
         dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -100,12 +100,12 @@ class DesignBatch:
 class PreparedDesign:
     VALUE_FIELDS = ("cell_feat", "net_feat", "image", "arrival_time")
 
-    def __init__(self, step, host, device, graph=None):
+    def __init__(self, step, host, device, graph=None, pool=None):
         self.batch = DesignBatch.from_host(host, device, graph=graph)
         self.static = {"cell_feat": self.batch.cell_feat, "net_feat": self.batch.net_feat,
                        "image": self.batch.image, "arrival_time": self.batch.arrival_time}
         torch.cuda.synchronize()
-        self.replay = step.capture(self.batch)
+        self.replay = step.capture(self.batch, pool=pool)
 
     def upload(self, host, stream=None):
         """Host -> device copy of the per-step values into the graph's static inputs."""
@@ -132,7 +132,8 @@ class DesignStep:
         # both are chains of small latency-bound kernels: they run on two streams, forward and backward.
         self.image_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
         self.overlap = True
-        self._pending = []
+        self._buckets = {}            # name -> tm_dp.FlatBucket (persistent flat gradient buffers)
+        self._graphs = []             # captured CUDA graphs (released by close())
         g = model.gnn
         sd = dict(g.named_parameters())
         self.gnn_params = [sd[k] for k in tm_ops.GNN_PARAM_NAMES]
@@ -179,7 +180,10 @@ class DesignStep:
         sched = b.graph.schedule()
         gp = [p.detach() for p in self.gnn_params]
         # the longer chain is enqueued first so the host's launch time for the other one overlaps it
-        H, saved = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat, gp, save=True)
+        # (per-level kernels while the image stream runs next to them: measured 5.07 ms/step against 5.49 ms
+        #  with the persistent forward, which owns all SMs for 0.9 ms and serialises the U-Net behind it)
+        H, saved = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat, gp, save=True,
+                                      impl=0 if side is not main and os.environ.get("TM_GNN_IMPL") is None else None)
         with torch.cuda.stream(side):
             fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
             feat = fmap.reshape(-1)
@@ -202,7 +206,7 @@ class DesignStep:
         head = [(f0.weight, dw1), (f0.bias, db1), (f2.weight, dw2), (f2.bias, db2), (a0.weight, da1),
                 (a0.bias, dab1), (a2.weight, da2), (a2.bias, dab2), (m.fcn.weight, dfw), (m.fcn.bias, dfb)]
         self._assign(head)
-        self._post_allreduce([p for p, _ in head])
+        self._post_allreduce("head", [p for p, _ in head])
 
         # ---- GNN backward (main stream) next to the U-Net backward (image stream)
         side.wait_stream(main)                               # dF is ready
@@ -211,45 +215,46 @@ class DesignStep:
         ggrads = tm_ops.gnn_backward(sched, saved, gp, G)
         pairs = list(zip(self.gnn_params, ggrads))
         self._assign(pairs)
-        self._post_allreduce([p for p, _ in pairs])
+        self._post_allreduce("gnn", [p for p, _ in pairs])
         with torch.cuda.stream(side):
             ug = tm_unet.unet_backward(cnn, ust, dF.reshape(fmap.shape))
             upairs = [(self.cnn_params[k], ug[k]) for k in self.cnn_names]
             self._assign(upairs)
-            self._post_allreduce([p for p, _ in upairs])
+            self._post_allreduce("unet", [p for p, _ in upairs])
         main.wait_stream(side)                               # join: every gradient exists on `main`
         self._wait_allreduce()
         return loss, pred.squeeze(-1)
 
     # ---------------------------------------------------------------- CUDA graph
-    def capture(self, b, warmup=2):
+    def capture(self, b, warmup=2, pool=None):
         """Capture ``run(b)`` (about 500 launches on two streams) into one CUDA graph.  The batch's
         tensors become the graph's static inputs: refresh them in place (``tensor.copy_``) and call
         the returned function, which replays the graph and returns the same (loss, pred) tensors;
         ``param.grad`` tensors are rewritten in place by every replay.  On the data-parallel path the
-        graph holds the rank's compute only; the NCCL gradient all-reduce (one bucket, 11.6 MB) is
-        posted right after each replay."""
-        if self.world > 1 and os.environ.get("TM_DP_GRAPH", "0") == "1":
-            # experimental: capture the three bucketed NCCL all-reduces (overlapping the backward) inside the graph
-            return self._capture_local(b, warmup)
+        three bucketed NCCL all-reduces are captured INSIDE the graph (persistent flat buffers,
+        ``tm_dp.FlatBucket``), where they overlap the backward as in the eager schedule; with
+        ``TM_DP_GRAPH=0`` the graph holds the rank's compute only and one exchange is posted after each
+        replay.  ``pool``: a ``torch.cuda.graph_pool_handle()`` shared by graphs that are replayed one
+        after the other (several prepared designs of one rank share their activation memory).
+        Call ``close()`` before ``torch.distributed.destroy_process_group()``."""
+        if self.world <= 1 or os.environ.get("TM_DP_GRAPH", "1") != "0":
+            return self._capture_local(b, warmup, pool)
         world, self.world = self.world, 1                  # no collectives inside the captured region
         try:
-            replay_local = self._capture_local(b, warmup)
+            replay_local = self._capture_local(b, warmup, pool)
         finally:
             self.world = world
-        if world <= 1:
-            return replay_local
         params = [p for p in list(self.model.parameters()) + list(self.cnn.parameters())]
 
         def replay():
             out = replay_local()
-            self._post_allreduce([p for p in params if p.grad is not None])
+            self._post_allreduce("all", [p for p in params if p.grad is not None])
             self._wait_allreduce()
             return out
         replay.graph = replay_local.graph
         return replay
 
-    def _capture_local(self, b, warmup=2):
+    def _capture_local(self, b, warmup=2, pool=None):
         cur = torch.cuda.current_stream()
         s = torch.cuda.Stream(priority=int(os.environ.get("TM_MAIN_PRIORITY", "0")))   # (a higher priority for the netlist branch was measured: no effect)
         s.wait_stream(cur)
@@ -259,8 +264,9 @@ class DesignStep:
         cur.wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, pool=pool):
             loss, pred = self.run(b)
+        self._graphs.append(g)
         grads = [(p, p.grad) for p in list(self.model.parameters()) + list(self.cnn.parameters()) if p.grad is not None]
 
         def replay():
@@ -271,13 +277,13 @@ class DesignStep:
         replay.graph = g
         return replay
 
-    def prepare(self, host, device, graph=None):
+    def prepare(self, host, device, graph=None, pool=None):
         """A design made resident for repeated steps: uploads everything once, builds the structure
         that depends only on the netlist and the endpoint batch (level schedule, CSRs, mask runs / CSC)
         and captures the step as a CUDA graph.  Returns a ``PreparedDesign``; its ``step(host)``
         refreshes the per-step VALUES (features, image, labels) from pinned host memory and replays.
         The structure (edges, endpoints, masks) must be the one given here."""
-        return PreparedDesign(self, host, device, graph)
+        return PreparedDesign(self, host, device, graph, pool)
 
     @staticmethod
     def _assign(pairs):
@@ -285,16 +291,26 @@ class DesignStep:
             p.grad = g.reshape(p.shape)
 
     # ---------------------------------------------------------------- data parallel
-    def _post_allreduce(self, params):
+    def _post_allreduce(self, name, params):
         if self.world <= 1:
             return
-        bucket = tm_dp.GradBucket(params, self.world, self.pg)
-        self._pending.append((bucket, bucket.post(self.comm_stream)))
+        bucket = self._buckets.get(name)
+        if bucket is None:
+            bucket = self._buckets[name] = tm_dp.FlatBucket(params, self.world, self.pg)
+        bucket.post(self.comm_stream)
 
     def _wait_allreduce(self):
-        for bucket, work in self._pending:
-            bucket.finish(work)
-        self._pending = []
+        if self.world > 1 and self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def close(self):
+        """Release the captured graphs (they hold NCCL kernels of this step's communicator): call before
+        ``torch.distributed.destroy_process_group()``."""
+        torch.cuda.synchronize()
+        for g in self._graphs:
+            g.reset()
+        self._graphs = []
+        torch.cuda.synchronize()
 
     def adam_step(self, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         """Fused Adam over every parameter that has a gradient (train.py:431-435,555)."""

@@ -245,9 +245,13 @@ GNN_PARAM_NAMES = ("fc_cell_self.layers.0.weight", "fc_cell_self.layers.0.bias",
                    "fc_cell_neigh.layers.2.weight", "fc_cell_neigh.layers.2.bias")
 
 
-def gnn_forward(sched, cell_feat, net_feat, params, save=True):
+def gnn_forward(sched, cell_feat, net_feat, params, save=True, impl=None):
     """Full propagation over every level.  ``params``: the 12 tensors of GNN_PARAM_NAMES.
-    Returns ``(H, saved)``; H is (N, 128) with zeros on pins outside the schedule."""
+    Returns ``(H, saved)``; H is (N, 128) with zeros on pins outside the schedule.
+    ``impl``: back end for this call (``tm_gnn_set_impl`` bits; None = the process default, which runs the
+    forward as ONE persistent cluster kernel).  The persistent kernel owns every SM while it runs, so a
+    caller that overlaps the propagation with other streams (``DesignStep``) asks for 0, the chain of
+    small per-level kernels that co-resides with them."""
     (cs1w, cs1b, cs2w, cs2b, ns1w, ns1b, ns2w, ns2b, cn1w, cn1b, cn2w, cn2b) = [_f32c(p) for p in params]
     if cn2w.shape[0] != D or cs2w.shape[0] != D or ns2w.shape[0] != D or cn1w.shape != (256, D):
         raise RuntimeError("the CUDA propagation kernels are built for out_feat_dim = hidden_feat_dim = 128 "
@@ -271,8 +275,13 @@ def gnn_forward(sched, cell_feat, net_feat, params, save=True):
         HID = torch.empty(max(ncr, 1), 256, dtype=torch.float32, device=dev)
     w1t, w2t = transpose(cn1w), transpose(cn2w)
     nb = tm_lib.ws_bytes("tm_gnn_ws_bytes")
-    call("tm_gnn_forward", sched.struct, 0, sched.num_levels, H, S, w1t, cn1b, w2t, cn2b, A, LSE, HID,
-         tm_lib.workspace(nb, dev), nb, stream())
+    old = tm_lib.lib().tm_gnn_set_impl(impl) if impl is not None else None
+    try:
+        call("tm_gnn_forward", sched.struct, 0, sched.num_levels, H, S, w1t, cn1b, w2t, cn2b, A, LSE, HID,
+             tm_lib.workspace(nb, dev), nb, stream())
+    finally:
+        if old is not None:
+            tm_lib.lib().tm_gnn_set_impl(old)
     saved = dict(H=H, A=A, LSE=LSE, HID=HID, hc=hc, hn=hn, cell_feat=cell_feat, net_feat=net_feat) if save else None
     return H, saved
 

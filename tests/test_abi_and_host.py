@@ -152,6 +152,10 @@ params[1].grad = None                                  # unused parameter (fc_ne
 b = tm_dp.GradBucket(params, world)
 work = b.post(None)
 b.finish(work)
+flat_ptr = b.flat.data_ptr()
+for i, p in enumerate(params):
+    if p.grad is not None:
+        assert p.grad.data_ptr() >= flat_ptr                # .grad is a view of the persistent flat buffer
 exp = sum(r + 1 for r in range(world)) / world
 assert torch.allclose(params[0].grad, torch.full((3, 5), exp)), params[0].grad
 assert params[1].grad is None

@@ -1,27 +1,22 @@
 """BASELINE.json configurations 2, 3 and 4 at FULL size (the headline bench runs config 2; the
 other configs are parity-test cases).
 
-* config 2 (100k cells, 331 819 pins, 101 levels): forward propagation H against the oracle on the
-  whole design (the oracle's forward takes a few seconds), schedule bit-exact.
-* config 3 (300k cells, ~1M pins, 101 levels): the oracle would take minutes, so the check is the
-  size-independent property of the recurrence itself -- EVERY pin must satisfy its own level equation
-  given the H rows of its predecessors (src/model.py:88-116,138-153) -- evaluated in fp64 on a random
-  sample of pins of every kind, plus bit-determinism of a second run and the schedule invariants.
-* config 4 (U-Net, batch 32 of 512x512, bf16 tensor-core operands): batch 2 against the oracle at
-  the bf16 bar (rtol 2e-2) on the OUTPUT; batch 32 forward+backward for shapes, finiteness and
-  determinism.  Parameter gradients of this network are not a 2e-2 quantity at 8-bit operands for
-  ANY implementation: 18 layers of max-pool arg-max and ReLU gates re-route the upstream gradient
-  whenever an activation moves across a tie, so they are checked by direction and size (cosine
-  >= 0.85, norm within 25 %); `profiles/diag_c4.py` prints the per-mode figures (3xTF32: 3e-3
-  relative L2, two-term bf16: 1e-2, single TF32: 1e-1, bf16: 3e-1).  The fp32-class default mode is
-  held to rtol 1e-3 on every gradient in test_gpu_parity.py::test_unet_vs_oracle.
+* config 2 (100k cells, 331 819 pins, 101 levels, 3x256x256 image, 1 350 endpoints): the WHOLE design step --
+  predictions, loss and every parameter gradient of the netlist branch, head, fusion and U-Net -- against the
+  oracle's step on the same design (4 s of CPU), rtol 1e-3; plus forward H alone and the schedule bit-exact.
+* config 3 (300k cells, ~1M pins, 101 levels): propagation forward AND backward (H and the twelve parameter
+  gradients) against the oracle at full size (10 s of CPU), rtol 1e-3; plus the size-independent property that
+  EVERY pin satisfies its own level equation (fp64 on sampled pins), bit-determinism, schedule invariants.
+* config 4 (U-Net, batch 32 of 512x512, bf16 tensor-core operands): batch 2 against the bf16-rounded oracle at
+  the bf16 bar (rtol 2e-2) on the output and -- teacher-forced, see the test -- on EVERY gradient; batch 32
+  forward+backward for shapes, finiteness and determinism.
 """
 import numpy as np
 import pytest
 import torch
 
 import tm_synth
-from conftest import assert_close, design_to_oracle
+from conftest import assert_close, assert_grad_close_given_flips, design_to_oracle, relu_gate_flips
 from oracle import restate
 
 pytestmark = pytest.mark.gpu
@@ -140,32 +135,159 @@ def test_config3_million_pin_recurrence(mods):
     assert res < 1e-4, f"a pin violates its level equation: relative residual {res:.3e}"
 
 
+def test_config2_full_step_vs_oracle(mods):
+    """The headline workload end to end: one design step of config 2 (fused two-stream DesignStep, default
+    arithmetic) against oracle.restate.design_step on the same design and weights."""
+    import tm_engine
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["c2"])
+    model, cnn = tm_engine.build_models(d.map_size, seed=0, device=DEV)
+    sd_m = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    sd_c = {k: v.detach().cpu().clone() for k, v in cnn.state_dict().items()}
+    batch = tm_engine.DesignBatch.from_synth(d, DEV)
+    loss, pred = tm_engine.DesignStep(model, cnn).run(batch)
+    with torch.no_grad():
+        H = model.gnn.propagate(batch.graph)                  # the same kernels: bit-identical to the step's H
+        _, ust = mods["unet"].unet_forward(cnn, batch.image, need_bwd=False, update_stats=False)
+    # The image branch's 3.5 M ReLU gates / max-pool windows at 256x256 re-route its gradients whenever two
+    # evaluations disagree about a tie (0.4 % of the gradient's scale, measured): the oracle's U-Net is
+    # teacher-forced with the product's contraction outputs (restate._force), so both differentiate the same
+    # piecewise-linear function and every element can be held to rtol 1e-3.
+    ref = restate.design_step(sd_m, sd_c, design_to_oracle(d), unet_forced=_unet_forced_tensors(ust, 1, 2 * d.map_size))
+    assert_close(pred, ref["pred"], 1e-3, 1e-4, "pred")
+    assert_close(loss.reshape(()), ref["loss"], 1e-3, 1e-4, "loss")
+    assert_close(H, ref["H"], 1e-3, 1e-4, "H")
+    flips = relu_gate_flips(H, ref["H"])
+    for k, p in model.named_parameters():
+        g = ref["grads"][k]
+        if g is None:
+            assert p.grad is None, k
+        elif k.startswith("gnn."):
+            assert_grad_close_given_flips(p.grad, g, k, flips, atol_scale=2e-4)
+        else:
+            assert_close(p.grad, g, 1e-3, 2e-4, k)
+    cg = dict(cnn.named_parameters())
+    for k, p in cnn.named_parameters():
+        if k.endswith(".up.bias"):
+            # a bias in front of conv3x3 + train-mode BatchNorm: only the image border keeps its gradient from being
+            # absorbed by the batch mean, so it is a cancelling sum over 65k pixels, ~20x below the layer's weight
+            # gradient -- its absolute tolerance is scaled to that weight gradient, not to its own (noise-sized) maximum
+            r = ref["grads"]["cnn." + k].double()
+            wscale = float(ref["grads"]["cnn." + k[:-4] + "weight"].abs().max())
+            err = (p.grad.double().cpu() - r).abs()
+            assert bool((err <= 1e-3 * r.abs() + 2e-4 * wscale).all()), f"{k}: max abs err {float(err.max()):.3e}"
+            continue
+        assert_close(p.grad, ref["grads"]["cnn." + k], 1e-3, 2e-4, "cnn." + k)
+
+
+def test_config3_forward_backward_vs_oracle(mods):
+    """GNN-only, ~1M pins, 101 levels: H and the twelve parameter gradients against the oracle at full size.
+    127 M output gates: the few whose pre-activation is ~0 and on whose sign the two evaluations disagree are
+    PROVEN to be such (conftest.relu_gate_flips) and the oracle's backward is then taken through the product's
+    branch of exactly those gates (restate.gnn_propagate(gate=...)); every gradient element is held to rtol 1e-3."""
+    ops = mods["ops"]
+    d = tm_synth.make_design(seed=0, n_endpoints=64, **tm_synth.CONFIGS["c3"])
+    gnn = _gnn(3)
+    od = design_to_oracle(d)
+    gen = torch.Generator().manual_seed(3)
+    Gout = 1e-3 * torch.randn(d.n, 128, generator=gen)
+    names = ["gnn." + k for k in ops.GNN_PARAM_NAMES]
+    gd = gnn.to(DEV)
+    g = _graph(mods, d)
+    H = gd.propagate(g)
+    H.backward(Gout.to(DEV))
+    sd = {"gnn." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in gd.state_dict().items()}
+    with torch.no_grad():
+        Hfree = restate.gnn_propagate(sd, "gnn", d.n, od["levels"], od["net_csr"], od["cell_csr"], od["cell_feat"], od["net_feat"])
+    assert_close(H, Hfree, 1e-3, 1e-4, "H")
+    flips = relu_gate_flips(H, Hfree, max_flips=64)
+    gate = (H.detach() > 0).cpu() if flips else None
+    Href = restate.gnn_propagate(sd, "gnn", d.n, od["levels"], od["net_csr"], od["cell_csr"], od["cell_feat"], od["net_feat"], gate=gate)
+    gref = torch.autograd.grad(Href, [sd[k] for k in names], Gout)
+    # what is left are ties of HIDDEN units (77 M inside the recurrence, 255 M in the hoisted MLPs): one flipped hidden
+    # unit of one pin moves one row of a layers.0.weight / one column of a layers.2.weight (128 elements; the <= 4
+    # elements its one-hot features select in fc_cell_self.layers.0).  Measured at this size: 2 units (267 of 32 768
+    # elements of fc_cell_neigh.layers.0.weight, by 2.4e-3 of the tensor's scale; 4 of 9 216 of fc_cell_self.layers.0).
+    # At most 4 units' worth of elements per tensor may exceed the tolerance, by <= 50x; everything else is strict.
+    for k, r in zip(ops.GNN_PARAM_NAMES, gref):
+        assert_close(dict(gd.named_parameters())[k].grad, r, 1e-3, 2e-4, k, max_bad=512)
+
+
+def _unet_forced_tensors(st, B, H):
+    """The product's contraction outputs (NHWC rows) as the oracle's NCHW tensors, keyed like restate._force."""
+    chans = [16, 32, 64, 128]
+    enc = ["inc.double_conv", "down1.maxpool_conv.1.double_conv", "down2.maxpool_conv.1.double_conv",
+           "down3.maxpool_conv.1.double_conv"]
+
+    def nchw(t, C, h):
+        return t.detach().float().reshape(B, h, h, C).permute(0, 3, 1, 2).contiguous().cpu()
+    f = {}
+    for i in range(4):
+        e = st[f"enc{i}"]
+        f[enc[i] + ".0"], f[enc[i] + ".3"] = nchw(e["r1"], chans[i], H >> i), nchw(e["r2"], chans[i], H >> i)
+    for j, nm in enumerate(["up1", "up2", "up3"]):
+        i = 2 - j
+        e = st[f"dec{j}"]
+        f[nm + ".conv.double_conv.0"], f[nm + ".conv.double_conv.3"] = nchw(e["r1"], chans[i], H >> i), nchw(e["r2"], chans[i], H >> i)
+        f[nm + ".up"] = nchw(st["cat"][i][:, chans[i]:].contiguous(), chans[i], H >> i)
+    return f
+
+
 def test_config4_unet_bf16(mods):
+    """BASELINE config 4: the bf16 image branch (TMA-fed tcgen05 convolutions) at the north_star bar, rtol 2e-2.
+
+    Oracle: restate.unet_forward(rounding="bf16") -- the reference network with the operands of every
+    convolution rounded to bf16 at the product's rounding points.
+      * output: per element at rtol 2e-2 against that oracle run freely;
+      * EVERY parameter gradient: per element at rtol 2e-2 against that oracle TEACHER-FORCED with the product's
+        own contraction outputs, i.e. differentiating the same piecewise-linear function (same ReLU gates, same
+        max-pool winners, same batch statistics).  Free-running, two bf16 evaluations of this 18-layer network
+        are ~10 % apart in their gradients however exact each contraction is: bf16 quantisation noise regenerates
+        at every layer (relative L2 fixed point 2^-8) and re-routes ~0.3 % of the gates per layer --
+        tests/test_oracle_pinning.py::test_bf16_unet_free_running_gradients_are_tie_limited shows the oracle doing
+        that to ITSELF (fp32 against fp64 accumulation).  The free-running distance is bounded here as well."""
     import Unet as U
     unet = mods["unet"]
     torch.manual_seed(4)
     net = U.UNet("max").train()
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    # ---- batch 2 of 512x512 against the oracle at the bf16 bar
-    x = torch.rand(2, 3, 512, 512)
-    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
-    ref, _ = restate.unet_forward(P, x, "max")
-    g = torch.randn_like(ref)
+    B, H = 2, 512
+    x = torch.rand(B, 3, H, H)
     names = [k for k, _ in net.named_parameters()]
-    gref = torch.autograd.grad(ref, [P[k] for k in names], g)
+
+    def oracle(forced):
+        P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+        ref, _ = restate.unet_forward(P, x, "max", rounding="bf16", forced=forced)
+        return ref, P
+
     net = net.to(DEV)
     old = unet.MATH
     try:
         unet.MATH = "bf16"
-        out = net(x.to(DEV))
-        assert_close(out, ref, 2e-2, 2e-2, "unet out (bf16 operands)")
-        out.backward(g.to(DEV))
+        out, st = unet.unet_forward(net, x.to(DEV), need_bwd=True, update_stats=False)
+        assert all(st[k].get("tma") for k in ("enc0", "enc1", "enc2", "enc3", "dec0", "dec1", "dec2")), "not on the TMA path"
+        free, _ = oracle(None)
+        assert_close(out, free, 2e-2, 2e-2, "unet out (bf16 operands) vs free-running bf16 oracle")
+        g = torch.randn(B, 1, H // 2, H // 2, generator=torch.Generator().manual_seed(9))
+        grads = unet.unet_backward(net, st, g.to(DEV))
+        ref, P = oracle(_unet_forced_tensors(st, B, H))
+        assert_close(out, ref, 2e-2, 2e-2, "unet out vs forced bf16 oracle")
+        gref = torch.autograd.grad(ref, [P[k] for k in names], g)
+        gmap = dict(zip(names, gref))
         for k, r in zip(names, gref):
-            a = dict(net.named_parameters())[k].grad.double().cpu().reshape(-1)
-            r = r.double().reshape(-1)
-            cos = float((a @ r) / (a.norm() * r.norm() + 1e-300))
-            ratio = float(a.norm() / (r.norm() + 1e-300))
-            assert cos >= 0.85 and 0.75 <= ratio <= 1.25, f"{k}: cosine {cos:.3f}, norm ratio {ratio:.3f}"
+            if k.endswith(".up.bias"):
+                # cancelling sum (see test_config2_full_step_vs_oracle): tolerance scaled to the layer's weight gradient
+                wscale = float(gmap[k[:-4] + "weight"].abs().max())
+                err = (grads[k].double().cpu().reshape(r.shape) - r.double()).abs()
+                assert bool((err <= 2e-2 * r.abs() + 2e-2 * wscale).all()), f"{k}: max abs err {float(err.max()):.3e}"
+                continue
+            assert_close(grads[k].reshape(r.shape), r, 2e-2, 2e-2, f"grad {k} (bf16, teacher-forced oracle)")
+        # free-running distance (no forcing): bounded, and reported by profiles/diag_unet_bf16.py
+        freeP = oracle(None)
+        gfree = torch.autograd.grad(freeP[0], [freeP[1][k] for k in names], g)
+        for k, r in zip(names, gfree):
+            a, r = grads[k].double().cpu().reshape(-1), r.double().reshape(-1)
+            rel = float((a - r).norm() / (r.norm() + 1e-300))
+            assert rel <= 0.25, f"{k}: free-running relative L2 distance {rel:.3f}"
         # ---- the BASELINE shape: batch 32 of 512x512, forward + backward
         net.zero_grad()
         torch.manual_seed(5)

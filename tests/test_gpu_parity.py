@@ -10,7 +10,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import GOLD, assert_close, design_to_oracle, load_golden_step
+from conftest import (GOLD, assert_close, assert_grad_close_given_flips, design_to_oracle, load_golden_step,
+                      relu_gate_flips)
 from oracle import levelize, restate
 import tm_synth
 
@@ -206,10 +207,12 @@ def test_gnn_forward_backward(mods, math_mode, cfg, seed):
     H = gnn.propagate(g)
     assert_close(H, Href, 1e-3, 1e-4, "H")
     H.backward(Gout.to(DEV))
-    # ~2 M ReLU gates (pins x channels + hidden units): allow the handful of boundary flips any
-    # reordered fp32-class evaluation produces (see conftest.assert_close); H above is held exactly.
+    # every gradient element at rtol 1e-3 -- except the rows a PROVEN output-gate flip lands in (a pin whose
+    # pre-activation is within 1e-5 of zero and whose sign the two evaluations disagree on: 0-2 of 2.1 M gates,
+    # see conftest.relu_gate_flips; profiles/diag_gnn_flips.py lists them per back end)
+    flips = relu_gate_flips(H, Href)
     for k, r in zip(ops.GNN_PARAM_NAMES, gref):
-        assert_close(dict(gnn.named_parameters())[k].grad, r, 1e-3, 1e-4, k, flip_frac=5e-3)
+        assert_grad_close_given_flips(dict(gnn.named_parameters())[k].grad, r, k, flips)
     assert gnn.fc_net_drive.layers[0].weight.grad is None and gnn.fc_attn2.weight.grad is None
     # a second backward through retained buffers gives the same gradients (retain_graph, D9)
     first = {k: p.grad.clone() for k, p in gnn.named_parameters() if p.grad is not None}
@@ -717,8 +720,9 @@ def test_gnn_kernel_variants_vs_oracle(mods, impl, flow, cfg, seed):
             H.backward(Gout.to(DEV))
             runs.append((H.detach().clone(), {k: p.grad.clone() for k, p in gnn.named_parameters() if p.grad is not None}))
         assert_close(runs[0][0], Href, 1e-3, 1e-4, "H")
+        flips = relu_gate_flips(runs[0][0], Href)
         for k, r in zip(ops.GNN_PARAM_NAMES, gref):
-            assert_close(runs[0][1][k], r, 1e-3, 1e-4, k, flip_frac=5e-3)
+            assert_grad_close_given_flips(runs[0][1][k], r, k, flips)
         assert torch.equal(runs[0][0], runs[1][0])
         for k in runs[0][1]:
             assert torch.equal(runs[0][1][k], runs[1][1][k]), k

@@ -113,3 +113,44 @@ def test_restatement_vs_live_reference(tiny):
             assert_close(out["grads"][k], p.grad, 1e-4, 1e-5, k)
     for k, p in cnn.named_parameters():
         assert_close(out["grads"]["cnn." + k], p.grad, 1e-4, 1e-5, k)
+
+
+def test_bf16_unet_free_running_gradients_are_tie_limited(pkg):
+    """Evidence for the way tests/test_gpu_configs.py::test_config4_unet_bf16 checks gradients.  The bf16-rounded
+    oracle against ITSELF -- same network, same rounding points, fp32 against fp64 accumulation (differences of
+    1e-7 before the first rounding): the outputs agree at the bf16 bar, the parameter gradients do not (relative
+    L2 distance of several per cent), because bf16 quantisation noise regenerates at every layer and re-routes
+    ReLU / max-pool gates.  No implementation can therefore meet rtol 2e-2 per element on free-running gradients;
+    teacher-forcing the gates (restate._force) removes the ambiguity and is what the GPU test does."""
+    import Unet as U
+    torch.manual_seed(4)
+    sd = {k: v.detach().clone() for k, v in U.UNet("max").state_dict().items()}
+    x = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(1))
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+
+    def run(dtype, forced=None):
+        P = {k: (v.to(dtype).clone().requires_grad_(True) if k in names else (v.to(dtype) if v.is_floating_point() else v.clone()))
+             for k, v in sd.items()}
+        out, _ = restate.unet_forward(P, x.to(dtype), "max", rounding="bf16", forced=forced)
+        g = torch.randn(out.shape, generator=torch.Generator().manual_seed(2)).to(dtype)
+        return out.detach(), torch.autograd.grad(out, [P[k] for k in names], g)
+
+    o32, g32 = run(torch.float32)
+    # the fp64 run, its contraction outputs captured through the hook the GPU test forces through
+    cap = {}
+    orig_force = restate._force
+    restate._force = lambda y, forced, key: (cap.setdefault(key, y.detach()), y)[1]
+    try:
+        o64, g64 = run(torch.float64)
+    finally:
+        restate._force = orig_force
+    scale = float(o64.abs().max())
+    assert float((o32.double() - o64).abs().max()) <= 2e-2 * scale            # forward: fine at the bf16 bar
+    rels = [float((a.double() - b).norm() / b.norm()) for a, b in zip(g32, g64)]
+    assert max(rels) > 2e-2, f"free-running bf16 gradients unexpectedly agree ({max(rels):.3e})"
+    # with the gates forced to the fp64 run's, the fp32 run's gradients agree per element at the bar
+    _, g32f = run(torch.float32, forced=cap)
+    for k, a, b in zip(names, g32f, g64):
+        err = (a.double() - b).abs()
+        tol = 2e-2 * float(b.abs().max()) + 2e-2 * b.abs()
+        assert bool((err <= tol).all()), f"{k}: forced fp32 run differs from the fp64 run ({float(err.max()):.3e})"
