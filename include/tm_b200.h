@@ -230,6 +230,19 @@ int tm_mask_count(int64_t n, int64_t E, const int32_t* src, const int32_t* dst, 
 int tm_mask_fill(int64_t n, int64_t T, int64_t map_size, const int32_t* indptr, int32_t* cols, void* ws,
                  size_t ws_bytes, void* stream);
 
+/* Row selection of a path-mask CSR for one endpoint batch -- th.index_select(path_masks, 0, th.tensor(paths)),
+ * src/train.py:500 (and :213, test.py:201) -- entirely on the device: no host round trip, every size a bound the
+ * host already has, so it can be replayed inside a CUDA graph with `rows` as an input.
+ *   rows[T]: mask row (path id) of every endpoint of the batch, repeats allowed (oversampled paths, train.py:377-380);
+ *   run_ptr[T+1], run_lo / run_hi [cap]: run-length form of the selected rows (tm_fuse_forward_runs);
+ *   csc_ptr[J+1], csc_t[cap]: column-major transpose, t ascending inside a column (tm_fuse_backward), built as a
+ *            stable counting sort: deterministic without sorting;
+ *   cap >= sum of the selected rows' lengths (e.g. T * longest row), J * 4 bytes <= 200 KB of shared memory. */
+size_t tm_mask_select_ws(int64_t T, int64_t J);
+int tm_mask_select(int64_t T, int64_t J, const int32_t* indptr, const int32_t* cols, const int32_t* rows,
+                   int32_t* run_ptr, int32_t* run_lo, int32_t* run_hi, int32_t* csc_ptr, int32_t* csc_t,
+                   void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * G6  head helpers (src/model.py:280-292, src/train.py:513-522)
  * ---------------------------------------------------------------------------------- */

@@ -150,3 +150,191 @@ extern "C" int tm_mask_fill(int64_t n, int64_t T, int64_t map_size, const int32_
   mask_fill_kernel<<<(unsigned)T, MT, 0, (cudaStream_t)stream>>>(bitmaps, words, indptr, cols);
   return check_launch("mask_fill");
 }
+
+// =============================================================================================
+// Row selection of a path-mask CSR for one endpoint batch, on the device, with no host round trip:
+//   th.index_select(path_masks, 0, th.tensor(paths))        (src/train.py:500, once per level and batch)
+// rows[T] picks mask rows (a shuffled DataLoader batch; repeats allowed: oversampled critical paths,
+// train.py:377-380).  Produces the two forms the fusion kernels read:
+//   * run-length form of the selected rows (forward, tm_fuse_forward_runs);
+//   * their column-major transpose csc_ptr[J+1], csc_t[] with t ascending inside every column
+//     (backward pull, tm_fuse_backward) -- built as a STABLE counting sort (per-block histograms, a
+//     column-wise scan over the blocks, then a row-by-row fill), so the result and hence the order of the
+//     backward's floating-point sums is deterministic without sorting anything.
+// Every size the host needs is an upper bound it already knows (cap >= selected nnz), so the whole
+// selection can sit inside a captured CUDA graph with `rows` as a graph input.
+// =============================================================================================
+namespace {
+constexpr int SEL_R = 8;            // rows per block in the counting sort
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += y;
+  }
+  return v;
+}
+
+// one warp per selected row: number of runs of consecutive columns
+__global__ void sel_count_runs_kernel(int T, const int* __restrict__ indptr, const int* __restrict__ cols,
+                                      const int* __restrict__ rows, int* __restrict__ nruns) {
+  const int lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= T) return;
+  const int r = rows[t], s = indptr[r], e = indptr[r + 1];
+  int cnt = 0;
+  for (int i = s + lane; i < e; i += 32) cnt += (i == s || cols[i] != cols[i - 1] + 1) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) nruns[t] = cnt;
+}
+
+// single block: out[0] = 0, out[i+1] = in[0] + ... + in[i]
+__global__ void __launch_bounds__(1024) sel_scan_kernel(int n, const int* __restrict__ in, int* __restrict__ out) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { carry = 0; out[0] = 0; }
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const int v = i < n ? in[i] : 0;
+    int x = warp_incl_scan(v, lane);
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = wsum[lane];
+      wsum[lane] = warp_incl_scan(w, lane) - w;
+    }
+    __syncthreads();
+    x += wsum[warp] + carry;
+    if (i < n) out[i + 1] = x;
+    __syncthreads();
+    if (tid == 1023) carry = x;
+    __syncthreads();
+  }
+}
+
+// one warp per selected row: write its runs at run_ptr[t]
+__global__ void sel_fill_runs_kernel(int T, const int* __restrict__ indptr, const int* __restrict__ cols,
+                                     const int* __restrict__ rows, const int* __restrict__ run_ptr,
+                                     int* __restrict__ run_lo, int* __restrict__ run_hi) {
+  const int lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= T) return;
+  const int r = rows[t], s = indptr[r], e = indptr[r + 1];
+  int out = run_ptr[t];
+  for (int i0 = s; i0 < e; i0 += 32) {
+    const int i = i0 + lane;
+    const bool in = i < e;
+    const int c = in ? cols[i] : 0;
+    const bool start = in && (i == s || cols[i - 1] + 1 != c);
+    const bool last = in && (i == e - 1 || cols[i + 1] != c + 1);
+    const unsigned ms = __ballot_sync(0xffffffffu, start), ml = __ballot_sync(0xffffffffu, last);
+    // the run an entry starts / ends: runs opened before this chunk are counted in `out`
+    if (start) run_lo[out + __popc(ms & ((1u << lane) - 1u))] = c;
+    if (last) {
+      // index of the run this entry closes = (#starts at or before this lane) - 1, relative to `out`, or the run
+      // carried in from the previous chunk (then no start precedes it here and the index is out - 1)
+      const int k = __popc(ms & ((2u << lane) - 1u)) - 1;
+      run_hi[out + k] = c + 1;
+    }
+    out += __popc(ms);
+    (void)ml;
+  }
+}
+
+// counting sort by column, pass 1: per-block histogram of the columns of SEL_R consecutive selected rows
+__global__ void __launch_bounds__(1024) sel_hist_kernel(int T, int J, const int* __restrict__ indptr, const int* __restrict__ cols,
+                                                        const int* __restrict__ rows, int* __restrict__ hist) {
+  extern __shared__ int sh[];                                    // [J]
+  for (int j = threadIdx.x; j < J; j += blockDim.x) sh[j] = 0;
+  __syncthreads();
+  const int t0 = blockIdx.x * SEL_R;
+  for (int q = 0; q < SEL_R; ++q) {
+    const int t = t0 + q;
+    if (t >= T) break;
+    const int r = rows[t], s = indptr[r], e = indptr[r + 1];
+    for (int i = s + threadIdx.x; i < e; i += blockDim.x) sh[cols[i]] += 1;      // columns are unique inside a row
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < J; j += blockDim.x) hist[(size_t)blockIdx.x * J + j] = sh[j];
+}
+
+// pass 2a: per column, exclusive scan over the blocks (in place) and the column total
+__global__ void sel_colscan_kernel(int nb, int J, int* __restrict__ hist, int* __restrict__ total) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= J) return;
+  int acc = 0;
+  for (int b = 0; b < nb; ++b) {
+    const int v = hist[(size_t)b * J + j];
+    hist[(size_t)b * J + j] = acc;
+    acc += v;
+  }
+  total[j] = acc;
+}
+
+// pass 3: row by row inside a block (rows ascending), every entry goes to its column's next slot
+__global__ void __launch_bounds__(1024) sel_scatter_kernel(int T, int J, const int* __restrict__ indptr, const int* __restrict__ cols,
+                                                           const int* __restrict__ rows, const int* __restrict__ hist,
+                                                           const int* __restrict__ csc_ptr, int* __restrict__ csc_t) {
+  extern __shared__ int cur[];                                   // [J] next free slot of every column for this block
+  for (int j = threadIdx.x; j < J; j += blockDim.x) cur[j] = csc_ptr[j] + hist[(size_t)blockIdx.x * J + j];
+  __syncthreads();
+  const int t0 = blockIdx.x * SEL_R;
+  for (int q = 0; q < SEL_R; ++q) {
+    const int t = t0 + q;
+    if (t >= T) break;
+    const int r = rows[t], s = indptr[r], e = indptr[r + 1];
+    for (int i = s + threadIdx.x; i < e; i += blockDim.x) {
+      const int j = cols[i];
+      csc_t[cur[j]] = t;
+      cur[j] += 1;
+    }
+    __syncthreads();
+  }
+}
+}  // namespace
+
+extern "C" size_t tm_mask_select_ws(int64_t T, int64_t J) {
+  const int64_t nb = cdiv(T > 0 ? T : 1, SEL_R);
+  return (size_t)(nb * J + J + T + 64) * sizeof(int) + 1024;
+}
+
+extern "C" int tm_mask_select(int64_t T, int64_t J, const int32_t* indptr, const int32_t* cols, const int32_t* rows,
+                              int32_t* run_ptr, int32_t* run_lo, int32_t* run_hi, int32_t* csc_ptr, int32_t* csc_t,
+                              void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(T >= 0 && J > 0 && J * sizeof(int) <= 200 * 1024, "tm_mask_select: bad sizes (J = %lld)", (long long)J);
+  TM_REQUIRE(ws && ws_bytes >= tm_mask_select_ws(T, J), "tm_mask_select: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (int)cdiv(T > 0 ? T : 1, SEL_R);
+  Carver c(ws);
+  int* hist = c.take<int>((size_t)nb * J);
+  int* total = c.take<int>(J);
+  int* nruns = c.take<int>(T + 1);
+  if (T == 0) {
+    TM_CUDA(cudaMemsetAsync(run_ptr, 0, sizeof(int), st));
+    TM_CUDA(cudaMemsetAsync(csc_ptr, 0, sizeof(int) * (J + 1), st));
+    return 0;
+  }
+  const unsigned wblocks = (unsigned)cdiv(T * 32, 256);
+  sel_count_runs_kernel<<<wblocks, 256, 0, st>>>((int)T, indptr, cols, rows, nruns);
+  TM_TRY(check_launch("sel_count_runs"));
+  sel_scan_kernel<<<1, 1024, 0, st>>>((int)T, nruns, run_ptr);
+  TM_TRY(check_launch("sel_scan(runs)"));
+  sel_fill_runs_kernel<<<wblocks, 256, 0, st>>>((int)T, indptr, cols, rows, run_ptr, run_lo, run_hi);
+  TM_TRY(check_launch("sel_fill_runs"));
+  const size_t sm = (size_t)J * sizeof(int);
+  TM_CUDA(cudaFuncSetAttribute(sel_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  TM_CUDA(cudaFuncSetAttribute(sel_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  sel_hist_kernel<<<nb, 1024, sm, st>>>((int)T, (int)J, indptr, cols, rows, hist);
+  TM_TRY(check_launch("sel_hist"));
+  sel_colscan_kernel<<<(unsigned)cdiv(J, 256), 256, 0, st>>>(nb, (int)J, hist, total);
+  TM_TRY(check_launch("sel_colscan"));
+  sel_scan_kernel<<<1, 1024, 0, st>>>((int)J, total, csc_ptr);
+  TM_TRY(check_launch("sel_scan(columns)"));
+  sel_scatter_kernel<<<nb, 1024, sm, st>>>((int)T, (int)J, indptr, cols, rows, hist, csc_ptr, csc_t);
+  TM_TRY(check_launch("sel_scatter"));
+  return 0;
+}

@@ -67,7 +67,8 @@ class HostDesign:
 class DesignBatch:
     """Device-resident batch of one design."""
 
-    def __init__(self, graph, mask_csr, endpoints, endpoint_level, arrival_time, image, cell_feat=None, net_feat=None):
+    def __init__(self, graph, mask_csr, endpoints, endpoint_level, arrival_time, image, cell_feat=None, net_feat=None,
+                 rows=None, dynamic=False):
         self.graph, self.mask_csr = graph, mask_csr
         # per-batch feature tensors (a prefetched batch must not disturb the one in flight through
         # the shared graph object); default: whatever the graph carries
@@ -77,7 +78,20 @@ class DesignBatch:
         self.endpoint_level = endpoint_level       # float32 (T,)
         self.arrival_time = arrival_time           # float32 (T,)
         self.image = image                         # (C,H,W)
-        self.mask_rows = mask_csr.select_all()
+        # rows: the mask row (path id) of every endpoint -- th.index_select(path_masks, 0, paths), train.py:500;
+        # None: endpoint t owns row t (one design's endpoints in one batch, test.py:176)
+        self.mask_rows = mask_csr.select(rows) if rows is not None else mask_csr.select_all()
+        # dynamic: the endpoint batch (endpoints / levels / labels / mask rows) is refreshed IN PLACE between steps, so
+        # the step re-runs the on-device row selection every time (captured into its CUDA graph): one capture per
+        # design serves every shuffled batch of the reference's DataLoader (train.py:470-486)
+        self.dynamic = bool(dynamic)
+
+    def set_endpoints(self, endpoints, endpoint_level, arrival_time, rows):
+        """Refresh the endpoint batch in place (same batch size): what changes between two DataLoader batches."""
+        self.endpoints.copy_(endpoints, non_blocking=True)
+        self.endpoint_level.copy_(endpoint_level, non_blocking=True)
+        self.arrival_time.copy_(arrival_time, non_blocking=True)
+        self.mask_rows.rows.copy_(rows, non_blocking=True)
 
     @staticmethod
     def from_host(h, device, graph=None):
@@ -175,6 +189,8 @@ class DesignStep:
         m, cnn = self.model, self.cnn
         dev = b.image.device
         main = torch.cuda.current_stream()
+        if getattr(b, "dynamic", False):
+            b.mask_rows.rebuild()                            # this batch's mask-row selection (7 small kernels, no host sync)
         side = self.image_stream if (self.overlap and self.image_stream is not None) else main
         side.wait_stream(main)                               # fork: inputs / parameters are ready on `main`
         sched = b.graph.schedule()

@@ -40,6 +40,17 @@ class TimingGraph:
         self._topo_levels = None
         self._schedule = None
 
+    # ---- pickling (the reference stores the graph inside its per-design tuple, generate_data.py:50-54) ----
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_schedule"] = None                     # device-side, rebuilt on first use
+        st.pop("nodes", None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self.nodes = {"pin": _View(self.ndata)}
+
     # ---- DGL surface -------------------------------------------------------------------------
     class _EdgeAccessor:
         def __init__(self, g):
@@ -251,6 +262,13 @@ class MaskCSR:
         self.cols = torch.as_tensor(cols, dtype=torch.int32)
         self.width = int(width)
         self.num_rows = int(self.indptr.numel()) - 1
+        self._max_row = None
+
+    def max_row_len(self):
+        """Longest row (one host read per design; bounds the buffers of every row selection)."""
+        if self._max_row is None:
+            self._max_row = int((self.indptr[1:] - self.indptr[:-1]).max().item()) if self.num_rows else 0
+        return self._max_row
 
     @staticmethod
     def from_sparse_coo(t):
@@ -308,62 +326,51 @@ def rasterize_path_masks(n, src, dst, level, endpoints, pin_xy, map_size):
 
 
 class MaskRows:
-    """A row selection of a MaskCSR plus its column-major transpose (built lazily on the GPU)."""
+    """A row selection of a MaskCSR -- ``th.index_select(path_masks, 0, paths)`` (train.py:500) -- in the two forms
+    the fusion kernels read: the run-length form of the selected rows (forward) and their column-major transpose
+    (backward pull).  Both are built by ``tm_mask_select`` on the device with no host synchronisation into
+    buffers sized by bounds the host already knows, so ``rebuild()`` can be replayed inside a CUDA graph after the
+    caller refreshed ``rows`` in place (a new shuffled endpoint batch costs O(1) host work)."""
 
     def __init__(self, csr, rows, identity=False):
         self.csr = csr
         dev = csr.indptr.device
-        self.rows = torch.as_tensor(rows, dtype=torch.int32).to(dev)
+        self.rows = torch.as_tensor(rows, dtype=torch.int32).to(dev).contiguous()
         self.T = int(self.rows.numel())
-        self.identity = bool(identity)        # rows == arange(num_rows): skip the gather when building runs
-        self._csc = None
-        self._runs = None
+        self.identity = bool(identity)        # rows == arange(num_rows)
+        self._buf = None
+
+    def _alloc(self):
+        csr, dev = self.csr, self.csr.indptr.device
+        tm_lib.require_cuda(csr.indptr, "path masks")
+        cap = int(csr.cols.numel()) if self.identity else self.T * csr.max_row_len()
+        cap = max(cap, 1)
+        i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)      # noqa: E731
+        nb = tm_lib.ws_bytes("tm_mask_select_ws", self.T, csr.width)
+        self._buf = dict(run_ptr=i32(self.T + 1), run_lo=i32(cap), run_hi=i32(cap), csc_ptr=i32(csr.width + 1),
+                         csc_t=i32(cap), ws=tm_lib.workspace(nb, dev), nb=nb)
+
+    def rebuild(self):
+        """(Re)run the selection kernels for the current contents of ``rows`` on the current stream."""
+        if self._buf is None:
+            self._alloc()
+        b, csr = self._buf, self.csr
+        tm_lib.call("tm_mask_select", self.T, csr.width, csr.indptr, csr.cols, self.rows, b["run_ptr"], b["run_lo"],
+                    b["run_hi"], b["csc_ptr"], b["csc_t"], b["ws"], b["nb"], tm_lib.stream())
+        self._built = True
+
+    def _ensure(self):
+        if self._buf is None or not getattr(self, "_built", False):
+            self.rebuild()
+        return self._buf
 
     def runs(self):
-        """Run-length form of the selected rows: (run_ptr int32[T+1], run_lo, run_hi int32[<= nnz]) with
-        run r = columns [run_lo[r], run_hi[r]).  Needs ascending columns inside a row (the CSR
-        convention); built with asynchronous device ops only when the selection is the identity,
-        otherwise the rows are gathered first.  A row boundary always starts a new run; two adjacent
-        runs that touch are harmless (their prefix differences add up to the same sum)."""
-        if self._runs is None:
-            csr = self.csr
-            dev = csr.indptr.device
-            if self.identity:
-                indptr, cols = csr.indptr.long(), csr.cols.long()
-            else:
-                rl = self.rows.long()
-                start = csr.indptr[rl].long()
-                deg = csr.indptr[rl + 1].long() - start
-                indptr = torch.zeros(self.T + 1, dtype=torch.int64, device=dev)
-                indptr[1:] = torch.cumsum(deg, 0)
-                t_of = torch.repeat_interleave(torch.arange(self.T, device=dev), deg)
-                slot = torch.repeat_interleave(start, deg) + (torch.arange(int(deg.sum()), device=dev) - indptr[:-1][t_of])
-                cols = csr.cols[slot].long()
-            nnz = int(cols.numel())
-            if nnz == 0:
-                z = torch.zeros(1, dtype=torch.int32, device=dev)
-                self._runs = (torch.zeros(self.T + 1, dtype=torch.int32, device=dev), z, z)
-                return self._runs
-            brk = torch.ones(nnz, dtype=torch.int64, device=dev)
-            brk[1:] = (cols[1:] != cols[:-1] + 1).long()
-            brk.index_fill_(0, indptr[:-1].clamp(max=nnz - 1), 1)          # every row starts a run
-            ridx = torch.cumsum(brk, 0) - 1                                  # run index of every entry
-            run_lo = torch.full((nnz,), 1 << 30, dtype=torch.int64, device=dev).scatter_reduce_(0, ridx, cols, "amin")
-            run_hi = torch.full((nnz,), -1, dtype=torch.int64, device=dev).scatter_reduce_(0, ridx, cols + 1, "amax")
-            excl = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(brk, 0)])
-            run_ptr = excl[indptr]                                           # runs before the row's first entry
-            self._runs = (run_ptr.to(torch.int32), run_lo.to(torch.int32), run_hi.to(torch.int32))
-        return self._runs
+        """(run_ptr int32[T+1], run_lo, run_hi): endpoint t owns runs run_ptr[t]..run_ptr[t+1], run r covers columns
+        [run_lo[r], run_hi[r]).  Needs ascending columns inside a row (the CSR convention)."""
+        b = self._ensure()
+        return b["run_ptr"], b["run_lo"], b["run_hi"]
 
     def csc(self):
-        if self._csc is None:
-            csr = self.csr
-            rl = self.rows.long()
-            start = csr.indptr[rl].long()
-            deg = csr.indptr[rl + 1].long() - start
-            t_of = torch.repeat_interleave(torch.arange(self.T, device=deg.device), deg)
-            first = torch.cumsum(deg, 0) - deg
-            slot = torch.repeat_interleave(start, deg) + (torch.arange(int(deg.sum()), device=deg.device) - first[t_of])
-            cols = csr.cols[slot].long()
-            self._csc = build_csr(csr.width, cols, t_of)
-        return self._csc
+        """(csc_ptr int32[J+1], csc_t): positions t (0..T-1, ascending) whose mask contains column j."""
+        b = self._ensure()
+        return b["csc_ptr"], b["csc_t"]

@@ -729,3 +729,105 @@ def test_gnn_kernel_variants_vs_oracle(mods, impl, flow, cfg, seed):
     finally:
         lib.tm_gnn_set_impl(old_impl)
         lib.tm_gnn_set_sync(old_flow)
+
+
+def test_mask_row_selection_on_device(mods):
+    """tm_mask_select (th.index_select(path_masks, 0, paths), train.py:500, with repeats = oversampled paths) against
+    the definition: run-length form reproduces every selected row bit-exactly, the column-major transpose lists
+    exactly the positions t whose row holds the column, ascending."""
+    g = mods["graph"]
+    d = tm_synth.make_design(seed=2, **tm_synth.CONFIGS["c1"])
+    csr = g.MaskCSR(d.mask_indptr, d.mask_cols, d.map_size ** 2).to(DEV)
+    rng = np.random.default_rng(0)
+    P = len(d.endpoints)
+    for rows in (rng.integers(0, P, 777), np.arange(P)[::-1].copy(), np.array([5, 5, 5, 0]), np.array([], dtype=np.int64)):
+        mr = csr.select(torch.from_numpy(rows.astype(np.int32)))
+        run_ptr, run_lo, run_hi = [t.cpu().numpy() for t in mr.runs()]
+        cptr, ct = [t.cpu().numpy() for t in mr.csc()]
+        want_cols = [d.mask_cols[d.mask_indptr[r]:d.mask_indptr[r + 1]] for r in rows]
+        for t, wc in enumerate(want_cols):
+            got = np.concatenate([np.arange(run_lo[k], run_hi[k]) for k in range(run_ptr[t], run_ptr[t + 1])] or [np.zeros(0, np.int64)])
+            assert np.array_equal(got, wc), f"row {t}"
+        J = d.map_size ** 2
+        assert cptr[0] == 0 and cptr[J] == sum(len(w) for w in want_cols)
+        member = {}
+        for t, wc in enumerate(want_cols):
+            for c in wc:
+                member.setdefault(int(c), []).append(t)
+        for j in range(J):
+            assert ct[cptr[j]:cptr[j + 1]].tolist() == member.get(j, []), f"column {j}"
+
+
+def test_loader_train_loop_shape(mods, tmp_path):
+    """N3 + N1: a design written in the reference's per-design tuple format (generate_data.py:50-54, raw 42 / 3
+    feature columns), read back by tm_loader.load_single_design (train.py:335-388: feat_reduce trim, oversampling)
+    and driven by a RESTATEMENT of the reference's batch loop (train.py:468-562; the file itself cannot run on the
+    GPU box: /root/reference is absent there and it imports tkinter / lib2to3 / dgl / torchmetrics): shuffled
+    DataLoader batches, per-level model(graph, nodes, eids, targets, level_id, level_th, dense path_map) calls,
+    MSELoss, backward(retain_graph=True), Adam, h rebinding, CNN forward again.  The SAME batches through the fused
+    step (LoadedDesign.prepare: one CUDA-graph capture, endpoint batch refreshed in place) must give the same loss."""
+    import tm_loader
+    from torch.utils.data import DataLoader
+    eng = mods["engine"]
+    d = tm_synth.make_design(seed=4, **tm_synth.CONFIGS["tiny"])
+    tm_loader.save_design(str(tmp_path / "tiny.pkl"), tm_loader.design_tuple_from_synth(d))
+    opts = dict(out_dim=128, os_rate=1, feat_reduce=[6, 1], norm=False, batch_size=16)
+    path_dataset, graph, path2level, path2endpoint, topo_levels, cnn_inputs, path_masks = tm_loader.load_single_design(
+        "train", str(tmp_path), "tiny", opts["out_dim"], opts["os_rate"], opts["feat_reduce"], opts["norm"])
+    assert graph.ndata["cell_feat"].shape[1] == 36 and graph.ndata["net_feat"].shape[1] == 2
+    assert len(path_dataset) == len(d.endpoints) + len(path_dataset.paths) - len(set(path_dataset.paths))   # oversampled
+    model, cnn = eng.build_models(d.map_size, seed=1, device=DEV)
+    sd_m = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sd_c = {k: v.detach().clone() for k, v in cnn.state_dict().items()}
+    optim = torch.optim.Adam(list(model.parameters()) + list(cnn.parameters()), 1e-3)
+    loss_fn = torch.nn.MSELoss()
+    device = torch.device(DEV)
+    feat_map = cnn(cnn_inputs.to(device)).reshape((1, -1))                                   # train.py:465 (3-D input)
+    graph = graph.to(device)                                                                   # :467
+    loader = DataLoader(path_dataset, batch_size=opts["batch_size"], shuffle=True, drop_last=True,
+                        generator=torch.Generator().manual_seed(0))
+    seen, losses = [], []
+    for bidx, path_ids in enumerate(loader):                                                   # :475
+        path_ids = list(path_ids.numpy().tolist())
+        seen.append(path_ids)
+        sampled_ends, sampled_paths = {}, {}
+        for pathid in path_ids:                                                                # :477-484
+            sampled_ends.setdefault(path2level[pathid], []).append(path2endpoint[pathid])
+            sampled_paths.setdefault(path2level[pathid], []).append(pathid)
+        label_hats, target_list = None, []
+        for level_id, level in enumerate(topo_levels):                                         # :490
+            nodes, eids = level[:2]
+            targets, paths = sampled_ends.get(level_id, []), sampled_paths.get(level_id, [])
+            target_list.extend(targets)
+            if len(paths) == 0:
+                path_map = None
+            else:
+                path_mask = torch.index_select(path_masks, 0, torch.tensor(paths)).to(device)  # :500
+                path_map = path_mask.to_dense() * feat_map                                     # :501
+            cur = model(graph, nodes, eids, targets, level_id,
+                        torch.tensor(level_id, dtype=torch.float).unsqueeze(0).to(device), path_map)   # :503
+            if len(paths) == 0:
+                continue
+            label_hats = cur if label_hats is None else torch.cat((label_hats, cur), dim=0)
+        arrival_time = graph.ndata["arrival_time"][target_list].squeeze()
+        train_loss = loss_fn(label_hats, arrival_time)                                         # :520-522
+        losses.append(float(train_loss.item()))
+        optim.zero_grad()
+        train_loss.backward(retain_graph=True)                                                 # :553
+        optim.step()
+        graph.ndata["h"] = torch.zeros((graph.number_of_nodes(), opts["out_dim"]), dtype=torch.float).to(device)   # :559
+        feat_map = cnn(cnn_inputs.to(device)).reshape((1, -1))                                 # :562
+        if bidx == 1:
+            break
+    assert len(losses) == 2 and all(np.isfinite(losses))
+    # the fused path on the same two batches, from the same initial weights, Adam included
+    model.load_state_dict(sd_m)
+    cnn.load_state_dict(sd_c)
+    ld = tm_loader.load_design(str(tmp_path / "tiny.pkl"), DEV)
+    step = eng.DesignStep(model, cnn)
+    run = ld.prepare(step, batch_size=opts["batch_size"])
+    state = {}
+    for ids, want in zip(seen, losses):
+        loss, _ = run(ids)
+        assert_close(loss.reshape(()), torch.tensor(want), 1e-3, 1e-4, "loss of a shuffled batch")
+        step.adam_step(state, lr=1e-3)
