@@ -579,7 +579,7 @@ def main():
             del H, saved, S, G, GA, GH, GZ
             torch.cuda.empty_cache()
             try:
-                extra["other_configs"] = {"config3": bc.config3(), "config4": bc.config4()[0]}
+                extra["other_configs"] = {"config3": bc.config3(), "config4": bc.config4()[0], "layoutnet": bc.layoutnet()}
             except Exception as e:                                   # noqa: BLE001  (report, do not lose the headline line)
                 extra["other_configs"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:

@@ -326,6 +326,11 @@ int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64_t ldx, con
                        const float* beta, float* running_mean, float* running_var, float momentum,
                        float eps, float* y, int64_t ldy, float* save_mean, float* save_invstd,
                        void* y_bf16, const void* stats_part, int64_t nparts, void* ws, size_t ws_bytes, void* stream);
+/* The same pair with nn.BatchNorm2d in EVAL mode (module.eval()): y = relu(gamma * (x - running_mean) *
+ * rsqrt(running_var + eps) + beta); save_mean / save_invstd receive the statistics used (inference only). */
+int tm_bn_relu_eval(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* gamma, const float* beta,
+                    const float* running_mean, const float* running_var, float eps, float* y, int64_t ldy,
+                    float* save_mean, float* save_invstd, void* y_bf16, void* stream);
 /* Backward of the pair: dy is the gradient w.r.t. the ReLU output y.
  * dx = BN'( dy * (y>0) ), dgamma, dbeta [C].  dx may be NULL when only dx_bf16 is wanted; y may be NULL:
  * the ReLU mask is then rebuilt bit-for-bit from x, the saved statistics, gamma and beta (one tensor less to
@@ -473,6 +478,16 @@ int tm_conv3x3_bf16_wgrad(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t 
 int tm_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                  void* stream);
+/* The same update for EVERY parameter tensor in ONE launch.  table: device array of
+ * {float* p; const float* g; float* m; float* v; int64 n} (40 bytes each); chunk c of tm_adam_chunk() elements
+ * starts at element chunk_off[c] of tensor chunk_tensor[c]. */
+int tm_adam_chunk(void);
+int tm_adam_multi(int64_t n_chunks, const void* table, const int32_t* chunk_tensor, const int32_t* chunk_off, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                  void* stream);
+/* loss[0] = NaN if the device flag *err (set by a tensor-core kernel whose mbarrier wait timed out) is non-zero:
+ * a failed tile can then not pass silently into the optimizer; the host still clears / reports the flag. */
+int tm_poison_on_error(float* loss, const int32_t* err, void* stream);
 
 #ifdef __cplusplus
 }

@@ -671,6 +671,29 @@ extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64
   return check_launch("bn_relu_apply");
 }
 
+namespace {
+__global__ void bn_eval_stats_kernel(int C, const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                     float* __restrict__ mean, float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { mean[c] = rm[c]; invstd[c] = rsqrtf(rv[c] + eps); }
+}
+}  // namespace
+
+/* nn.BatchNorm2d in EVAL mode + ReLU: y = relu(gamma * (x - running_mean) * rsqrt(running_var + eps) + beta) */
+extern "C" int tm_bn_relu_eval(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* gamma, const float* beta,
+                               const float* running_mean, const float* running_var, float eps, float* y, int64_t ldy,
+                               float* save_mean, float* save_invstd, void* y_bf16, void* stream) {
+  TM_REQUIRE(npix > 0 && C > 0 && C <= 256, "tm_bn_relu_eval: bad sizes (C <= 256)");
+  TM_REQUIRE(y || y_bf16, "tm_bn_relu_eval: neither y nor y_bf16 given");
+  TM_REQUIRE(running_mean && running_var && save_mean && save_invstd, "tm_bn_relu_eval: statistics missing");
+  bn_eval_stats_kernel<<<(unsigned)cdiv(C, 128), 128, 0, ST>>>((int)C, running_mean, running_var, eps, save_mean, save_invstd);
+  TM_TRY(check_launch("bn_eval_stats"));
+  const bool v4 = bn_vec4(C, {{x, ldx}, {y, ldy}});
+  if (v4) bn_relu_apply_kernel<4><<<blocks_for(npix * (C / 4)), 256, 0, ST>>>(npix, (int)C, x, ldx, gamma, beta, save_mean, save_invstd, y, ldy, (__nv_bfloat16*)y_bf16);
+  else bn_relu_apply_kernel<1><<<blocks_for(npix * C), 256, 0, ST>>>(npix, (int)C, x, ldx, gamma, beta, save_mean, save_invstd, y, ldy, (__nv_bfloat16*)y_bf16);
+  return check_launch("bn_relu_apply(eval)");
+}
+
 /* dx_bf16 (optional): compact bf16 copy [npix][C] of dx, written by the same pass */
 extern "C" int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int64_t ldx, const float* y,
                                    int64_t ldy, const float* dy, int64_t lddy, const float* gamma, const float* beta,

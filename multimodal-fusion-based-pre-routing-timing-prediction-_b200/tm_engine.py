@@ -239,6 +239,9 @@ class DesignStep:
             self._post_allreduce("unet", [p for p, _ in upairs])
         main.wait_stream(side)                               # join: every gradient exists on `main`
         self._wait_allreduce()
+        # a tensor-core kernel whose barrier timed out leaves garbage: the step's loss becomes NaN (loud in any
+        # training loop, also under graph replay); tm_lib.check_err_flags() names the cause on the host
+        call("tm_poison_on_error", loss, tm_lib.err_flag(dev), stream())
         return loss, pred.squeeze(-1)
 
     # ---------------------------------------------------------------- CUDA graph
@@ -329,14 +332,33 @@ class DesignStep:
         torch.cuda.synchronize()
 
     def adam_step(self, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        """Fused Adam over every parameter that has a gradient (train.py:431-435,555)."""
+        """Fused Adam over every parameter that has a gradient (train.py:431-435,555): ONE launch for all ~70
+        tensors (``tm_adam_multi``).  The pointer / chunk tables live on the device and are rebuilt only when a
+        ``.grad`` tensor moved (never under CUDA-graph replay, where gradients are rewritten in place)."""
+        import numpy as np
         state["step"] = state.get("step", 0) + 1
-        for p in list(self.model.parameters()) + list(self.cnn.parameters()):
-            if p.grad is None:
-                continue
-            st = state.setdefault(id(p), None)
-            if st is None:
-                st = state[id(p)] = (torch.zeros_like(p), torch.zeros_like(p))
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            call("tm_adam_step", p.numel(), p.data, g, st[0], st[1], lr, betas[0], betas[1], eps, weight_decay,
-                 state["step"], 1.0, stream())
+        ps = [p for p in list(self.model.parameters()) + list(self.cnn.parameters()) if p.grad is not None]
+        if not ps:
+            return
+        for p in ps:
+            if id(p) not in state:
+                state[id(p)] = (torch.zeros_like(p), torch.zeros_like(p))
+            if not p.grad.is_contiguous():
+                p.grad = p.grad.contiguous()
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        tab = state.get("_table")
+        if tab is None or tab[0] != key:
+            chunk = int(tm_lib.lib().tm_adam_chunk())
+            rows = np.zeros((len(ps), 5), dtype=np.int64)
+            ct, co = [], []
+            for i, p in enumerate(ps):
+                m, v = state[id(p)]
+                rows[i] = (p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
+                for off in range(0, p.numel(), chunk):
+                    ct.append(i)
+                    co.append(off)
+            dev = ps[0].device
+            tab = state["_table"] = (key, torch.from_numpy(rows).to(dev), torch.tensor(ct, dtype=torch.int32, device=dev),
+                                     torch.tensor(co, dtype=torch.int32, device=dev))
+        call("tm_adam_multi", int(tab[2].numel()), tab[1], tab[2], tab[3], lr, betas[0], betas[1], eps, weight_decay,
+             state["step"], 1.0, stream())

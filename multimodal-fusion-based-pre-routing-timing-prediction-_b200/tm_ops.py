@@ -312,7 +312,7 @@ def gnn_backward(sched, saved, params, G):
     cf, nf = saved["cell_feat"], saved["net_feat"]
     nc, nn_ = int(sched.cell_class.numel()), int(sched.net_class.numel())
     dcs1w, dcs1b, dcs2w, dcs2b, _ = mlp2_backward(cf, cf.stride(0), sched.cell_class, nc, cs1w, cs2w,
-                                                  saved["hc"], G, D, g_rows=sched.cell_class)
+                                                  saved["hc"], G, D, g_rows=sched.cell_class, b1=cs1b)
     dns1w, dns1b, dns2w, dns2b, _ = mlp2_backward(nf, nf.stride(0), sched.net_class, nn_, ns1w, ns2w,
                                                   saved["hn"], G, D, g_rows=sched.net_class, b1=ns1b)
     return (dcs1w, dcs1b, dcs2w, dcs2b, dns1w, dns1b, dns2w, dns2b, dcn1w, dcn1b, dcn2w, dcn2b)

@@ -147,9 +147,18 @@ def _pack(w, need_bwd=True):
     return wf, wb
 
 
+EVAL = False          # set by unet_forward: nn.Module.eval() -> BatchNorm uses its running statistics
+
+
 def _bn_relu_fwd(ws, x, ldx, npix, C, bn, y, ldy, update_stats, yb=None, stats=None):
     dev = x.device
     mean, invstd = _empty(C, dev=dev), _empty(C, dev=dev)
+    if EVAL:
+        if bn.running_mean is None:
+            raise NotImplementedError("eval-mode BatchNorm without running statistics (track_running_stats=False)")
+        call("tm_bn_relu_eval", npix, C, x, ldx, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+             float(bn.eps), y, ldy, mean, invstd, yb, stream())
+        return mean, invstd
     nb = tm_lib.ws_bytes("tm_bn_ws", npix, C)
     rm = bn.running_mean if update_stats else None
     rv = bn.running_var if update_stats else None
@@ -257,6 +266,11 @@ def unet_forward(net, x, need_bwd=True, update_stats=True):
     """``net``: the UNet module (parameter container).  x: (B,3,H,W) or (3,H,W) on a CUDA device.
     Returns (out (B,1,H/2,W/2), state)."""
     _enter(net)
+    global EVAL
+    EVAL = not net.training
+    if EVAL and need_bwd:
+        raise NotImplementedError("UNet in eval mode is inference only here (BatchNorm backward with frozen statistics is not "
+                                  "built): call it under torch.no_grad(), or keep the module in train mode like the reference")
     if x.dim() == 3:                                   # train.py:465 passes (C,H,W)
         x = x.unsqueeze(0)
     x = x.detach().float().contiguous()

@@ -171,6 +171,55 @@ def config4(batch=32, size=512, modes=("bf16",)):
     return out
 
 
+def layoutnet(size=512, cpu=True):
+    """LayoutNet (model.py:216-247), the reference's DEFAULT image branch (train.py:70 without --unet): 2 x 512 x 512
+    input, forward + backward, device time and algorithmic TFLOP/s (2*R*S*Cin*Cout*Hout*Wout per convolution:
+    9x9 2->32 @512, 7x7 32->64 @256, 9x9 64->32 @128, 7x7 32->1 @128 = 21.4 GFLOP forward), with the oracle port on
+    the host cores beside it."""
+    import model as M
+    from oracle import restate
+    torch.manual_seed(1)
+    net = M.LayoutNet("max").to(DEV).train()
+    x = torch.rand(1, 2, size, size, device=DEV)
+    sc = (size / 512) ** 2
+    flop_f = sc * 2.0 * (81 * 2 * 32 * 512 * 512 + 49 * 32 * 64 * 256 * 256 + 81 * 64 * 32 * 128 * 128 + 49 * 32 * 1 * 128 * 128)
+    out = {"config": "LayoutNet %dx%dx2, batch 1 (reference default CNN)" % (size, size), "fwd_GFLOP": flop_f / 1e9}
+    res = {}
+    for math in ("tf32x3", "bf16"):
+        old = tm_unet.MATH
+        try:
+            tm_unet.MATH = math
+            with torch.no_grad():
+                t_f = timed(lambda: net(x), reps=5, warm=3)
+
+            def both():
+                net.zero_grad()
+                net(x).sum().backward()
+            t_fb = timed(both, reps=5, warm=3)
+        finally:
+            tm_unet.MATH = old
+        _, tpk = peaks()
+        res[math] = {"fwd_ms": t_f, "fwd_bwd_ms": t_fb, "fwd_TFLOPs": flop_f / t_f / 1e9, "fwd_bwd_TFLOPs": 3 * flop_f / t_fb / 1e9,
+                     "fwd_bwd_frac_of_bf16_peak": 3 * flop_f / t_fb / 1e9 / tpk}
+    out["modes"] = res
+    if cpu:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+        xc = x.cpu()
+
+        def cpu_both():
+            y = restate.layoutnet_forward(sd, xc, "max")
+            torch.autograd.grad(y.sum(), list(sd.values()))
+        cpu_both()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            cpu_both()
+        out["cpu_port_fwd_bwd_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        out["cpu_threads"] = threads
+    return out
+
+
 def config5(n_designs=64, distinct=8):
     """64 design steps on one GPU.  `distinct` different designs are made resident (structure +
     captured step); the 64 steps cycle through them (the generator is the same for all seeds, so the
@@ -268,6 +317,8 @@ if __name__ == "__main__":
     if "c4" in want:
         for r in config4(modes=("bf16", "tf32x3") if "--c4-all" in sys.argv else ("bf16",)):
             print(json.dumps(r), flush=True)
+    if "layoutnet" in want:
+        print(json.dumps(layoutnet()), flush=True)
     if "c5" in want:
         print(json.dumps(config5()), flush=True)
     if "cpu" in want:

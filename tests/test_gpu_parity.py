@@ -831,3 +831,76 @@ def test_loader_train_loop_shape(mods, tmp_path):
         loss, _ = run(ids)
         assert_close(loss.reshape(()), torch.tensor(want), 1e-3, 1e-4, "loss of a shuffled batch")
         step.adam_step(state, lr=1e-3)
+
+
+def test_unet_eval_mode_matches_batchnorm_eval(mods):
+    """a drop-in nn.Module must honour .eval(): BatchNorm then normalises with its RUNNING statistics."""
+    import Unet as U
+    torch.manual_seed(3)
+    net = U.UNet("max")
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.2, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.rand(2, 3, 32, 32)
+    # oracle in eval mode: batch_norm with training=False
+    import torch.nn.functional as F
+
+    def dc(p, t):
+        for ic, ib in ((0, 1), (3, 4)):
+            t = F.conv2d(t, sd[f"{p}.{ic}.weight"], None, padding=1)
+            t = F.relu(F.batch_norm(t, sd[f"{p}.{ib}.running_mean"], sd[f"{p}.{ib}.running_var"], sd[f"{p}.{ib}.weight"],
+                                    sd[f"{p}.{ib}.bias"], training=False, eps=1e-5))
+        return t
+    x1 = dc("inc.double_conv", x)
+    x2 = dc("down1.maxpool_conv.1.double_conv", F.max_pool2d(x1, 2))
+    x3 = dc("down2.maxpool_conv.1.double_conv", F.max_pool2d(x2, 2))
+    y = dc("down3.maxpool_conv.1.double_conv", F.max_pool2d(x3, 2))
+    for name, skip in (("up1", x3), ("up2", x2), ("up3", x1)):
+        y = F.conv_transpose2d(y, sd[f"{name}.up.weight"], sd[f"{name}.up.bias"], stride=2)
+        y = dc(f"{name}.conv.double_conv", torch.cat([skip, y], 1))
+    ref = F.relu(F.max_pool2d(F.conv2d(y, sd["outc.conv.0.weight"], sd["outc.conv.0.bias"]), 2))
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        out = net(x.to(DEV))
+    assert_close(out, ref, 1e-3, 1e-4, "UNet.eval() output")
+    assert torch.equal(net.state_dict()["inc.double_conv.1.running_mean"].cpu(), sd["inc.double_conv.1.running_mean"])
+    with pytest.raises(NotImplementedError):
+        net(x.to(DEV).requires_grad_(True)).sum().backward()
+
+
+def test_adam_multi_tensor_and_loss_poison(mods):
+    """DesignStep.adam_step = ONE tm_adam_multi launch == torch.optim.Adam over all parameters; and a raised
+    tensor-core error flag turns the step's loss into NaN."""
+    eng, lib = mods["engine"], mods["lib"]
+    d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["tiny"])
+    model, cnn = eng.build_models(d.map_size, seed=2, device=DEV)
+    import copy
+    model2, cnn2 = copy.deepcopy(model), copy.deepcopy(cnn)
+    step = eng.DesignStep(model, cnn)
+    batch = eng.DesignBatch.from_synth(d, DEV)
+    opt = torch.optim.Adam(list(model2.parameters()) + list(cnn2.parameters()), 1e-3)
+    state = {}
+    for _ in range(3):
+        step.run(batch)
+        for (p, q) in zip(list(model.parameters()) + list(cnn.parameters()), list(model2.parameters()) + list(cnn2.parameters())):
+            q.grad = None if p.grad is None else p.grad.detach().clone()
+        before = lib.launch_count()
+        step.adam_step(state, lr=1e-3)
+        assert lib.launch_count() - before == 1
+        opt.step()
+        # keep both replicas on identical weights so that the next step's gradients are identical too
+        for (p, q) in zip(list(model.parameters()) + list(cnn.parameters()), list(model2.parameters()) + list(cnn2.parameters())):
+            assert_close(p.detach(), q.detach(), 1e-5, 1e-6, "Adam update")
+            q.data.copy_(p.data)
+    flag = lib.err_flag(torch.device(DEV))
+    try:
+        flag.fill_(1)
+        loss, _ = step.run(batch)
+        assert bool(torch.isnan(loss).all()), "a raised error flag must poison the loss"
+    finally:
+        flag.zero_()
+    loss, _ = step.run(batch)
+    assert bool(torch.isfinite(loss).all())
