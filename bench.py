@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the config-3 / config-4 device timings")
     ap.add_argument("--no-graph", action="store_true", help="time the resident loop eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained repeat of the resident loop")
+    ap.add_argument("--no-shuffled", action="store_true", help="skip the fresh-endpoint-batch-every-step end-to-end loop")
     ap.add_argument("--config5", type=int, default=64, help="designs of the config-5 run (0 = skip)")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit "
@@ -346,6 +347,50 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+
+    # ---- end to end with a FRESH shuffled endpoint batch every step (the reference's DataLoader, train.py:468-486):
+    # a design with 3 x 1350 timing paths in the reference's tuple format, read by tm_loader, ONE CUDA-graph capture;
+    # per step the host draws the next 1350 path ids, uploads them + the step's values (features, image), the graph
+    # re-selects the mask rows on the device (tm_mask_select) and the loss is read back -- all inside the timed region
+    e2e_shuffled = None
+    if not args.no_shuffled and use_graph and args.config == "c2":
+        import tm_loader
+        d3 = tm_synth.make_design(seed=1000 + rank, n_endpoints=3 * 1350, **tm_synth.CONFIGS["c2"])
+        ld = tm_loader.load_design(tm_loader.design_tuple_from_synth(d3), dev)
+        run_b = ld.prepare(step, batch_size=1350)
+        bt = run_b.batch
+        hb = {"cell_feat": torch.from_numpy(d3.cell_feat).pin_memory(), "net_feat": torch.from_numpy(d3.net_feat).pin_memory(),
+              "image": torch.from_numpy(d3.image).pin_memory()}
+        all_paths = torch.as_tensor(ld.paths, dtype=torch.int64)
+        gen = torch.Generator().manual_seed(rank)
+
+        def shuffled_loop(n):
+            perm, k, out = torch.randperm(all_paths.numel(), generator=gen), 0, 0.0
+            for _ in range(n):
+                if k + 1350 > perm.numel():
+                    perm, k = torch.randperm(all_paths.numel(), generator=gen), 0
+                ids = all_paths[perm[k:k + 1350]]
+                k += 1350
+                bt.cell_feat.copy_(hb["cell_feat"], non_blocking=True)
+                bt.net_feat.copy_(hb["net_feat"], non_blocking=True)
+                bt.image.copy_(hb["image"], non_blocking=True)
+                out = float(run_b(ids)[0].item())
+            return out
+        shuffled_loop(2)
+        sync_all()
+        t0 = time.perf_counter()
+        lsh = shuffled_loop(args.steps)
+        torch.cuda.synchronize()
+        sh_s = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(sh_s, op=dist.ReduceOp.MAX)
+        h2d_sh = int(sum(v.numel() * v.element_size() for v in hb.values())) + 1350 * (8 + 4 + 4 + 4 + 4)
+        e2e_shuffled = {"value": world * args.steps / float(sh_s.item()), "unit": "designs/s", "h2d_bytes_per_step": h2d_sh,
+                        "d2h_bytes_per_step": 4, "paths_per_design": int(all_paths.numel()), "batch": 1350, "loss": lsh,
+                        "note": "new shuffled 1350-path batch every step through tm_loader.LoadedDesign.prepare(): synchronous loop "
+                                "(no upload prefetch), one capture per design, mask rows re-selected on the device inside the graph"}
+        del run_b, ld, d3
+        torch.cuda.empty_cache()
 
     # ---- the same resident loop for >= 3 s: does the number survive sustained clocks?
     sustained = None
@@ -610,7 +655,7 @@ def main():
                 "e2e": {"value": world * args.steps / e2e_s, "unit": "designs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "note": e2e_note},
                 "gpu_launches": launches, "clocks": clocks, "loss": lv, "sustained": sustained, "allreduce": allreduce,
-                "config5": config5}
+                "config5": config5, "e2e_shuffled": e2e_shuffled}
         line.update(extra)
         tm_lib.check_err_flags()                 # no tensor-core barrier timed out anywhere in this run
         print(json.dumps(line), flush=True)
