@@ -132,6 +132,8 @@ class PathConv(nn.Module):
                 len(cur_nodes) != int(sched.h_level_ptr[level_id + 1] - sched.h_level_ptr[level_id]):
             raise RuntimeError(f"level {level_id}: the caller's node list does not match the level schedule; "
                                "pass the batch's own levels with graph.set_topo_levels(topo_levels)")
+        if len(targets) == 0:                                     # most levels carry no sampled endpoint: no launch, no copy
+            return H[:0]
         idx = th.as_tensor(targets, dtype=th.int64, device=H.device)
         return H[idx]
 

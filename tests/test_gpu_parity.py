@@ -904,3 +904,31 @@ def test_adam_multi_tensor_and_loss_poison(mods):
         flag.zero_()
     loss, _ = step.run(batch)
     assert bool(torch.isfinite(loss).all())
+
+
+def test_foreign_heterograph_object_is_adapted(mods):
+    """tm_graph.as_timing_graph on an object that only has DGL's heterograph SURFACE (edges(etype=), ndata,
+    number_of_nodes) -- what a real dgl.DGLGraph offers (dataset.py:274-287); DGL itself is not in the image."""
+    class Hetero:
+        def __init__(self, d):
+            self._e = {"net": (torch.from_numpy(d.net_src).to(DEV), torch.from_numpy(d.net_dst).to(DEV)),
+                       "cell": (torch.from_numpy(d.cell_src).to(DEV), torch.from_numpy(d.cell_dst).to(DEV))}
+            self.ndata = {"cell_feat": torch.from_numpy(d.cell_feat).to(DEV), "net_feat": torch.from_numpy(d.net_feat).to(DEV)}
+            self._n = d.n
+
+        def edges(self, etype=None):
+            return self._e[etype]
+
+        def number_of_nodes(self):
+            return self._n
+
+    d = tm_synth.make_design(seed=6, **tm_synth.CONFIGS["tiny"])
+    gnn = _gnn_params(6).to(DEV)
+    with torch.no_grad():
+        H_foreign = gnn.propagate(Hetero(d))          # PIs inferred: pins without any in-edge
+        H_native = gnn.propagate(_graph(mods, d))
+    assert torch.equal(H_foreign, H_native)
+    foreign = Hetero(d)
+    with torch.no_grad():
+        out = gnn(foreign, d.level_lists()[0].tolist(), None, [int(d.endpoints[0])], 0)
+    assert out.shape == (1, 128) and "h" in foreign.ndata          # model.py:208 leaves ndata['h'] behind
