@@ -629,8 +629,10 @@ int gnn_impl() {
     // bit 0: forward persistent, bit 1: backward persistent.  Default 1: measured on B200 the persistent
     // forward beats the per-level chain (config 2: 0.89 vs 1.01 ms, config 3: 1.92 vs 2.64 ms) while the
     // persistent backward does not (1.24 vs 1.00 ms, 2.61 vs 2.59 ms).
+    //   C3: 2.31 vs 2.61 ms in favour of the persistent backward).  Bit 2 = "auto" (default): persistent forward;
+    //   persistent backward only on wide schedules (>= 6 000 pins per level on average).
     const char* e = getenv("TM_GNN_IMPL");
-    v = !e ? 1 : (e[0] == 'l' ? 0 : (e[0] == 'p' ? 3 : (atoi(e) & 3)));
+    v = !e ? 4 : (e[0] == 'l' ? 0 : (e[0] == 'p' ? 3 : (atoi(e) & 7)));
     g_impl.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -644,7 +646,7 @@ int count_levels(const tm_schedule* s, int lb, int le) {
 
 extern "C" int tm_gnn_set_impl(int impl) {
   const int prev = gnn_impl();
-  if (impl >= 0) g_impl.store(impl & 3, std::memory_order_relaxed);
+  if (impl >= 0) g_impl.store(impl & 7, std::memory_order_relaxed);
   return prev;
 }
 extern "C" int tm_gnn_last_barriers() { return g_last_barriers; }
@@ -680,7 +682,7 @@ extern "C" int tm_gnn_forward(const tm_schedule* s, int32_t lb, int32_t le, floa
   TM_REQUIRE((A == nullptr) == (LSE == nullptr) && (A == nullptr) == (HIDb == nullptr),
              "tm_gnn_forward: A, LSE, HID must be all set or all NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  if (gnn_impl() & 1) {
+  if (gnn_impl() & 5) {
     TM_REQUIRE(ws && ws_bytes >= tm_gnn_ws_bytes(), "tm_gnn_forward: workspace too small (tm_gnn_ws_bytes)");
     g_last_barriers = count_levels(s, lb, le);
     return tmk::gnn_persist_forward(s, lb, le, H, S, W1t_in, b1, W2t_in, b2, A, LSE, HIDb, ws, st);
@@ -712,7 +714,8 @@ extern "C" int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, c
                                float* GA, float* GHID, float* GZC, void* ws, size_t ws_bytes, void* stream) {
   TM_REQUIRE(s && s->h_level_ptr && s->bn_ptr && s->bc_ptr, "tm_gnn_backward: bad schedule");
   cudaStream_t st = (cudaStream_t)stream;
-  if (gnn_impl() & 2) {
+  const bool wide = s->num_levels > 0 && s->h_level_ptr[s->num_levels] / s->num_levels >= 6000;
+  if ((gnn_impl() & 2) || ((gnn_impl() & 4) && wide)) {
     TM_REQUIRE(ws && ws_bytes >= tm_gnn_ws_bytes(), "tm_gnn_backward: workspace too small (tm_gnn_ws_bytes)");
     g_last_barriers = count_levels(s, 0, s->num_levels);
     return tmk::gnn_persist_backward(s, H, G, W1_in, W2_in, A, LSE, HIDb, GA, GHID, GZC, ws, st);

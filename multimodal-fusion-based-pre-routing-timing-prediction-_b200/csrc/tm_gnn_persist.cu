@@ -505,7 +505,34 @@ struct FwdArgs {
   unsigned int* ready;             // [n] by pin id: H[v] is final
   long long* prof;
   int lb, le, prefetch;
+  // net-level fusion ("push"): when every net-level pin has exactly ONE driver, its row
+  //   h[s] = relu(S[s] + h[driver])                         (model.py:103-108 with a mean over one edge)
+  // is written by whoever produces h[driver] -- level 0 for primary inputs, the cell tile's epilogue for cell
+  // outputs -- over the driver's net out-edge list.  Odd levels then need no pass and no barrier: 51 barriers
+  // instead of 101 for config 2.
+  const int* bn_ptr; const int* bn_dst;
+  int fuse;
 };
+
+// rows of the sinks driven by one pin; lane layout of the caller: `cols` = this lane's float4 columns (NV of them)
+template <int NV>
+__device__ __forceinline__ void push_sinks(const FwdArgs& a, int pos, const float4 (&h)[NV], int col0, int colstride) {
+  const int e0 = __ldg(a.bn_ptr + pos), e1 = __ldg(a.bn_ptr + pos + 1);
+  for (int i = e0; i < e1; i += 2) {
+    const int s0 = __ldg(a.bn_dst + i), s1 = (i + 1 < e1) ? __ldg(a.bn_dst + i + 1) : -1;
+    float4 v0[NV], v1[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      v0[j] = ldg4(a.S + (int64_t)s0 * D + col0 + j * colstride);
+      if (s1 >= 0) v1[j] = ldg4(a.S + (int64_t)s1 * D + col0 + j * colstride);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      *reinterpret_cast<float4*>(a.H + (int64_t)s0 * D + col0 + j * colstride) = f4relu(f4add(v0[j], h[j]));
+      if (s1 >= 0) *reinterpret_cast<float4*>(a.H + (int64_t)s1 * D + col0 + j * colstride) = f4relu(f4add(v1[j], h[j]));
+    }
+  }
+}
 
 // issue the loads the prefetch of level l1 depends on (pass k); consumed by pf_end_fwd
 __device__ __forceinline__ PfState pf_begin_fwd(const FwdArgs& a, int l1, int k) {
@@ -520,10 +547,11 @@ __device__ __forceinline__ PfState pf_begin_fwd(const FwdArgs& a, int l1, int k)
     st.e1 = __ldg(a.f_ptr + p0 + q0 + qn);
     st.qn = qn;
   }
-  if (k == 0 && l1 + 1 < a.le) {               // pointer lines of the level after
-    const int p2 = __ldg(a.level_ptr + l1 + 1), cnt2 = __ldg(a.level_ptr + l1 + 2) - p2;
+  const int l2 = a.fuse ? l1 + 2 : l1 + 1;
+  if (k == 0 && l2 < a.le) {                   // pointer lines of the level after
+    const int p2 = __ldg(a.level_ptr + l2), cnt2 = __ldg(a.level_ptr + l2 + 1) - p2;
     int r0, rn;
-    cta_range(l1 + 1, cnt2, 0, r0, rn);
+    cta_range(l2, cnt2, 0, r0, rn);
     const int t = threadIdx.x;
     if (rn > 0 && t < 8 && (t & 3) * 32 <= rn) pf_l2((t < 4 ? a.f_ptr : a.order) + p2 + r0 + (t & 3) * 32);
   }
@@ -586,9 +614,13 @@ __device__ __forceinline__ void fwd_net_level(const FwdArgs& a, int p0, int cnt,
         for (int j = 0; j < NV; ++j) acc[j] = f4add(acc[j], m[q][j]);
     }
     const float rdeg = (e > s) ? 1.f / (float)(e - s) : 0.f;
+    float4 hv[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-      *reinterpret_cast<float4*>(a.H + (int64_t)v * D + (j * G + lg) * 4) = f4relu(f4fma(acc[j], rdeg, sv[j]));
+    for (int j = 0; j < NV; ++j) {
+      hv[j] = f4relu(f4fma(acc[j], rdeg, sv[j]));
+      *reinterpret_cast<float4*>(a.H + (int64_t)v * D + (j * G + lg) * 4) = hv[j];
+    }
+    if (!FLOW && a.fuse) push_sinks<NV>(a, p0 + p, hv, lg * 4, G * 4);
     if (FLOW) {
       __syncwarp(gmask);
       if (lg == 0) set_flag(a.ready + v);
@@ -614,8 +646,11 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_fwd_kernel(const FwdAr
   for (int l = a.lb; l < a.le; ++l) {
     const int p0 = __ldg(a.level_ptr + l), cnt = __ldg(a.level_ptr + l + 1) - p0;
     if (cnt <= 0) continue;
+    const bool fused = !FLOW && a.fuse;
+    if (fused && (l & 1)) continue;                          // written by their drivers' producers
     {
-      const PfState pf0 = pf_begin_fwd(a, l + 1, 0), pf1 = pf_begin_fwd(a, l + 1, 1);
+      const int ln = fused ? (l == 0 ? 2 : l + 2) : l + 1;    // the next level this kernel processes
+      const PfState pf0 = pf_begin_fwd(a, ln, 0), pf1 = pf_begin_fwd(a, ln, 1);
       pf_end_fwd(a, pf0);
       pf_end_fwd(a, pf1);
     }
@@ -732,7 +767,25 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_fwd_kernel(const FwdAr
       mlp_tile(c, N, [] {}, epi1, pre2);
       auto fin = [&](int n, int m, int slot, float val) {
         const int v = c.pin_s[n];
-        if (v >= 0) a.H[(int64_t)v * D + m] = fmaxf(val + b2m + sreg[slot], 0.f);
+        if (v >= 0) {
+          const float h = fmaxf(val + b2m + sreg[slot], 0.f);
+          a.H[(int64_t)v * D + m] = h;
+          if (fused) {                                       // the sinks this pin drives (warp-uniform edge range)
+            const int pos = p0 + t0 + n;
+            const int e0 = __ldg(a.bn_ptr + pos), e1 = __ldg(a.bn_ptr + pos + 1);
+            for (int i = e0; i < e1; i += 4) {
+              int sk[4];
+              float sv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) sk[u] = (i + u < e1) ? __ldg(a.bn_dst + i + u) : -1;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) sv[u] = sk[u] >= 0 ? __ldg(a.S + (int64_t)sk[u] * D + m) : 0.f;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (sk[u] >= 0) a.H[(int64_t)sk[u] * D + m] = fmaxf(sv[u] + h, 0.f);
+            }
+          }
+        }
       };
       exchange_tile(c, N, fin);
       if (FLOW) {
@@ -809,6 +862,14 @@ __device__ __forceinline__ void pf_end_bwd(const BwdArgs& a, const PfState& st, 
       if (st.row0 >= 0) pf_l2(a.HIDb + (int64_t)(st.row0 + (int)threadIdx.x) * HID + rank * 128 + j * 32);
     }
   }
+}
+
+// hraw[k] with a k that is a compile-time constant after unrolling for each of the three 8-column chunks
+__device__ __forceinline__ float hsel(const float (&h)[NMAX / 4], int k) {
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < NMAX / 4; ++i) r = (i == k) ? h[i] : r;
+  return r;
 }
 
 template <int NV, bool FLOW>
@@ -1030,12 +1091,13 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_bwd_kernel(const BwdAr
       // g_hid = (W2^T g_z) * (hid > 0), in units of the pin's scale.  The ReLU mask of this thread's hidden unit
       // for the warp's pins is fetched (one bit per pin) while the first product runs.
       const int cg = warp >> 2, nper = N >> 2, qd = warp & 3;
-      uint32_t hmask = 0;
+      float hraw[NMAX / 4];                                  // raw loads: consumed only in the epilogue, after the MMA wait
       auto pre1 = [&]() {
 #pragma unroll
         for (int j = 0; j < NMAX / 4; ++j) {
+          hraw[j] = 0.f;
           if (j < nper && t0 + cg * nper + j < cnt)
-            hmask |= (__ldg(a.HIDb + (int64_t)(crow0 + t0 + cg * nper + j) * HID + c.rank * 128 + qd * 32 + lane) > 0.f ? 1u : 0u) << j;
+            hraw[j] = __ldg(a.HIDb + (int64_t)(crow0 + t0 + cg * nper + j) * HID + c.rank * 128 + qd * 32 + lane);
         }
       };
       auto epi1 = [&](int n0, int m, float (&vm)[8], const float (&vc)[8]) {
@@ -1043,7 +1105,7 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_bwd_kernel(const BwdAr
         for (int j = 0; j < 8; ++j) {
           float gh = 0.f;
           if (t0 + n0 + j < cnt) {
-            gh = ((hmask >> (n0 - cg * nper + j)) & 1u) ? fmaf(vc[j], LO_INV, vm[j]) : 0.f;
+            gh = hsel(hraw, n0 - cg * nper + j) > 0.f ? fmaf(vc[j], LO_INV, vm[j]) : 0.f;
             a.GHID[(int64_t)(crow0 + t0 + n0 + j) * HID + c.rank * 128 + m] = gh * c.inv_s[n0 + j];
           }
           vm[j] = gh;
@@ -1122,15 +1184,16 @@ int prefetch_on() {
   static const int v = getenv("TM_GNN_PREFETCH") ? atoi(getenv("TM_GNN_PREFETCH")) : 1;
   return v;
 }
-std::atomic<int> g_flow{-1};
-bool flow_sync() {
+std::atomic<int> g_flow{-1};      // 0 = grid barrier per level, 1 = per-pin ready flags, 2 = grid barrier + net-level push fusion
+int sync_mode() {
   int v = g_flow.load(std::memory_order_relaxed);
   if (v < 0) {
-    v = (getenv("TM_GNN_SYNC") && getenv("TM_GNN_SYNC")[0] == 'f') ? 1 : 0;
+    v = (getenv("TM_GNN_SYNC") && getenv("TM_GNN_SYNC")[0] == 'f') ? 1 : ((getenv("TM_GNN_FUSE") && atoi(getenv("TM_GNN_FUSE"))) ? 2 : 0);
     g_flow.store(v, std::memory_order_relaxed);
   }
-  return v != 0;
+  return v;
 }
+bool flow_sync() { return sync_mode() == 1; }
 }  // namespace
 
 namespace tmk {
@@ -1139,8 +1202,8 @@ static long long* g_prof = nullptr;
 void gnn_persist_set_profile(long long* p) { g_prof = p; }
 int gnn_persist_profile_slots() { return PH_COUNT; }
 int gnn_persist_set_flow(int flow) {
-  const int prev = flow_sync() ? 1 : 0;
-  if (flow >= 0) g_flow.store(flow ? 1 : 0, std::memory_order_relaxed);
+  const int prev = sync_mode();
+  if (flow >= 0) g_flow.store(flow > 2 ? 0 : flow, std::memory_order_relaxed);
   return prev;
 }
 
@@ -1160,8 +1223,15 @@ int gnn_persist_forward(const tm_schedule* s, int lb, int le, float* H, const fl
   }
   gnn_pack_planes_kernel<<<2 * 2 * 128 * 128 / 256, 256, 0, st>>>(W1t, W2t, planes);
   TM_TRY(check_launch("gnn_pack_planes"));
+  // opt-in (TM_GNN_FUSE=1): measured SLOWER on B200 (config 2 forward 1.20 ms against 0.89 ms unfused): the sinks' S rows
+  // are cold in HBM and the epilogue's lane-per-channel layout walks a pin's sinks one DRAM round trip at a time, so the
+  // slowest cluster of a level (largest fan-out) sets the pace; see DESIGN.md section 4
+  const int fuse_env = sync_mode() == 2;
+  // push fusion needs every net-level pin single-driven from an even level (tm_schedule.single_driver), the whole
+  // pass in one call and the barrier ordering
+  const int fuse = (fuse_env && s->single_driver && lb == 0 && le == s->num_levels && !flow_sync() && s->bn_ptr && s->bn_dst) ? 1 : 0;
   FwdArgs a{s->level_ptr, s->cell_base, s->order, s->f_ptr, s->f_src, S, H, planes, b1, b2, A, LSE, HIDb, ready, g_prof,
-            lb, le, prefetch_on()};
+            lb, le, prefetch_on(), s->bn_ptr, s->bn_dst, fuse};
   return flow_sync() ? launch_persist(gnn_persist_fwd_kernel<true>, a, st, "gnn_persist_fwd<flow>")
                      : launch_persist(gnn_persist_fwd_kernel<false>, a, st, "gnn_persist_fwd");
 }
