@@ -176,3 +176,41 @@ def test_data_parallel_buckets_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_loader_reference_semantics(tmp_path):
+    """tm_loader.load_single_design == the reference function (train.py:335-388) on a synthetic design written in
+    the reference's tuple format: feat_reduce trim 42/3 -> 36/2, ndata['h'] / edata['a'] zeros, min-max norm from
+    column num_ctypes on, critical-path oversampling (os_rate x when negatives outnumber positives 2:1), the 1/5
+    validation split written once and reused; LoadedDesign orders a batch like the reference loop (levels ascending,
+    DataLoader order inside a level)."""
+    import tm_loader
+    import tm_synth
+    d = tm_synth.make_design(seed=3, **tm_synth.CONFIGS["tiny"])
+    tup = tm_loader.design_tuple_from_synth(d, seed=1)
+    tm_loader.save_design(str(tmp_path / "x.pkl"), tup)
+    raw_cf = tup[0].ndata["cell_feat"].clone()
+    ds, g, p2l, p2e, tl, img, pm = tm_loader.load_single_design("train", str(tmp_path), "x", 128, 2, [6, 1], False)
+    P, crit = len(d.endpoints), tup[5]
+    assert len(ds) == P + 2 * len(crit) and ds.paths[P:P + len(crit)] == crit
+    assert torch.equal(g.ndata["cell_feat"], raw_cf[:, :-6]) and g.ndata["net_feat"].shape[1] == 2
+    assert g.ndata["h"].shape == (d.n, 128) and float(g.ndata["h"].abs().sum()) == 0.0
+    assert g.edges["cell"].data["a"].shape == (len(d.cell_src), 1)
+    assert isinstance(img, torch.Tensor) and img.dtype == torch.float32 and tuple(pm.shape) == (P, d.map_size ** 2)
+    # norm: columns >= num_ctypes scaled to [0, 1] by their own min / max, the one-hot block untouched
+    gn = tm_loader.load_single_design("train", str(tmp_path), "x", 128, 0, [6, 1], True)[1]
+    cf = gn.ndata["cell_feat"]
+    assert torch.equal(cf[:, :34], raw_cf[:, :34])
+    col = raw_cf[:, 35]
+    assert torch.allclose(cf[:, 35], (col - col.min()) / (col.max() - col.min()))
+    # test usage: split written once, then reused
+    v1 = tm_loader.load_single_design("test", str(tmp_path), "x", 128, 1, [6, 1], False)[0].paths
+    v2 = tm_loader.load_single_design("test", str(tmp_path), "x", 128, 1, [6, 1], False)[0].paths
+    assert v1 == v2 and abs(len(v1) - P // 5) <= 2 and (tmp_path / "x_split.pkl").exists()
+    # batch order of the fused path == order of the reference loop's predictions
+    ld = tm_loader.LoadedDesign(str(tmp_path / "x.pkl"), "cpu")
+    ids = [7, 3, 11, 0, 3, 25]
+    want = []
+    for lid in range(len(tl)):
+        want += [p for p in ids if p2l[p] == lid]
+    assert ld.order_batch(ids).tolist() == want
