@@ -124,6 +124,10 @@ __device__ __forceinline__ void set_flag(unsigned int* p) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
 }
 
+// programmatic dependent launch (per-level launches of the same kernels, tm_gnn_set_impl bit 3)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -512,6 +516,7 @@ struct FwdArgs {
   // instead of 101 for config 2.
   const int* bn_ptr; const int* bn_dst;
   int fuse;
+  int pdl;                         // one launch per cell level: wait for the previous grid (griddepcontrol) instead of a grid barrier
 };
 
 // rows of the sinks driven by one pin; lane layout of the caller: `cols` = this lane's float4 columns (NV of them)
@@ -681,7 +686,11 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_fwd_kernel(const FwdAr
       }
       const int E0 = __shfl_sync(0xffffffffu, ptrs, 0), E1 = __shfl_sync(0xffffffffu, ptrs, max(npin, 0));
       int idx = (E0 + (lane & 7) < E1) ? __ldg(a.f_src + E0 + (lane & 7)) : 0;
-      if (!FLOW && !waited) gb.wait();                       // (ends with a CTA barrier)
+      if (!FLOW && !waited) {
+        if (a.pdl) pdl_wait();                               // per-level launch: the previous level's grid has completed
+        gb.wait();                                           // (ends with a CTA barrier; no-op for a launch's first level)
+        if (a.pdl) __syncthreads();
+      }
       else __syncthreads();                                  // the previous tile's epilogue / publication still reads pin_s
       waited = true;
       c.stamp(PH_CPRE);
@@ -765,6 +774,7 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_fwd_kernel(const FwdAr
         }
       };
       mlp_tile(c, N, [] {}, epi1, pre2);
+      if (a.pdl) pdl_launch_dependents();                    // the next level's launch may start its prologue (weights, TMEM)
       auto fin = [&](int n, int m, int slot, float val) {
         const int v = c.pin_s[n];
         if (v >= 0) {
@@ -822,6 +832,8 @@ struct BwdArgs {
   unsigned int* ready_c;           // [n_cell_rows] by compact row: GA[row] is final
   long long* prof;
   int num_levels, prefetch;
+  int lb, le;                      // levels [lb, le) are processed (downwards)
+  int pdl;
 };
 
 __device__ __forceinline__ PfState pf_begin_bwd(const BwdArgs& a, int l1, int k) {
@@ -971,7 +983,7 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_bwd_kernel(const BwdAr
   float* scratch = reinterpret_cast<float*>(smem + OFF_B);      // [N][128] fp32 gradient accumulators during the gather
   GridBar gb{a.ready_n, gridDim.x, 0u};                    // barrier mode: the first flag word is the counter
 
-  for (int l = a.num_levels - 1; l >= 0; --l) {
+  for (int l = a.le - 1; l >= a.lb; --l) {
     const int p0 = __ldg(a.level_ptr + l), cnt = __ldg(a.level_ptr + l + 1) - p0;
     if (cnt <= 0) continue;
     {
@@ -1006,7 +1018,11 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_bwd_kernel(const BwdAr
       int idx = 0;
       float wt = 0.f;
       if (E0 + (lane & 7) < E1) { idx = __ldg(a.bn_dst + E0 + (lane & 7)); wt = __ldg(a.bn_w + E0 + (lane & 7)); }
-      if (!FLOW && !waited) gb.wait();                       // (ends with a CTA barrier)
+      if (!FLOW && !waited) {
+        if (a.pdl) pdl_wait();                               // per-level launch: the previous level's grid has completed
+        gb.wait();                                           // (ends with a CTA barrier; no-op for a launch's first level)
+        if (a.pdl) __syncthreads();
+      }
       else __syncthreads();                                  // the previous tile's epilogue still reads the scales
       waited = true;
       c.stamp(PH_CPRE);
@@ -1112,6 +1128,7 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_bwd_kernel(const BwdAr
         }
       };
       mlp_tile(c, N, pre1, epi1, [] {});
+      if (a.pdl) pdl_launch_dependents();
       auto fin = [&](int n, int m, int, float val) {
         if (t0 + n < cnt) a.GA[(int64_t)(crow0 + t0 + n) * D + m] = val;
       };
@@ -1148,7 +1165,7 @@ __global__ void gnn_mark_ready_kernel(const int* __restrict__ order, int count, 
 // host
 // ---------------------------------------------------------------------------------------------
 template <class Args>
-int launch_persist(void (*kern)(const Args), const Args& args, cudaStream_t st, const char* what) {
+int launch_persist(void (*kern)(const Args), const Args& args, cudaStream_t st, const char* what, int want_clusters = 0, bool pdl = false) {
   TM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   static const int coop = getenv("TM_GNN_COOP") ? atoi(getenv("TM_GNN_COOP")) : 0;
   static const int max_ctas = getenv("TM_GNN_CTAS") ? atoi(getenv("TM_GNN_CTAS")) : 0;
@@ -1173,8 +1190,14 @@ int launch_persist(void (*kern)(const Args), const Args& args, cudaStream_t st, 
   TM_REQUIRE(ncl >= 1, "%s: no 2-CTA cluster with %u bytes of shared memory fits this device", what, SMEM_BYTES);
   int nblk = 2 * std::min(ncl, sm_count() / 2);
   if (max_ctas >= 2) nblk = std::min(nblk, max_ctas & ~1);
+  if (want_clusters > 0) nblk = std::min(nblk, 2 * want_clusters);
   cfg.gridDim = dim3((unsigned)nblk);
   cfg.numAttrs = coop ? 2 : 1;
+  if (pdl) {                                   // one launch per level, chained by programmatic dependent launch
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
@@ -1207,46 +1230,56 @@ int gnn_persist_set_flow(int flow) {
   return prev;
 }
 
-int gnn_persist_forward(const tm_schedule* s, int lb, int le, float* H, const float* S, const float* W1t, const float* b1,
-                        const float* W2t, const float* b2, float* A, float* LSE, float* HIDb, void* ws, cudaStream_t st) {
+// pack the fc_cell_neigh planes and clear the synchronisation words: once per pass
+int gnn_persist_begin(const tm_schedule* s, const float* Wa, const float* Wb, void* ws, bool flags_all, size_t nflags, cudaStream_t st) {
   TM_REQUIRE(s->level_ptr && s->cell_base && s->sync_flags,
-             "tm_gnn_forward: schedule lacks the device level_ptr / cell_base / sync_flags arrays");
+             "tm_gnn: schedule lacks the device level_ptr / cell_base / sync_flags arrays");
+  uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  TM_CUDA(cudaMemsetAsync(s->sync_flags, 0, flags_all ? sizeof(unsigned int) * nflags : 256, st));
+  gnn_pack_planes_kernel<<<2 * 2 * 128 * 128 / 256, 256, 0, st>>>(Wa, Wb, planes);
+  return check_launch("gnn_pack_planes");
+}
+
+int gnn_persist_forward(const tm_schedule* s, int lb, int le, float* H, const float* S, const float* W1t, const float* b1,
+                        const float* W2t, const float* b2, float* A, float* LSE, float* HIDb, void* ws, cudaStream_t st,
+                        bool begin, bool per_level) {
   uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   unsigned int* ready = reinterpret_cast<unsigned int*>(s->sync_flags);
-  TM_CUDA(cudaMemsetAsync(ready, 0, flow_sync() ? sizeof(unsigned int) * (size_t)s->n : 256, st));
-  if (flow_sync() && lb > 0) {
+  if (begin) TM_TRY(gnn_persist_begin(s, W1t, W2t, ws, flow_sync() && !per_level, (size_t)s->n, st));
+  if (!per_level && flow_sync() && lb > 0) {
     const int count = s->h_level_ptr[lb];
     if (count > 0) {
       gnn_mark_ready_kernel<<<(count + 255) / 256, 256, 0, st>>>(s->order, count, ready);
       TM_TRY(check_launch("gnn_mark_ready"));
     }
   }
-  gnn_pack_planes_kernel<<<2 * 2 * 128 * 128 / 256, 256, 0, st>>>(W1t, W2t, planes);
-  TM_TRY(check_launch("gnn_pack_planes"));
-  // opt-in (TM_GNN_FUSE=1): measured SLOWER on B200 (config 2 forward 1.20 ms against 0.89 ms unfused): the sinks' S rows
-  // are cold in HBM and the epilogue's lane-per-channel layout walks a pin's sinks one DRAM round trip at a time, so the
-  // slowest cluster of a level (largest fan-out) sets the pace; see DESIGN.md section 4
   const int fuse_env = sync_mode() == 2;
   // push fusion needs every net-level pin single-driven from an even level (tm_schedule.single_driver), the whole
   // pass in one call and the barrier ordering
-  const int fuse = (fuse_env && s->single_driver && lb == 0 && le == s->num_levels && !flow_sync() && s->bn_ptr && s->bn_dst) ? 1 : 0;
+  const int fuse = (!per_level && fuse_env && s->single_driver && lb == 0 && le == s->num_levels && !flow_sync() && s->bn_ptr && s->bn_dst) ? 1 : 0;
   FwdArgs a{s->level_ptr, s->cell_base, s->order, s->f_ptr, s->f_src, S, H, planes, b1, b2, A, LSE, HIDb, ready, g_prof,
-            lb, le, prefetch_on(), s->bn_ptr, s->bn_dst, fuse};
+            lb, le, per_level ? 0 : prefetch_on(), s->bn_ptr, s->bn_dst, fuse, per_level ? 1 : 0};
+  if (per_level) {                             // ONE cell level: a cluster per 32-pin tile (more pins per tile past 74 clusters)
+    const int cnt = s->h_level_ptr[lb + 1] - s->h_level_ptr[lb];
+    return launch_persist(gnn_persist_fwd_kernel<false>, a, st, "gnn_cell_level_fwd", (cnt + 31) / 32, true);
+  }
   return flow_sync() ? launch_persist(gnn_persist_fwd_kernel<true>, a, st, "gnn_persist_fwd<flow>")
                      : launch_persist(gnn_persist_fwd_kernel<false>, a, st, "gnn_persist_fwd");
 }
 
 int gnn_persist_backward(const tm_schedule* s, const float* H, float* G, const float* W1, const float* W2, const float* A,
-                         const float* LSE, const float* HIDb, float* GA, float* GHID, float* GZC, void* ws, cudaStream_t st) {
-  TM_REQUIRE(s->level_ptr && s->cell_base && s->sync_flags,
-             "tm_gnn_backward: schedule lacks the device level_ptr / cell_base / sync_flags arrays");
+                         const float* LSE, const float* HIDb, float* GA, float* GHID, float* GZC, void* ws, cudaStream_t st,
+                         int lb, int le, bool begin, bool per_level) {
   uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   unsigned int* ready = reinterpret_cast<unsigned int*>(s->sync_flags);
-  TM_CUDA(cudaMemsetAsync(ready, 0, flow_sync() ? sizeof(unsigned int) * ((size_t)s->n + (size_t)s->n_cell_rows) : 256, st));
-  gnn_pack_planes_kernel<<<2 * 2 * 128 * 128 / 256, 256, 0, st>>>(W2, W1, planes);
-  TM_TRY(check_launch("gnn_pack_planes"));
+  if (begin) TM_TRY(gnn_persist_begin(s, W2, W1, ws, flow_sync() && !per_level, (size_t)s->n + (size_t)s->n_cell_rows, st));
   BwdArgs a{s->level_ptr, s->cell_base, s->order, s->bn_ptr, s->bn_dst, s->bn_w, s->bc_ptr, s->bc_row, H, G, planes,
-            A, LSE, HIDb, GA, GHID, GZC, ready, ready + s->n, g_prof, s->num_levels, prefetch_on()};
+            A, LSE, HIDb, GA, GHID, GZC, ready, ready + s->n, g_prof, s->num_levels, per_level ? 0 : prefetch_on(), lb, le,
+            per_level ? 1 : 0};
+  if (per_level) {
+    const int cnt = s->h_level_ptr[lb + 1] - s->h_level_ptr[lb];
+    return launch_persist(gnn_persist_bwd_kernel<false>, a, st, "gnn_cell_level_bwd", (cnt + 31) / 32, true);
+  }
   return flow_sync() ? launch_persist(gnn_persist_bwd_kernel<true>, a, st, "gnn_persist_bwd<flow>")
                      : launch_persist(gnn_persist_bwd_kernel<false>, a, st, "gnn_persist_bwd");
 }

@@ -692,11 +692,12 @@ def test_cpu_inputs_fail_loudly(mods):
         M.MLP(4, 8, 2)(torch.randn(3, 4))
 
 
-@pytest.mark.parametrize("impl,flow", [(0, 0), (3, 0), (3, 1), (3, 2)])
+@pytest.mark.parametrize("impl,flow", [(0, 0), (3, 0), (3, 1), (3, 2), (8, 0)])
 @pytest.mark.parametrize("cfg,seed", [("tiny", 2), ("c1", 3)])
 def test_gnn_kernel_variants_vs_oracle(mods, impl, flow, cfg, seed):
     """The propagation back ends -- per-level launches (0), persistent cluster kernels with a grid barrier per level
-    (3, flow 0), with per-pin ready flags (3, flow 1) and with net-level push fusion (3, flow 2) -- against the oracle, forward
+    (3, flow 0), with per-pin ready flags (3, flow 1), with net-level push fusion (3, flow 2), and the same cluster tile
+    kernel launched once per cell level (8) -- against the oracle, forward
     (no allowance) and backward, and bit-deterministic from run to run."""
     ops, lib = mods["ops"], mods["lib"].lib()
     d = tm_synth.make_design(seed=seed, **tm_synth.CONFIGS[cfg])
