@@ -164,7 +164,9 @@ size_t tm_gnn_ws_bytes(void);   /* workspace of tm_gnn_forward / tm_gnn_backward
  *   bit set   = ONE persistent kernel for the whole pass: 2-CTA clusters, fc_cell_neigh resident in shared memory,
  *               the tile MLP transposed on tcgen05 (fp16 two-term split, fp32 accumulate in TMEM), one grid-wide
  *               barrier per level (or, with TM_GNN_SYNC=flow, per-pin ready flags and no barrier);
- *   bit clear = one launch per level (mma.sync 3xTF32 tile MLP, weights streamed per level, PDL-chained).
+ *   bit clear = one launch per level (mma.sync 3xTF32 tile MLP, weights streamed per level, PDL-chained);
+ *   8         = one launch per level with the CELL levels on the cluster tile kernel (tcgen05, fp16 split); measured
+ *               slower than both.
  * Returns the previous value; impl < 0 only queries. */
 int tm_gnn_set_impl(int impl);
 /* Level ordering inside the persistent kernels: 0 = grid barrier per level (default), 1 = per-pin ready flags
