@@ -171,8 +171,10 @@ size_t tm_gnn_ws_bytes(void);   /* workspace of tm_gnn_forward / tm_gnn_backward
 int tm_gnn_set_impl(int impl);
 /* Level ordering inside the persistent kernels: 0 = grid barrier per level (default), 1 = per-pin ready flags
  * (dataflow; also env TM_GNN_SYNC=flow), 2 = grid barrier + net-level "push" fusion in the forward (rows of
- * single-driver net pins written by their driver's producer, odd levels skipped; also env TM_GNN_FUSE=1).  Both
- * alternatives measured slower than 0 on B200.  Returns the previous value; flow < 0 only queries. */
+ * single-driver net pins written by their driver's producer, odd levels skipped; also env TM_GNN_FUSE=1), 3 = sentinel
+ * dataflow in the forward (H pre-filled with 0xFFFFFFFF words, every gathered 16-byte piece validates itself: no flag,
+ * no fence; the backward uses the flags).  All alternatives measured slower than 0 on B200.
+ * Returns the previous value; flow < 0 only queries. */
 int tm_gnn_set_sync(int flow);
 /* Grid-wide barriers inside the last tm_gnn_forward / tm_gnn_backward call of this thread (persistent kernel:
  * one per non-empty level; per-level kernels: 0, they synchronise by kernel boundaries). */

@@ -120,6 +120,18 @@ __device__ __forceinline__ void wait_flag(const unsigned int* p) {
   for (uint32_t spin = 0; ld_flag(p) == 0u; ++spin)
     if (spin > (1u << 22)) __trap();
 }
+// Sentinel dataflow (forward, sync mode 3): H is pre-filled with the bit pattern 0xFFFFFFFF (a NaN no arithmetic
+// produces); a row needs no flag and no fence -- every 16-byte piece a consumer lane loads validates itself, and a
+// piece that still holds a sentinel word (not yet written, or torn) is simply loaded again.
+__device__ __forceinline__ float4 ld_poll4(const float* p) {       // re-load that the compiler may neither hoist nor fold
+  float4 r;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ bool f4_pending(float4 v) {
+  return __float_as_uint(v.x) == 0xFFFFFFFFu || __float_as_uint(v.y) == 0xFFFFFFFFu ||
+         __float_as_uint(v.z) == 0xFFFFFFFFu || __float_as_uint(v.w) == 0xFFFFFFFFu;
+}
 __device__ __forceinline__ void set_flag(unsigned int* p) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
 }
@@ -517,6 +529,7 @@ struct FwdArgs {
   const int* bn_ptr; const int* bn_dst;
   int fuse;
   int pdl;                         // one launch per cell level: wait for the previous grid (griddepcontrol) instead of a grid barrier
+  int sentinel;                    // FLOW kernels: validate the gathered data itself instead of per-pin flags
 };
 
 // rows of the sinks driven by one pin; lane layout of the caller: `cols` = this lane's float4 columns (NV of them)
@@ -606,13 +619,28 @@ __device__ __forceinline__ void fwd_net_level(const FwdArgs& a, int p0, int cnt,
       }
 #pragma unroll
       for (int q = 0; q < UN; ++q)
-        if (FLOW && i + q < e) wait_flag(a.ready + idx[q]);
+        if (FLOW && !a.sentinel && i + q < e) wait_flag(a.ready + idx[q]);
       float4 m[UN][NV];
 #pragma unroll
       for (int q = 0; q < UN; ++q)
 #pragma unroll
         for (int j = 0; j < NV; ++j)
           m[q][j] = (i + q < e) ? ldcg4(a.H + (int64_t)idx[q] * D + (j * G + lg) * 4) : f4zero();
+      if (FLOW && a.sentinel) {
+        for (uint32_t spin = 0;; ++spin) {
+          bool pending = false;
+#pragma unroll
+          for (int q = 0; q < UN; ++q)
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+              if (i + q < e && f4_pending(m[q][j])) {
+                m[q][j] = ld_poll4(a.H + (int64_t)idx[q] * D + (j * G + lg) * 4);
+                pending = true;
+              }
+          if (!pending) break;
+          if (spin > (1u << 22)) __trap();
+        }
+      }
 #pragma unroll
       for (int q = 0; q < UN; ++q)
 #pragma unroll
@@ -626,7 +654,7 @@ __device__ __forceinline__ void fwd_net_level(const FwdArgs& a, int p0, int cnt,
       *reinterpret_cast<float4*>(a.H + (int64_t)v * D + (j * G + lg) * 4) = hv[j];
     }
     if (!FLOW && a.fuse) push_sinks<NV>(a, p0 + p, hv, lg * 4, G * 4);
-    if (FLOW) {
+    if (FLOW && !a.sentinel) {
       __syncwarp(gmask);
       if (lg == 0) set_flag(a.ready + v);
     }
@@ -719,15 +747,30 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_fwd_kernel(const FwdAr
         int bnd = __shfl_sync(0xffffffffu, ptrs, 1);
         for (int i = E0; i < E1; i += 8) {
           if (i > E0) idx = (i + (lane & 7) < E1) ? __ldg(a.f_src + i + (lane & 7)) : 0;
-          if (FLOW) {
+          if (FLOW && !a.sentinel) {
             if (i + (lane & 7) < E1) wait_flag(a.ready + idx);     // every source row of the batch is final
             __syncwarp();
           }
           float4 m[8];
+          int srcs[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int src = __shfl_sync(0xffffffffu, idx, u);
-            m[u] = (i + u < E1) ? ldcg4(a.H + (int64_t)src * D + lane * 4) : f4zero();
+            srcs[u] = __shfl_sync(0xffffffffu, idx, u);
+            m[u] = (i + u < E1) ? ldcg4(a.H + (int64_t)srcs[u] * D + lane * 4) : f4zero();
+          }
+          if (FLOW && a.sentinel) {
+            for (uint32_t spin = 0;; ++spin) {
+              bool pending = false;
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (i + u < E1 && f4_pending(m[u])) {
+                  m[u] = ld_poll4(a.H + (int64_t)srcs[u] * D + lane * 4);
+                  pending = true;
+                }
+              if (!pending) break;
+              if (spin > (1u << 22)) __trap();
+            }
+            __syncwarp();
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -798,7 +841,7 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_fwd_kernel(const FwdAr
         }
       };
       exchange_tile(c, N, fin);
-      if (FLOW) {
+      if (FLOW && !a.sentinel) {
         __syncthreads();                                     // every warp's H stores precede the publication
         if (tid < half) {
           const int v = c.pin_s[(int)c.rank * half + tid];
@@ -1155,6 +1198,15 @@ __global__ void __launch_bounds__(THREADS, 1) gnn_persist_bwd_kernel(const BwdAr
   ctx_teardown(c);
 }
 
+// sentinel mode: rows of pins that are not scheduled (or beyond the processed levels) go back to zero
+__global__ void gnn_clear_pending_kernel(int64_t n, const int* __restrict__ level, int le, float* __restrict__ H) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const int l = level[w];
+  if (l < 0 || l >= le) *reinterpret_cast<float4*>(H + w * D + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // pins of levels < lb were produced by an earlier call: mark them ready
 __global__ void gnn_mark_ready_kernel(const int* __restrict__ order, int count, unsigned int* __restrict__ ready) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1216,7 +1268,8 @@ int sync_mode() {
   }
   return v;
 }
-bool flow_sync() { return sync_mode() == 1; }
+bool flow_sync() { return sync_mode() == 1 || sync_mode() == 3; }
+bool sentinel_sync() { return sync_mode() == 3; }
 }  // namespace
 
 namespace tmk {
@@ -1226,7 +1279,7 @@ void gnn_persist_set_profile(long long* p) { g_prof = p; }
 int gnn_persist_profile_slots() { return PH_COUNT; }
 int gnn_persist_set_flow(int flow) {
   const int prev = sync_mode();
-  if (flow >= 0) g_flow.store(flow > 2 ? 0 : flow, std::memory_order_relaxed);
+  if (flow >= 0) g_flow.store(flow > 3 ? 0 : flow, std::memory_order_relaxed);
   return prev;
 }
 
@@ -1258,13 +1311,23 @@ int gnn_persist_forward(const tm_schedule* s, int lb, int le, float* H, const fl
   // pass in one call and the barrier ordering
   const int fuse = (!per_level && fuse_env && s->single_driver && lb == 0 && le == s->num_levels && !flow_sync() && s->bn_ptr && s->bn_dst) ? 1 : 0;
   FwdArgs a{s->level_ptr, s->cell_base, s->order, s->f_ptr, s->f_src, S, H, planes, b1, b2, A, LSE, HIDb, ready, g_prof,
-            lb, le, per_level ? 0 : prefetch_on(), s->bn_ptr, s->bn_dst, fuse, per_level ? 1 : 0};
+            lb, le, per_level ? 0 : prefetch_on(), s->bn_ptr, s->bn_dst, fuse, per_level ? 1 : 0,
+            (!per_level && sentinel_sync() && lb == 0) ? 1 : 0};
+  if (a.sentinel) {
+    // every row the kernel will read starts as "pending"; rows of pins outside the schedule are zeroed afterwards
+    TM_CUDA(cudaMemsetAsync(H, 0xFF, sizeof(float) * (size_t)s->n * D, st));
+  }
   if (per_level) {                             // ONE cell level: a cluster per 32-pin tile (more pins per tile past 74 clusters)
     const int cnt = s->h_level_ptr[lb + 1] - s->h_level_ptr[lb];
     return launch_persist(gnn_persist_fwd_kernel<false>, a, st, "gnn_cell_level_fwd", (cnt + 31) / 32, true);
   }
-  return flow_sync() ? launch_persist(gnn_persist_fwd_kernel<true>, a, st, "gnn_persist_fwd<flow>")
-                     : launch_persist(gnn_persist_fwd_kernel<false>, a, st, "gnn_persist_fwd");
+  TM_TRY(flow_sync() ? launch_persist(gnn_persist_fwd_kernel<true>, a, st, "gnn_persist_fwd<flow>")
+                     : launch_persist(gnn_persist_fwd_kernel<false>, a, st, "gnn_persist_fwd"));
+  if (a.sentinel && (s->h_level_ptr[s->num_levels] < s->n || le < s->num_levels)) {
+    gnn_clear_pending_kernel<<<(unsigned)cdiv((int64_t)s->n * 32, 256), 256, 0, st>>>(s->n, s->level, le, H);
+    TM_TRY(check_launch("gnn_clear_pending"));
+  }
+  return 0;
 }
 
 int gnn_persist_backward(const tm_schedule* s, const float* H, float* G, const float* W1, const float* W2, const float* A,

@@ -144,6 +144,8 @@ def time_cfg(name, g, n):
 
 if __name__ == "__main__":
     what = sys.argv[1:] or ["compare"]
+    if os.environ.get("TM_DEV_SYNC"):
+        tm_lib.lib().tm_gnn_set_sync(int(os.environ["TM_DEV_SYNC"]))
     if "compare" in what:
         for cfg, seed in (("tiny", 0), ("tiny", 5), ("c1", 1)):
             compare(cfg, seed)
