@@ -510,12 +510,13 @@ def test_design_step_vs_golden(mods, math_mode):
 
 
 def test_design_step_mixed_precision_vs_golden(mods):
-    """The fused step with the image branch in its bf16 mode (TMA-fed tcgen05 convolutions; `cnn.math = "bf16"`)
-    against the fixture of the unmodified reference at the bf16 bar: predictions and loss per element at rtol 2e-2
-    (atol 2e-2 x max|ref|); the gradients of the netlist branch / head / fusion at 2e-2 relative L2 error per tensor
-    (their error is the image branch's bf16 rounding spread over a whole tensor: a few of 166k elements of the
-    widest head layer sit at 5 % of the tensor's scale); the U-Net's own parameter gradients by direction
-    (cosine >= 0.85), as in tests/test_gpu_configs.py."""
+    """The fused step with the image branch in its bf16 mode (`cnn.math = "bf16"`; the tiny 16x16 image runs the
+    cp.async-fed bf16 tensor-core convolutions, the full-size TMA path is held in tests/test_gpu_configs.py).
+      * against the fixture of the UNMODIFIED reference (fp32): predictions and loss per element at the bf16 bar,
+        rtol 2e-2;
+      * against the oracle whose U-Net rounds its operands to bf16 at the product's rounding points and is
+        teacher-forced with the product's contraction outputs (oracle/restate.py): predictions, loss and EVERY
+        parameter gradient -- netlist branch, head, fusion and U-Net -- per element at rtol 2e-2."""
     eng = mods["engine"]
     d = tm_synth.make_design(seed=0, **tm_synth.CONFIGS["tiny"])
     z, sd_m, sd_c = load_golden_step("tiny")
@@ -523,20 +524,44 @@ def test_design_step_mixed_precision_vs_golden(mods):
     cnn.math = "bf16"
     batch = eng.DesignBatch.from_synth(d, DEV)
     loss, pred = eng.DesignStep(model, cnn).run(batch)
-    assert_close(pred, z["pred"], 2e-2, 2e-2, "pred (bf16 image branch)")
-    assert_close(loss.reshape(()), z["loss"], 2e-2, 2e-2, "loss (bf16 image branch)")
+    assert_close(pred, z["pred"], 2e-2, 2e-2, "pred (bf16 image branch) vs reference fixture")
+    assert_close(loss.reshape(()), z["loss"], 2e-2, 2e-2, "loss (bf16 image branch) vs reference fixture")
+    # the product's contraction outputs of the same forward (deterministic), as the oracle's forced tensors
+    import tm_unet
+    with torch.no_grad():
+        _, ust = tm_unet.unet_forward(cnn, batch.image, need_bwd=False, update_stats=False)
+    H = 2 * d.map_size
+    chans = [16, 32, 64, 128]
+    enc = ["inc.double_conv", "down1.maxpool_conv.1.double_conv", "down2.maxpool_conv.1.double_conv", "down3.maxpool_conv.1.double_conv"]
+
+    def nchw(t, C, h):
+        return t.detach().float().reshape(1, h, h, C).permute(0, 3, 1, 2).contiguous().cpu()
+    forced = {}
+    for i in range(4):
+        e = ust[f"enc{i}"]
+        forced[enc[i] + ".0"], forced[enc[i] + ".3"] = nchw(e["r1"], chans[i], H >> i), nchw(e["r2"], chans[i], H >> i)
+    for j, nm in enumerate(["up1", "up2", "up3"]):
+        i = 2 - j
+        e = ust[f"dec{j}"]
+        forced[nm + ".conv.double_conv.0"], forced[nm + ".conv.double_conv.3"] = nchw(e["r1"], chans[i], H >> i), nchw(e["r2"], chans[i], H >> i)
+        forced[nm + ".up"] = nchw(ust["cat"][i][:, chans[i]:].contiguous(), chans[i], H >> i)
+    ref = restate.design_step(sd_m, sd_c, design_to_oracle(d), unet_rounding="bf16", unet_forced=forced)
+    assert_close(pred, ref["pred"], 2e-2, 2e-2, "pred vs bf16-rounded oracle")
+    assert_close(loss.reshape(()), ref["loss"], 2e-2, 2e-2, "loss vs bf16-rounded oracle")
     for k, p in model.named_parameters():
-        ref = z["grad.model." + k]
-        if ref.size:
-            a, b = p.grad.double().cpu().reshape(-1), torch.from_numpy(ref).double().reshape(-1)
-            rel = float((a - b).norm() / (b.norm() + 1e-300))
-            assert rel <= 2e-2, f"model.{k}: relative L2 error {rel:.3e}"
+        g = ref["grads"][k]
+        if g is None:
+            assert p.grad is None, k
+        else:
+            assert_close(p.grad, g, 2e-2, 2e-2, "model." + k)
     for k, p in cnn.named_parameters():
-        if p.numel() == 1:
+        g = ref["grads"]["cnn." + k]
+        if k.endswith(".up.bias"):                       # cancelling sum: tolerance scaled to the layer's weight gradient
+            wscale = float(ref["grads"]["cnn." + k[:-4] + "weight"].abs().max())
+            err = (p.grad.double().cpu() - g.double()).abs()
+            assert bool((err <= 2e-2 * g.abs() + 2e-2 * wscale).all()), f"cnn.{k}: max abs err {float(err.max()):.3e}"
             continue
-        a, b = p.grad.double().cpu().reshape(-1), torch.from_numpy(z["grad.cnn." + k]).double().reshape(-1)
-        cos = float((a @ b) / (a.norm() * b.norm() + 1e-300))
-        assert cos >= 0.85, f"cnn.{k}: cosine {cos:.3f}"
+        assert_close(p.grad, g, 2e-2, 2e-2, "cnn." + k)
 
 
 def test_prepared_design_graph_replay(mods):
