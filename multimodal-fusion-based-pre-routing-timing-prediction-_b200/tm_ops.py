@@ -163,6 +163,9 @@ def _recurrence_math():
     """Arithmetic of the hoisted self-term MLPs.  Their output S seeds the 101-level recurrence, whose
     ReLU masks turn forward rounding differences into gradient differences, so they keep 24-bit
     products ("tc6") when the default mode is one of the ~21-bit / 16-bit ones."""
+    forced = os.environ.get("TM_RECURRENCE_MATH")
+    if forced:
+        return None if forced == "default" else forced
     return "tc6" if MATH in ("tf32x3", "tf32", "tc3") else None
 
 
