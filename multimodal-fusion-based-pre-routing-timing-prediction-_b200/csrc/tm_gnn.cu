@@ -17,6 +17,7 @@
 // A warp owns a pin (lane = 4 channels, 128-bit loads); cell levels are processed in 16-pin tiles:
 // the aggregated rows are staged in shared memory and pushed through the 128->256->128 MLP by the
 // same CTA, so `a` and the hidden layer never round-trip through HBM on the forward critical path.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "tm_common.cuh"
@@ -100,6 +101,10 @@ constexpr int CHUNK_B = 32 * WB_ROW;    // floats per chunk of Wb (32 k-rows)  =
 constexpr int SLOT = CHUNK_B > CHUNK_A ? CHUNK_B : CHUNK_A;
 constexpr size_t PACK_FLOATS = (size_t)D * WA_ROW + (size_t)HID * WB_ROW;   // one (Wa, Wb) pair
 constexpr int TILE_FLOATS = 3 * TILE * IN_LD + 2 * TILE * MID_LD;
+constexpr int IN_LDH = D / 2 + 4;     // 68 half2 words per row:  bank(g*68 + t) = 4g + t  -> conflict-free A fragments (m16n8k16)
+constexpr int MID_LDH = HID / 2 + 4;  // 132
+static_assert(TILE * MID_LD + 2 * TILE * IN_LDH + 2 * TILE * MID_LDH + 2 * TILE <= 2 * TILE * IN_LD + 2 * TILE * MID_LD,
+              "the fp16-split tiles must fit the area of the fp32 hi / lo tiles");
 constexpr size_t CELL_SMEM = (size_t)(TILE_FLOATS + NSTAGE * SLOT) * sizeof(float) + TILE * sizeof(int) + 64;
 
 struct Tiles {                    // shared-memory carve-up of one CTA
@@ -111,12 +116,28 @@ struct Tiles {                    // shared-memory carve-up of one CTA
   float* wbuf;                    // NSTAGE x SLOT
   int* v_s;                       // [TILE]
   uint64_t* wfull;                // [NSTAGE] mbarriers
+  // fp16-split variant (H16): the same area behind scr holds the fp32 hidden tile, the half2 (hi, lo') planes of the
+  // input / hidden tiles and the per-pin scales instead of the four fp32 hi / lo tiles
+  float* hid_f;                   // [TILE][MID_LD] fp32 hidden (unscaled: what the backward needs)
+  uint32_t* ah_hi;                // [TILE][IN_LDH] half2 words, k pairs
+  uint32_t* ah_lo;
+  uint32_t* mh_hi;                // [TILE][MID_LDH]
+  uint32_t* mh_lo;
+  float* sc_s;                    // [TILE] scale, [TILE] 1/scale
+  float* inv_s;
   __device__ explicit Tiles(float* smem) {
     scr = smem;
     in_hi = scr + TILE * IN_LD;
     in_lo = in_hi + TILE * IN_LD;
     mid_hi = in_lo + TILE * IN_LD;
     mid_lo = mid_hi + TILE * MID_LD;
+    hid_f = in_hi;
+    ah_hi = reinterpret_cast<uint32_t*>(hid_f + TILE * MID_LD);
+    ah_lo = ah_hi + TILE * IN_LDH;
+    mh_hi = ah_lo + TILE * IN_LDH;
+    mh_lo = mh_hi + TILE * MID_LDH;
+    sc_s = reinterpret_cast<float*>(mh_lo + TILE * MID_LDH);
+    inv_s = sc_s + TILE;
     wbuf = mid_lo + TILE * MID_LD;
     v_s = reinterpret_cast<int*>(wbuf + NSTAGE * SLOT);
     wfull = reinterpret_cast<uint64_t*>(v_s + TILE);
@@ -262,9 +283,156 @@ __device__ __forceinline__ void mlp_tile(const Tiles& T, const float* Wa, const 
   __syncthreads();
 }
 
+// =============================================================================================
+// fp16 two-term split variant of the tile MLP (TM_GNN_CELL_MATH=h16, round 2; see tm_gnn_persist.cu):
+//   x s = hi + lo,  hi = fp16(x s),  lo' = fp16((x s - hi) 2^11),  s = per-pin power of two (row maximum -> [1, 2))
+//   acc_main += hi hi;  acc_corr += hi lo' + lo' hi;  result = (acc_main + 2^-11 acc_corr) / s
+// on mma.sync.m16n8k16 (f16 operands, fp32 accumulate): 3 tensor instructions per k16 step and n-tile instead of the 6 of
+// 3xTF32 (m16n8k8), and the operand fragments are single 32-bit shared-memory words (half2 k-pairs), no on-the-fly split.
+// The weights are packed ONCE per call into the same chunk geometry as the fp32 path (so the cp.async.bulk ring is
+// unchanged): chunk c < 8 = k16 step c of Wa as [plane hi | lo'][8 k-pairs][264 words], chunk 8 + c = two k16 steps of
+// Wb as [plane][16 k-pairs][136 words].
+// =============================================================================================
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+__device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void row_scale(float rowmax, int emin, float& sc, float& inv) {
+  int e = (int)((__float_as_uint(rowmax) >> 23) & 0xffu) - 127;
+  e = max(emin, min(e, 100));
+  sc = __uint_as_float((uint32_t)(127 - e) << 23);
+  inv = __uint_as_float((uint32_t)(127 + e) << 23);
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// one tile row (this lane: channels 4 lane .. 4 lane + 3) -> scale, split, half2 planes
+__device__ __forceinline__ void store_row_h(const Tiles& T, int row, int lane, float4 x, int emin) {
+  const float rm = warp_max_f(fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+  float sc, inv;
+  row_scale(rm, emin, sc, inv);
+  __half h0, h1, h2, h3, l0, l1, l2, l3;
+  split_h(x.x * sc, h0, l0); split_h(x.y * sc, h1, l1); split_h(x.z * sc, h2, l2); split_h(x.w * sc, h3, l3);
+  *reinterpret_cast<uint2*>(&T.ah_hi[row * IN_LDH + 2 * lane]) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+  *reinterpret_cast<uint2*>(&T.ah_lo[row * IN_LDH + 2 * lane]) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+  if (lane == 0) { T.sc_s[row] = sc; T.inv_s[row] = inv; }
+}
+// (Wa [128][256], Wb [256][128]) fp32 -> the chunked half2 planes described above.  One thread per (k pair, n).
+__global__ void gnn_pack_h_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, uint32_t* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (D / 2) * HID) {                                   // Wa: k pair kq < 64, n < 256
+    const int kq = i / HID, n = i - kq * HID;
+    __half h0, l0, h1, l1;
+    split_h(Wa[(size_t)(2 * kq) * HID + n], h0, l0);
+    split_h(Wa[(size_t)(2 * kq + 1) * HID + n], h1, l1);
+    uint32_t* c = dst + (size_t)(kq >> 3) * CHUNK_A + (kq & 7) * WA_ROW + n;
+    c[0] = pack_h2(h0, h1);
+    c[8 * WA_ROW] = pack_h2(l0, l1);
+  } else if (i < (D / 2) * HID + (HID / 2) * D) {            // Wb: k pair kq < 128, n < 128
+    const int j = i - (D / 2) * HID;
+    const int kq = j / D, n = j - kq * D;
+    __half h0, l0, h1, l1;
+    split_h(Wb[(size_t)(2 * kq) * D + n], h0, l0);
+    split_h(Wb[(size_t)(2 * kq + 1) * D + n], h1, l1);
+    uint32_t* c = dst + (size_t)8 * CHUNK_A + (size_t)(kq >> 4) * CHUNK_B + (kq & 15) * WB_ROW + n;
+    c[0] = pack_h2(h0, h1);
+    c[16 * WB_ROW] = pack_h2(l0, l1);
+  }
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// one k16 step of a 16 x (8*NT) product: A words from the tile planes (row stride a_ld words, k-pair offset kp0),
+// B words from a chunk's planes (w_hi / w_lo, k-pair row kpw0, row stride w_row words)
+template <int NT>
+__device__ __forceinline__ void mma_kstep_h(float (&am)[NT][4], float (&ac)[NT][4], const uint32_t* a_hi, const uint32_t* a_lo,
+                                            int a_ld, int kp0, const uint32_t* w_hi, const uint32_t* w_lo, int w_row, int kpw0,
+                                            int n_base, int g, int t) {
+  uint32_t ah[4], al[4];
+  const int i0 = g * a_ld + kp0 + t, i1 = (g + 8) * a_ld + kp0 + t;
+  ah[0] = a_hi[i0]; ah[1] = a_hi[i1]; ah[2] = a_hi[i0 + 4]; ah[3] = a_hi[i1 + 4];
+  al[0] = a_lo[i0]; al[1] = a_lo[i1]; al[2] = a_lo[i0 + 4]; al[3] = a_lo[i1 + 4];
+  const int o0 = (kpw0 + t) * w_row + n_base + g, o1 = o0 + 4 * w_row;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const uint32_t bh0 = w_hi[o0 + j * 8], bh1 = w_hi[o1 + j * 8], bl0 = w_lo[o0 + j * 8], bl1 = w_lo[o1 + j * 8];
+    mma_f16(ac[j], al, bh0, bh1);          // small terms
+    mma_f16(ac[j], ah, bl0, bl1);
+    mma_f16(am[j], ah, bh0, bh1);
+  }
+}
+// The fp16-split tile MLP.  T.ah_hi / ah_lo: the scaled, split input tile (store_row_h); epi1(row, col, v0, v1) maps the
+// first product's (still scaled) values of columns col, col+1 to the scaled hidden values; T.hid_f receives the UNSCALED
+// hidden tile, T.scr the unscaled second product.  Ends with a __syncthreads().
+template <class Epi1>
+__device__ __forceinline__ void mlp_tile_h(const Tiles& T, const float* Wa, const float* Wb, int tid, Epi1 epi1) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  constexpr int NT1 = HID / 8 / (CT / 32), NT2 = D / 8 / (CT / 32);   // n-tiles per warp: 4 and 2
+  float m1[NT1][4], c1[NT1][4], m2[NT2][4], c2[NT2][4];
+#pragma unroll
+  for (int j = 0; j < NT1; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { m1[j][c] = 0.f; c1[j][c] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < NT2; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { m2[j][c] = 0.f; c2[j][c] = 0.f; }
+  for (int c = 0; c < NCHUNK; ++c) {
+    __syncthreads();                      // everybody is done with chunk c-1 (its slot is free); tiles visible
+    if (tid == 0) issue_chunk(T, Wa, Wb, c + NSTAGE - 1);
+    wait_chunk(T, c);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(T.wbuf + (c % NSTAGE) * SLOT);
+    if (c < 8) {                          // GEMM1: k16 step c of Wa
+      mma_kstep_h<NT1>(m1, c1, T.ah_hi, T.ah_lo, IN_LDH, c * 8, w, w + 8 * WA_ROW, WA_ROW, 0, warp * NT1 * 8, g, t);
+      if (c == 7) {
+#pragma unroll
+        for (int j = 0; j < NT1; ++j) {
+          const int col = warp * NT1 * 8 + j * 8 + 2 * t;
+          const float2 e0 = epi1(g, col, fmaf(c1[j][0], LO_INV, m1[j][0]), fmaf(c1[j][1], LO_INV, m1[j][1]));
+          const float2 e1 = epi1(g + 8, col, fmaf(c1[j][2], LO_INV, m1[j][2]), fmaf(c1[j][3], LO_INV, m1[j][3]));
+          const float i0 = T.inv_s[g], i1 = T.inv_s[g + 8];
+          *reinterpret_cast<float2*>(&T.hid_f[g * MID_LD + col]) = make_float2(e0.x * i0, e0.y * i0);
+          *reinterpret_cast<float2*>(&T.hid_f[(g + 8) * MID_LD + col]) = make_float2(e1.x * i1, e1.y * i1);
+          __half h0, l0, h1, l1;
+          split_h(e0.x, h0, l0); split_h(e0.y, h1, l1);
+          T.mh_hi[g * MID_LDH + (col >> 1)] = pack_h2(h0, h1);
+          T.mh_lo[g * MID_LDH + (col >> 1)] = pack_h2(l0, l1);
+          split_h(e1.x, h0, l0); split_h(e1.y, h1, l1);
+          T.mh_hi[(g + 8) * MID_LDH + (col >> 1)] = pack_h2(h0, h1);
+          T.mh_lo[(g + 8) * MID_LDH + (col >> 1)] = pack_h2(l0, l1);
+        }
+      }
+    } else {                              // GEMM2: two k16 steps of Wb
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma_kstep_h<NT2>(m2, c2, T.mh_hi, T.mh_lo, MID_LDH, (c - 8) * 16 + ks * 8, w, w + 16 * WB_ROW, WB_ROW, ks * 8,
+                         warp * NT2 * 8, g, t);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NT2; ++j) {
+    const int col = warp * NT2 * 8 + j * 8 + 2 * t;
+    const float i0 = T.inv_s[g], i1 = T.inv_s[g + 8];
+    *reinterpret_cast<float2*>(&T.scr[g * IN_LD + col]) =
+        make_float2(fmaf(c2[j][0], LO_INV, m2[j][0]) * i0, fmaf(c2[j][1], LO_INV, m2[j][1]) * i0);
+    *reinterpret_cast<float2*>(&T.scr[(g + 8) * IN_LD + col]) =
+        make_float2(fmaf(c2[j][2], LO_INV, m2[j][2]) * i1, fmaf(c2[j][3], LO_INV, m2[j][3]) * i1);
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward, even level > 0: gather + per-channel softmax-weighted sum + MLP, 16 pins per CTA
 // ---------------------------------------------------------------------------------------------
+template <bool H16>
 __global__ void __launch_bounds__(CT)
 gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
                     const int* __restrict__ f_ptr, const int* __restrict__ f_src,
@@ -303,10 +471,14 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
         av = make_float4(tw[0] / sm[0], tw[1] / sm[1], tw[2] / sm[2], tw[3] / sm[3]);
         lse = make_float4(mx[0] + logf(sm[0]), mx[1] + logf(sm[1]), mx[2] + logf(sm[2]), mx[3] + logf(sm[3]));
       }
-      float4 avh, avl;
-      split4(av, avh, avl);
-      *reinterpret_cast<float4*>(&T.in_hi[(r0 + q) * IN_LD + lane * 4]) = avh;
-      *reinterpret_cast<float4*>(&T.in_lo[(r0 + q) * IN_LD + lane * 4]) = avl;
+      if constexpr (H16) {
+        store_row_h(T, r0 + q, lane, av, -4);
+      } else {
+        float4 avh, avl;
+        split4(av, avh, avl);
+        *reinterpret_cast<float4*>(&T.in_hi[(r0 + q) * IN_LD + lane * 4]) = avh;
+        *reinterpret_cast<float4*>(&T.in_lo[(r0 + q) * IN_LD + lane * 4]) = avl;
+      }
       if (A) {
         st4(A + (int64_t)(crow0 + t0 + r0 + q) * D + lane * 4, av);
         st4(LSE + (int64_t)(crow0 + t0 + r0 + q) * D + lane * 4, lse);
@@ -346,26 +518,43 @@ gnn_cell_fwd_kernel(const int* __restrict__ order, int p0, int cnt, int crow0,
       while (q < npin) finish_pin();
     }
     for (int r = max(npin, 0); r < PPW; ++r) {                   // rows past the end of the level
-      *reinterpret_cast<float4*>(&T.in_hi[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(&T.in_lo[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (H16) {
+        store_row_h(T, r0 + r, lane, make_float4(0.f, 0.f, 0.f, 0.f), -4);
+      } else {
+        *reinterpret_cast<float4*>(&T.in_hi[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(&T.in_lo[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
 
   // phases 2+3: hidden = relu(a @ W1t + b1);  h = relu(S + hidden @ W2t + b2)
-  auto epi1 = [&](int row, int col, float v0, float v1) {
-    const float2 bb = __ldg(reinterpret_cast<const float2*>(b1 + col));
-    return make_float2(fmaxf(v0 + bb.x, 0.f), fmaxf(v1 + bb.y, 0.f));
-  };
-  mlp_tile(T, W1t, W2t, tid, epi1);
+  if constexpr (H16) {
+    auto epi1 = [&](int row, int col, float v0, float v1) {      // v = sc[row] (a @ W1t): add the scaled bias
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(b1 + col));
+      const float sc = T.sc_s[row];
+      return make_float2(fmaxf(fmaf(bb.x, sc, v0), 0.f), fmaxf(fmaf(bb.y, sc, v1), 0.f));
+    };
+    mlp_tile_h(T, W1t, W2t, tid, epi1);
+  } else {
+    auto epi1 = [&](int row, int col, float v0, float v1) {
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(b1 + col));
+      return make_float2(fmaxf(v0 + bb.x, 0.f), fmaxf(v1 + bb.y, 0.f));
+    };
+    mlp_tile(T, W1t, W2t, tid, epi1);
+  }
   pdl_launch_dependents();                           // the next level may be scheduled while the epilogue drains
   // coalesced epilogues from shared memory: hidden rows (saved for backward; hi + lo is exact), then h rows
   if (HIDb) {
 #pragma unroll
     for (int i = 0; i < TILE * HID / 4 / CT; ++i) {
       const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
-      if (t0 + row < cnt)
-        st4(HIDb + (int64_t)(crow0 + t0 + row) * HID + c4,
-            f4add(*reinterpret_cast<const float4*>(&T.mid_hi[row * MID_LD + c4]), *reinterpret_cast<const float4*>(&T.mid_lo[row * MID_LD + c4])));
+      if (t0 + row < cnt) {
+        if constexpr (H16)
+          st4(HIDb + (int64_t)(crow0 + t0 + row) * HID + c4, *reinterpret_cast<const float4*>(&T.hid_f[row * MID_LD + c4]));
+        else
+          st4(HIDb + (int64_t)(crow0 + t0 + row) * HID + c4,
+              f4add(*reinterpret_cast<const float4*>(&T.mid_hi[row * MID_LD + c4]), *reinterpret_cast<const float4*>(&T.mid_lo[row * MID_LD + c4])));
+      }
     }
   }
 #pragma unroll
@@ -449,6 +638,7 @@ gnn_net_bwd_kernel(SchedDev s, int p0, int cnt, const float* __restrict__ H, flo
   st4(G + off, relu_mask(hv, g));
 }
 
+template <bool H16>
 __global__ void __launch_bounds__(CT)
 gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restrict__ H, float* G,
                     const float* __restrict__ W1, const float* __restrict__ W2, float* GA,
@@ -457,7 +647,7 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
   extern __shared__ __align__(16) float smem[];
   const Tiles T(smem);
   float (*gz_s)[IN_LD] = reinterpret_cast<float (*)[IN_LD]>(T.scr);          // gradient accumulation scratch
-  float (*gh_s)[MID_LD] = reinterpret_cast<float (*)[MID_LD]>(T.mid_hi);     // the pins' own h rows until the MLP runs
+  float (*gh_s)[MID_LD] = reinterpret_cast<float (*)[MID_LD]>(H16 ? T.hid_f : T.mid_hi);   // the pins' own h rows until the MLP runs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * TILE;
   // g_hid = (g_z @ W2) * (hid > 0): W2 is [128][256] as stored by nn.Linear(256,128)  -> "Wa"
@@ -537,12 +727,18 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
       if (r < npin) {
         const float4 hv = *reinterpret_cast<const float4*>(&gh_s[r0 + r][lane * 4]);
         const float4 gz = relu_mask(hv, *reinterpret_cast<const float4*>(&gz_s[r0 + r][lane * 4]));
-        float4 gzh, gzl;
-        split4(gz, gzh, gzl);
-        *reinterpret_cast<float4*>(&T.in_hi[(r0 + r) * IN_LD + lane * 4]) = gzh;
-        *reinterpret_cast<float4*>(&T.in_lo[(r0 + r) * IN_LD + lane * 4]) = gzl;
+        if constexpr (H16) {
+          store_row_h(T, r0 + r, lane, gz, -100);
+        } else {
+          float4 gzh, gzl;
+          split4(gz, gzh, gzl);
+          *reinterpret_cast<float4*>(&T.in_hi[(r0 + r) * IN_LD + lane * 4]) = gzh;
+          *reinterpret_cast<float4*>(&T.in_lo[(r0 + r) * IN_LD + lane * 4]) = gzl;
+        }
         st4(G + (int64_t)__shfl_sync(0xffffffffu, vv, r) * D + lane * 4, gz);
         st4(GZC + (int64_t)(crow0 + t0 + r0 + r) * D + lane * 4, gz);
+      } else if constexpr (H16) {
+        store_row_h(T, r0 + r, lane, make_float4(0.f, 0.f, 0.f, 0.f), -100);
       } else {
         *reinterpret_cast<float4*>(&T.in_hi[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(&T.in_lo[(r0 + r) * IN_LD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -559,14 +755,19 @@ gnn_cell_bwd_kernel(SchedDev s, int p0, int cnt, int crow0, const float* __restr
     }
     return o;
   };
-  mlp_tile(T, W2, W1, tid, epi1);
+  if constexpr (H16) mlp_tile_h(T, W2, W1, tid, epi1);       // (the ReLU mask commutes with the per-pin scale)
+  else mlp_tile(T, W2, W1, tid, epi1);
   pdl_launch_dependents();
 #pragma unroll
   for (int i = 0; i < TILE * HID / 4 / CT; ++i) {
     const int q = tid + i * CT, row = q >> 6, c4 = (q & 63) * 4;
-    if (t0 + row < cnt)
-      st4(GHID + (int64_t)(crow0 + t0 + row) * HID + c4,
-          f4add(*reinterpret_cast<const float4*>(&T.mid_hi[row * MID_LD + c4]), *reinterpret_cast<const float4*>(&T.mid_lo[row * MID_LD + c4])));
+    if (t0 + row < cnt) {
+      if constexpr (H16)
+        st4(GHID + (int64_t)(crow0 + t0 + row) * HID + c4, *reinterpret_cast<const float4*>(&T.hid_f[row * MID_LD + c4]));
+      else
+        st4(GHID + (int64_t)(crow0 + t0 + row) * HID + c4,
+            f4add(*reinterpret_cast<const float4*>(&T.mid_hi[row * MID_LD + c4]), *reinterpret_cast<const float4*>(&T.mid_lo[row * MID_LD + c4])));
+    }
   }
 #pragma unroll
   for (int i = 0; i < TILE * D / 4 / CT; ++i) {
@@ -597,8 +798,10 @@ int launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t sme
 
 int cell_smem_optin() {
   // the attribute is per function AND per device: set it on every call (cheap), so a second device works
-  TM_CUDA(cudaFuncSetAttribute(gnn_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
-  TM_CUDA(cudaFuncSetAttribute(gnn_cell_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
+  TM_CUDA(cudaFuncSetAttribute(gnn_cell_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
+  TM_CUDA(cudaFuncSetAttribute(gnn_cell_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
+  TM_CUDA(cudaFuncSetAttribute(gnn_cell_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
+  TM_CUDA(cudaFuncSetAttribute(gnn_cell_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
   return 0;
 }
 
@@ -634,7 +837,8 @@ int gnn_impl() {
     //   C3: 2.31 vs 2.61 ms in favour of the persistent backward).  Bit 2 = "auto" (default): persistent forward;
     //   persistent backward only on wide schedules (>= 6 000 pins per level on average).
     const char* e = getenv("TM_GNN_IMPL");
-    v = !e ? 4 : (e[0] == 'l' ? 0 : (e[0] == 'p' ? 3 : (atoi(e) & 15)));
+    //   Bit 4 (16): the per-level cell kernels run the fp16 two-term split (mma.sync.m16n8k16) instead of 3xTF32.
+    v = !e ? 20 : (e[0] == 'l' ? 0 : (e[0] == 'p' ? 3 : (atoi(e) & 31)));
     g_impl.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -648,7 +852,7 @@ int count_levels(const tm_schedule* s, int lb, int le) {
 
 extern "C" int tm_gnn_set_impl(int impl) {
   const int prev = gnn_impl();
-  if (impl >= 0) g_impl.store(impl & 15, std::memory_order_relaxed);
+  if (impl >= 0) g_impl.store(impl & 31, std::memory_order_relaxed);
   return prev;
 }
 extern "C" int tm_gnn_last_barriers() { return g_last_barriers; }
@@ -662,10 +866,17 @@ extern "C" size_t tm_gnn_ws_bytes() { return PACK_FLOATS * sizeof(float) + 256 +
 
 namespace {
 // (Wa [128][256], Wb [256][128]) -> padded, hi/lo pre-split rows in the caller's workspace
-int pack_pair(const float* Wa, const float* Wb, void* ws, size_t ws_bytes, const float** pa, const float** pb, cudaStream_t st) {
+int pack_pair(const float* Wa, const float* Wb, void* ws, size_t ws_bytes, const float** pa, const float** pb, cudaStream_t st,
+              bool h16) {
   TM_REQUIRE(ws && ws_bytes >= tm_gnn_ws_bytes(), "tm_gnn: workspace too small (tm_gnn_ws_bytes)");
   float* a = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   float* b = a + (size_t)D * WA_ROW;
+  *pa = a;
+  *pb = b;
+  if (h16) {                               // same chunk geometry, half2 (hi | lo') planes inside each chunk
+    gnn_pack_h_kernel<<<(D * HID + 255) / 256, 256, 0, st>>>(Wa, Wb, reinterpret_cast<uint32_t*>(a));
+    return check_launch("gnn_pack_h");
+  }
   gnn_pack_kernel<<<(D * WA_ROW + 255) / 256, 256, 0, st>>>(Wa, D, HID, a);
   TM_TRY(check_launch("gnn_pack(Wa)"));
   gnn_pack_kernel<<<(HID * WB_ROW + 255) / 256, 256, 0, st>>>(Wb, HID, D, b);
@@ -693,7 +904,8 @@ extern "C" int tm_gnn_forward(const tm_schedule* s, int32_t lb, int32_t le, floa
   const bool tc_levels = (gnn_impl() & 8) && s->level_ptr && s->cell_base && s->sync_flags;   // cell levels on the tcgen05 cluster tile kernel
   TM_TRY(cell_smem_optin());
   const float *W1t = nullptr, *W2t = nullptr;
-  if (!tc_levels) TM_TRY(pack_pair(W1t_in, W2t_in, ws, ws_bytes, &W1t, &W2t, st));
+  const bool h16 = gnn_impl() & 16;
+  if (!tc_levels) TM_TRY(pack_pair(W1t_in, W2t_in, ws, ws_bytes, &W1t, &W2t, st, h16));
   int crow0 = cell_base_of(s, lb + (lb & 1));
   bool tc_begun = false;
   for (int l = lb; l < le; ++l) {
@@ -708,7 +920,7 @@ extern "C" int tm_gnn_forward(const tm_schedule* s, int32_t lb, int32_t le, floa
         TM_TRY(launch_pdl(gnn_net_fwd_kernel, (unsigned)cdiv(cnt, 8), 256, 0, st, "gnn_net_fwd", s->order, p0, cnt, s->f_ptr,
                           s->f_src, S, H));
       } else {
-        TM_TRY(launch_pdl(gnn_cell_fwd_kernel, (unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st, "gnn_cell_fwd", s->order, p0, cnt,
+        TM_TRY(launch_pdl(h16 ? gnn_cell_fwd_kernel<true> : gnn_cell_fwd_kernel<false>, (unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st, "gnn_cell_fwd", s->order, p0, cnt,
                           crow0, s->f_ptr, s->f_src, S, H, W1t, b1, W2t, b2, A, LSE, HIDb));
       }
     }
@@ -733,7 +945,8 @@ extern "C" int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, c
   TM_TRY(cell_smem_optin());
   // backward products: g_hid = g_z @ W2 (W2 [128][256] is "Wa"), g_a = g_hid @ W1 (W1 [256][128] is "Wb")
   const float *W2 = nullptr, *W1 = nullptr;
-  if (!tc_levels) TM_TRY(pack_pair(W2_in, W1_in, ws, ws_bytes, &W2, &W1, st));
+  const bool h16 = gnn_impl() & 16;
+  if (!tc_levels) TM_TRY(pack_pair(W2_in, W1_in, ws, ws_bytes, &W2, &W1, st, h16));
   bool tc_begun = false;
   SchedDev d{s->order, s->bn_ptr, s->bn_dst, s->bn_w, s->bc_ptr, s->bc_row};
   int crow_end = cell_base_of(s, s->num_levels + (s->num_levels & 1));  // total cell rows
@@ -749,7 +962,7 @@ extern "C" int tm_gnn_backward(const tm_schedule* s, const float* H, float* G, c
     } else if (!cell) {
       TM_TRY(launch_pdl(gnn_net_bwd_kernel, (unsigned)cdiv(cnt, 8), 256, 0, st, "gnn_net_bwd", d, p0, cnt, H, G, (const float*)GA, A, LSE));
     } else {
-      TM_TRY(launch_pdl(gnn_cell_bwd_kernel, (unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st, "gnn_cell_bwd", d, p0, cnt, crow_end, H,
+      TM_TRY(launch_pdl(h16 ? gnn_cell_bwd_kernel<true> : gnn_cell_bwd_kernel<false>, (unsigned)cdiv(cnt, TILE), CT, CELL_SMEM, st, "gnn_cell_bwd", d, p0, cnt, crow_end, H,
                         G, W1, W2, GA, A, LSE, HIDb, GHID, GZC));
     }
   }

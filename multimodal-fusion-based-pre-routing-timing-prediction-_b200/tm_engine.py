@@ -199,7 +199,7 @@ class DesignStep:
         # (per-level kernels while the image stream runs next to them: measured 5.07 ms/step against 5.49 ms
         #  with the persistent forward, which owns all SMs for 0.9 ms and serialises the U-Net behind it)
         H, saved = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat, gp, save=True,
-                                      impl=0 if side is not main and os.environ.get("TM_GNN_IMPL") is None else None)
+                                      impl=16 if side is not main and os.environ.get("TM_GNN_IMPL") is None else None)
         with torch.cuda.stream(side):
             fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
             feat = fmap.reshape(-1)

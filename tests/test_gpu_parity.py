@@ -717,7 +717,7 @@ def test_cpu_inputs_fail_loudly(mods):
         M.MLP(4, 8, 2)(torch.randn(3, 4))
 
 
-@pytest.mark.parametrize("impl,flow", [(0, 0), (3, 0), (3, 1), (3, 2), (3, 3), (8, 0)])
+@pytest.mark.parametrize("impl,flow", [(0, 0), (16, 0), (3, 0), (3, 1), (3, 2), (3, 3), (8, 0)])
 @pytest.mark.parametrize("cfg,seed", [("tiny", 2), ("c1", 3)])
 def test_gnn_kernel_variants_vs_oracle(mods, impl, flow, cfg, seed):
     """The propagation back ends -- per-level launches (0), persistent cluster kernels with a grid barrier per level
