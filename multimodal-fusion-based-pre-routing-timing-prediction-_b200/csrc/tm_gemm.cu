@@ -5,15 +5,36 @@
 using namespace tmk;
 
 namespace tmk {
-__global__ void split_reduce_kernel(const float* __restrict__ P, int64_t count, int splits,
-                                    float* __restrict__ C, int64_t N, int64_t ldc, int accumulate) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+// C[m][n] (+)= sum_k P[k][m*N + n].  Block = 64 elements x 4 split groups: group y adds splits y, y+4, ... (eight
+// independent loads in flight), the four groups are folded in a fixed order -- deterministic, and four times fewer
+// dependent additions per thread than one thread per element (the reductions sit between the weight-gradient GEMMs of
+// the backward chain, where their latency is exposed).  Launch with split_reduce_grid(count) blocks of 256 threads.
+__global__ void __launch_bounds__(256)
+split_reduce_kernel(const float* __restrict__ P, int64_t count, int splits,
+                    float* __restrict__ C, int64_t N, int64_t ldc, int accumulate) {
+  __shared__ float sm[4][64];
+  const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
+  const int64_t i = (int64_t)blockIdx.x * 64 + x;
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += P[(int64_t)k * count + i];  // fixed order: deterministic
-  const int64_t m = i / N, n = i - m * N;
-  float* p = C + m * ldc + n;
-  *p = accumulate ? (*p + s) : s;
+  if (i < count) {
+    int k = y;
+    for (; k + 28 < splits; k += 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = P[(int64_t)(k + 4 * u) * count + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; k < splits; k += 4) s += P[(int64_t)k * count + i];
+  }
+  sm[y][x] = s;
+  __syncthreads();
+  if (y == 0 && i < count) {
+    s = ((sm[0][x] + sm[1][x]) + sm[2][x]) + sm[3][x];
+    const int64_t m = i / N, n = i - m * N;
+    float* p = C + m * ldc + n;
+    *p = accumulate ? (*p + s) : s;
+  }
 }
 }  // namespace tmk
 

@@ -481,16 +481,16 @@ int launch_gemm_tn(const AL& al, bool veca, const BL& bl, bool vecb, int64_t M, 
   TM_TRY(check_launch("gemm_tn"));
   {
     const int64_t count = M * N;
-    unsigned blocks = (unsigned)cdiv(count, 256);
+    unsigned blocks = (unsigned)cdiv(count, 64);
     split_reduce_kernel<<<blocks, 256, 0, st>>>(P, count, splits, C, N, ldc, accumulate);
     TM_TRY(check_launch("split_reduce"));
   }
   if (colsum) {
-    split_reduce_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(Pcs, N, splits, colsum, N, N, accumulate);
+    split_reduce_kernel<<<(unsigned)cdiv(N, 64), 256, 0, st>>>(Pcs, N, splits, colsum, N, N, accumulate);
     TM_TRY(check_launch("split_reduce_cs"));
   }
   if (colsum_a) {
-    split_reduce_kernel<<<(unsigned)cdiv(M, 256), 256, 0, st>>>(PcsA, M, splits, colsum_a, M, M, accumulate);
+    split_reduce_kernel<<<(unsigned)cdiv(M, 64), 256, 0, st>>>(PcsA, M, splits, colsum_a, M, M, accumulate);
     TM_TRY(check_launch("split_reduce_csa"));
   }
   return 0;
