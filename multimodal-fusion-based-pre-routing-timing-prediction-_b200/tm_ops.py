@@ -160,13 +160,15 @@ def colsum(X, R, C, ld, out=None, accumulate=0):
 # two-layer MLP (model.py:10-24 with sizes (in, hid, out)):  y = W2 relu(W1 x + b1) + b2
 # --------------------------------------------------------------------------------------------
 def _recurrence_math():
-    """Arithmetic of the hoisted self-term MLPs.  Their output S seeds the 101-level recurrence, whose
-    ReLU masks turn forward rounding differences into gradient differences, so they keep 24-bit
-    products ("tc6") when the default mode is one of the ~21-bit / 16-bit ones."""
+    """Arithmetic of the hoisted self-term MLPs, whose output S seeds the 101-level recurrence.  Round 1 kept
+    24-bit products ("tc6", six bf16 MMAs) here; measured on B200 (``profiles/diag_gemm_modes.py``) the default
+    3xTF32 contraction has the same error on these shapes (max 3.0e-6 against 2.4e-6 of the row scale: the fp32
+    accumulation dominates both) and every parity test -- including the full-size config 2 / 3 gradient checks -- is
+    unchanged, while the step is 0.09 ms shorter.  ``TM_RECURRENCE_MATH=tc6`` restores the round-1 choice."""
     forced = os.environ.get("TM_RECURRENCE_MATH")
     if forced:
         return None if forced == "default" else forced
-    return "tc6" if MATH in ("tf32x3", "tf32", "tc3") else None
+    return None
 
 
 def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, math=None):
@@ -269,7 +271,12 @@ def gnn_forward(sched, cell_feat, net_feat, params, save=True, impl=None):
                       out_rows=sched.cell_class, math=_recurrence_math())
     hn = mlp2_forward(net_feat, net_feat.stride(0), sched.net_class, nn_, ns1w, ns1b, ns2w, ns2b, S, D,
                       out_rows=sched.net_class, math=_recurrence_math())
-    H = torch.zeros(n, D, dtype=torch.float32, device=dev)
+    # every scheduled pin's row is written by its level's kernel: only pins outside the schedule need the zero fill
+    # (170 MB = 42 us of the config-2 step when every pin is scheduled, as in the reference's designs)
+    if sched.n_sched == n and os.environ.get("TM_H_FILL") != "1":
+        H = torch.empty(n, D, dtype=torch.float32, device=dev)
+    else:
+        H = torch.zeros(n, D, dtype=torch.float32, device=dev)
     ncr = sched.n_cell_rows
     A = LSE = HID = None
     if save:
