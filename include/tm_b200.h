@@ -427,6 +427,14 @@ int tm_tc_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, int64_t lda, 
 int tm_tc_conv2d_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k,
                       const float* x, int64_t ldx, const float* wf, const float* bias, float* y,
                       int64_t ldy, int flags, int precision, int* err, void* stream);
+/* The same convolution with the K = k*k*Cin range split over CTAs when the layer has too few 128-pixel tiles to
+ * fill the GPU (the 64 x 64 and 32 x 32 maps of one 256 x 256 design); partial tiles in `ws`, folded in a fixed
+ * order.  Falls through to tm_tc_conv2d_nhwc when no split pays (ws may then be NULL / 0 bytes). */
+size_t tm_tc_conv2d_splitk_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k, int precision);
+int tm_tc_conv2d_nhwc_splitk(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k,
+                             const float* x, int64_t ldx, const float* wf, const float* bias, float* y,
+                             int64_t ldy, int flags, int precision, void* ws, size_t ws_bytes, int* err,
+                             void* stream);
 size_t tm_tc_conv2d_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k);
 int tm_tc_conv2d_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k,
                             const float* x, int64_t ldx, const float* dy, int64_t lddy, float* dwf,

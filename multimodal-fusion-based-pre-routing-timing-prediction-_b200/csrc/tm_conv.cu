@@ -627,7 +627,19 @@ extern "C" int tm_convt2x2_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t C
 }
 
 namespace {
-inline int bn_blocks(int64_t npix) { return (int)(npix < BN_BLOCKS ? npix : BN_BLOCKS); }
+// Blocks of the statistics sweep: at most BN_BLOCKS, and at least two pixels per pixel lane of a block (a block of
+// 256 threads has 256 / (C / VEC) lanes).  The small deep maps (32 x 32 x 128: 1 024 pixels) ran 592 blocks of one
+// or two pixels each, whose fixed fp64 fold cost more than the sweep (14 - 16 us against 6 - 9 us for 256 x 256 x 16).
+inline int bn_blocks(int64_t npix, int64_t C = 0, bool v4 = false) {
+  int64_t n = npix < BN_BLOCKS ? npix : BN_BLOCKS;
+  if (C > 0) {
+    const int64_t groups = v4 ? C / 4 : C;
+    const int64_t lanes = groups < BN_THREADS ? BN_THREADS / groups : 1;
+    const int64_t cap = npix / (2 * lanes);
+    if (n > cap) n = cap;
+  }
+  return (int)(n < 1 ? 1 : n);
+}
 inline bool bn_vec4(int64_t C, std::initializer_list<std::pair<const void*, int64_t>> ts) {
   if (C % 4 != 0 || C > 1024) return false;
   for (auto& t : ts)
@@ -648,9 +660,9 @@ extern "C" int tm_bn_relu_forward(int64_t npix, int64_t C, const float* x, int64
                                   size_t ws_bytes, void* stream) {
   TM_REQUIRE(npix > 0 && C > 0 && C <= 256, "tm_bn_relu_forward: bad sizes (C <= 256)");
   TM_REQUIRE(ws_bytes >= tm_bn_ws(npix, C), "tm_bn_relu_forward: workspace too small");
-  const int nblk = bn_blocks(npix);
   double* part = (double*)ws;
   const bool v4 = bn_vec4(C, {{x, ldx}, {y, ldy}});
+  const int nblk = bn_blocks(npix, C, v4);
   const int groups = v4 ? (int)C / 4 : (int)C;
   const size_t sh = (size_t)(BN_THREADS / groups) * C * 2 * sizeof(double);
   TM_REQUIRE(y || y_bf16, "tm_bn_relu_forward: neither y nor y_bf16 given");
@@ -704,9 +716,9 @@ extern "C" int tm_bn_relu_backward(int64_t npix, int64_t C, const float* x, int6
   TM_REQUIRE(dx || dx_bf16, "tm_bn_relu_backward: neither dx nor dx_bf16 given");
   TM_REQUIRE(y || beta, "tm_bn_relu_backward: without the stored activation y the mask is rebuilt from beta");
   TM_REQUIRE(ws_bytes >= tm_bn_ws(npix, C), "tm_bn_relu_backward: workspace too small");
-  const int nblk = bn_blocks(npix);
   double* part = (double*)ws;
   const bool v4 = bn_vec4(C, {{x, ldx}, {y, ldy}, {dy, lddy}, {dx, lddx}});
+  const int nblk = bn_blocks(npix, C, v4);
   const int groups = v4 ? (int)C / 4 : (int)C;
   const size_t sh = (size_t)(BN_THREADS / groups) * C * 2 * sizeof(double);
   if (v4) bn_stats_kernel<4, true><<<nblk, BN_THREADS, sh, ST>>>(npix, (int)C, x, ldx, y, ldy, dy, lddy, save_mean, save_invstd, gamma, beta, part);

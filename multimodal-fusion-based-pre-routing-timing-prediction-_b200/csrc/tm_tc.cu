@@ -181,6 +181,89 @@ extern "C" int tm_tc_conv2d_nhwc(int64_t B, int64_t H, int64_t W, int64_t Cin, i
   return tc::launch(al, bl, ep, M, Cout, K, 1, cdiv(K, tc::BK) * tc::BK, precision, err, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split-K form of the convolution for the deep, small-map layers.  One U-Net step at 256 x 256 has layers of
+// 64 x 64 and 32 x 32 pixels: 32 and 8 output tiles of 128 pixels -- 22 % and 5 % of the SMs -- each walking
+// K = 9 Cin = 576 .. 1152 (measured 34 - 74 us per layer on 8 - 32 CTAs).  Here the K range is cut so that
+// tiles x splits fills the GPU; every CTA writes an fp32 partial tile, and one pass adds them in a fixed order
+// (deterministic) with the bias / ReLU of the plain epilogue.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+conv_split_reduce_kernel(const float* __restrict__ P, int64_t M, int64_t N, int splits, const float* __restrict__ bias,
+                         int relu, float* __restrict__ Y, int64_t ldy) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // one float4 of the M x N result
+  const int64_t n4 = N >> 2;
+  if (i >= M * n4) return;
+  const int64_t m = i / n4, n = (i - m * n4) << 2;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* p = reinterpret_cast<const float4*>(P + m * N + n);
+  const int64_t stride4 = (M * N) >> 2;
+#pragma unroll 4
+  for (int k = 0; k < splits; ++k) {
+    const float4 v = p[(int64_t)k * stride4];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  if (bias) { s.x += bias[n]; s.y += bias[n + 1]; s.z += bias[n + 2]; s.w += bias[n + 3]; }
+  if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+  float* y = Y + m * ldy + n;
+  if ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) *reinterpret_cast<float4*>(y) = s;
+  else { y[0] = s.x; y[1] = s.y; y[2] = s.z; y[3] = s.w; }
+}
+
+// number of K splits of a convolution GEMM (1 = the plain kernel) and the K range of one split
+inline int conv_splits(int64_t M, int64_t N, int64_t K, int precision, int64_t* kps) {
+  *kps = cdiv(K, tc::BK) * tc::BK;
+  static const bool off = getenv("TM_CONV_SPLITK") && atoi(getenv("TM_CONV_SPLITK")) == 0;
+  if (off || precision < 3 || (N & 3) || M <= 0) return 1;
+  const int64_t tiles = cdiv(M, tc::BM) * cdiv(N, tc::pick_bn(N, precision));
+  const int64_t nkb = cdiv(K, tc::BK);
+  int64_t want = (int64_t)sm_count() / tiles;
+  if (want > nkb / 2) want = nkb / 2;                   // at least two k-blocks per split
+  if (want < 2) return 1;
+  *kps = cdiv(nkb, want) * tc::BK;
+  return (int)cdiv(K, *kps);
+}
+}  // namespace
+
+extern "C" size_t tm_tc_conv2d_splitk_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k, int precision) {
+  int64_t kps;
+  const int splits = conv_splits(B * H * W, Cout, k * k * Cin, precision, &kps);
+  return splits > 1 ? (size_t)splits * (size_t)(B * H * W) * (size_t)Cout * sizeof(float) + 256 : 0;
+}
+
+extern "C" int tm_tc_conv2d_nhwc_splitk(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k,
+                                        const float* x, int64_t ldx, const float* wf, const float* bias, float* y,
+                                        int64_t ldy, int flags, int precision, void* ws, size_t ws_bytes, int* err,
+                                        void* stream) {
+  TM_REQUIRE(k >= 1 && (k & 1), "tm_tc_conv2d_nhwc_splitk: odd kernel sizes only");
+  const int64_t M = B * H * W, K = k * k * Cin;
+  int64_t kps;
+  const int splits = conv_splits(M, Cout, K, precision, &kps);
+  if (splits <= 1) return tm_tc_conv2d_nhwc(B, H, W, Cin, Cout, k, x, ldx, wf, bias, y, ldy, flags, precision, err, stream);
+  TM_REQUIRE(ws && ws_bytes >= tm_tc_conv2d_splitk_ws(B, H, W, Cin, Cout, k, precision),
+             "tm_tc_conv2d_nhwc_splitk: workspace too small (tm_tc_conv2d_splitk_ws)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  tc::Im2colLoader8 al{x, ldx, (int)H, (int)W, (int)Cin, (int)k, (int)(k / 2), M, K,
+                       (Cin % 4 == 0) ? vec_mode(x, ldx) : 0};
+  tc::ColLoader bl{wf, Cout, nullptr, Cout, K, vec_mode(wf, Cout)};
+  tc::PartialEpilogue ep{part, M, Cout};
+  const int bn = tc::pick_bn(Cout, precision);
+#define TM_CONV_SPLIT_CASE(BN_)                                                                                              \
+  TM_TRY((precision == 3 ? tc::launch_tf<tc::Im2colLoader8, tc::ColLoader, tc::PartialEpilogue, BN_, 2>(al, bl, ep, M, Cout, K, splits, kps, err, st) \
+                         : tc::launch_tf<tc::Im2colLoader8, tc::ColLoader, tc::PartialEpilogue, BN_, 1>(al, bl, ep, M, Cout, K, splits, kps, err, st)))
+  switch (bn) {
+    case 128: TM_CONV_SPLIT_CASE(128); break;
+    case 64: TM_CONV_SPLIT_CASE(64); break;
+    default: TM_CONV_SPLIT_CASE(32); break;
+  }
+#undef TM_CONV_SPLIT_CASE
+  conv_split_reduce_kernel<<<(unsigned)cdiv(M * (Cout >> 2), 256), 256, 0, st>>>(part, M, Cout, splits, bias,
+                                                                                  (flags & TM_EPI_RELU) ? 1 : 0, y, ldy);
+  return check_launch("conv_split_reduce");
+}
+
 extern "C" size_t tm_tc_conv2d_wgrad_ws(int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t k) {
   return tm_tc_gemm_tn_ws(k * k * Cin, Cout, B * H * W);
 }

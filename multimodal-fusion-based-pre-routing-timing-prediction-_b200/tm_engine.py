@@ -155,24 +155,36 @@ class DesignStep:
         self.cnn_params = dict(cnn.named_parameters())
 
     # ---------------------------------------------------------------- forward pieces
-    def _head_forward(self, H, b, feat):
+    def _head_image_side(self, b, feat, X):
+        """The head's inputs that do not depend on the propagation: mask fusion of the feature map and the level
+        embedding (``mlp_alpha``), written into columns D.. of the head matrix X.  Runs on the image stream."""
         m = self.model
         T = int(b.endpoints.numel())
-        dev = H.device
-        gd = m.global_dim
-        width = D + D + gd
-        X = torch.empty(T, width, dtype=torch.float32, device=dev)
-        call("tm_gather_cols", T, D, H, D, b.endpoints, X, width, 0, stream())
+        width = X.shape[1]
         wt = tm_ops.fusion_forward(b.mask_rows, feat, m.fcn.weight.detach(), m.fcn.bias.detach(), X[:, D:], width)
         a0, a2 = m.mlp_alpha.layers[0], m.mlp_alpha.layers[2]
         lv = b.endpoint_level.reshape(T, 1)
         ha = tm_ops.mlp2_forward(lv, 1, None, T, a0.weight.detach(), a0.bias.detach(), a2.weight.detach(),
                                  a2.bias.detach(), X[:, 2 * D:], width)
+        return dict(X=X, wt=wt, ha=ha, lv=lv, width=width)
+
+    def _head_netlist_side(self, H, b, hs):
+        """Endpoint rows of H into columns 0..D of X, then ``mlp_fuse``."""
+        m = self.model
+        T = int(b.endpoints.numel())
+        X, width = hs["X"], hs["width"]
+        call("tm_gather_cols", T, D, H, D, b.endpoints, X, width, 0, stream())
         f0, f2 = m.mlp_fuse.layers[0], m.mlp_fuse.layers[2]
-        pred = torch.empty(T, f2.weight.shape[0], dtype=torch.float32, device=dev)
-        hf = tm_ops.mlp2_forward(X, width, None, T, f0.weight.detach(), f0.bias.detach(), f2.weight.detach(),
-                                 f2.bias.detach(), pred, pred.shape[1])
-        return pred, dict(X=X, wt=wt, ha=ha, hf=hf, lv=lv, width=width)
+        pred = torch.empty(T, f2.weight.shape[0], dtype=torch.float32, device=H.device)
+        hs["hf"] = tm_ops.mlp2_forward(X, width, None, T, f0.weight.detach(), f0.bias.detach(), f2.weight.detach(),
+                                       f2.bias.detach(), pred, pred.shape[1])
+        return pred
+
+    def _head_forward(self, H, b, feat):
+        T = int(b.endpoints.numel())
+        X = torch.empty(T, D + D + self.model.global_dim, dtype=torch.float32, device=H.device)
+        hs = self._head_image_side(b, feat, X)
+        return self._head_netlist_side(H, b, hs), hs
 
     def forward(self, b):
         """Inference: predictions for the batch's endpoints (validate(), train.py:137-291)."""
@@ -198,35 +210,42 @@ class DesignStep:
         # the longer chain is enqueued first so the host's launch time for the other one overlaps it
         # (per-level kernels while the image stream runs next to them: measured 5.07 ms/step against 5.49 ms
         #  with the persistent forward, which owns all SMs for 0.9 ms and serialises the U-Net behind it)
+        T = int(b.endpoints.numel())
+        X = torch.empty(T, D + D + m.global_dim, dtype=torch.float32, device=dev)     # head input [H rows | fused map | level]
+        G = torch.empty(sched.n, D, dtype=torch.float32, device=dev)                 # dLoss/dH, seeded at the endpoints
         H, saved = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat, gp, save=True,
                                       impl=16 if side is not main and os.environ.get("TM_GNN_IMPL") is None else None)
         with torch.cuda.stream(side):
             fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
             feat = fmap.reshape(-1)
-        main.wait_stream(side)                               # join: the fusion needs the feature map
-        pred, hs = self._head_forward(H, b, feat)
-        T = int(b.endpoints.numel())
+            # everything of the head that does not read H runs here, off the netlist branch's critical path
+            # (the image stream is idle long before the 101 levels finish): mask fusion, level embedding, G = 0
+            hs = self._head_image_side(b, feat, X)
+            G.zero_()
+        main.wait_stream(side)                               # join: the head needs the fused feature map
+        pred = self._head_netlist_side(H, b, hs)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         gpred = torch.empty(T, 1, dtype=torch.float32, device=dev)
         call("tm_mse", T, pred, b.arrival_time, loss, gpred, float(grad_scale), stream())
 
-        # ---- head backward
-        width, X = hs["width"], hs["X"]
+        # ---- head backward: mlp_fuse on the netlist stream (its dX seeds the backward sweep) ...
+        width = hs["width"]
         f0, f2 = m.mlp_fuse.layers[0], m.mlp_fuse.layers[2]
         dw1, db1, dw2, db2, dX = tm_ops.mlp2_backward(X, width, None, T, f0.weight.detach(), f2.weight.detach(),
                                                       hs["hf"], gpred, 1, need_dx=True)
+        side.wait_stream(main)                               # dX is ready
+        # ... the level embedding and the mask fusion (whose dF starts the U-Net backward) on the image stream
         a0, a2 = m.mlp_alpha.layers[0], m.mlp_alpha.layers[2]
-        da1, dab1, da2, dab2, _ = tm_ops.mlp2_backward(hs["lv"], 1, None, T, a0.weight.detach(), a2.weight.detach(),
-                                                       hs["ha"], dX[:, 2 * D:], width, b1=a0.bias.detach())
-        dF, dfw, dfb = tm_ops.fusion_backward(b.mask_rows, feat, hs["wt"], dX[:, D:], width)
-        head = [(f0.weight, dw1), (f0.bias, db1), (f2.weight, dw2), (f2.bias, db2), (a0.weight, da1),
-                (a0.bias, dab1), (a2.weight, da2), (a2.bias, dab2), (m.fcn.weight, dfw), (m.fcn.bias, dfb)]
-        self._assign(head)
-        self._post_allreduce("head", [p for p, _ in head])
+        with torch.cuda.stream(side):
+            da1, dab1, da2, dab2, _ = tm_ops.mlp2_backward(hs["lv"], 1, None, T, a0.weight.detach(), a2.weight.detach(),
+                                                           hs["ha"], dX[:, 2 * D:], width, b1=a0.bias.detach())
+            dF, dfw, dfb = tm_ops.fusion_backward(b.mask_rows, feat, hs["wt"], dX[:, D:], width)
+            head = [(f0.weight, dw1), (f0.bias, db1), (f2.weight, dw2), (f2.bias, db2), (a0.weight, da1),
+                    (a0.bias, dab1), (a2.weight, da2), (a2.bias, dab2), (m.fcn.weight, dfw), (m.fcn.bias, dfb)]
+            self._assign(head)
+            self._post_allreduce("head", [p for p, _ in head])
 
         # ---- GNN backward (main stream) next to the U-Net backward (image stream)
-        side.wait_stream(main)                               # dF is ready
-        G = torch.zeros(sched.n, D, dtype=torch.float32, device=dev)
         call("tm_scatter_add_cols", T, D, dX, width, 0, b.endpoints, G, D, stream())
         ggrads = tm_ops.gnn_backward(sched, saved, gp, G)
         pairs = list(zip(self.gnn_params, ggrads))

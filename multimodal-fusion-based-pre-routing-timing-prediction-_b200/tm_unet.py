@@ -113,8 +113,9 @@ def _conv(x, ldx, B, H, W, cin, cout, k, wf, bias, y, ldy, flags=0, math=None):
     if prec is None:
         call("tm_conv2d_nhwc", B, H, W, cin, cout, k, x, ldx, wf, bias, y, ldy, flags, stream())
     else:
-        call("tm_tc_conv2d_nhwc", B, H, W, cin, cout, k, x, ldx, wf, bias, y, ldy, flags, prec,
-             tm_lib.err_flag(y.device), stream())
+        nb = tm_lib.ws_bytes("tm_tc_conv2d_splitk_ws", B, H, W, cin, cout, k, prec)   # 0: the layer fills the GPU unsplit
+        call("tm_tc_conv2d_nhwc_splitk", B, H, W, cin, cout, k, x, ldx, wf, bias, y, ldy, flags, prec,
+             tm_lib.workspace(nb, y.device) if nb else None, nb, tm_lib.err_flag(y.device), stream())
 
 
 def _conv_wgrad(ws, x, ldx, dy, lddy, B, H, W, cin, cout, k, want_bias, math=None):
