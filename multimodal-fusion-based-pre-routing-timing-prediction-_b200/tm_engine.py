@@ -232,7 +232,8 @@ class DesignStep:
         width = hs["width"]
         f0, f2 = m.mlp_fuse.layers[0], m.mlp_fuse.layers[2]
         dw1, db1, dw2, db2, dX = tm_ops.mlp2_backward(X, width, None, T, f0.weight.detach(), f2.weight.detach(),
-                                                      hs["hf"], gpred, 1, need_dx=True)
+                                                      hs["hf"], gpred, 1, need_dx=True,
+                                                      wgrad_stream=side if side is not main else None)
         side.wait_stream(main)                               # dX is ready
         # ... the level embedding and the mask fusion (whose dF starts the U-Net backward) on the image stream
         a0, a2 = m.mlp_alpha.layers[0], m.mlp_alpha.layers[2]

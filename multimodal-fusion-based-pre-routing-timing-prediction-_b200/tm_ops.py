@@ -34,6 +34,7 @@ BIAS, RELU, MASK, ACCUM = 1, 2, 4, 8
 MATH = os.environ.get("TM_MATH", "tf32x3")
 GEN_HIDDEN = os.environ.get("TM_GEN_HIDDEN", "1") != "0"  # generate Linear(<=2, hid) hidden layers instead of storing them
 FUSE_RUNS = os.environ.get("TM_FUSE_RUNS", "1") != "0"    # run-length / prefix-table mask fusion forward
+TC_MIN_N = 4           # Linear(hid, 1) (the head's last layer): a 128 x 32 tensor-core tile would be 97 % padding
 TC_MIN_K = 16          # contractions shorter than this stay on the CUDA-core kernel (K = 1, 2: pure bandwidth)
 
 
@@ -108,7 +109,7 @@ def gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, a_rows=None, c_rows=None, bias=None
     if mask is not None:
         flags |= MASK
     prec = _precision(math)
-    if prec is None or K < TC_MIN_K:
+    if prec is None or K < TC_MIN_K or N < TC_MIN_N:
         if b_is_nk:
             B, ldb = transpose(B[:, :K] if B.shape[1] != K else B), N
         call("tm_gemm_nn", M, N, K, A, lda, a_rows, B, ldb, C, ldc, c_rows, bias, mask, ldmask, flags, stream())
@@ -190,10 +191,12 @@ def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, 
     return h
 
 
-def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=False, b1=None):
+def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=False, b1=None, wgrad_stream=None):
     """Gradients of a two-layer MLP.  ``g``: dLoss/d(out) rows (optionally gathered by ``g_rows``).
     ``h``: the hidden activations mlp2_forward returned, or None when they were generated on the fly
-    (then ``b1`` is required).  Returns (dw1, db1, dw2, db2, dx or None)."""
+    (then ``b1`` is required).  Returns (dw1, db1, dw2, db2, dx or None).
+    ``wgrad_stream`` (with ``need_dx``): the data gradient is computed first on the current stream and the four
+    parameter gradients on ``wgrad_stream`` (which waits for it); the caller joins that stream before reading them."""
     hid, kin = w1.shape
     nout = w2.shape[0]
     dev = g.device
@@ -219,6 +222,17 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
              _f32c(w1), _f32c(b1), dw1, db1, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
         aux_join()
         return dw1, db1, dw2, db2, None
+    if need_dx and wgrad_stream is not None:
+        dh = torch.empty(n_rows, hid, dtype=torch.float32, device=dev)
+        gemm_nn(n_rows, hid, nout, g, ldg, _f32c(w2), hid, dh, hid, a_rows=g_rows, mask=h, ldmask=hid)
+        dx = torch.empty(n_rows, kin, dtype=torch.float32, device=dev)
+        gemm_nn(n_rows, kin, hid, dh, hid, _f32c(w1), kin, dx, kin)
+        wgrad_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(wgrad_stream):
+            gemm_tn(nout, hid, n_rows, g, ldg, h, hid, dw2, hid, a_rows=g_rows, colsum_a=db2)
+            gemm_tn(hid, kin, n_rows, dh, hid, x, ldx, dw1, kin, b_rows=rows, colsum_a=db1)
+            aux_join()
+        return dw1, db1, dw2, db2, dx
     gemm_tn(nout, hid, n_rows, g, ldg, h, hid, dw2, hid, a_rows=g_rows, colsum_a=db2)
     if kin <= 2 and hid <= 256 and hid % 4 == 0 and not need_dx and _precision() == 3:
         # Linear(<=2, hid) first layer: its whole backward (dW1, db1) is a reduction of the hidden
