@@ -21,7 +21,7 @@ import tm_dp
 import tm_lib
 import tm_ops
 import tm_unet
-from tm_graph import MaskCSR, TimingGraph
+from tm_graph import BackwardCone, MaskCSR, TimingGraph
 from tm_lib import call, stream
 from tm_ops import D, RELU, gemm_nn, gemm_tn, transpose
 
@@ -85,6 +85,16 @@ class DesignBatch:
         # the step re-runs the on-device row selection every time (captured into its CUDA graph): one capture per
         # design serves every shuffled batch of the reference's DataLoader (train.py:470-486)
         self.dynamic = bool(dynamic)
+        self._cone = None
+
+    def cone(self):
+        """``tm_graph.BackwardCone`` of this batch's endpoints (cached), or None for a dynamic batch, whose endpoints
+        change between replays of one captured step (the weight gradients then run over every row)."""
+        if self.dynamic or os.environ.get("TM_CONE", "1") == "0":
+            return None
+        if self._cone is None:
+            self._cone = BackwardCone(self.graph, self.graph.schedule(), self.endpoints)
+        return self._cone
 
     def set_endpoints(self, endpoints, endpoint_level, arrival_time, rows):
         """Refresh the endpoint batch in place (same batch size): what changes between two DataLoader batches."""
@@ -92,6 +102,7 @@ class DesignBatch:
         self.endpoint_level.copy_(endpoint_level, non_blocking=True)
         self.arrival_time.copy_(arrival_time, non_blocking=True)
         self.mask_rows.rows.copy_(rows, non_blocking=True)
+        self._cone = None
 
     @staticmethod
     def from_host(h, device, graph=None):
@@ -248,7 +259,7 @@ class DesignStep:
 
         # ---- GNN backward (main stream) next to the U-Net backward (image stream)
         call("tm_scatter_add_cols", T, D, dX, width, 0, b.endpoints, G, D, stream())
-        ggrads = tm_ops.gnn_backward(sched, saved, gp, G)
+        ggrads = tm_ops.gnn_backward(sched, saved, gp, G, cone=b.cone())
         pairs = list(zip(self.gnn_params, ggrads))
         self._assign(pairs)
         self._post_allreduce("gnn", [p for p, _ in pairs])

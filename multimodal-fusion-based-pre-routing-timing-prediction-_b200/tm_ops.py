@@ -191,12 +191,15 @@ def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, 
     return h
 
 
-def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=False, b1=None, wgrad_stream=None):
+def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=False, b1=None, wgrad_stream=None,
+                  h_rows=None):
     """Gradients of a two-layer MLP.  ``g``: dLoss/d(out) rows (optionally gathered by ``g_rows``).
     ``h``: the hidden activations mlp2_forward returned, or None when they were generated on the fly
     (then ``b1`` is required).  Returns (dw1, db1, dw2, db2, dx or None).
     ``wgrad_stream`` (with ``need_dx``): the data gradient is computed first on the current stream and the four
-    parameter gradients on ``wgrad_stream`` (which waits for it); the caller joins that stream before reading them."""
+    parameter gradients on ``wgrad_stream`` (which waits for it); the caller joins that stream before reading them.
+    ``h_rows``: row of ``h`` that belongs to MLP row i (default i) -- set when ``rows`` / ``g_rows`` are a subset of
+    the rows the forward pass ran on (``tm_graph.BackwardCone``)."""
     hid, kin = w1.shape
     nout = w2.shape[0]
     dev = g.device
@@ -233,7 +236,16 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
             gemm_tn(hid, kin, n_rows, dh, hid, x, ldx, dw1, kin, b_rows=rows, colsum_a=db1)
             aux_join()
         return dw1, db1, dw2, db2, dx
-    gemm_tn(nout, hid, n_rows, g, ldg, h, hid, dw2, hid, a_rows=g_rows, colsum_a=db2)
+    gemm_tn(nout, hid, n_rows, g, ldg, h, hid, dw2, hid, a_rows=g_rows, b_rows=h_rows, colsum_a=db2)
+    if h_rows is not None:
+        if need_dx:
+            raise RuntimeError("mlp2_backward: h_rows has no dx path")
+        # dh lives in the rows of h it belongs to, so the ReLU mask of the epilogue reads the matching row
+        dh = torch.empty(h.shape[0], hid, dtype=torch.float32, device=dev)
+        gemm_nn(n_rows, hid, nout, g, ldg, _f32c(w2), hid, dh, hid, a_rows=g_rows, c_rows=h_rows, mask=h, ldmask=hid)
+        gemm_tn(hid, kin, n_rows, dh, hid, x, ldx, dw1, kin, a_rows=h_rows, b_rows=rows, colsum_a=db1)
+        aux_join()
+        return dw1, db1, dw2, db2, None
     if kin <= 2 and hid <= 256 and hid % 4 == 0 and not need_dx and _precision() == 3:
         # Linear(<=2, hid) first layer: its whole backward (dW1, db1) is a reduction of the hidden
         # gradient, fused into the data-gradient GEMM's epilogue -- dh is never written or re-read
@@ -310,9 +322,11 @@ def gnn_forward(sched, cell_feat, net_feat, params, save=True, impl=None):
     return H, saved
 
 
-def gnn_backward(sched, saved, params, G):
+def gnn_backward(sched, saved, params, G, cone=None):
     """``G`` (N,128): dLoss/dH, consumed (overwritten with dLoss/d pre-activation).
-    Returns the 12 parameter gradients in GNN_PARAM_NAMES order."""
+    Returns the 12 parameter gradients in GNN_PARAM_NAMES order.
+    ``cone`` (``tm_graph.BackwardCone`` of the endpoints that seeded G): the weight-gradient contractions run over
+    the cone's rows only -- every other row of dLoss/dz is exactly zero."""
     (cs1w, cs1b, cs2w, cs2b, ns1w, ns1b, ns2w, ns2b, cn1w, cn1b, cn2w, cn2b) = [_f32c(p) for p in params]
     dev = G.device
     ncr = sched.n_cell_rows
@@ -326,19 +340,27 @@ def gnn_backward(sched, saved, params, G):
     dcn2b = torch.empty(D, dtype=torch.float32, device=dev)
     dcn1w = torch.empty(256, D, dtype=torch.float32, device=dev)
     dcn1b = torch.empty(256, dtype=torch.float32, device=dev)
+    cr = cone.crows if cone is not None else None
+    if cr is not None:
+        ncr = int(cr.numel())
     if ncr > 0:
-        gemm_tn(D, 256, ncr, GZC, D, saved["HID"], 256, dcn2w, 256, colsum_a=dcn2b)
-        gemm_tn(256, D, ncr, GHID, 256, saved["A"], D, dcn1w, D, colsum_a=dcn1b)
+        gemm_tn(D, 256, ncr, GZC, D, saved["HID"], 256, dcn2w, 256, a_rows=cr, b_rows=cr, colsum_a=dcn2b)
+        gemm_tn(256, D, ncr, GHID, 256, saved["A"], D, dcn1w, D, a_rows=cr, b_rows=cr, colsum_a=dcn1b)
         aux_join()
     else:
         for t in (dcn2w, dcn2b, dcn1w, dcn1b):
             t.zero_()
     cf, nf = saved["cell_feat"], saved["net_feat"]
-    nc, nn_ = int(sched.cell_class.numel()), int(sched.net_class.numel())
-    dcs1w, dcs1b, dcs2w, dcs2b, _ = mlp2_backward(cf, cf.stride(0), sched.cell_class, nc, cs1w, cs2w,
-                                                  saved["hc"], G, D, g_rows=sched.cell_class, b1=cs1b)
-    dns1w, dns1b, dns2w, dns2b, _ = mlp2_backward(nf, nf.stride(0), sched.net_class, nn_, ns1w, ns2w,
-                                                  saved["hn"], G, D, g_rows=sched.net_class, b1=ns1b)
+    cpins, npins, cpos = sched.cell_class, sched.net_class, None
+    if cone is not None:
+        cpins, npins = cone.cell_pins, cone.net_pins
+        cpos = cone.cell_pos if saved["hc"] is not None else None
+    nc, nn_ = int(cpins.numel()), int(npins.numel())
+    dcs1w, dcs1b, dcs2w, dcs2b, _ = mlp2_backward(cf, cf.stride(0), cpins, nc, cs1w, cs2w,
+                                                  saved["hc"], G, D, g_rows=cpins, b1=cs1b, h_rows=cpos)
+    dns1w, dns1b, dns2w, dns2b, _ = mlp2_backward(nf, nf.stride(0), npins, nn_, ns1w, ns2w,
+                                                  saved["hn"], G, D, g_rows=npins, b1=ns1b,
+                                                  h_rows=(cone.net_pos if cone is not None and saved["hn"] is not None else None))
     return (dcs1w, dcs1b, dcs2w, dcs2b, dns1w, dns1b, dns2w, dns2b, dcn1w, dcn1b, dcn2w, dcn2b)
 
 

@@ -757,6 +757,52 @@ def test_gnn_kernel_variants_vs_oracle(mods, impl, flow, cfg, seed):
         lib.tm_gnn_set_sync(old_flow)
 
 
+@pytest.mark.parametrize("cfg,seed,frac", [("tiny", 4, 0.1), ("c1", 5, 0.02), ("c1", 6, 1.0)])
+def test_backward_cone_weight_gradients(mods, cfg, seed, frac):
+    """tm_graph.BackwardCone: pins outside the cone of the endpoint batch have an exactly zero dLoss/dz row (checked),
+    the cone lists are what their definitions say, and the 12 parameter gradients over the cone's rows only equal the
+    all-rows gradients (same sums minus zero terms: 1e-5 of the gradient scale covers the different tile boundaries)
+    and the oracle's."""
+    ops, g_ = mods["ops"], mods["graph"]
+    d = tm_synth.make_design(seed=seed, **tm_synth.CONFIGS[cfg])
+    gnn = _gnn_params(seed).to(DEV)
+    g = _graph(mods, d)
+    sched = g.schedule()
+    rng = np.random.default_rng(seed)
+    ep = np.sort(rng.choice(d.endpoints, size=max(1, int(len(d.endpoints) * frac)), replace=False)).astype(np.int32)
+    ept = torch.from_numpy(ep).to(DEV)
+    ps = [dict(gnn.named_parameters())[k].detach() for k in ops.GNN_PARAM_NAMES]
+    H, saved = ops.gnn_forward(sched, g.ndata["cell_feat"], g.ndata["net_feat"], ps, save=True)
+    torch.manual_seed(seed)
+    G0 = torch.zeros(d.n, 128, device=DEV)
+    G0[ept.long()] = torch.randn(len(ep), 128, device=DEV)
+    Ga = G0.clone()
+    full = ops.gnn_backward(sched, saved, ps, Ga)
+    cone = g_.BackwardCone(g, sched, ept)
+    assert not bool((Ga[~cone.active] != 0).any()), "a pin outside the cone received a gradient"
+    cc, nc = sched.cell_class.long(), sched.net_class.long()
+    assert torch.equal(cone.cell_pins.long(), cc[cone.active[cc]]) and torch.equal(cc[cone.cell_pos.long()], cone.cell_pins.long())
+    assert torch.equal(cone.net_pins.long(), nc[cone.active[nc]]) and torch.equal(nc[cone.net_pos.long()], cone.net_pins.long())
+    want_rows = torch.sort(sched.crow[cone.active & (sched.crow >= 0)]).values
+    assert torch.equal(cone.crows, want_rows.int())
+    if frac < 1.0:
+        assert cone.fraction < 1.0
+    Gb = G0.clone()
+    part = ops.gnn_backward(sched, saved, ps, Gb, cone=cone)
+    assert torch.equal(Ga, Gb)
+    for k, a, b in zip(ops.GNN_PARAM_NAMES, part, full):
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 1e-5 * max(scale, 1e-30), (k, float((a - b).abs().max()), scale)
+    # and against the oracle
+    sd = {"gnn." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in gnn.state_dict().items()}
+    od = design_to_oracle(d)
+    Href = restate.gnn_propagate(sd, "gnn", d.n, od["levels"], od["net_csr"], od["cell_csr"], od["cell_feat"], od["net_feat"])
+    gref = torch.autograd.grad(Href, [sd["gnn." + k] for k in ops.GNN_PARAM_NAMES], G0.cpu())
+    flips = relu_gate_flips(H, Href)
+    for k, a, r in zip(ops.GNN_PARAM_NAMES, part, gref):
+        assert_grad_close_given_flips(a, r, k, flips)
+
+
 def test_mask_row_selection_on_device(mods):
     """tm_mask_select (th.index_select(path_masks, 0, paths), train.py:500, with repeats = oversampled paths) against
     the definition: run-length form reproduces every selected row bit-exactly, the column-major transpose lists
