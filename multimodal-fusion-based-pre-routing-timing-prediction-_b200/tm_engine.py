@@ -21,7 +21,7 @@ import tm_dp
 import tm_lib
 import tm_ops
 import tm_unet
-from tm_graph import BackwardCone, MaskCSR, TimingGraph
+from tm_graph import ConeGraph, MaskCSR, TimingGraph
 from tm_lib import call, stream
 from tm_ops import D, RELU, gemm_nn, gemm_tn, transpose
 
@@ -88,12 +88,14 @@ class DesignBatch:
         self._cone = None
 
     def cone(self):
-        """``tm_graph.BackwardCone`` of this batch's endpoints (cached), or None for a dynamic batch, whose endpoints
-        change between replays of one captured step (the weight gradients then run over every row)."""
-        if self.dynamic or os.environ.get("TM_CONE", "1") == "0":
+        """``tm_graph.ConeGraph`` of this batch's endpoints (cached): the sub-netlist that can reach an endpoint, on
+        which ``DesignStep(..., prune=True)`` runs -- same predictions, loss and gradients over a fraction of the pins.
+        None for a dynamic batch, whose endpoints change between replays of one captured step (the step then runs on
+        the whole netlist).  The endpoints of a non-dynamic batch must not be modified in place."""
+        if self.dynamic:
             return None
         if self._cone is None:
-            self._cone = BackwardCone(self.graph, self.graph.schedule(), self.endpoints)
+            self._cone = ConeGraph(self.graph, self.endpoints)
         return self._cone
 
     def set_endpoints(self, endpoints, endpoint_level, arrival_time, rows):
@@ -149,8 +151,14 @@ class PreparedDesign:
 
 
 class DesignStep:
-    def __init__(self, model, cnn, process_group=None, world_size=1):
+    def __init__(self, model, cnn, process_group=None, world_size=1, prune=None):
+        """``prune`` (default: environment ``TM_CONE=1``, else off): run the netlist branch on the sub-netlist that can
+        reach the batch's endpoints (``tm_graph.ConeGraph``) instead of the whole netlist.  Predictions, loss and every
+        gradient are unchanged (``tests/test_gpu_parity.py::test_design_step_on_cone_subnetlist``); pins that no
+        endpoint of the batch depends on are simply not evaluated.  Off by default: the headline step evaluates every
+        pin, as the reference does."""
         self.model, self.cnn = model, cnn
+        self.prune = (os.environ.get("TM_CONE", "0") == "1") if prune is None else bool(prune)
         self.pg, self.world = process_group, world_size
         self.comm_stream = torch.cuda.Stream() if world_size > 1 else None
         # The image branch (U-Net) and the netlist branch (GNN) are independent until the fusion, and
@@ -179,12 +187,12 @@ class DesignStep:
                                  a2.bias.detach(), X[:, 2 * D:], width)
         return dict(X=X, wt=wt, ha=ha, lv=lv, width=width)
 
-    def _head_netlist_side(self, H, b, hs):
+    def _head_netlist_side(self, H, b, hs, endpoints=None):
         """Endpoint rows of H into columns 0..D of X, then ``mlp_fuse``."""
         m = self.model
         T = int(b.endpoints.numel())
         X, width = hs["X"], hs["width"]
-        call("tm_gather_cols", T, D, H, D, b.endpoints, X, width, 0, stream())
+        call("tm_gather_cols", T, D, H, D, b.endpoints if endpoints is None else endpoints, X, width, 0, stream())
         f0, f2 = m.mlp_fuse.layers[0], m.mlp_fuse.layers[2]
         pred = torch.empty(T, f2.weight.shape[0], dtype=torch.float32, device=H.device)
         hs["hf"] = tm_ops.mlp2_forward(X, width, None, T, f0.weight.detach(), f0.bias.detach(), f2.weight.detach(),
@@ -216,7 +224,11 @@ class DesignStep:
             b.mask_rows.rebuild()                            # this batch's mask-row selection (7 small kernels, no host sync)
         side = self.image_stream if (self.overlap and self.image_stream is not None) else main
         side.wait_stream(main)                               # fork: inputs / parameters are ready on `main`
-        sched = b.graph.schedule()
+        # the netlist branch runs on the sub-netlist that can reach this batch's endpoints (tm_graph.ConeGraph)
+        cone = b.cone() if self.prune else None
+        sched = (cone.graph if cone is not None else b.graph).schedule()
+        endpoints = cone.endpoints if cone is not None else b.endpoints
+        x_rows = (cone.cell_x_rows, cone.net_x_rows) if cone is not None else None
         gp = [p.detach() for p in self.gnn_params]
         # the longer chain is enqueued first so the host's launch time for the other one overlaps it
         # (per-level kernels while the image stream runs next to them: measured 5.07 ms/step against 5.49 ms
@@ -224,7 +236,7 @@ class DesignStep:
         T = int(b.endpoints.numel())
         X = torch.empty(T, D + D + m.global_dim, dtype=torch.float32, device=dev)     # head input [H rows | fused map | level]
         G = torch.empty(sched.n, D, dtype=torch.float32, device=dev)                 # dLoss/dH, seeded at the endpoints
-        H, saved = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat, gp, save=True,
+        H, saved = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat, gp, save=True, x_rows=x_rows,
                                       impl=16 if side is not main and os.environ.get("TM_GNN_IMPL") is None else None)
         with torch.cuda.stream(side):
             fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
@@ -234,7 +246,7 @@ class DesignStep:
             hs = self._head_image_side(b, feat, X)
             G.zero_()
         main.wait_stream(side)                               # join: the head needs the fused feature map
-        pred = self._head_netlist_side(H, b, hs)
+        pred = self._head_netlist_side(H, b, hs, endpoints)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         gpred = torch.empty(T, 1, dtype=torch.float32, device=dev)
         call("tm_mse", T, pred, b.arrival_time, loss, gpred, float(grad_scale), stream())
@@ -258,8 +270,8 @@ class DesignStep:
             self._post_allreduce("head", [p for p, _ in head])
 
         # ---- GNN backward (main stream) next to the U-Net backward (image stream)
-        call("tm_scatter_add_cols", T, D, dX, width, 0, b.endpoints, G, D, stream())
-        ggrads = tm_ops.gnn_backward(sched, saved, gp, G, cone=b.cone())
+        call("tm_scatter_add_cols", T, D, dX, width, 0, endpoints, G, D, stream())
+        ggrads = tm_ops.gnn_backward(sched, saved, gp, G)
         pairs = list(zip(self.gnn_params, ggrads))
         self._assign(pairs)
         self._post_allreduce("gnn", [p for p, _ in pairs])

@@ -276,13 +276,15 @@ GNN_PARAM_NAMES = ("fc_cell_self.layers.0.weight", "fc_cell_self.layers.0.bias",
                    "fc_cell_neigh.layers.2.weight", "fc_cell_neigh.layers.2.bias")
 
 
-def gnn_forward(sched, cell_feat, net_feat, params, save=True, impl=None):
+def gnn_forward(sched, cell_feat, net_feat, params, save=True, impl=None, x_rows=None):
     """Full propagation over every level.  ``params``: the 12 tensors of GNN_PARAM_NAMES.
     Returns ``(H, saved)``; H is (N, 128) with zeros on pins outside the schedule.
     ``impl``: back end for this call (``tm_gnn_set_impl`` bits; None = the process default, which runs the
     forward as ONE persistent cluster kernel).  The persistent kernel owns every SM while it runs, so a
     caller that overlaps the propagation with other streams (``DesignStep``) asks for 0, the chain of
-    small per-level kernels that co-resides with them."""
+    small per-level kernels that co-resides with them.
+    ``x_rows`` = (rows of ``cell_feat`` for ``sched.cell_class``, rows of ``net_feat`` for ``sched.net_class``) when the
+    schedule is a sub-netlist whose pins are renumbered (``tm_graph.ConeGraph``); default: the pin ids themselves."""
     (cs1w, cs1b, cs2w, cs2b, ns1w, ns1b, ns2w, ns2b, cn1w, cn1b, cn2w, cn2b) = [_f32c(p) for p in params]
     if cn2w.shape[0] != D or cs2w.shape[0] != D or ns2w.shape[0] != D or cn1w.shape != (256, D):
         raise RuntimeError("the CUDA propagation kernels are built for out_feat_dim = hidden_feat_dim = 128 "
@@ -293,9 +295,10 @@ def gnn_forward(sched, cell_feat, net_feat, params, save=True, impl=None):
     n = sched.n
     S = torch.empty(n, D, dtype=torch.float32, device=dev)
     nc, nn_ = int(sched.cell_class.numel()), int(sched.net_class.numel())
-    hc = mlp2_forward(cell_feat, cell_feat.stride(0), sched.cell_class, nc, cs1w, cs1b, cs2w, cs2b, S, D,
+    xc, xn = x_rows if x_rows is not None else (sched.cell_class, sched.net_class)
+    hc = mlp2_forward(cell_feat, cell_feat.stride(0), xc, nc, cs1w, cs1b, cs2w, cs2b, S, D,
                       out_rows=sched.cell_class, math=_recurrence_math())
-    hn = mlp2_forward(net_feat, net_feat.stride(0), sched.net_class, nn_, ns1w, ns1b, ns2w, ns2b, S, D,
+    hn = mlp2_forward(net_feat, net_feat.stride(0), xn, nn_, ns1w, ns1b, ns2w, ns2b, S, D,
                       out_rows=sched.net_class, math=_recurrence_math())
     # every scheduled pin's row is written by its level's kernel: only pins outside the schedule need the zero fill
     # (170 MB = 42 us of the config-2 step when every pin is scheduled, as in the reference's designs)
@@ -318,7 +321,7 @@ def gnn_forward(sched, cell_feat, net_feat, params, save=True, impl=None):
     finally:
         if old is not None:
             tm_lib.lib().tm_gnn_set_impl(old)
-    saved = dict(H=H, A=A, LSE=LSE, HID=HID, hc=hc, hn=hn, cell_feat=cell_feat, net_feat=net_feat) if save else None
+    saved = dict(H=H, A=A, LSE=LSE, HID=HID, hc=hc, hn=hn, cell_feat=cell_feat, net_feat=net_feat, x_rows=x_rows) if save else None
     return H, saved
 
 
@@ -352,13 +355,17 @@ def gnn_backward(sched, saved, params, G, cone=None):
             t.zero_()
     cf, nf = saved["cell_feat"], saved["net_feat"]
     cpins, npins, cpos = sched.cell_class, sched.net_class, None
+    xc, xn = saved.get("x_rows") or (cpins, npins)            # feature rows of the two classes
     if cone is not None:
+        if saved.get("x_rows") is not None:
+            raise RuntimeError("gnn_backward: a BackwardCone on top of a renumbered sub-netlist is not supported")
         cpins, npins = cone.cell_pins, cone.net_pins
+        xc, xn = cpins, npins
         cpos = cone.cell_pos if saved["hc"] is not None else None
     nc, nn_ = int(cpins.numel()), int(npins.numel())
-    dcs1w, dcs1b, dcs2w, dcs2b, _ = mlp2_backward(cf, cf.stride(0), cpins, nc, cs1w, cs2w,
+    dcs1w, dcs1b, dcs2w, dcs2b, _ = mlp2_backward(cf, cf.stride(0), xc, nc, cs1w, cs2w,
                                                   saved["hc"], G, D, g_rows=cpins, b1=cs1b, h_rows=cpos)
-    dns1w, dns1b, dns2w, dns2b, _ = mlp2_backward(nf, nf.stride(0), npins, nn_, ns1w, ns2w,
+    dns1w, dns1b, dns2w, dns2b, _ = mlp2_backward(nf, nf.stride(0), xn, nn_, ns1w, ns2w,
                                                   saved["hn"], G, D, g_rows=npins, b1=ns1b,
                                                   h_rows=(cone.net_pos if cone is not None and saved["hn"] is not None else None))
     return (dcs1w, dcs1b, dcs2w, dcs2b, dns1w, dns1b, dns2w, dns2b, dcn1w, dcn1b, dcn2w, dcn2b)

@@ -564,6 +564,59 @@ def test_design_step_mixed_precision_vs_golden(mods):
         assert_close(p.grad, g, 2e-2, 2e-2, "cnn." + k)
 
 
+@pytest.mark.parametrize("cfg,seed,keep", [("tiny", 3, 0.15), ("c1", 4, 0.03), ("c1", 5, 1.0)])
+def test_design_step_on_cone_subnetlist(mods, cfg, seed, keep):
+    """tm_graph.ConeGraph: the fused step on the sub-netlist that can reach the batch's endpoints gives the same
+    predictions and loss (each pin's arithmetic is unchanged: 1e-6) and the same gradient of EVERY parameter (sums over
+    the same non-zero rows, different tile boundaries: 2e-5 of the gradient's scale) as the step on the whole netlist;
+    the sub-netlist keeps every in-edge of its pins and their original levels."""
+    eng, g_ = mods["engine"], mods["graph"]
+    d = tm_synth.make_design(seed=seed, **tm_synth.CONFIGS[cfg])
+    rng = np.random.default_rng(seed)
+    T = len(d.endpoints)
+    sel = np.sort(rng.choice(T, size=max(2, int(T * keep)), replace=False))
+    model, cnn = eng.build_models(d.map_size, seed=seed, device=DEV)
+    host = eng.HostDesign(d, pin=False)
+
+    def batch():
+        b = eng.DesignBatch.from_host(host, DEV)
+        idx = torch.from_numpy(sel).to(DEV)
+        return eng.DesignBatch(b.graph, b.mask_csr, b.endpoints[idx].contiguous(), b.endpoint_level[idx].contiguous(),
+                               b.arrival_time[idx].contiguous(), b.image, cell_feat=b.cell_feat, net_feat=b.net_feat,
+                               rows=idx.int().contiguous())
+
+    params = list(model.named_parameters()) + [("cnn." + k, p) for k, p in cnn.named_parameters()]
+    out = {}
+    for mode in ("0", "1"):
+        step = eng.DesignStep(model, cnn, prune=(mode == "1"))
+        b = batch()
+        for _, p in params:
+            p.grad = None
+        loss, pred = step.run(b)
+        torch.cuda.synchronize()
+        assert (b._cone is not None) == (mode == "1")         # the sub-netlist is only built (and used) when asked for
+        out[mode] = (loss.clone(), pred.clone(), {k: p.grad.clone() for k, p in params if p.grad is not None}, b.cone())
+    cone = out["1"][3]
+    if keep < 1.0:
+        assert cone.fraction < 1.0
+    # structure: every in-edge of a cone pin is inside the cone, levels are the original ones
+    full = b.graph.schedule()
+    for et, (s_, d_) in b.graph._edges.items():
+        s_, d_ = s_.to(DEV).long(), d_.to(DEV).long()
+        k = cone.active[d_]
+        assert bool(cone.active[s_[k]].all())
+        assert int(k.sum()) == int(cone.graph._edges[et][0].numel())
+    assert torch.equal(cone.graph.schedule().level, full.level[cone.pins.long()])
+    assert torch.equal(cone.pins[cone.endpoints.long()].long(), b.endpoints.long())
+    assert_close(out["1"][1], out["0"][1], 1e-6, 1e-6, "pred")
+    assert_close(out["1"][0], out["0"][0], 1e-6, 1e-7, "loss")
+    assert set(out["1"][2]) == set(out["0"][2])
+    for k, gfull in out["0"][2].items():
+        scale = max(float(gfull.abs().max()), 1e-30)
+        err = float((out["1"][2][k] - gfull).abs().max())
+        assert err <= 2e-5 * scale, (k, err, scale)
+
+
 def test_prepared_design_graph_replay(mods):
     """DesignStep.prepare(): the captured CUDA-graph step, fed new per-step VALUES from host memory,
     reproduces the eager two-stream step bit for bit (loss, predictions, every gradient), also when two
