@@ -645,6 +645,32 @@ def main():
                 extra["mixed_precision_step"] = {"error": repr(e)}
             finally:
                 cnn.math = None
+            # the same fp32-class step with the netlist branch restricted to the sub-netlist that can reach this batch's
+            # endpoints (DesignStep(prune=True), tm_graph.ConeGraph): identical loss / predictions / gradients, pins no
+            # endpoint depends on are not evaluated.  Reported NEXT to the headline, which evaluates every pin.
+            try:
+                step_p = tm_engine.DesignStep(model, cnn, prune=True)
+                batch_p = tm_engine.DesignBatch.from_host(host, dev, graph=batch.graph)
+                run_p = step_p.capture(batch_p)
+                for _ in range(3):
+                    run_p()
+                torch.cuda.synchronize()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(args.steps):
+                    loss_p, _ = run_p()
+                p1.record()
+                torch.cuda.synchronize()
+                ms_p = p0.elapsed_time(p1) / args.steps
+                cone = batch_p.cone()
+                extra["pruned_step"] = {"value": 1e3 / ms_p, "unit": "designs/s", "ms_per_step": ms_p, "loss": float(loss_p.item()),
+                                        "pins_evaluated": cone.n_active, "pins": int(sched.n), "fraction": cone.fraction,
+                                        "note": "not the headline: DesignStep(prune=True) evaluates only the pins from which one of "
+                                                "the batch's 1 350 endpoints is reachable (same loss, predictions and gradients: "
+                                                "tests/test_gpu_parity.py::test_design_step_on_cone_subnetlist)"}
+                step_p.close()
+            except Exception as e:                                   # noqa: BLE001
+                extra["pruned_step"] = {"error": repr(e)}
         if world == 1 and not args.no_configs and args.config == "c2":
             # BASELINE configs 3 (GNN only, ~1M pins) and 4 (U-Net alone, 32 x 512x512, bf16): device timings next to
             # the headline (profiles/bench_configs.py; parity for both lives in tests/test_gpu_configs.py)
