@@ -518,6 +518,100 @@ __device__ __forceinline__ void store4<PlainEpilogue>(const PlainEpilogue& ep, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-direct epilogue (tf_gemm_kernel): a lane owns ONE row of the tile (TMEM lane = tile row) and writes the 32
+// columns of a chunk straight from the tcgen05.ld registers as eight 128-bit stores -- no shared-memory transpose, the
+// row handle and the vector-path predicates resolved once per tile.  Measured on the 229 819 x 128 x 256 product the
+// transposing epilogue was the critical path of the whole kernel: 23 000 cycles per 128 x 128 tile (a single warp per
+// scheduler walking ~1 500 dependent 64-bit index / predicate instructions) against 17 000 for the main loop.  The
+// eight stores of a lane fill one 128-byte line, so L2 sees whole lines.
+// ---------------------------------------------------------------------------------------------
+template <class EP>
+struct RowStore {                 // generic: element-wise through EP::store
+  typename EP::Row rw;
+  __device__ __forceinline__ void open(const EP& ep, int64_t m, int z, int64_t N) { rw = epi_row<EP>(ep, m, z); }
+  __device__ __forceinline__ void chunk(const EP& ep, int64_t n, int64_t N, const float (&v)[32]) const {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (n + i < N) ep.store(rw, n + i, v[i]);
+  }
+};
+template <>
+struct RowStore<PartialEpilogue> {
+  float* p;
+  bool vec;
+  __device__ __forceinline__ void open(const PartialEpilogue& ep, int64_t m, int z, int64_t N) {
+    p = ep.P + ((int64_t)z * ep.M + m) * ep.N;
+    vec = (N & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.P) & 15) == 0;
+  }
+  __device__ __forceinline__ void chunk(const PartialEpilogue& ep, int64_t n, int64_t N, const float (&v)[32]) const {
+    float* q = p + n;
+    if (vec && n + 32 <= N) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st4(q + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n + i < N) q[i] = v[i];
+    }
+  }
+};
+template <>
+struct RowStore<PlainEpilogue> {
+  float* p;
+  const float* mp;
+  bool vec;
+  __device__ __forceinline__ void open(const PlainEpilogue& ep, int64_t m, int z, int64_t N) {
+    const int64_t r = ep.c_rows ? (int64_t)ep.c_rows[m] : m;
+    p = ep.C + r * ep.ldc;
+    mp = (ep.flags & TM_EPI_MASK) ? ep.mask + r * ep.ldmask : nullptr;
+    vec = (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0 &&
+          (!(ep.flags & TM_EPI_BIAS) || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
+          (!mp || ((ep.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0));
+  }
+  __device__ __forceinline__ void chunk(const PlainEpilogue& ep, int64_t n, int64_t N, const float (&v)[32]) const {
+    const int flags = ep.flags;
+    if (vec && n + 32 <= N) {
+      float4 mk[8], old[8];
+      if (flags & TM_EPI_MASK) {                   // row operands first: all loads in flight before the first store
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mk[j] = ld4(mp + n + 4 * j);
+      }
+      if (flags & TM_EPI_ACCUM) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) old[j] = ld4(p + n + 4 * j);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (flags & TM_EPI_BIAS) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4 * j));
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (flags & TM_EPI_ACCUM) { o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w; }
+        if (flags & TM_EPI_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (flags & TM_EPI_MASK) {
+          o.x = mk[j].x > 0.f ? o.x : 0.f; o.y = mk[j].y > 0.f ? o.y : 0.f;
+          o.z = mk[j].z > 0.f ? o.z : 0.f; o.w = mk[j].w > 0.f ? o.w : 0.f;
+        }
+        st4(p + n + 4 * j, o);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (n + i < N) {
+          float o = v[i];
+          if (flags & TM_EPI_BIAS) o += ep.bias[n + i];
+          if (flags & TM_EPI_ACCUM) o += p[n + i];
+          if (flags & TM_EPI_RELU) o = fmaxf(o, 0.f);
+          if (flags & TM_EPI_MASK) o = (mp[n + i] > 0.f) ? o : 0.f;
+          p[n + i] = o;
+        }
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // kernel configuration
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int parts_of(int split) { return split == 1 ? 1 : (split == 3 ? 2 : 3); }
@@ -1279,45 +1373,17 @@ tf_gemm_kernel(AL al, BL bl, EP ep, int64_t M, int64_t N, TileMap tm, int* __res
       int64_t m0, nq, kb0; int zi, nkb;
       tm.decode(t, m0, nq, zi, kb0, nkb);
       const int64_t n0 = nq * BN;
-      typename EP::Row rws[8];                                            // this lane's rows of the 8 store passes
-#pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
-        rws[pass] = epi_row<EP>(ep, m < M ? m : M - 1, zi);
-      }
+      const int64_t m = m0 + warp * 32 + lane;                            // this lane's row of the tile (TMEM lane)
+      const bool live = m < M && !(TM_DBGBITS & 1);
+      RowStore<EP> rs;
+      rs.open(ep, m < M ? m : M - 1, zi, N);
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         if (n0 + c >= N) break;
-        const float4 b4 = epi_bias4<EP>(ep, n0 + c + (lane & 7) * 4, N);
         float v[32];
-        tmem_ld32(trow + (uint32_t)c, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
-        __syncwarp();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          EpiAux aux[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {                                   // row operands first (loads in flight together)
-            const int pass = half * 4 + q;
-            const int64_t m = m0 + warp * 32 + pass * 4 + (lane >> 3);
-            const int64_t n = n0 + c + (lane & 7) * 4;
-            aux[q] = (m < M && n < N) ? epi_aux<EP>(ep, rws[pass], n, N) : EpiAux{};
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {                                   // 8 lanes x 4 columns per row, 4 rows per pass
-            const int pass = half * 4 + q;
-            const int r = pass * 4 + (lane >> 3), cq = (lane & 7) * 4;
-            const int64_t m = m0 + warp * 32 + r;
-            const int64_t n = n0 + c + cq;
-            if (m < M && n < N && !(TM_DBGBITS & 1)) {
-              const float o[4] = {scr[r * 33 + cq], scr[r * 33 + cq + 1], scr[r * 33 + cq + 2], scr[r * 33 + cq + 3]};
-              store4<EP>(ep, rws[pass], n, N, o, b4, aux[q]);
-            }
-          }
-        }
-        __syncwarp();
+        tmem_ld32(trow + (uint32_t)c, v);                                 // (warp-collective: every lane takes part)
+        if (live) rs.chunk(ep, n0 + c, N, v);
       }
       tc_fence_before();
       __syncwarp();
