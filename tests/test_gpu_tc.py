@@ -93,3 +93,54 @@ def test_tc_conv(lib, B, H, W, Cin, Cout, k, precision):
     lib.call("tm_conv_unpack_wgrad", Cout, Cin, k, dwf, dw, lib.stream())
     assert_close(dw, gw, *TOL[precision], "tc wgrad")
     assert int(err.item()) == 0
+
+
+@pytest.mark.parametrize("precision", [3, 4])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,relu", [(1, 32, 32, 128, 128, 3, False), (1, 64, 64, 64, 64, 3, True),
+                                                   (1, 32, 32, 256, 64, 3, False), (2, 16, 16, 64, 128, 3, False),
+                                                   (1, 256, 256, 16, 16, 3, False)])
+def test_tc_conv_splitk(lib, B, H, W, Cin, Cout, k, relu, precision):
+    """tm_tc_conv2d_nhwc_splitk: the K = 9 Cin range split over CTAs on the small deep maps of one 256 x 256 design
+    (forward and the data gradient through the same entry), bias / ReLU applied by the folding pass, into a strided
+    output (a concat buffer); the last shape is large enough that no split is chosen (workspace size 0)."""
+    torch.manual_seed(H + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, device=DEV)
+    w = torch.randn(Cout, Cin, k, k, device=DEV) * 0.05
+    bias = torch.randn(Cout, device=DEV)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)
+    if relu:
+        ref = ref.relu()
+    xs = x.permute(0, 2, 3, 1).contiguous()
+    wf = torch.empty(k * k * Cin, Cout, device=DEV)
+    wb = torch.empty(k * k * Cout, Cin, device=DEV)
+    lib.call("tm_conv_pack_weight", Cout, Cin, k, w.contiguous(), wf, wb, lib.stream())
+    err = _err()
+    ldy = Cout + 8
+    y = torch.full((B, H, W, ldy), 7.0, device=DEV)
+    nb = lib.ws_bytes("tm_tc_conv2d_splitk_ws", B, H, W, Cin, Cout, k, precision)
+    assert (nb == 0) == (H * W * B >= 148 * 128 // 2)
+    lib.call("tm_tc_conv2d_nhwc_splitk", B, H, W, Cin, Cout, k, xs, Cin, wf, bias, y, ldy, 2 if relu else 0, precision,
+             lib.workspace(nb, DEV) if nb else None, nb, err, lib.stream())
+    assert_close(y[..., :Cout].permute(0, 3, 1, 2), ref, *TOL[precision], "split-K fprop")
+    assert bool((y[..., Cout:] == 7.0).all()), "columns past Cout were touched"
+    assert int(err.item()) == 0
+
+
+@pytest.mark.parametrize("R,C,gather", [(5000, 128, False), (70001, 256, True), (3, 128, False), (4097, 36, False), (300, 130, True)])
+def test_colsum(lib, R, C, gather):
+    """tm_colsum: vectorised path (C % 4 == 0, 256-row chunks) and the scalar fall-back, with and without a row list,
+    accumulate on and off, bit-deterministic."""
+    torch.manual_seed(R + C)
+    X = torch.randn(R + 50, C, device=DEV)
+    rows = torch.randint(0, R + 50, (R,), device=DEV, dtype=torch.int32) if gather else None
+    ref = (X[rows.long()] if gather else X[:R]).double().sum(0)
+    nb = lib.ws_bytes("tm_colsum_ws", R, C)
+    out = torch.full((C,), 3.0, device=DEV)
+    lib.call("tm_colsum", R, C, X, C, rows, out, 0, lib.workspace(nb, DEV), nb, lib.stream())
+    assert_close(out, ref, 1e-5, 1e-4, "colsum")
+    out2 = torch.full((C,), 3.0, device=DEV)
+    lib.call("tm_colsum", R, C, X, C, rows, out2, 1, lib.workspace(nb, DEV), nb, lib.stream())
+    assert_close(out2, ref + 3.0, 1e-5, 1e-4, "colsum accumulate")
+    out3 = torch.empty(C, device=DEV)
+    lib.call("tm_colsum", R, C, X, C, rows, out3, 0, lib.workspace(nb, DEV), nb, lib.stream())
+    assert torch.equal(out, out3)
