@@ -412,6 +412,14 @@ int tm_tc_mlp1_bwd_fused(int64_t M, int64_t N, int64_t K, const float* G, int64_
  * instead of stored (2 FMAs per element; H = NULL above then regenerates the ReLU mask from W1, b1):
  *   forward:  out[out_rows[m], 0:N] = relu(X[x_rows[m]] @ W1^T + b1) @ W2^T + b2     (W2: [N,K] as stored)
  *   wgrad2:   dW2[Mo, hid] = G[g_rows]^T @ relu(X[x_rows] @ W1^T + b1)               (ws: tm_tc_gemm_tn_ws) */
+/* The forward of that MLP for the reference's sizes (hidden 256, 128 outputs: fc_net_self, model.py:46,151) as ONE
+ * fused kernel: generator warps write the hidden tile straight into fp16 two-term-split operand planes, W2 is split
+ * once and stays resident in shared memory, tcgen05.mma with the accumulators in TMEM (csrc/tm_selfmlp.cu).
+ * ws: tm_selfmlp_ws_bytes(). */
+size_t tm_selfmlp_ws_bytes(void);
+int tm_selfmlp_gen_forward(int64_t M, const float* X, int64_t ldx, const int32_t* x_rows, int64_t kx,
+                           const float* W1, const float* b1, const float* W2, const float* b2, float* out,
+                           int64_t ldo, const int32_t* out_rows, void* ws, size_t ws_bytes, void* stream);
 int tm_tc_mlp2_smallk_forward(int64_t M, int64_t K, int64_t N, const float* X, int64_t ldx, const int32_t* x_rows,
                               int64_t kx, const float* W1, const float* b1, const float* W2, const float* b2,
                               float* out, int64_t ldo, const int32_t* out_rows, int precision, int* err,

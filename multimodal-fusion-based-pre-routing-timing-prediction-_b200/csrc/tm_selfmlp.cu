@@ -1,0 +1,350 @@
+// Hoisted self-term MLP of the net pins, fused (round 2):  out[out_rows[m]] = W2 relu(W1 x[x_rows[m]] + b1) + b2
+// with x of width 1 or 2 (fc_net_self, model.py:46,151: Linear(2, 256) -> ReLU -> Linear(256, 128) over every odd-level
+// pin -- 229 819 rows in config 2).  The hidden layer costs two FMAs per element, so it is never stored: generator
+// warps write it straight into the tensor-core operand planes, chunk by chunk, and the second layer runs on
+// tcgen05.mma with the accumulator in TMEM.
+//
+// Why a kernel of its own: the generic streaming GEMM (tm_tc.cuh) is bound by the shared-memory traffic of fp32-sized
+// operands -- 2 100 cycles per 32-wide k-block, 266 us for this product.  Here
+//   * operands are the fp16 two-term split of tm_gnn_persist.cu (x s = hi + lo, lo' = fp16((x s - hi) 2^11), per-row
+//     power-of-two scale s; hi hi -> acc_main, hi lo' + lo' hi -> acc_corr, result = (main + 2^-11 corr) / s: ~22-bit
+//     products at the fp16 MMA rate and half the operand bytes);
+//   * W2 is split ONCE (tm_selfmlp_pack) and stays resident in shared memory (2 x 64 KB planes), so a k-step reads
+//     8 KB instead of 24 KB and nothing is re-staged per tile;
+//   * the per-row scale comes from a bound (|x0| max|w0| + |x1| max|w1| + max|b1| >= every hidden unit of the row), so
+//     the row is generated once, with no maximum pass.
+// Roles of the 416 threads of a persistent CTA (one per SM): warps 0-3 epilogue (TMEM lane quarter = warp, a lane
+// owns one output row and writes it as 128-bit stores), warp 4 issues the MMAs, warps 5-12 generate.  The hidden
+// tile moves through two 64-wide chunk buffers (full / empty mbarriers), the accumulators (main + corr, 128 columns
+// each) are double-buffered in TMEM so the epilogue of tile t overlaps the products of tile t+1.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "tm_common.cuh"
+
+using namespace tmk;
+
+namespace {
+constexpr int TM = 128;            // rows per tile (MMA M)
+constexpr int HIDF = 256;          // hidden width (MMA K)
+constexpr int NOUT = 128;          // outputs (MMA N)
+constexpr int KC = 64;             // hidden units per chunk buffer
+constexpr int NCH = HIDF / KC;     // chunks per tile
+constexpr int EPI_W = 4, GEN_W = 8;
+constexpr int MMA_WARP = EPI_W, GEN_WARP0 = EPI_W + 1;
+constexpr int THREADS = (EPI_W + 1 + GEN_W) * 32;    // 416
+static_assert(GEN_W * 32 == 2 * TM, "two generator threads per tile row");
+
+// K-major SWIZZLE_NONE operand planes (core matrix = 8 rows x 16 bytes):
+//   off(row, k) = (row / 8) * SBO + (k / 8) * LBO + (row % 8) * 16 + (k % 8) * 2          [bytes, fp16]
+constexpr uint32_t W_LBO = 128, W_SBO = (HIDF / 8) * W_LBO, W_PLANE = (NOUT / 8) * W_SBO;   // 64 KB
+constexpr uint32_t H_LBO = 128, H_SBO = (KC / 8) * H_LBO, H_PLANE = (TM / 8) * H_SBO;      // 16 KB
+constexpr uint32_t OFF_W = 0;                              // Whi, Wlo
+constexpr uint32_t OFF_H = OFF_W + 2 * W_PLANE;            // [buffer 2][hi, lo]
+constexpr uint32_t OFF_P = OFF_H + 4 * H_PLANE;            // w0[256], w1[256], b1[256], b2[128], maxima[4]
+constexpr uint32_t OFF_BAR = OFF_P + (3 * HIDF + NOUT + 4) * 4;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 16 * 8 + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+constexpr uint32_t TM_COLS = 512;                          // [acc buffer 2][main 128 | corr 128]
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (spin > (1u << 22)) __trap();       // a lost arrival must fail the launch, not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = fp16 (format 0), both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// s = 2^-e, inv = 2^e with 2^e <= bound < 2^(e+1): every |value| <= bound lands in [0, 2) after scaling
+__device__ __forceinline__ void bound_scale(float bound, float& s, float& inv) {
+  int e = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 127;
+  e = max(-100, min(e, 100));
+  s = __uint_as_float((uint32_t)(127 - e) << 23);
+  inv = __uint_as_float((uint32_t)(127 + e) << 23);
+}
+
+// W2 [NOUT][HIDF] fp32 (nn.Linear layout: K-major as it is) -> the shared-memory image of the (hi, lo') planes
+__global__ void selfmlp_pack_kernel(const float* __restrict__ W2, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NOUT * HIDF) return;
+  const int n = i / HIDF, k = i - n * HIDF;
+  __half h, l;
+  split_h(W2[i], h, l);
+  const uint32_t off = (uint32_t)(n >> 3) * W_SBO + (uint32_t)(k >> 3) * W_LBO + (uint32_t)(n & 7) * 16 + (uint32_t)(k & 7) * 2;
+  *reinterpret_cast<__half*>(out + off) = h;
+  *reinterpret_cast<__half*>(out + W_PLANE + off) = l;
+}
+
+struct Args {
+  int64_t M;
+  const float* X;
+  int64_t ldx;
+  const int* x_rows;
+  int kx;
+  const float* W1;      // [HIDF][kx]
+  const float* b1;
+  const float* b2;
+  const uint8_t* wplanes;
+  float* out;
+  int64_t ldo;
+  const int* out_rows;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* w0_s = reinterpret_cast<float*>(smem + OFF_P);
+  float* w1_s = w0_s + HIDF;
+  float* b1_s = w1_s + HIDF;
+  float* b2_s = b1_s + HIDF;
+  float* max_s = b2_s + NOUT;                                  // max|w0|, max|w1|, max|b1|
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t *h_full = bars, *h_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6, *wbar = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.M + TM - 1) / TM;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], GEN_W); mbar_init(&h_empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_W);
+    }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+    // resident weight planes: 128 KB in four bulk copies
+    const uint32_t bar = smem_u32(wbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * W_PLANE) : "memory");
+    for (int i = 0; i < 4; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(smem + OFF_W + i * (W_PLANE / 2))), "l"(a.wplanes + (size_t)i * (W_PLANE / 2)), "r"(W_PLANE / 2), "r"(bar)
+                   : "memory");
+  }
+  for (int j = tid; j < HIDF; j += THREADS) {
+    w0_s[j] = a.W1[(size_t)j * a.kx];
+    w1_s[j] = a.kx > 1 ? a.W1[(size_t)j * a.kx + 1] : 0.f;
+    b1_s[j] = a.b1[j];
+  }
+  for (int j = tid; j < NOUT; j += THREADS) b2_s[j] = a.b2 ? a.b2[j] : 0.f;
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {                                            // bounds of the first layer (for the per-row scale)
+    float m0 = 0.f, m1 = 0.f, mb = 0.f;
+    for (int j = lane; j < HIDF; j += 32) { m0 = fmaxf(m0, fabsf(w0_s[j])); m1 = fmaxf(m1, fabsf(w1_s[j])); mb = fmaxf(mb, fabsf(b1_s[j])); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    if (lane == 0) { max_s[0] = m0; max_s[1] = m1; max_s[2] = mb; }
+  }
+  __syncthreads();
+  const uint32_t tmem_base = *tmem_slot;
+  const float wm0 = max_s[0], wm1 = max_s[1], bm = max_s[2];
+  auto row_x = [&](int64_t m, float& x0, float& x1) {
+    x0 = 0.f; x1 = 0.f;
+    if (m < a.M) {
+      const float* xp = a.X + (a.x_rows ? (int64_t)a.x_rows[m] : m) * a.ldx;
+      x0 = xp[0];
+      if (a.kx > 1) x1 = xp[1];
+    }
+  };
+
+  if (warp >= GEN_WARP0) {
+    // ======================= generators: hidden chunks -> operand planes =======================
+    const int gt = tid - GEN_WARP0 * 32;
+    const int row = gt & (TM - 1), kh = gt >> 7;              // this thread: one tile row, k-groups 4 kh .. 4 kh + 3 of a chunk
+    uint32_t g = 0;                                           // chunk counter (buffer = g & 1)
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      float x0, x1;
+      row_x(t * TM + row, x0, x1);
+      float s, inv;
+      bound_scale(fmaf(fabsf(x0), wm0, fmaf(fabsf(x1), wm1, bm)), s, inv);
+      for (int c = 0; c < NCH; ++c, ++g) {
+        const uint32_t buf = g & 1u;
+        mbar_wait(&h_empty[buf], ((g >> 1) & 1u) ^ 1u);       // the MMAs that read this buffer two chunks ago are done
+        uint8_t* hi_p = smem + OFF_H + buf * 2 * H_PLANE;
+        uint8_t* lo_p = hi_p + H_PLANE;
+        const uint32_t rbase = (uint32_t)(row >> 3) * H_SBO + (uint32_t)(row & 7) * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int kg = kh * 4 + q, j0 = c * KC + kg * 8;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const float p0 = fmaf(w0_s[j0 + e], x0, fmaf(w1_s[j0 + e], x1, b1_s[j0 + e]));
+            const float p1 = fmaf(w0_s[j0 + e + 1], x0, fmaf(w1_s[j0 + e + 1], x1, b1_s[j0 + e + 1]));
+            __half h0, l0, h1, l1;
+            split_h(fmaxf(p0, 0.f) * s, h0, l0);
+            split_h(fmaxf(p1, 0.f) * s, h1, l1);
+            hw[e >> 1] = pack_h2(h0, h1);
+            lw[e >> 1] = pack_h2(l0, l1);
+          }
+          const uint32_t off = rbase + (uint32_t)kg * H_LBO;
+          *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        fence_async_smem();                                   // generic stores -> async proxy (UMMA reads)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_full[buf]);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = make_idesc_f16(NOUT);
+      const uint32_t w_hi = smem_u32(smem + OFF_W), w_lo = w_hi + W_PLANE;
+      uint32_t g = 0;
+      int li = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+        const uint32_t ab = (uint32_t)li & 1u;
+        mbar_wait(&acc_empty[ab], (((uint32_t)li >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator pair
+        tc_fence_after();
+        const uint32_t t_main = tmem_base + ab * 256u, t_corr = t_main + 128u;
+        for (int c = 0; c < NCH; ++c, ++g) {
+          const uint32_t buf = g & 1u;
+          mbar_wait(&h_full[buf], (g >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t h_hi = smem_u32(smem + OFF_H + buf * 2 * H_PLANE), h_lo = h_hi + H_PLANE;
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint32_t wk = (uint32_t)(c * (KC / 8) + ks * 2) * W_LBO;
+            const uint64_t ah = make_desc(h_hi + ks * 2 * H_LBO, H_LBO, H_SBO), al = make_desc(h_lo + ks * 2 * H_LBO, H_LBO, H_SBO);
+            const uint64_t bh = make_desc(w_hi + wk, W_LBO, W_SBO), bl = make_desc(w_lo + wk, W_LBO, W_SBO);
+            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+            umma_f16(t_main, ah, bh, idesc, acc);
+            umma_f16(t_corr, ah, bl, idesc, acc);
+            umma_f16(t_corr, al, bh, idesc, 1u);
+          }
+          umma_commit(&h_empty[buf]);                          // buffer reusable once these MMAs retire
+        }
+        umma_commit(&acc_full[ab]);                            // covers every MMA of the tile
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue: a lane owns one output row =======================
+    int li = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+      const uint32_t ab = (uint32_t)li & 1u;
+      const int64_t m = t * TM + warp * 32 + lane;
+      float x0, x1;
+      row_x(m, x0, x1);
+      float s, inv;
+      bound_scale(fmaf(fabsf(x0), wm0, fmaf(fabsf(x1), wm1, bm)), s, inv);
+      float* op = nullptr;
+      if (m < a.M) op = a.out + (a.out_rows ? (int64_t)a.out_rows[m] : m) * a.ldo;
+      mbar_wait(&acc_full[ab], ((uint32_t)li >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + ab * 256u;
+#pragma unroll 1
+      for (int c = 0; c < NOUT; c += 32) {
+        float vm[32], vc[32];
+        tmem_ld32(trow + (uint32_t)c, vm);
+        tmem_ld32(trow + 128u + (uint32_t)c, vc);
+        if (op) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            o.x = fmaf(fmaf(vc[4 * j], LO_INV, vm[4 * j]), inv, b2_s[c + 4 * j]);
+            o.y = fmaf(fmaf(vc[4 * j + 1], LO_INV, vm[4 * j + 1]), inv, b2_s[c + 4 * j + 1]);
+            o.z = fmaf(fmaf(vc[4 * j + 2], LO_INV, vm[4 * j + 2]), inv, b2_s[c + 4 * j + 2]);
+            o.w = fmaf(fmaf(vc[4 * j + 3], LO_INV, vm[4 * j + 3]), inv, b2_s[c + 4 * j + 3]);
+            st4(op + c + 4 * j, o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, TM_COLS);
+}
+}  // namespace
+
+extern "C" size_t tm_selfmlp_ws_bytes() { return 2 * (size_t)W_PLANE + 256; }
+
+/* out[out_rows[m], 0:128] = W2 relu(W1 X[x_rows[m], 0:kx] + b1) + b2 for m < M, with W1 [256][kx] (kx = 1 or 2),
+ * W2 [128][256] as nn.Linear stores them.  `ws`: tm_selfmlp_ws_bytes() bytes (the split planes of W2). */
+extern "C" int tm_selfmlp_gen_forward(int64_t M, const float* X, int64_t ldx, const int32_t* x_rows, int64_t kx,
+                                      const float* W1, const float* b1, const float* W2, const float* b2, float* out,
+                                      int64_t ldo, const int32_t* out_rows, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(kx == 1 || kx == 2, "tm_selfmlp_gen_forward: the first layer must have 1 or 2 inputs");
+  TM_REQUIRE(ws && ws_bytes >= tm_selfmlp_ws_bytes(), "tm_selfmlp_gen_forward: workspace too small (tm_selfmlp_ws_bytes)");
+  TM_REQUIRE((ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tm_selfmlp_gen_forward: out rows must be 16-byte aligned");
+  if (M <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  selfmlp_pack_kernel<<<(NOUT * HIDF + 255) / 256, 256, 0, st>>>(W2, planes);
+  TM_TRY(check_launch("selfmlp_pack"));
+  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES + 1024));
+  Args a{M, X, ldx, x_rows, (int)kx, W1, b1, b2, planes, out, ldo, out_rows};
+  const int64_t ntiles = (M + TM - 1) / TM;
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  selfmlp_gen_fwd_kernel<<<grid, THREADS, SMEM_BYTES + 1024, st>>>(a);
+  return check_launch("selfmlp_gen_fwd");
+}

@@ -33,6 +33,7 @@ BIAS, RELU, MASK, ACCUM = 1, 2, 4, 8
 #   "fp32" the CUDA-core FFMA kernels (tm_gemm_nn / tm_gemm_tn).
 MATH = os.environ.get("TM_MATH", "tf32x3")
 GEN_HIDDEN = os.environ.get("TM_GEN_HIDDEN", "1") != "0"  # generate Linear(<=2, hid) hidden layers instead of storing them
+FUSED_SELF_MLP = os.environ.get("TM_FUSED_SELF_MLP", "1") != "0"   # tm_selfmlp.cu for the 2 -> 256 -> 128 net-pin MLP
 FUSE_RUNS = os.environ.get("TM_FUSE_RUNS", "1") != "0"    # run-length / prefix-table mask fusion forward
 TC_MIN_N = 4           # Linear(hid, 1) (the head's last layer): a 128 x 32 tensor-core tile would be 97 % padding
 TC_MIN_K = 16          # contractions shorter than this stay on the CUDA-core kernel (K = 1, 2: pure bandwidth)
@@ -182,6 +183,12 @@ def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, 
         # Linear(<=2, hid) first layer: the hidden activations cost 2 FMAs each to recompute, so they are
         # generated inside the GEMM's operand loader and never stored (returns None; mlp2_backward
         # regenerates them the same way)
+        if FUSED_SELF_MLP and hid == 256 and nout == 128 and prec == 3 and ldo % 4 == 0 and out.data_ptr() % 16 == 0:
+            # the reference's sizes: fused kernel, fp16 two-term split operands generated in place (tm_selfmlp.cu)
+            nb = tm_lib.ws_bytes("tm_selfmlp_ws_bytes")
+            call("tm_selfmlp_gen_forward", n_rows, x, ldx, rows, kin, _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2), out, ldo,
+                 out_rows, tm_lib.workspace(nb, out.device), nb, stream())
+            return None
         call("tm_tc_mlp2_smallk_forward", n_rows, hid, nout, x, ldx, rows, kin, _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2),
              out, ldo, out_rows, prec, tm_lib.err_flag(out.device), stream())
         return None

@@ -221,7 +221,8 @@ def layoutnet_forward(sd, x, pooling="max"):
 # ---------------------------------------------------------------------------
 # one design step (train.py:465,490-522,552-553): predictions, loss, gradients
 # ---------------------------------------------------------------------------
-def design_step(sd_model, sd_cnn, d, pooling="max", with_grad=True, cnn="unet", unet_rounding=None, unet_forced=None):
+def design_step(sd_model, sd_cnn, d, pooling="max", with_grad=True, cnn="unet", unet_rounding=None, unet_forced=None,
+                gnn_gate=None):
     """``d`` is a dict of CPU tensors:
     n, levels (list of int64 tensors), net_csr, cell_csr (indptr, src int64),
     cell_feat, net_feat, image (C,H,W), endpoints (int64, grouped by level in
@@ -239,7 +240,7 @@ def design_step(sd_model, sd_cnn, d, pooling="max", with_grad=True, cnn="unet", 
         fmap, stats = layoutnet_forward(C, d["image"], pooling), {}
     feat = fmap.reshape(1, -1)                                                  # train.py:465
     H = gnn_propagate(P, "gnn", d["n"], d["levels"], d["net_csr"], d["cell_csr"],
-                      d["cell_feat"], d["net_feat"])
+                      d["cell_feat"], d["net_feat"], gate=gnn_gate)             # gnn_gate: teacher-forced output gates
     preds = []
     ep, el = d["endpoints"], d["endpoint_level"]
     for lid in torch.unique(el).tolist():                                        # ascending levels

@@ -144,3 +144,33 @@ def test_colsum(lib, R, C, gather):
     out3 = torch.empty(C, device=DEV)
     lib.call("tm_colsum", R, C, X, C, rows, out3, 0, lib.workspace(nb, DEV), nb, lib.stream())
     assert torch.equal(out, out3)
+
+
+@pytest.mark.parametrize("M,kx,gather,xscale", [(1000, 2, False, 1.0), (40000, 2, True, 1.0), (129, 1, True, 30.0),
+                                                 (5000, 2, False, 1e-4), (70000, 2, True, 1e3)])
+def test_selfmlp_gen_forward(lib, M, kx, gather, xscale):
+    """tm_selfmlp_gen_forward (Linear(kx,256) -> ReLU -> Linear(256,128), hidden layer generated into fp16 two-term
+    split tcgen05 operands): against the fp64 definition at the fp32-class bar, inputs of very different magnitudes
+    (the per-row scale), gathered / scattered rows, untouched rows stay untouched."""
+    torch.manual_seed(M + kx)
+    n_src, n_dst = M + 77, M + 33
+    X = torch.randn(n_src, kx, device=DEV) * xscale
+    W1 = torch.randn(256, kx, device=DEV) * 0.5
+    b1 = torch.randn(256, device=DEV) * 0.3
+    W2 = torch.randn(128, 256, device=DEV) * 0.1
+    b2 = torch.randn(128, device=DEV) * 0.1
+    xr = torch.randperm(n_src, device=DEV)[:M].int().contiguous() if gather else None
+    orow = torch.randperm(n_dst, device=DEV)[:M].int().contiguous() if gather else None
+    xs = X[xr.long()] if gather else X[:M]
+    ref = (xs.double() @ W1.double().t() + b1.double()).relu() @ W2.double().t() + b2.double()
+    out = torch.full((n_dst, 128), -5.0, device=DEV)
+    nb = lib.ws_bytes("tm_selfmlp_ws_bytes")
+    lib.call("tm_selfmlp_gen_forward", M, X, kx, xr, kx, W1, b1, W2, b2, out, 128, orow, lib.workspace(nb, DEV), nb, lib.stream())
+    got = out[orow.long()] if gather else out[:M]
+    assert_close(got, ref, 1e-4, 2e-5, "fused self MLP")
+    touched = torch.zeros(n_dst, dtype=torch.bool, device=DEV)
+    touched[orow.long() if gather else torch.arange(M, device=DEV)] = True
+    assert bool((out[~touched] == -5.0).all())
+    out2 = torch.full((n_dst, 128), -5.0, device=DEV)
+    lib.call("tm_selfmlp_gen_forward", M, X, kx, xr, kx, W1, b1, W2, b2, out2, 128, orow, lib.workspace(nb, DEV), nb, lib.stream())
+    assert torch.equal(out, out2)
