@@ -33,7 +33,7 @@ constexpr int NCH = HIDF / KC;     // chunks per tile
 constexpr int EPI_W = 4, GEN_W = 8;
 constexpr int MMA_WARP = EPI_W, GEN_WARP0 = EPI_W + 1;
 constexpr int THREADS = (EPI_W + 1 + GEN_W) * 32;    // 416
-static_assert(GEN_W * 32 == 2 * TM, "two generator threads per tile row");
+static_assert(GEN_W == KC / 8, "one generator warp per k-group of a chunk");
 
 // K-major SWIZZLE_NONE operand planes (core matrix = 8 rows x 16 bytes):
 //   off(row, k) = (row / 8) * SBO + (k / 8) * LBO + (row % 8) * 16 + (k % 8) * 2          [bytes, fp16]
@@ -110,8 +110,18 @@ __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
 }
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+// Two values in [0, 2) -> packed (hi, hi) and (lo', lo') words.  hi is taken by Veltkamp's splitting (x rounded to 11
+// significant bits in fp32: exactly an fp16 number when x >= 2^-14) so that only TWO packed conversions are issued
+// per pair instead of six scalar ones -- the conversions, not the FMAs, bounded the generator; below 2^-14 the
+// conversion of hi rounds once more, by at most 2^-25 of the row's scale.
+__device__ __forceinline__ void split_pair(float y0, float y1, uint32_t& hi, uint32_t& lo) {
+  const float C = 8193.f;                                     // 2^13 + 1
+  const float t0 = __fmul_rn(y0, C), t1 = __fmul_rn(y1, C);
+  const float h0 = __fsub_rn(t0, __fsub_rn(t0, y0)), h1 = __fsub_rn(t1, __fsub_rn(t1, y1));
+  const __half2 hh = __floats2half2_rn(h0, h1);
+  const __half2 ll = __floats2half2_rn(__fmul_rn(__fsub_rn(y0, h0), LO_SCALE), __fmul_rn(__fsub_rn(y1, h1), LO_SCALE));
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
 // s = 2^-e, inv = 2^e with 2^e <= bound < 2^(e+1): every |value| <= bound lands in [0, 2) after scaling
 __device__ __forceinline__ void bound_scale(float bound, float& s, float& inv) {
@@ -212,35 +222,44 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
 
   if (warp >= GEN_WARP0) {
     // ======================= generators: hidden chunks -> operand planes =======================
-    const int gt = tid - GEN_WARP0 * 32;
-    const int row = gt & (TM - 1), kh = gt >> 7;              // this thread: one tile row, k-groups 4 kh .. 4 kh + 3 of a chunk
+    // Warp gw owns k-group gw of EVERY chunk (hidden units c*64 + 8 gw .. + 7): their first-layer parameters live in
+    // registers for the whole kernel (96 values, identical in every lane), a lane owns four rows of the tile.  No
+    // shared-memory reads in the loop: it shares the shared-memory pipe with the MMA operand fetch.
+    const int gw = warp - GEN_WARP0;
+    float pw0[NCH][8], pw1[NCH][8], pb[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = c * KC + gw * 8 + e;
+        pw0[c][e] = w0_s[j]; pw1[c][e] = w1_s[j]; pb[c][e] = b1_s[j];
+      }
     uint32_t g = 0;                                           // chunk counter (buffer = g & 1)
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      float x0, x1;
-      row_x(t * TM + row, x0, x1);
-      float s, inv;
-      bound_scale(fmaf(fabsf(x0), wm0, fmaf(fabsf(x1), wm1, bm)), s, inv);
+      float x0[4], x1[4], sc[4];
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) {
+        row_x(t * TM + rb * 32 + lane, x0[rb], x1[rb]);
+        float inv;
+        bound_scale(fmaf(fabsf(x0[rb]), wm0, fmaf(fabsf(x1[rb]), wm1, bm)), sc[rb], inv);
+      }
+#pragma unroll
       for (int c = 0; c < NCH; ++c, ++g) {
         const uint32_t buf = g & 1u;
         mbar_wait(&h_empty[buf], ((g >> 1) & 1u) ^ 1u);       // the MMAs that read this buffer two chunks ago are done
-        uint8_t* hi_p = smem + OFF_H + buf * 2 * H_PLANE;
+        uint8_t* hi_p = smem + OFF_H + buf * 2 * H_PLANE + (uint32_t)gw * H_LBO;
         uint8_t* lo_p = hi_p + H_PLANE;
-        const uint32_t rbase = (uint32_t)(row >> 3) * H_SBO + (uint32_t)(row & 7) * 16;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int kg = kh * 4 + q, j0 = c * KC + kg * 8;
+        for (int rb = 0; rb < 4; ++rb) {
+          const int row = rb * 32 + lane;
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
-            const float p0 = fmaf(w0_s[j0 + e], x0, fmaf(w1_s[j0 + e], x1, b1_s[j0 + e]));
-            const float p1 = fmaf(w0_s[j0 + e + 1], x0, fmaf(w1_s[j0 + e + 1], x1, b1_s[j0 + e + 1]));
-            __half h0, l0, h1, l1;
-            split_h(fmaxf(p0, 0.f) * s, h0, l0);
-            split_h(fmaxf(p1, 0.f) * s, h1, l1);
-            hw[e >> 1] = pack_h2(h0, h1);
-            lw[e >> 1] = pack_h2(l0, l1);
+            const float y0 = fmaxf(fmaf(pw0[c][e], x0[rb], fmaf(pw1[c][e], x1[rb], pb[c][e])), 0.f) * sc[rb];
+            const float y1 = fmaxf(fmaf(pw0[c][e + 1], x0[rb], fmaf(pw1[c][e + 1], x1[rb], pb[c][e + 1])), 0.f) * sc[rb];
+            split_pair(y0, y1, hw[e >> 1], lw[e >> 1]);
           }
-          const uint32_t off = rbase + (uint32_t)kg * H_LBO;
+          const uint32_t off = (uint32_t)(row >> 3) * H_SBO + (uint32_t)(row & 7) * 16;
           *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
