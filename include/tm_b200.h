@@ -267,6 +267,9 @@ int tm_scatter_add_cols(int64_t T, int64_t w, const float* src, int64_t lds, int
 size_t tm_colsum_ws(int64_t R, int64_t C);
 int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, const int32_t* rows, float* out,
               int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* tm_colsum (accumulate = 0) that also returns max |X[rows]| in absmax[0] (C % 4 == 0, 16-byte aligned rows). */
+int tm_colsum_absmax(int64_t R, int64_t C, const float* X, int64_t ld, const int32_t* rows, float* out,
+                     float* absmax, void* ws, size_t ws_bytes, void* stream);
 /* loss[0] = mean((pred-y)^2); grad[i] = 2*(pred[i]-y[i])/T * grad_scale  (nn.MSELoss) */
 int tm_mse(int64_t T, const float* pred, const float* y, float* loss, float* grad,
            float grad_scale, void* stream);
@@ -417,6 +420,15 @@ int tm_tc_mlp1_bwd_fused(int64_t M, int64_t N, int64_t K, const float* G, int64_
  * once and stays resident in shared memory, tcgen05.mma with the accumulators in TMEM (csrc/tm_selfmlp.cu).
  * ws: tm_selfmlp_ws_bytes(). */
 size_t tm_selfmlp_ws_bytes(void);
+/* Its second-layer weight gradient dW2[128][256] = G[g_rows]^T relu(W1 X[x_rows] + b1) as ONE fused kernel of the same
+ * kind (the hidden layer generated as the B operand, G transposed into the A operand on the way in, contraction over
+ * the rows on tcgen05 with the accumulators resident in TMEM for the whole kernel).  A contraction over rows cannot
+ * use per-row scales: `gmax` = device scalar holding max|G| over the rows (tm_colsum_absmax computes it in the pass
+ * that takes the bias gradient).  ws: tm_selfmlp_wgrad2_ws_bytes(). */
+size_t tm_selfmlp_wgrad2_ws_bytes(void);
+int tm_selfmlp_gen_wgrad2(int64_t M, const float* G, int64_t ldg, const int32_t* g_rows, const float* X, int64_t ldx,
+                          const int32_t* x_rows, int64_t kx, const float* W1, const float* b1, const float* gmax,
+                          float* dW2, void* ws, size_t ws_bytes, void* stream);
 int tm_selfmlp_gen_forward(int64_t M, const float* X, int64_t ldx, const int32_t* x_rows, int64_t kx,
                            const float* W1, const float* b1, const float* W2, const float* b2, float* out,
                            int64_t ldo, const int32_t* out_rows, void* ws, size_t ws_bytes, void* stream);

@@ -201,13 +201,14 @@ colsum_partial_kernel(int64_t R, int64_t C, const float* __restrict__ X, int64_t
 constexpr int CS_ROWS_V4 = 256;   // rows per chunk: ~900 blocks on a 230 000-row matrix, 32 KB of loads in flight per block
 __global__ void __launch_bounds__(256)
 colsum_partial_v4_kernel(int64_t R, int64_t C, const float* __restrict__ X, int64_t ld, const int* __restrict__ rows,
-                         float* __restrict__ part) {
+                         float* __restrict__ part, unsigned int* __restrict__ amax) {
   __shared__ float4 sm[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 128 + lane * 4;
   const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS_V4;
   const int64_t r1 = (r0 + CS_ROWS_V4 < R) ? r0 + CS_ROWS_V4 : R;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float mx = 0.f;                                    // largest magnitude seen (amax != NULL: tm_colsum_absmax)
   if (c < C) {
     int64_t r = r0 + warp;
     for (; r + 56 < r1; r += 64) {
@@ -218,12 +219,20 @@ colsum_partial_v4_kernel(int64_t R, int64_t C, const float* __restrict__ X, int6
         v[u] = __ldg(reinterpret_cast<const float4*>(X + (rows ? (int64_t)rows[rr] : rr) * ld + c));
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+      for (int u = 0; u < 8; ++u) {
+        s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+      }
     }
     for (; r < r1; r += 8) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(X + (rows ? (int64_t)rows[r] : r) * ld + c));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     }
+  }
+  if (amax) {                                        // non-negative floats order like their bit patterns; max is order-free
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx > 0.f) atomicMax(amax, __float_as_uint(mx));
   }
   sm[warp][lane] = s;
   __syncthreads();
@@ -413,11 +422,29 @@ extern "C" int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, const
   const bool v4 = v4_on && C % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
   const int nchunk = (int)cdiv(R > 0 ? R : 1, v4 ? CS_ROWS_V4 : CS_ROWS);
   if (v4)
-    colsum_partial_v4_kernel<<<dim3((unsigned)cdiv(C, 128), (unsigned)nchunk), 256, 0, st>>>(R, C, X, ld, rows, (float*)ws);
+    colsum_partial_v4_kernel<<<dim3((unsigned)cdiv(C, 128), (unsigned)nchunk), 256, 0, st>>>(R, C, X, ld, rows, (float*)ws, nullptr);
   else
     colsum_partial_kernel<<<dim3((unsigned)cdiv(C, 32), (unsigned)nchunk), dim3(32, 8), 0, st>>>(R, C, X, ld, rows, (float*)ws);
   TM_TRY(check_launch("colsum_partial"));
   colsum_final_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, st>>>(C, nchunk, (const float*)ws, out, accumulate);
+  return check_launch("colsum_final");
+}
+
+/* tm_colsum that also returns the largest magnitude of the summed rows in absmax[0] (the global operand scale of
+ * tm_selfmlp_gen_wgrad2, taken from the pass that reads the rows anyway).  Needs C % 4 == 0 and 16-byte aligned rows. */
+extern "C" int tm_colsum_absmax(int64_t R, int64_t C, const float* X, int64_t ld, const int32_t* rows, float* out,
+                                float* absmax, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(C > 0 && C % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && ws &&
+                 (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && absmax,
+             "tm_colsum_absmax: needs C % 4 == 0, 16-byte aligned rows and workspace, absmax != NULL");
+  TM_REQUIRE(ws_bytes >= tm_colsum_ws(R, C), "tm_colsum_absmax: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunk = (int)cdiv(R > 0 ? R : 1, CS_ROWS_V4);
+  TM_CUDA(cudaMemsetAsync(absmax, 0, sizeof(float), st));
+  colsum_partial_v4_kernel<<<dim3((unsigned)cdiv(C, 128), (unsigned)nchunk), 256, 0, st>>>(R, C, X, ld, rows, (float*)ws,
+                                                                                           reinterpret_cast<unsigned int*>(absmax));
+  TM_TRY(check_launch("colsum_partial(absmax)"));
+  colsum_final_kernel<<<(unsigned)cdiv(C * 32, 128), 128, 0, st>>>(C, nchunk, (const float*)ws, out, 0);
   return check_launch("colsum_final");
 }
 

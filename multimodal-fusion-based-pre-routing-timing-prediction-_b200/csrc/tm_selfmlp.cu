@@ -24,6 +24,11 @@
 
 using namespace tmk;
 
+namespace tmk {   // tm_gemm.cu: C[m][n] (+)= sum_k P[k][m*N + n], fixed order
+__global__ void split_reduce_kernel(const float* __restrict__ P, int64_t count, int splits, float* __restrict__ C, int64_t N,
+                                    int64_t ldc, int accumulate);
+}
+
 namespace {
 constexpr int TM = 128;            // rows per tile (MMA M)
 constexpr int HIDF = 256;          // hidden width (MMA K)
@@ -343,6 +348,259 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, TM_COLS);
 }
+
+// =============================================================================================
+// Second-layer weight gradient:  dW2[o][j] = sum_r G[g_rows[r]][o] * relu(w0_j x0[r] + w1_j x1[r] + b_j)
+//   D[M = 128 o][N = 256 j] += A[o][k = row] . B[j][k = row]^T, 64 rows per step, both operands K-major with k = row:
+//   A = G transposed on the way in (a lane owns one o and eight consecutive rows: eight coalesced 128-byte loads per
+//       warp, one 16-byte store per plane), B = the hidden layer generated by the thread that owns hidden unit j
+//       (its three first-layer parameters in registers, the step's 64 inputs broadcast from shared memory).
+// The contraction runs over the rows, so the operand scales must not depend on the row: G is scaled by a power of two
+// from max|G| (gmax, device scalar), the hidden layer by one from the largest row bound (a small pass over X).  Values
+// 2^-14 below the maximum keep fewer than 22 bits (absolute error <= 2^-36 of the maximum per product).
+// One accumulator pair (main / corr, 256 columns each) stays in TMEM for the whole kernel; every CTA owns a contiguous
+// range of steps and writes one partial dW2 at the end (folded by split_reduce in a fixed order: deterministic).
+// =============================================================================================
+constexpr int WG_KS = 64;                                   // rows per step (MMA K = 4 x 16)
+constexpr int WG_TR_W = 4;                                  // transposer warps
+constexpr int WG_THREADS = (1 + GEN_W + WG_TR_W) * 32;      // warp 0 MMA, 1..8 generators, 9..12 transposers = 416
+constexpr uint32_t WG_LBO = 128, WG_SBO = (WG_KS / 8) * WG_LBO;             // 1024
+// A planes: the 8-row-group stride is padded by 16 bytes so that the transposers' stores (lane = 4 outputs) hit 8
+// different 16-byte columns per quarter warp
+constexpr uint32_t WG_A_SBO = WG_SBO + 16;
+constexpr uint32_t WG_A_PLANE = (NOUT / 8) * WG_A_SBO, WG_B_PLANE = (HIDF / 8) * WG_SBO;   // 16.25 KB, 32 KB
+constexpr uint32_t WG_BUF = 2 * WG_A_PLANE + 2 * WG_B_PLANE;                // 96 KB: Ahi, Alo, Bhi, Blo
+constexpr uint32_t WG_OFF_X = 2 * WG_BUF;                                   // [buffer 2][x0 64 | x1 64] fp32
+constexpr uint32_t WG_OFF_BAR = WG_OFF_X + 2 * 2 * WG_KS * 4;
+constexpr uint32_t WG_SMEM = WG_OFF_BAR + 8 * 8 + 16;
+static_assert(WG_SMEM <= 232448, "shared memory budget");
+
+__device__ __forceinline__ uint32_t make_idesc_f16_n(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// max |x0|, max |x1| over the rows (non-negative floats order like their bit patterns)
+__global__ void selfmlp_xmax_kernel(int64_t M, const float* __restrict__ X, int64_t ldx, const int* __restrict__ x_rows, int kx,
+                                    unsigned int* __restrict__ out2) {
+  float m0 = 0.f, m1 = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* xp = X + (x_rows ? (int64_t)x_rows[r] : r) * ldx;
+    m0 = fmaxf(m0, fabsf(xp[0]));
+    if (kx > 1) m1 = fmaxf(m1, fabsf(xp[1]));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (m0 > 0.f) atomicMax(out2, __float_as_uint(m0));
+    if (m1 > 0.f) atomicMax(out2 + 1, __float_as_uint(m1));
+  }
+}
+
+struct WgArgs {
+  int64_t M;
+  const float* G;
+  int64_t ldg;
+  const int* g_rows;
+  const float* X;
+  int64_t ldx;
+  const int* x_rows;
+  int kx;
+  const float* W1;
+  const float* b1;
+  const float* gmax;      // device: max |G|
+  const float* xmax;      // device: max |x0|, max |x1|
+  float* part;            // [grid][128][256]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) selfmlp_gen_wgrad2_kernel(WgArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_OFF_BAR);
+  uint64_t *full = bars, *empty = bars + 2, *done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  __shared__ float wmax_s[3];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t nsteps = (a.M + WG_KS - 1) / WG_KS;
+  const int64_t per = (nsteps + gridDim.x - 1) / gridDim.x;
+  const int64_t s0 = (int64_t)blockIdx.x * per, s1 = (s0 + per < nsteps) ? s0 + per : nsteps;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], GEN_W + WG_TR_W); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
+  if (warp == 1) {                                            // bounds of the first layer
+    float m0 = 0.f, m1 = 0.f, mb = 0.f;
+    for (int j = lane; j < HIDF; j += 32) {
+      m0 = fmaxf(m0, fabsf(a.W1[(size_t)j * a.kx]));
+      if (a.kx > 1) m1 = fmaxf(m1, fabsf(a.W1[(size_t)j * a.kx + 1]));
+      mb = fmaxf(mb, fabsf(a.b1[j]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    if (lane == 0) { wmax_s[0] = m0; wmax_s[1] = m1; wmax_s[2] = mb; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // global operand scales (powers of two)
+  float sg, ig, sh, ih;
+  bound_scale(fmaxf(a.gmax[0], 1e-37f), sg, ig);
+  bound_scale(fmaf(a.xmax[0], wmax_s[0], fmaf(a.xmax[1], wmax_s[1], wmax_s[2])), sh, ih);
+
+  if (warp == 0) {
+    // ======================= MMA issuer =======================
+    if (lane == 0 && s1 > s0) {
+      const uint32_t idesc = make_idesc_f16_n(HIDF);
+      const uint32_t t_main = tmem_base, t_corr = tmem_base + 256u;
+      uint32_t g = 0;
+      for (int64_t st = s0; st < s1; ++st, ++g) {
+        const uint32_t buf = g & 1u;
+        mbar_wait(&full[buf], (g >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + buf * WG_BUF), a_lo = a_hi + WG_A_PLANE;
+        const uint32_t b_hi = a_hi + 2 * WG_A_PLANE, b_lo = b_hi + WG_B_PLANE;
+#pragma unroll
+        for (int ks = 0; ks < WG_KS / 16; ++ks) {
+          const uint64_t ah = make_desc(a_hi + ks * 2 * WG_LBO, WG_LBO, WG_A_SBO), al = make_desc(a_lo + ks * 2 * WG_LBO, WG_LBO, WG_A_SBO);
+          const uint64_t bh = make_desc(b_hi + ks * 2 * WG_LBO, WG_LBO, WG_SBO), bl = make_desc(b_lo + ks * 2 * WG_LBO, WG_LBO, WG_SBO);
+          const uint32_t acc = (g > 0 || ks > 0) ? 1u : 0u;
+          umma_f16(t_main, ah, bh, idesc, acc);
+          umma_f16(t_corr, ah, bl, idesc, acc);
+          umma_f16(t_corr, al, bh, idesc, 1u);
+        }
+        umma_commit(&empty[buf]);
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else if (warp <= GEN_W) {
+    // ======================= generators: thread = hidden unit j, B[j][k = row] =======================
+    const int j = tid - 32;
+    const float w0 = a.W1[(size_t)j * a.kx], w1 = a.kx > 1 ? a.W1[(size_t)j * a.kx + 1] : 0.f, bj = a.b1[j];
+    const uint32_t jbase = (uint32_t)(j >> 3) * WG_SBO + (uint32_t)(j & 7) * 16;
+    uint32_t g = 0;
+    for (int64_t st = s0; st < s1; ++st, ++g) {
+      const uint32_t buf = g & 1u;
+      mbar_wait(&empty[buf], ((g >> 1) & 1u) ^ 1u);
+      float* xs = reinterpret_cast<float*>(smem + WG_OFF_X) + buf * 2 * WG_KS;
+      if (j < WG_KS) {                                        // the step's inputs (rows past M: 0, and G is 0 there too)
+        const int64_t r = st * WG_KS + j;
+        float x0 = 0.f, x1 = 0.f;
+        if (r < a.M) {
+          const float* xp = a.X + (a.x_rows ? (int64_t)a.x_rows[r] : r) * a.ldx;
+          x0 = xp[0];
+          if (a.kx > 1) x1 = xp[1];
+        }
+        xs[j] = x0; xs[WG_KS + j] = x1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(GEN_W * 32) : "memory");
+      uint8_t* hi_p = smem + buf * WG_BUF + 2 * WG_A_PLANE + jbase;
+      uint8_t* lo_p = hi_p + WG_B_PLANE;
+#pragma unroll 2
+      for (int rg = 0; rg < WG_KS / 8; ++rg) {
+        const float4 xa = *reinterpret_cast<const float4*>(xs + rg * 8), xb = *reinterpret_cast<const float4*>(xs + rg * 8 + 4);
+        const float4 ya = *reinterpret_cast<const float4*>(xs + WG_KS + rg * 8), yb = *reinterpret_cast<const float4*>(xs + WG_KS + rg * 8 + 4);
+        const float x0v[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float x1v[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float y0 = fmaxf(fmaf(w0, x0v[e], fmaf(w1, x1v[e], bj)), 0.f) * sh;
+          const float y1 = fmaxf(fmaf(w0, x0v[e + 1], fmaf(w1, x1v[e + 1], bj)), 0.f) * sh;
+          split_pair(y0, y1, hw[e >> 1], lw[e >> 1]);
+        }
+        *reinterpret_cast<uint4*>(hi_p + rg * WG_LBO) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(lo_p + rg * WG_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[buf]);
+    }
+  } else {
+    // ======================= transposers: A[o][k = row] from G rows =======================
+    // Warp tw owns row groups tw and tw + 4 of the step (8 consecutive rows each).  A lane reads 16 bytes (4 outputs
+    // o = 4 lane ..) of each row -- a warp-wide load is one whole 512-byte row -- and then holds, for each of its four
+    // outputs, eight consecutive rows: one 16-byte store per output and plane.  The rows of the NEXT step are loaded
+    // into registers right after this step's stores, so they are in flight while the generators and the MMAs work.
+    const int tw = warp - (1 + GEN_W);
+    float4 v[2][8];
+    auto fetch = [&](int64_t st) {
+      const int64_t r0 = st * WG_KS;
+      int id0 = -1, id1 = -1;                               // row ids: two coalesced index loads, handed round by shuffles
+      if (r0 + lane < a.M) id0 = a.g_rows ? a.g_rows[r0 + lane] : (int)(r0 + lane);
+      if (r0 + 32 + lane < a.M) id1 = a.g_rows ? a.g_rows[r0 + 32 + lane] : (int)(r0 + 32 + lane);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int row = (tw + 4 * h) * 8 + e;               // 0 .. 63; h == 1 rows are >= 32
+          const int src = __shfl_sync(0xffffffffu, h ? id1 : id0, row & 31);
+          v[h][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src >= 0) v[h][e] = __ldg(reinterpret_cast<const float4*>(a.G + (int64_t)src * a.ldg) + lane);
+        }
+    };
+    if (s0 < s1) fetch(s0);
+    uint32_t g = 0;
+    for (int64_t st = s0; st < s1; ++st, ++g) {
+      const uint32_t buf = g & 1u;
+      mbar_wait(&empty[buf], ((g >> 1) & 1u) ^ 1u);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int rg = tw + 4 * h;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                         // output o = 4 lane + c, rows rg*8 .. rg*8 + 7
+          const int o = lane * 4 + c;
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = (c == 0 ? v[h][e].x : c == 1 ? v[h][e].y : c == 2 ? v[h][e].z : v[h][e].w) * sg;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) split_pair(x[e], x[e + 1], hw[e >> 1], lw[e >> 1]);
+          uint8_t* hi_p = smem + buf * WG_BUF + (uint32_t)(o >> 3) * WG_A_SBO + (uint32_t)(o & 7) * 16 + (uint32_t)rg * WG_LBO;
+          *reinterpret_cast<uint4*>(hi_p) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(hi_p + WG_A_PLANE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[buf]);
+      if (st + 1 < s1) fetch(st + 1);
+    }
+  }
+  // ======================= epilogue: warps 1..4 (TMEM lane quarter = warp % 4), once =======================
+  if (warp >= 1 && warp <= 4) {
+    const int q = warp & 3;
+    float* prow = a.part + ((size_t)blockIdx.x * NOUT + (q * 32 + lane)) * HIDF;
+    if (s1 > s0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const float unscale = ig * ih;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < HIDF; c += 32) {
+        float vm[32], vc[32];
+        tmem_ld32(trow + (uint32_t)c, vm);
+        tmem_ld32(trow + 256u + (uint32_t)c, vc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          st4(prow + c + 4 * e, make_float4(fmaf(vc[4 * e], LO_INV, vm[4 * e]) * unscale, fmaf(vc[4 * e + 1], LO_INV, vm[4 * e + 1]) * unscale,
+                                            fmaf(vc[4 * e + 2], LO_INV, vm[4 * e + 2]) * unscale, fmaf(vc[4 * e + 3], LO_INV, vm[4 * e + 3]) * unscale));
+      }
+    } else {
+      for (int c = 0; c < HIDF; c += 4) st4(prow + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
+}
 }  // namespace
 
 extern "C" size_t tm_selfmlp_ws_bytes() { return 2 * (size_t)W_PLANE + 256; }
@@ -366,4 +624,34 @@ extern "C" int tm_selfmlp_gen_forward(int64_t M, const float* X, int64_t ldx, co
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   selfmlp_gen_fwd_kernel<<<grid, THREADS, SMEM_BYTES + 1024, st>>>(a);
   return check_launch("selfmlp_gen_fwd");
+}
+
+extern "C" size_t tm_selfmlp_wgrad2_ws_bytes() { return (size_t)sm_count() * NOUT * HIDF * sizeof(float) + 1024; }
+
+extern "C" int tm_selfmlp_gen_wgrad2(int64_t M, const float* G, int64_t ldg, const int32_t* g_rows, const float* X, int64_t ldx,
+                                     const int32_t* x_rows, int64_t kx, const float* W1, const float* b1, const float* gmax,
+                                     float* dW2, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(kx == 1 || kx == 2, "tm_selfmlp_gen_wgrad2: the first layer must have 1 or 2 inputs");
+  TM_REQUIRE(ws && ws_bytes >= tm_selfmlp_wgrad2_ws_bytes(), "tm_selfmlp_gen_wgrad2: workspace too small (tm_selfmlp_wgrad2_ws_bytes)");
+  TM_REQUIRE(gmax, "tm_selfmlp_gen_wgrad2: gmax (device scalar, max |G|: tm_colsum_absmax) missing");
+  TM_REQUIRE((ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0, "tm_selfmlp_gen_wgrad2: G rows must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M <= 0) {
+    TM_CUDA(cudaMemsetAsync(dW2, 0, (size_t)NOUT * HIDF * sizeof(float), st));
+    return 0;
+  }
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  unsigned int* xmax = reinterpret_cast<unsigned int*>(base);
+  float* part = reinterpret_cast<float*>(base + 256);
+  TM_CUDA(cudaMemsetAsync(xmax, 0, 2 * sizeof(float), st));
+  selfmlp_xmax_kernel<<<(unsigned)(sm_count() * 2), 256, 0, st>>>(M, X, ldx, x_rows, (int)kx, xmax);
+  TM_TRY(check_launch("selfmlp_xmax"));
+  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM + 1024));
+  const int64_t nsteps = (M + WG_KS - 1) / WG_KS;
+  const int grid = (int)(nsteps < sm_count() ? nsteps : sm_count());
+  WgArgs a{M, G, ldg, g_rows, X, ldx, x_rows, (int)kx, W1, b1, gmax, reinterpret_cast<const float*>(xmax), part};
+  selfmlp_gen_wgrad2_kernel<<<grid, WG_THREADS, WG_SMEM + 1024, st>>>(a);
+  TM_TRY(check_launch("selfmlp_gen_wgrad2"));
+  split_reduce_kernel<<<(unsigned)cdiv((int64_t)NOUT * HIDF, 64), 256, 0, st>>>(part, (int64_t)NOUT * HIDF, grid, dW2, HIDF, HIDF, 0);
+  return check_launch("split_reduce(selfmlp wgrad2)");
 }

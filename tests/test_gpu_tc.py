@@ -174,3 +174,38 @@ def test_selfmlp_gen_forward(lib, M, kx, gather, xscale):
     out2 = torch.full((n_dst, 128), -5.0, device=DEV)
     lib.call("tm_selfmlp_gen_forward", M, X, kx, xr, kx, W1, b1, W2, b2, out2, 128, orow, lib.workspace(nb, DEV), nb, lib.stream())
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("M,kx,gather,gscale", [(1000, 2, False, 1.0), (40000, 2, True, 1e-4), (63, 1, True, 1.0),
+                                                 (70001, 2, True, 1e-8), (20000, 2, False, 1e3)])
+def test_selfmlp_gen_wgrad2(lib, M, kx, gather, gscale):
+    """tm_selfmlp_gen_wgrad2 (dW2 = G^T relu(W1 x + b1), hidden layer generated, contraction over the rows on
+    tcgen05 with global power-of-two operand scales) and tm_colsum_absmax (bias gradient + max |G| in one pass):
+    against the fp64 definition at the fp32-class bar, gradients of very different magnitudes, rows of G that differ
+    by six orders of magnitude, gathered rows, bit-deterministic."""
+    torch.manual_seed(M + kx)
+    n_src = M + 55
+    X = torch.randn(n_src, kx, device=DEV)
+    W1 = torch.randn(256, kx, device=DEV) * 0.5
+    b1 = torch.randn(256, device=DEV) * 0.3
+    G = torch.randn(n_src, 128, device=DEV) * gscale
+    G[::7] *= 1e-6                                   # rows far below the global scale
+    xr = torch.randperm(n_src, device=DEV)[:M].int().contiguous() if gather else None
+    gr = torch.randperm(n_src, device=DEV)[:M].int().contiguous() if gather else None
+    xs = X[xr.long()] if gather else X[:M]
+    gs = G[gr.long()] if gather else G[:M]
+    h = (xs.double() @ W1.double().t() + b1.double()).relu()
+    ref = gs.double().t() @ h
+    db = torch.empty(128, device=DEV)
+    gmax = torch.empty(1, device=DEV)
+    nbc = lib.ws_bytes("tm_colsum_ws", M, 128)
+    lib.call("tm_colsum_absmax", M, 128, G, 128, gr, db, gmax, lib.workspace(nbc, DEV), nbc, lib.stream())
+    assert float(gmax.item()) == float(gs.abs().max().item())
+    assert_close(db, gs.double().sum(0), 1e-4, 1e-4, "bias gradient")
+    nb = lib.ws_bytes("tm_selfmlp_wgrad2_ws_bytes")
+    dw = torch.empty(128, 256, device=DEV)
+    lib.call("tm_selfmlp_gen_wgrad2", M, G, 128, gr, X, kx, xr, kx, W1, b1, gmax, dw, lib.workspace(nb, DEV), nb, lib.stream())
+    assert_close(dw, ref, 1e-4, 2e-5, "fused dW2")
+    dw2 = torch.empty(128, 256, device=DEV)
+    lib.call("tm_selfmlp_gen_wgrad2", M, G, 128, gr, X, kx, xr, kx, W1, b1, gmax, dw2, lib.workspace(nb, DEV), nb, lib.stream())
+    assert torch.equal(dw, dw2)
