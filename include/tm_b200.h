@@ -425,6 +425,13 @@ size_t tm_selfmlp_ws_bytes(void);
  * the rows on tcgen05 with the accumulators resident in TMEM for the whole kernel).  A contraction over rows cannot
  * use per-row scales: `gmax` = device scalar holding max|G| over the rows (tm_colsum_absmax computes it in the pass
  * that takes the bias gradient).  ws: tm_selfmlp_wgrad2_ws_bytes(). */
+/* ... and its first-layer gradients db1[256], dW1[256][kx] = reductions of dh = (G[g_rows] W2) * (W1 x + b1 > 0) over
+ * the rows; dh is never written (per-lane column accumulators in registers).  W2: [128][256] as stored.
+ * ws: tm_selfmlp_bwd1_ws_bytes(). */
+size_t tm_selfmlp_bwd1_ws_bytes(void);
+int tm_selfmlp_gen_bwd1(int64_t M, const float* G, int64_t ldg, const int32_t* g_rows, const float* X, int64_t ldx,
+                        const int32_t* x_rows, int64_t kx, const float* W1, const float* b1, const float* W2,
+                        float* dW1, float* db1, void* ws, size_t ws_bytes, void* stream);
 size_t tm_selfmlp_wgrad2_ws_bytes(void);
 int tm_selfmlp_gen_wgrad2(int64_t M, const float* G, int64_t ldg, const int32_t* g_rows, const float* X, int64_t ldx,
                           const int32_t* x_rows, int64_t kx, const float* W1, const float* b1, const float* gmax,

@@ -601,6 +601,255 @@ __global__ void __launch_bounds__(WG_THREADS, 1) selfmlp_gen_wgrad2_kernel(WgArg
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
 }
+
+// =============================================================================================
+// First-layer gradients:  dh = (G W2) * (pre > 0),  db1[j] = sum_r dh[r][j],  dW1[j][c] = sum_r dh[r][j] x_c[r]
+//   D[M = 128 rows][N = 256 j] = A[row][k = o] . B[j][k = o]^T:  A = the G rows (per-row power-of-two scale: the
+//   contraction runs over o), B = W2 transposed, split once and resident (2 x 64 KB).  The 256 columns are two
+//   halves with their own accumulator pair, so the epilogue of one half overlaps the MMAs of the other and of the
+//   next tile.  dh is never written: an epilogue warp masks its 32 x 32 block with the regenerated pre-activation
+//   sign (the forward's own expression), transposes it through shared memory and adds it into per-lane column
+//   accumulators that live in registers for the whole kernel (8 columns x 3 sums per lane); one partial per warp at
+//   the end, folded in a fixed order.
+// =============================================================================================
+constexpr uint32_t B1_W_SBO = (NOUT / 8) * 128, B1_W_PLANE = (HIDF / 8) * B1_W_SBO;        // B[j][o]: 2048, 64 KB
+constexpr uint32_t B1_A_LBO = 144, B1_A_SBO = (NOUT / 8) * B1_A_LBO, B1_A_PLANE = (TM / 8) * B1_A_SBO;   // 2304, 36 KB
+constexpr uint32_t B1_OFF_W = 0;
+constexpr uint32_t B1_OFF_A = 2 * B1_W_PLANE;
+constexpr uint32_t B1_OFF_P = B1_OFF_A + 2 * B1_A_PLANE;                 // w0, w1, b1 [256]
+constexpr uint32_t B1_OFF_INV = B1_OFF_P + 3 * HIDF * 4;                 // [tile parity 2][128]
+constexpr uint32_t B1_OFF_SCR = B1_OFF_INV + 2 * TM * 4;                 // per epilogue warp: 32 x 33 block + x0[32] + x1[32]
+constexpr uint32_t B1_SCR_W = (32 * 33 + 64) * 4;
+constexpr uint32_t B1_OFF_BAR = B1_OFF_SCR + EPI_W * B1_SCR_W;
+constexpr uint32_t B1_SMEM = B1_OFF_BAR + 8 * 8 + 16;
+static_assert(B1_SMEM <= 232448, "shared memory budget");
+
+// W2 [NOUT o][HIDF j] fp32 -> planes of B[j][k = o]
+__global__ void selfmlp_pack_t_kernel(const float* __restrict__ W2, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NOUT * HIDF) return;
+  const int o = i / HIDF, j = i - o * HIDF;
+  __half h, l;
+  split_h(W2[i], h, l);
+  const uint32_t off = (uint32_t)(j >> 3) * B1_W_SBO + (uint32_t)(o >> 3) * 128 + (uint32_t)(j & 7) * 16 + (uint32_t)(o & 7) * 2;
+  *reinterpret_cast<__half*>(out + off) = h;
+  *reinterpret_cast<__half*>(out + B1_W_PLANE + off) = l;
+}
+
+// part [slots][3][HIDF] -> db1[j], dW1[j][kx]: 32 columns x 8 slot groups per block, fixed order
+__global__ void __launch_bounds__(256)
+selfmlp_bwd1_reduce_kernel(const float* __restrict__ part, int slots, int kx, float* __restrict__ dW1, float* __restrict__ db1) {
+  __shared__ float sm[8][3][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int g = w; g < slots; g += 8)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s[k] += part[((size_t)g * 3 + k) * HIDF + n];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) sm[w][k][lane] = s[k];
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      for (int i = 1; i < 8; ++i) s[k] += sm[i][k][lane];
+    db1[n] = s[0];
+    dW1[n * kx] = s[1];
+    if (kx > 1) dW1[n * kx + 1] = s[2];
+  }
+}
+
+struct B1Args {
+  int64_t M;
+  const float* G;
+  int64_t ldg;
+  const int* g_rows;
+  const float* X;
+  int64_t ldx;
+  const int* x_rows;
+  int kx;
+  const float* W1;
+  const float* b1;
+  const uint8_t* wplanes;
+  float* part;            // [grid * EPI_W][3][256]
+};
+
+__global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_bwd1_kernel(B1Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* w0_s = reinterpret_cast<float*>(smem + B1_OFF_P);
+  float* w1_s = w0_s + HIDF;
+  float* b1_s = w1_s + HIDF;
+  float* inv_s = reinterpret_cast<float*>(smem + B1_OFF_INV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B1_OFF_BAR);
+  uint64_t *a_full = bars, *a_empty = bars + 1, *acc_full = bars + 2, *acc_empty = bars + 4, *wbar = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.M + TM - 1) / TM;
+
+  if (tid == 0) {
+    mbar_init(a_full, GEN_W); mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_W); }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+    const uint32_t bar = smem_u32(wbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * B1_W_PLANE) : "memory");
+    for (int i = 0; i < 4; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(smem + B1_OFF_W + i * (B1_W_PLANE / 2))), "l"(a.wplanes + (size_t)i * (B1_W_PLANE / 2)),
+                     "r"(B1_W_PLANE / 2), "r"(bar) : "memory");
+  }
+  for (int j = tid; j < HIDF; j += THREADS) {
+    w0_s[j] = a.W1[(size_t)j * a.kx];
+    w1_s[j] = a.kx > 1 ? a.W1[(size_t)j * a.kx + 1] : 0.f;
+    b1_s[j] = a.b1[j];
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= GEN_WARP0) {
+    // ======================= loaders: G rows -> A planes (warp lw: rows 16 lw .. 16 lw + 15 of the tile) ==========
+    const int lw = warp - GEN_WARP0;
+    float4 v[16];
+    auto fetch = [&](int64_t t) {
+      const int64_t r = t * TM + lw * 16 + (lane & 15);
+      int id = -1;
+      if (r < a.M) id = a.g_rows ? a.g_rows[r] : (int)r;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int src = __shfl_sync(0xffffffffu, id, e);
+        v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src >= 0) v[e] = __ldg(reinterpret_cast<const float4*>(a.G + (int64_t)src * a.ldg) + lane);
+      }
+    };
+    if ((int64_t)blockIdx.x < ntiles) fetch(blockIdx.x);
+    uint32_t li = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+      mbar_wait(a_empty, (li & 1u) ^ 1u);                      // the MMAs of the previous tile are done with the planes
+      uint8_t* hi_p = smem + B1_OFF_A + (uint32_t)(lane >> 1) * B1_A_LBO + (uint32_t)(lane & 1) * 8;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int row = lw * 16 + e;
+        const float4 x = v[e];
+        float rm = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+        float sc, inv;
+        bound_scale(rm, sc, inv);
+        uint32_t h0, l0, h1, l1;
+        split_pair(x.x * sc, x.y * sc, h0, l0);
+        split_pair(x.z * sc, x.w * sc, h1, l1);
+        const uint32_t off = (uint32_t)(row >> 3) * B1_A_SBO + (uint32_t)(row & 7) * 16;
+        *reinterpret_cast<uint2*>(hi_p + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(hi_p + B1_A_PLANE + off) = make_uint2(l0, l1);
+        if (lane == 0) inv_s[(li & 1u) * TM + row] = inv;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+      if (t + gridDim.x < ntiles) fetch(t + gridDim.x);
+    }
+  } else if (warp == MMA_WARP) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = make_idesc_f16(NOUT);             // N = 128 columns per half
+      const uint32_t a_hi = smem_u32(smem + B1_OFF_A), a_lo = a_hi + B1_A_PLANE;
+      const uint32_t w_hi = smem_u32(smem + B1_OFF_W), w_lo = w_hi + B1_W_PLANE;
+      uint32_t li = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+        mbar_wait(a_full, li & 1u);
+        tc_fence_after();
+        for (uint32_t half = 0; half < 2; ++half) {
+          mbar_wait(&acc_empty[half], (li & 1u) ^ 1u);         // the epilogue drained this half's accumulators
+          tc_fence_after();
+          const uint32_t t_main = tmem_base + half * 256u, t_corr = t_main + 128u;
+          const uint32_t wh = w_hi + half * 16u * B1_W_SBO, wl = w_lo + half * 16u * B1_W_SBO;
+#pragma unroll
+          for (int ks = 0; ks < NOUT / 16; ++ks) {
+            const uint64_t ah = make_desc(a_hi + ks * 2 * B1_A_LBO, B1_A_LBO, B1_A_SBO), al = make_desc(a_lo + ks * 2 * B1_A_LBO, B1_A_LBO, B1_A_SBO);
+            const uint64_t bh = make_desc(wh + ks * 2 * 128u, 128u, B1_W_SBO), bl = make_desc(wl + ks * 2 * 128u, 128u, B1_W_SBO);
+            const uint32_t acc = ks > 0 ? 1u : 0u;
+            umma_f16(t_main, ah, bh, idesc, acc);
+            umma_f16(t_corr, ah, bl, idesc, acc);
+            umma_f16(t_corr, al, bh, idesc, 1u);
+          }
+          umma_commit(&acc_full[half]);
+        }
+        umma_commit(a_empty);                                  // planes reusable once both halves' MMAs retire
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue: mask, transpose, column sums in registers =======================
+    float* scr = reinterpret_cast<float*>(smem + B1_OFF_SCR + warp * B1_SCR_W);
+    float* xs0 = scr + 32 * 33;
+    float* xs1 = xs0 + 32;
+    float acc[8][3];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; }
+    uint32_t li = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+      const int64_t m = t * TM + warp * 32 + lane;
+      float x0 = 0.f, x1 = 0.f;
+      if (m < a.M) {
+        const float* xp = a.X + (a.x_rows ? (int64_t)a.x_rows[m] : m) * a.ldx;
+        x0 = xp[0];
+        if (a.kx > 1) x1 = xp[1];
+      }
+      __syncwarp();
+      xs0[lane] = x0; xs1[lane] = x1;
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&acc_full[half], li & 1u);
+        tc_fence_after();
+        const float inv = inv_s[(li & 1u) * TM + warp * 32 + lane];   // (written before a_full of this tile was signalled)
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)half * 256u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float vm[32], vc[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), vm);
+          tmem_ld32(trow + 128u + (uint32_t)(c * 32), vc);
+          const int j0 = half * 128 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float pre = fmaf(w0_s[j0 + i], x0, fmaf(w1_s[j0 + i], x1, b1_s[j0 + i]));
+            const float dh = fmaf(vc[i], LO_INV, vm[i]) * inv;
+            scr[lane * 33 + i] = pre > 0.f ? dh : 0.f;
+          }
+          __syncwarp();
+          float s = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; r += 4) {                    // (the rows' inputs: broadcast 16-byte reads)
+            const float4 p = *reinterpret_cast<const float4*>(xs0 + r), q = *reinterpret_cast<const float4*>(xs1 + r);
+            const float d0 = scr[r * 33 + lane], d1 = scr[(r + 1) * 33 + lane], d2 = scr[(r + 2) * 33 + lane], d3 = scr[(r + 3) * 33 + lane];
+            s += (d0 + d1) + (d2 + d3);
+            s0 = fmaf(d0, p.x, fmaf(d1, p.y, fmaf(d2, p.z, fmaf(d3, p.w, s0))));
+            s1 = fmaf(d0, q.x, fmaf(d1, q.y, fmaf(d2, q.z, fmaf(d3, q.w, s1))));
+          }
+          acc[half * 4 + c][0] += s; acc[half * 4 + c][1] += s0; acc[half * 4 + c][2] += s1;
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[half]);
+      }
+    }
+    float* pp = a.part + ((size_t)blockIdx.x * EPI_W + warp) * 3 * HIDF;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pp[(size_t)k * HIDF + i * 32 + lane] = acc[i][k];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, TM_COLS);
+}
 }  // namespace
 
 extern "C" size_t tm_selfmlp_ws_bytes() { return 2 * (size_t)W_PLANE + 256; }
@@ -654,4 +903,32 @@ extern "C" int tm_selfmlp_gen_wgrad2(int64_t M, const float* G, int64_t ldg, con
   TM_TRY(check_launch("selfmlp_gen_wgrad2"));
   split_reduce_kernel<<<(unsigned)cdiv((int64_t)NOUT * HIDF, 64), 256, 0, st>>>(part, (int64_t)NOUT * HIDF, grid, dW2, HIDF, HIDF, 0);
   return check_launch("split_reduce(selfmlp wgrad2)");
+}
+
+extern "C" size_t tm_selfmlp_bwd1_ws_bytes() { return 2 * (size_t)B1_W_PLANE + (size_t)sm_count() * EPI_W * 3 * HIDF * sizeof(float) + 1024; }
+
+extern "C" int tm_selfmlp_gen_bwd1(int64_t M, const float* G, int64_t ldg, const int32_t* g_rows, const float* X, int64_t ldx,
+                                   const int32_t* x_rows, int64_t kx, const float* W1, const float* b1, const float* W2,
+                                   float* dW1, float* db1, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(kx == 1 || kx == 2, "tm_selfmlp_gen_bwd1: the first layer must have 1 or 2 inputs");
+  TM_REQUIRE(ws && ws_bytes >= tm_selfmlp_bwd1_ws_bytes(), "tm_selfmlp_gen_bwd1: workspace too small (tm_selfmlp_bwd1_ws_bytes)");
+  TM_REQUIRE((ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0, "tm_selfmlp_gen_bwd1: G rows must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M <= 0) {
+    TM_CUDA(cudaMemsetAsync(dW1, 0, (size_t)HIDF * kx * sizeof(float), st));
+    TM_CUDA(cudaMemsetAsync(db1, 0, (size_t)HIDF * sizeof(float), st));
+    return 0;
+  }
+  uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* part = reinterpret_cast<float*>(planes + 2 * B1_W_PLANE);
+  selfmlp_pack_t_kernel<<<(NOUT * HIDF + 255) / 256, 256, 0, st>>>(W2, planes);
+  TM_TRY(check_launch("selfmlp_pack_t"));
+  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B1_SMEM + 1024));
+  const int64_t ntiles = (M + TM - 1) / TM;
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  B1Args a{M, G, ldg, g_rows, X, ldx, x_rows, (int)kx, W1, b1, planes, part};
+  selfmlp_gen_bwd1_kernel<<<grid, THREADS, B1_SMEM + 1024, st>>>(a);
+  TM_TRY(check_launch("selfmlp_gen_bwd1"));
+  selfmlp_bwd1_reduce_kernel<<<HIDF / 32, 256, 0, st>>>(part, grid * EPI_W, (int)kx, dW1, db1);
+  return check_launch("selfmlp_bwd1_reduce");
 }

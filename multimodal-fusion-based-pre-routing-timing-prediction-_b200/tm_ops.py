@@ -223,7 +223,8 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
             raise RuntimeError("mlp2_backward: generated hidden activations need b1 (and have no dx path)")
         prec = _precision()
         prec = 3 if prec is None else prec
-        if FUSED_SELF_MLP and hid == 256 and nout == 128 and prec == 3 and ldg % 4 == 0 and g.data_ptr() % 16 == 0:
+        fused = FUSED_SELF_MLP and hid == 256 and nout == 128 and prec == 3 and ldg % 4 == 0 and g.data_ptr() % 16 == 0
+        if fused:
             # the reference's sizes: bias gradient and max |g| in one pass, then the fused weight-gradient kernel
             # (hidden layer generated as a tcgen05 operand, accumulators resident in TMEM: tm_selfmlp.cu)
             gmax = torch.empty(1, dtype=torch.float32, device=dev)
@@ -237,9 +238,14 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
             nb = tm_lib.ws_bytes("tm_tc_gemm_tn_ws", nout, hid, n_rows)
             call("tm_tc_mlp2_smallk_wgrad2", nout, hid, n_rows, g, ldg, g_rows, x, ldx, rows, kin, _f32c(w1), _f32c(b1), dw2,
                  prec, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
-        nb = tm_lib.ws_bytes("tm_tc_mlp1_bwd_ws", hid)
-        call("tm_tc_mlp1_bwd_fused", n_rows, hid, nout, g, ldg, g_rows, transpose(_f32c(w2)), None, 0, x, ldx, rows, kin,
-             _f32c(w1), _f32c(b1), dw1, db1, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
+        if fused:
+            nb = tm_lib.ws_bytes("tm_selfmlp_bwd1_ws_bytes")
+            call("tm_selfmlp_gen_bwd1", n_rows, g, ldg, g_rows, x, ldx, rows, kin, _f32c(w1), _f32c(b1), _f32c(w2), dw1, db1,
+                 tm_lib.workspace(nb, dev), nb, stream())
+        else:
+            nb = tm_lib.ws_bytes("tm_tc_mlp1_bwd_ws", hid)
+            call("tm_tc_mlp1_bwd_fused", n_rows, hid, nout, g, ldg, g_rows, transpose(_f32c(w2)), None, 0, x, ldx, rows, kin,
+                 _f32c(w1), _f32c(b1), dw1, db1, tm_lib.workspace(nb, dev), nb, tm_lib.err_flag(dev), stream())
         aux_join()
         return dw1, db1, dw2, db2, None
     if need_dx and wgrad_stream is not None:

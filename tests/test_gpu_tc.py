@@ -209,3 +209,35 @@ def test_selfmlp_gen_wgrad2(lib, M, kx, gather, gscale):
     dw2 = torch.empty(128, 256, device=DEV)
     lib.call("tm_selfmlp_gen_wgrad2", M, G, 128, gr, X, kx, xr, kx, W1, b1, gmax, dw2, lib.workspace(nb, DEV), nb, lib.stream())
     assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("M,kx,gather,gscale", [(1000, 2, False, 1.0), (40000, 2, True, 1e-4), (129, 1, True, 1.0),
+                                                 (70001, 2, True, 1e-8)])
+def test_selfmlp_gen_bwd1(lib, M, kx, gather, gscale):
+    """tm_selfmlp_gen_bwd1: db1 / dW1 of Linear(kx,256) -> ReLU -> Linear(256,128) from dh = (G W2) * (pre > 0), dh
+    never stored; against the fp64 definition (mask taken from the fp32 pre-activation, as the forward takes it)."""
+    torch.manual_seed(M + 3 * kx)
+    n_src = M + 41
+    X = torch.randn(n_src, kx, device=DEV)
+    W1 = torch.randn(256, kx, device=DEV) * 0.5
+    b1 = torch.randn(256, device=DEV) * 0.3
+    W2 = torch.randn(128, 256, device=DEV) * 0.1
+    G = torch.randn(n_src, 128, device=DEV) * gscale
+    G[::5] *= 1e-5
+    xr = torch.randperm(n_src, device=DEV)[:M].int().contiguous() if gather else None
+    gr = torch.randperm(n_src, device=DEV)[:M].int().contiguous() if gather else None
+    xs = X[xr.long()] if gather else X[:M]
+    gs = G[gr.long()] if gather else G[:M]
+    pre = xs.double() @ W1.double().t() + b1.double()
+    dh = (gs.double() @ W2.double()) * (pre > 0)
+    ref_db = dh.sum(0)
+    ref_dw = dh.t() @ xs.double()
+    nb = lib.ws_bytes("tm_selfmlp_bwd1_ws_bytes")
+    dW1 = torch.empty(256, kx, device=DEV)
+    db1 = torch.empty(256, device=DEV)
+    lib.call("tm_selfmlp_gen_bwd1", M, G, 128, gr, X, kx, xr, kx, W1, b1, W2, dW1, db1, lib.workspace(nb, DEV), nb, lib.stream())
+    assert_close(db1, ref_db, 1e-3, 2e-4, "db1", max_bad=4)          # (a gate at |pre| ~ 1 ulp may go either way)
+    assert_close(dW1, ref_dw, 1e-3, 2e-4, "dW1", max_bad=8)
+    dW1b, db1b = torch.empty_like(dW1), torch.empty_like(db1)
+    lib.call("tm_selfmlp_gen_bwd1", M, G, 128, gr, X, kx, xr, kx, W1, b1, W2, dW1b, db1b, lib.workspace(nb, DEV), nb, lib.stream())
+    assert torch.equal(dW1, dW1b) and torch.equal(db1, db1b)
