@@ -673,8 +673,17 @@ struct B1Args {
   const float* b1;
   const uint8_t* wplanes;
   float* part;            // [grid * EPI_W][3][256]
+  // STORE form (tm_selfmlp_rows_dh): dh rows are written, masked by a STORED hidden activation
+  const float* H;         // [.][ldh] hidden activations of the forward
+  int64_t ldh;
+  const int* h_rows;      // row of H (and of DH) that belongs to row m (NULL: m)
+  float* DH;
+  int64_t lddh;
 };
 
+// STORE == false: first-layer gradients of the generated MLP (above).  STORE == true: the same product with the epilogue
+// of the general MLP backward -- dh = (G W2) * (H > 0) written to DH (fc_cell_self: 36 inputs, the hidden layer is stored).
+template <bool STORE>
 __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_bwd1_kernel(B1Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* w0_s = reinterpret_cast<float*>(smem + B1_OFF_P);
@@ -700,10 +709,12 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_bwd1_kernel(B1Args a) 
                    ::"r"(smem_u32(smem + B1_OFF_W + i * (B1_W_PLANE / 2))), "l"(a.wplanes + (size_t)i * (B1_W_PLANE / 2)),
                      "r"(B1_W_PLANE / 2), "r"(bar) : "memory");
   }
-  for (int j = tid; j < HIDF; j += THREADS) {
-    w0_s[j] = a.W1[(size_t)j * a.kx];
-    w1_s[j] = a.kx > 1 ? a.W1[(size_t)j * a.kx + 1] : 0.f;
-    b1_s[j] = a.b1[j];
+  if constexpr (!STORE) {
+    for (int j = tid; j < HIDF; j += THREADS) {
+      w0_s[j] = a.W1[(size_t)j * a.kx];
+      w1_s[j] = a.kx > 1 ? a.W1[(size_t)j * a.kx + 1] : 0.f;
+      b1_s[j] = a.b1[j];
+    }
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, TM_COLS);
   tc_fence_before();
@@ -784,6 +795,52 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_bwd1_kernel(B1Args a) 
       }
     }
     __syncwarp();
+  } else if constexpr (STORE) {
+    // ======================= epilogue (STORE): a lane owns one row: mask from H, 128-bit stores to DH ===============
+    uint32_t li = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+      const int64_t m = t * TM + warp * 32 + lane;
+      const float* hp = nullptr;
+      float* dp = nullptr;
+      if (m < a.M) {
+        const int64_t r = a.h_rows ? (int64_t)a.h_rows[m] : m;
+        hp = a.H + r * a.ldh;
+        dp = a.DH + r * a.lddh;
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&acc_full[half], li & 1u);
+        tc_fence_after();
+        const float inv = inv_s[(li & 1u) * TM + warp * 32 + lane];
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)half * 256u;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int j0 = half * 128 + c * 32;
+          float4 mk[8];
+          if (hp) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mk[e] = ld4(hp + j0 + 4 * e);        // (in flight under the TMEM loads)
+          }
+          float vm[32], vc[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), vm);
+          tmem_ld32(trow + 128u + (uint32_t)(c * 32), vc);
+          if (dp) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float4 o;
+              o.x = mk[e].x > 0.f ? fmaf(vc[4 * e], LO_INV, vm[4 * e]) * inv : 0.f;
+              o.y = mk[e].y > 0.f ? fmaf(vc[4 * e + 1], LO_INV, vm[4 * e + 1]) * inv : 0.f;
+              o.z = mk[e].z > 0.f ? fmaf(vc[4 * e + 2], LO_INV, vm[4 * e + 2]) * inv : 0.f;
+              o.w = mk[e].w > 0.f ? fmaf(vc[4 * e + 3], LO_INV, vm[4 * e + 3]) * inv : 0.f;
+              st4(dp + j0 + 4 * e, o);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[half]);
+      }
+    }
   } else {
     // ======================= epilogue: mask, transpose, column sums in registers =======================
     float* scr = reinterpret_cast<float*>(smem + B1_OFF_SCR + warp * B1_SCR_W);
@@ -923,12 +980,36 @@ extern "C" int tm_selfmlp_gen_bwd1(int64_t M, const float* G, int64_t ldg, const
   float* part = reinterpret_cast<float*>(planes + 2 * B1_W_PLANE);
   selfmlp_pack_t_kernel<<<(NOUT * HIDF + 255) / 256, 256, 0, st>>>(W2, planes);
   TM_TRY(check_launch("selfmlp_pack_t"));
-  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B1_SMEM + 1024));
+  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_bwd1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B1_SMEM + 1024));
   const int64_t ntiles = (M + TM - 1) / TM;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  B1Args a{M, G, ldg, g_rows, X, ldx, x_rows, (int)kx, W1, b1, planes, part};
-  selfmlp_gen_bwd1_kernel<<<grid, THREADS, B1_SMEM + 1024, st>>>(a);
+  B1Args a{M, G, ldg, g_rows, X, ldx, x_rows, (int)kx, W1, b1, planes, part, nullptr, 0, nullptr, nullptr, 0};
+  selfmlp_gen_bwd1_kernel<false><<<grid, THREADS, B1_SMEM + 1024, st>>>(a);
   TM_TRY(check_launch("selfmlp_gen_bwd1"));
   selfmlp_bwd1_reduce_kernel<<<HIDF / 32, 256, 0, st>>>(part, grid * EPI_W, (int)kx, dW1, db1);
   return check_launch("selfmlp_bwd1_reduce");
+}
+
+extern "C" size_t tm_selfmlp_rows_dh_ws_bytes() { return 2 * (size_t)B1_W_PLANE + 256; }
+
+/* DH[r, 0:256] = (G[g_rows[m], 0:128] @ W2) * (H[r, 0:256] > 0), r = h_rows ? h_rows[m] : m, for m < M: the hidden-layer
+ * gradient of Linear(., 256) -> ReLU -> Linear(256, 128) whose hidden activations H were stored (fc_cell_self). */
+extern "C" int tm_selfmlp_rows_dh(int64_t M, const float* G, int64_t ldg, const int32_t* g_rows, const float* W2, const float* H,
+                                  int64_t ldh, const int32_t* h_rows, float* DH, int64_t lddh, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  TM_REQUIRE(ws && ws_bytes >= tm_selfmlp_rows_dh_ws_bytes(), "tm_selfmlp_rows_dh: workspace too small (tm_selfmlp_rows_dh_ws_bytes)");
+  TM_REQUIRE((ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 && (ldh & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0 &&
+                 (lddh & 3) == 0 && (reinterpret_cast<uintptr_t>(DH) & 15) == 0,
+             "tm_selfmlp_rows_dh: G, H and DH rows must be 16-byte aligned");
+  if (M <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  selfmlp_pack_t_kernel<<<(NOUT * HIDF + 255) / 256, 256, 0, st>>>(W2, planes);
+  TM_TRY(check_launch("selfmlp_pack_t"));
+  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_bwd1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B1_SMEM + 1024));
+  const int64_t ntiles = (M + TM - 1) / TM;
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  B1Args a{M, G, ldg, g_rows, nullptr, 0, nullptr, 0, nullptr, nullptr, planes, nullptr, H, ldh, h_rows, DH, lddh};
+  selfmlp_gen_bwd1_kernel<true><<<grid, THREADS, B1_SMEM + 1024, st>>>(a);
+  return check_launch("selfmlp_rows_dh");
 }

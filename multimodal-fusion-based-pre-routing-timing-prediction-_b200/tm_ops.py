@@ -198,6 +198,18 @@ def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, 
     return h
 
 
+def _hidden_grad(n_rows, hid, nout, g, ldg, g_rows, w2, h, h_rows, dh):
+    """dh[r] = (g[g_rows] @ w2) * (h[r] > 0), r = h_rows or the row itself."""
+    if (FUSED_SELF_MLP and hid == 256 and nout == 128 and _precision() == 3 and ldg % 4 == 0 and g.data_ptr() % 16 == 0
+            and h.stride(0) % 4 == 0 and h.data_ptr() % 16 == 0 and dh.data_ptr() % 16 == 0):
+        # the reference's sizes: fp16 two-term split operands, W2 resident, tcgen05 (tm_selfmlp.cu)
+        nb = tm_lib.ws_bytes("tm_selfmlp_rows_dh_ws_bytes")
+        call("tm_selfmlp_rows_dh", n_rows, g, ldg, g_rows, _f32c(w2), h, h.stride(0), h_rows, dh, dh.stride(0),
+             tm_lib.workspace(nb, dh.device), nb, stream())
+        return
+    gemm_nn(n_rows, hid, nout, g, ldg, _f32c(w2), hid, dh, hid, a_rows=g_rows, c_rows=h_rows, mask=h, ldmask=hid)
+
+
 def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=False, b1=None, wgrad_stream=None,
                   h_rows=None):
     """Gradients of a two-layer MLP.  ``g``: dLoss/d(out) rows (optionally gathered by ``g_rows``).
@@ -265,7 +277,7 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
             raise RuntimeError("mlp2_backward: h_rows has no dx path")
         # dh lives in the rows of h it belongs to, so the ReLU mask of the epilogue reads the matching row
         dh = torch.empty(h.shape[0], hid, dtype=torch.float32, device=dev)
-        gemm_nn(n_rows, hid, nout, g, ldg, _f32c(w2), hid, dh, hid, a_rows=g_rows, c_rows=h_rows, mask=h, ldmask=hid)
+        _hidden_grad(n_rows, hid, nout, g, ldg, g_rows, w2, h, h_rows, dh)
         gemm_tn(hid, kin, n_rows, dh, hid, x, ldx, dw1, kin, a_rows=h_rows, b_rows=rows, colsum_a=db1)
         aux_join()
         return dw1, db1, dw2, db2, None
@@ -278,7 +290,7 @@ def mlp2_backward(x, ldx, rows, n_rows, w1, w2, h, g, ldg, g_rows=None, need_dx=
         aux_join()
         return dw1, db1, dw2, db2, None
     dh = torch.empty(n_rows, hid, dtype=torch.float32, device=dev)
-    gemm_nn(n_rows, hid, nout, g, ldg, _f32c(w2), hid, dh, hid, a_rows=g_rows, mask=h, ldmask=hid)
+    _hidden_grad(n_rows, hid, nout, g, ldg, g_rows, w2, h, None, dh)
     gemm_tn(hid, kin, n_rows, dh, hid, x, ldx, dw1, kin, b_rows=rows, colsum_a=db1)
     dx = None
     if need_dx:

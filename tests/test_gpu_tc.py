@@ -241,3 +241,28 @@ def test_selfmlp_gen_bwd1(lib, M, kx, gather, gscale):
     dW1b, db1b = torch.empty_like(dW1), torch.empty_like(db1)
     lib.call("tm_selfmlp_gen_bwd1", M, G, 128, gr, X, kx, xr, kx, W1, b1, W2, dW1b, db1b, lib.workspace(nb, DEV), nb, lib.stream())
     assert torch.equal(dW1, dW1b) and torch.equal(db1, db1b)
+
+
+@pytest.mark.parametrize("M,gather,gscale", [(1000, False, 1.0), (40000, True, 1e-5), (129, True, 1.0)])
+def test_selfmlp_rows_dh(lib, M, gather, gscale):
+    """tm_selfmlp_rows_dh: DH[r] = (G[g_rows] W2) * (H[r] > 0) with r through a row list (the cone's rows of a larger
+    hidden matrix); rows outside the list stay untouched."""
+    torch.manual_seed(M)
+    n_src, n_h = M + 41, M + 29
+    W2 = torch.randn(128, 256, device=DEV) * 0.1
+    G = torch.randn(n_src, 128, device=DEV) * gscale
+    G[::3] *= 1e-4
+    H = torch.randn(n_h, 256, device=DEV).relu_()
+    gr = torch.randperm(n_src, device=DEV)[:M].int().contiguous() if gather else None
+    hr = torch.randperm(n_h, device=DEV)[:M].int().contiguous() if gather else None
+    gs = G[gr.long()] if gather else G[:M]
+    hs = H[hr.long()] if gather else H[:M]
+    ref = (gs.double() @ W2.double()) * (hs > 0)
+    DH = torch.full((n_h, 256), 9.0, device=DEV)
+    nb = lib.ws_bytes("tm_selfmlp_rows_dh_ws_bytes")
+    lib.call("tm_selfmlp_rows_dh", M, G, 128, gr, W2, H, 256, hr, DH, 256, lib.workspace(nb, DEV), nb, lib.stream())
+    got = DH[hr.long()] if gather else DH[:M]
+    assert_close(got, ref, 1e-4, 2e-5, "dh")
+    touched = torch.zeros(n_h, dtype=torch.bool, device=DEV)
+    touched[hr.long() if gather else torch.arange(M, device=DEV)] = True
+    assert bool((DH[~touched] == 9.0).all())
