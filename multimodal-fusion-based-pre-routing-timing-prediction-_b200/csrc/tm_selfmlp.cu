@@ -907,6 +907,187 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_bwd1_kernel(B1Args a) 
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, TM_COLS);
 }
+
+// =============================================================================================
+// First layer of a stored-hidden MLP:  HID[m][0:256] = relu(X[x_rows[m]][0:kin] W1^T + b1), kin <= 48 (fc_cell_self: 36).
+// Output-bound (1 KB written per 144 bytes read): A = the x rows (a loader thread owns one row: per-row scale without
+// shuffles, K padded to 48 = three k-steps), B = W1 split once and resident (2 x 24 KB), two column halves with their
+// own accumulator pair, row-direct storing epilogue with bias + ReLU.
+// =============================================================================================
+constexpr int L1_K = 48;
+constexpr uint32_t L1_SBO = (L1_K / 8) * 128;                                   // 768
+constexpr uint32_t L1_A_PLANE = (TM / 8) * L1_SBO, L1_W_PLANE = (HIDF / 8) * L1_SBO;   // 12 KB, 24 KB
+constexpr uint32_t L1_OFF_W = 0, L1_OFF_A = 2 * L1_W_PLANE, L1_OFF_B = L1_OFF_A + 2 * L1_A_PLANE;
+constexpr uint32_t L1_OFF_INV = L1_OFF_B + HIDF * 4, L1_OFF_BAR = L1_OFF_INV + 2 * TM * 4;
+constexpr uint32_t L1_SMEM = L1_OFF_BAR + 8 * 8 + 16;
+constexpr int L1_LOAD_W = TM / 32;                                              // loader warps that own rows
+
+__global__ void selfmlp_pack_w1_kernel(const float* __restrict__ W1, int kin, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HIDF * L1_K) return;
+  const int j = i / L1_K, k = i - j * L1_K;
+  __half h, l;
+  split_h(k < kin ? W1[(size_t)j * kin + k] : 0.f, h, l);
+  const uint32_t off = (uint32_t)(j >> 3) * L1_SBO + (uint32_t)(k >> 3) * 128 + (uint32_t)(j & 7) * 16 + (uint32_t)(k & 7) * 2;
+  *reinterpret_cast<__half*>(out + off) = h;
+  *reinterpret_cast<__half*>(out + L1_W_PLANE + off) = l;
+}
+
+struct L1Args {
+  int64_t M;
+  const float* X;
+  int64_t ldx;
+  const int* x_rows;
+  int kin;                // multiple of 4, <= 48
+  const float* b1;
+  const uint8_t* wplanes;
+  float* out;
+  int64_t ldo;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) selfmlp_lin1_kernel(L1Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* b1_s = reinterpret_cast<float*>(smem + L1_OFF_B);
+  float* inv_s = reinterpret_cast<float*>(smem + L1_OFF_INV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L1_OFF_BAR);
+  uint64_t *a_full = bars, *a_empty = bars + 1, *acc_full = bars + 2, *acc_empty = bars + 4, *wbar = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.M + TM - 1) / TM;
+
+  if (tid == 0) {
+    mbar_init(a_full, L1_LOAD_W); mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_W); }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+    const uint32_t bar = smem_u32(wbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * L1_W_PLANE) : "memory");
+    for (int i = 0; i < 2; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(smem + L1_OFF_W + i * L1_W_PLANE)), "l"(a.wplanes + (size_t)i * L1_W_PLANE), "r"(L1_W_PLANE), "r"(bar)
+                   : "memory");
+  }
+  for (int j = tid; j < HIDF; j += THREADS) b1_s[j] = a.b1[j];
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= GEN_WARP0 && warp < GEN_WARP0 + L1_LOAD_W) {
+    // ======================= loaders: thread = one row of the tile =======================
+    const int row = tid - GEN_WARP0 * 32;
+    const int nq = a.kin >> 2;
+    float4 v[L1_K / 4];
+    auto fetch = [&](int64_t t) {
+      const int64_t m = t * TM + row;
+#pragma unroll
+      for (int q = 0; q < L1_K / 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < a.M) {
+        const float4* xp = reinterpret_cast<const float4*>(a.X + (a.x_rows ? (int64_t)a.x_rows[m] : m) * a.ldx);
+#pragma unroll
+        for (int q = 0; q < L1_K / 4; ++q)
+          if (q < nq) v[q] = __ldg(xp + q);
+      }
+    };
+    if ((int64_t)blockIdx.x < ntiles) fetch(blockIdx.x);
+    uint32_t li = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+      mbar_wait(a_empty, (li & 1u) ^ 1u);
+      float rm = 0.f;
+#pragma unroll
+      for (int q = 0; q < L1_K / 4; ++q) rm = fmaxf(rm, fmaxf(fmaxf(fabsf(v[q].x), fabsf(v[q].y)), fmaxf(fabsf(v[q].z), fabsf(v[q].w))));
+      float sc, inv;
+      bound_scale(rm, sc, inv);
+      uint8_t* hi_p = smem + L1_OFF_A + (uint32_t)(row >> 3) * L1_SBO + (uint32_t)(row & 7) * 16;
+#pragma unroll
+      for (int kg = 0; kg < L1_K / 8; ++kg) {
+        uint32_t hw[4], lw[4];
+        split_pair(v[2 * kg].x * sc, v[2 * kg].y * sc, hw[0], lw[0]);
+        split_pair(v[2 * kg].z * sc, v[2 * kg].w * sc, hw[1], lw[1]);
+        split_pair(v[2 * kg + 1].x * sc, v[2 * kg + 1].y * sc, hw[2], lw[2]);
+        split_pair(v[2 * kg + 1].z * sc, v[2 * kg + 1].w * sc, hw[3], lw[3]);
+        *reinterpret_cast<uint4*>(hi_p + kg * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(hi_p + L1_A_PLANE + kg * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      inv_s[(li & 1u) * TM + row] = inv;
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+      if (t + gridDim.x < ntiles) fetch(t + gridDim.x);
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = make_idesc_f16(NOUT);
+      const uint32_t a_hi = smem_u32(smem + L1_OFF_A), a_lo = a_hi + L1_A_PLANE;
+      const uint32_t w_hi = smem_u32(smem + L1_OFF_W), w_lo = w_hi + L1_W_PLANE;
+      uint32_t li = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+        mbar_wait(a_full, li & 1u);
+        tc_fence_after();
+        for (uint32_t half = 0; half < 2; ++half) {
+          mbar_wait(&acc_empty[half], (li & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t t_main = tmem_base + half * 256u, t_corr = t_main + 128u;
+          const uint32_t wh = w_hi + half * 16u * L1_SBO, wl = w_lo + half * 16u * L1_SBO;
+#pragma unroll
+          for (int ks = 0; ks < L1_K / 16; ++ks) {
+            const uint64_t ah = make_desc(a_hi + ks * 256u, 128u, L1_SBO), al = make_desc(a_lo + ks * 256u, 128u, L1_SBO);
+            const uint64_t bh = make_desc(wh + ks * 256u, 128u, L1_SBO), bl = make_desc(wl + ks * 256u, 128u, L1_SBO);
+            const uint32_t acc = ks > 0 ? 1u : 0u;
+            umma_f16(t_main, ah, bh, idesc, acc);
+            umma_f16(t_corr, ah, bl, idesc, acc);
+            umma_f16(t_corr, al, bh, idesc, 1u);
+          }
+          umma_commit(&acc_full[half]);
+        }
+        umma_commit(a_empty);
+      }
+    }
+    __syncwarp();
+  } else if (warp < EPI_W) {
+    // ======================= epilogue: a lane owns one row: bias, ReLU, 128-bit stores =======================
+    uint32_t li = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
+      const int64_t m = t * TM + warp * 32 + lane;
+      float* op = m < a.M ? a.out + m * a.ldo : nullptr;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&acc_full[half], li & 1u);
+        tc_fence_after();
+        const float inv = inv_s[(li & 1u) * TM + warp * 32 + lane];
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)half * 256u;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int j0 = half * 128 + c * 32;
+          float vm[32], vc[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), vm);
+          tmem_ld32(trow + 128u + (uint32_t)(c * 32), vc);
+          if (op) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 b = *reinterpret_cast<const float4*>(b1_s + j0 + 4 * e);
+              float4 o;
+              o.x = fmaxf(fmaf(fmaf(vc[4 * e], LO_INV, vm[4 * e]), inv, b.x), 0.f);
+              o.y = fmaxf(fmaf(fmaf(vc[4 * e + 1], LO_INV, vm[4 * e + 1]), inv, b.y), 0.f);
+              o.z = fmaxf(fmaf(fmaf(vc[4 * e + 2], LO_INV, vm[4 * e + 2]), inv, b.z), 0.f);
+              o.w = fmaxf(fmaf(fmaf(vc[4 * e + 3], LO_INV, vm[4 * e + 3]), inv, b.w), 0.f);
+              st4(op + j0 + 4 * e, o);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[half]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, TM_COLS);
+}
 }  // namespace
 
 extern "C" size_t tm_selfmlp_ws_bytes() { return 2 * (size_t)W_PLANE + 256; }
@@ -1012,4 +1193,26 @@ extern "C" int tm_selfmlp_rows_dh(int64_t M, const float* G, int64_t ldg, const 
   B1Args a{M, G, ldg, g_rows, nullptr, 0, nullptr, 0, nullptr, nullptr, planes, nullptr, H, ldh, h_rows, DH, lddh};
   selfmlp_gen_bwd1_kernel<true><<<grid, THREADS, B1_SMEM + 1024, st>>>(a);
   return check_launch("selfmlp_rows_dh");
+}
+
+extern "C" size_t tm_selfmlp_lin1_ws_bytes() { return 2 * (size_t)L1_W_PLANE + 256; }
+
+/* HID[m, 0:256] = relu(X[x_rows[m], 0:kin] @ W1^T + b1) for m < M (W1 [256][kin] as stored; kin % 4 == 0, kin <= 48). */
+extern "C" int tm_selfmlp_lin1_relu(int64_t M, const float* X, int64_t ldx, const int32_t* x_rows, int64_t kin, const float* W1,
+                                    const float* b1, float* HID, int64_t ldh, void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(kin > 0 && kin <= L1_K && (kin & 3) == 0, "tm_selfmlp_lin1_relu: kin must be a multiple of 4, <= 48");
+  TM_REQUIRE(ws && ws_bytes >= tm_selfmlp_lin1_ws_bytes(), "tm_selfmlp_lin1_relu: workspace too small (tm_selfmlp_lin1_ws_bytes)");
+  TM_REQUIRE((ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (ldh & 3) == 0 && (reinterpret_cast<uintptr_t>(HID) & 15) == 0,
+             "tm_selfmlp_lin1_relu: X and HID rows must be 16-byte aligned");
+  if (M <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  selfmlp_pack_w1_kernel<<<(HIDF * L1_K + 255) / 256, 256, 0, st>>>(W1, (int)kin, planes);
+  TM_TRY(check_launch("selfmlp_pack_w1"));
+  TM_CUDA(cudaFuncSetAttribute(selfmlp_lin1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1_SMEM + 1024));
+  const int64_t ntiles = (M + TM - 1) / TM;
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  L1Args a{M, X, ldx, x_rows, (int)kin, b1, planes, HID, ldh};
+  selfmlp_lin1_kernel<<<grid, THREADS, L1_SMEM + 1024, st>>>(a);
+  return check_launch("selfmlp_lin1");
 }

@@ -193,7 +193,14 @@ def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, 
              out, ldo, out_rows, prec, tm_lib.err_flag(out.device), stream())
         return None
     h = torch.empty(n_rows, hid, dtype=torch.float32, device=out.device)
-    gemm_nn(n_rows, hid, kin, x, ldx, _f32c(w1), kin, h, hid, a_rows=rows, bias=b1, flags=RELU, b_is_nk=True, math=math)
+    if (FUSED_SELF_MLP and hid == 256 and prec == 3 and kin % 4 == 0 and kin <= 48 and ldx % 4 == 0 and x.data_ptr() % 16 == 0
+            and n_rows > 0):
+        # fc_cell_self's first layer (36 inputs): output-bound, fp16 two-term split on tcgen05 (tm_selfmlp.cu)
+        nb = tm_lib.ws_bytes("tm_selfmlp_lin1_ws_bytes")
+        call("tm_selfmlp_lin1_relu", n_rows, x, ldx, rows, kin, _f32c(w1), _f32c(b1), h, hid, tm_lib.workspace(nb, out.device),
+             nb, stream())
+    else:
+        gemm_nn(n_rows, hid, kin, x, ldx, _f32c(w1), kin, h, hid, a_rows=rows, bias=b1, flags=RELU, b_is_nk=True, math=math)
     gemm_nn(n_rows, nout, hid, h, hid, _f32c(w2), hid, out, ldo, c_rows=out_rows, bias=b2, b_is_nk=True, math=math)
     return h
 

@@ -266,3 +266,22 @@ def test_selfmlp_rows_dh(lib, M, gather, gscale):
     touched = torch.zeros(n_h, dtype=torch.bool, device=DEV)
     touched[hr.long() if gather else torch.arange(M, device=DEV)] = True
     assert bool((DH[~touched] == 9.0).all())
+
+
+@pytest.mark.parametrize("M,kin,gather,xscale", [(1000, 36, False, 1.0), (40000, 36, True, 1e-3), (129, 48, True, 50.0), (777, 4, False, 1.0)])
+def test_selfmlp_lin1_relu(lib, M, kin, gather, xscale):
+    """tm_selfmlp_lin1_relu: HID = relu(X[x_rows] W1^T + b1) for up to 48 inputs (fc_cell_self: 36), fp32-class."""
+    torch.manual_seed(M + kin)
+    n_src = M + 19
+    X = torch.randn(n_src, kin, device=DEV) * xscale
+    X[::4] *= 1e-3
+    W1 = torch.randn(256, kin, device=DEV) * 0.3
+    b1 = torch.randn(256, device=DEV) * 0.2
+    xr = torch.randperm(n_src, device=DEV)[:M].int().contiguous() if gather else None
+    xs = X[xr.long()] if gather else X[:M]
+    ref = (xs.double() @ W1.double().t() + b1.double()).relu()
+    H = torch.full((M + 5, 256), -3.0, device=DEV)
+    nb = lib.ws_bytes("tm_selfmlp_lin1_ws_bytes")
+    lib.call("tm_selfmlp_lin1_relu", M, X, kin, xr, kin, W1, b1, H, 256, lib.workspace(nb, DEV), nb, lib.stream())
+    assert_close(H[:M], ref, 1e-4, 2e-5, "lin1")
+    assert bool((H[M:] == -3.0).all())
