@@ -458,6 +458,9 @@ int tm_tc_mlp2_smallk_wgrad2(int64_t Mo, int64_t hid, int64_t R, const float* G,
                              const float* X, int64_t ldx, const int32_t* x_rows, int64_t kx, const float* W1,
                              const float* b1, float* dW2, int precision, void* ws, size_t ws_bytes, int* err,
                              void* stream);
+/* At most `cap` persistent CTAs for the tcgen05 GEMM / convolution launches of the calling thread (0 = one per SM);
+ * returns the previous value.  Lets a caller keep SMs free for a latency-critical kernel chain on another stream. */
+int tm_tc_set_grid_cap(int cap);
 size_t tm_tc_gemm_tn_ws(int64_t M, int64_t N, int64_t R);
 int tm_tc_gemm_tn(int64_t M, int64_t N, int64_t R, const float* A, int64_t lda, const int32_t* a_rows,
                   const float* B, int64_t ldb, const int32_t* b_rows, float* C, int64_t ldc,

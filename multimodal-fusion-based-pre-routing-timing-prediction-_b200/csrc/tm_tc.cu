@@ -284,3 +284,11 @@ extern "C" int tm_tc_conv2d_wgrad_nhwc(int64_t B, int64_t H, int64_t W, int64_t 
   split_reduce_kernel<<<(unsigned)cdiv(M * N, 64), 256, 0, st>>>((const float*)ws, M * N, splits, dwf, N, N, 0);
   return check_launch("split_reduce(tc conv)");
 }
+
+/* At most `cap` persistent CTAs for the tcgen05 GEMM / convolution launches made by the calling thread from now on
+ * (0 = one per SM, the default).  Returns the previous value. */
+extern "C" int tm_tc_set_grid_cap(int cap) {
+  const int prev = tc::tc_grid_cap();
+  tc::tc_grid_cap() = cap < 0 ? 0 : cap;
+  return prev;
+}

@@ -1450,6 +1450,11 @@ int launch_one(const AL& al, const BL& bl, const EP& ep, int64_t M, int64_t N, i
   return check_launch("tc_gemm");
 }
 
+inline int& tc_grid_cap() {
+  static thread_local int cap = 0;
+  return cap;
+}
+
 template <class AL, class BL, class EP, int BN, int PLANES>
 int launch_tf(const AL& al, const BL& bl, const EP& ep, int64_t M, int64_t N, int64_t K, int splits,
               int64_t k_per_split, int* err, cudaStream_t st) {
@@ -1476,7 +1481,11 @@ int launch_tf(const AL& al, const BL& bl, const EP& ep, int64_t M, int64_t N, in
     cudaMemsetAsync(trace_buf, 0, 1024 * sizeof(long long), st);
     tm.trace = trace_buf;
   }
-  const int64_t grid = tm.total < sm_count() ? tm.total : sm_count();
+  // tm_tc_set_grid_cap(n): at most n persistent CTAs for the launches of the calling thread (0 = one per SM) -- lets
+  // a caller keep SMs free for a latency-critical kernel chain on another stream
+  int64_t lim = sm_count();
+  if (!IsReduce<EP>::value && tc_grid_cap() > 0 && tc_grid_cap() < lim) lim = tc_grid_cap();
+  const int64_t grid = tm.total < lim ? tm.total : lim;
   kern<<<(unsigned)grid, TF_THREADS, sm, st>>>(al, bl, ep, M, N, tm, err);
   if (trace_on) {
     static long long h[1024];

@@ -238,8 +238,11 @@ class DesignStep:
         G = torch.empty(sched.n, D, dtype=torch.float32, device=dev)                 # dLoss/dH, seeded at the endpoints
         H, saved = tm_ops.gnn_forward(sched, b.cell_feat, b.net_feat, gp, save=True, x_rows=x_rows,
                                       impl=16 if side is not main and os.environ.get("TM_GNN_IMPL") is None else None)
+        img_cap = int(os.environ.get("TM_IMAGE_SM_CAP", "0")) if side is not main else 0
         with torch.cuda.stream(side):
+            old_cap = tm_lib.lib().tm_tc_set_grid_cap(img_cap)
             fmap, ust = tm_unet.unet_forward(cnn, b.image, need_bwd=True, update_stats=cnn.training)
+            tm_lib.lib().tm_tc_set_grid_cap(old_cap)
             feat = fmap.reshape(-1)
             # everything of the head that does not read H runs here, off the netlist branch's critical path
             # (the image stream is idle long before the 101 levels finish): mask fusion, level embedding, G = 0
@@ -276,7 +279,9 @@ class DesignStep:
         self._assign(pairs)
         self._post_allreduce("gnn", [p for p, _ in pairs])
         with torch.cuda.stream(side):
+            old_cap = tm_lib.lib().tm_tc_set_grid_cap(img_cap)
             ug = tm_unet.unet_backward(cnn, ust, dF.reshape(fmap.shape))
+            tm_lib.lib().tm_tc_set_grid_cap(old_cap)
             upairs = [(self.cnn_params[k], ug[k]) for k in self.cnn_names]
             self._assign(upairs)
             self._post_allreduce("unet", [p for p, _ in upairs])
