@@ -267,6 +267,10 @@ int tm_scatter_add_cols(int64_t T, int64_t w, const float* src, int64_t lds, int
 size_t tm_colsum_ws(int64_t R, int64_t C);
 int tm_colsum(int64_t R, int64_t C, const float* X, int64_t ld, const int32_t* rows, float* out,
               int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* out[c_rows[m] * ldo] = act(X[a_rows[m], 0:K] . w + bias[0]): nn.Linear(K, 1) (mlp_fuse's last layer, model.py:292),
+ * one warp per row. */
+int tm_rowdot(int64_t M, int64_t K, const float* X, int64_t ldx, const int32_t* a_rows, const float* w,
+              const float* bias, float* out, int64_t ldo, const int32_t* c_rows, int relu, void* stream);
 /* tm_colsum (accumulate = 0) that also returns max |X[rows]| in absmax[0] (C % 4 == 0, 16-byte aligned rows). */
 int tm_colsum_absmax(int64_t R, int64_t C, const float* X, int64_t ld, const int32_t* rows, float* out,
                      float* absmax, void* ws, size_t ws_bytes, void* stream);

@@ -448,6 +448,43 @@ extern "C" int tm_colsum_absmax(int64_t R, int64_t C, const float* X, int64_t ld
   return check_launch("colsum_final");
 }
 
+namespace {
+// out[rows ? c_rows[m] : m] = act(X[a_rows ? a_rows[m] : m, 0:K] . w + bias): one warp per row (Linear(K, 1): the head's
+// last layer -- a 128 x 32 tensor-core tile or a 128 x 16 FFMA tile would be almost all padding)
+__global__ void __launch_bounds__(256)
+rowdot_kernel(int64_t M, int64_t K, const float* __restrict__ X, int64_t ldx, const int* __restrict__ a_rows,
+              const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int64_t ldo,
+              const int* __restrict__ c_rows, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const float* x = X + (a_rows ? (int64_t)a_rows[m] : m) * ldx;
+  float s = 0.f;
+  if ((K & 3) == 0 && (ldx & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    for (int64_t k = lane * 4; k < K; k += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + k)), b = __ldg(reinterpret_cast<const float4*>(w + k));
+      s = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s))));
+    }
+  } else {
+    for (int64_t k = lane; k < K; k += 32) s = fmaf(x[k], w[k], s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (bias) s += bias[0];
+    if (relu) s = fmaxf(s, 0.f);
+    out[(c_rows ? (int64_t)c_rows[m] : m) * ldo] = s;
+  }
+}
+}  // namespace
+
+/* out[c_rows[m]] = act(X[a_rows[m], 0:K] . w + bias[0]) -- nn.Linear(K, 1) (mlp_fuse's last layer, model.py:292). */
+extern "C" int tm_rowdot(int64_t M, int64_t K, const float* X, int64_t ldx, const int32_t* a_rows, const float* w,
+                         const float* bias, float* out, int64_t ldo, const int32_t* c_rows, int relu, void* stream) {
+  if (M <= 0) return 0;
+  rowdot_kernel<<<(unsigned)cdiv(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(M, K, X, ldx, a_rows, w, bias, out, ldo, c_rows, relu);
+  return check_launch("rowdot");
+}
+
 extern "C" int tm_mse(int64_t T, const float* pred, const float* y, float* loss, float* grad,
                       float grad_scale, void* stream) {
   TM_REQUIRE(T > 0, "tm_mse: empty batch");

@@ -110,6 +110,9 @@ def gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, a_rows=None, c_rows=None, bias=None
     if mask is not None:
         flags |= MASK
     prec = _precision(math)
+    if N == 1 and b_is_nk and mask is None and not (flags & ACCUM) and M > 0:
+        call("tm_rowdot", M, K, A, lda, a_rows, B, bias, C, ldc, c_rows, 1 if flags & RELU else 0, stream())
+        return
     if prec is None or K < TC_MIN_K or N < TC_MIN_N:
         if b_is_nk:
             B, ldb = transpose(B[:, :K] if B.shape[1] != K else B), N

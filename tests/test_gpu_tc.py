@@ -285,3 +285,23 @@ def test_selfmlp_lin1_relu(lib, M, kin, gather, xscale):
     lib.call("tm_selfmlp_lin1_relu", M, X, kin, xr, kin, W1, b1, H, 256, lib.workspace(nb, DEV), nb, lib.stream())
     assert_close(H[:M], ref, 1e-4, 2e-5, "lin1")
     assert bool((H[M:] == -3.0).all())
+
+
+@pytest.mark.parametrize("M,K,gather,relu", [(1350, 256, False, False), (77, 130, True, True), (5, 3, False, False)])
+def test_rowdot(lib, M, K, gather, relu):
+    """tm_rowdot: nn.Linear(K, 1) forward, one warp per row (vector and scalar paths, gathered / scattered rows)."""
+    torch.manual_seed(M + K)
+    X = torch.randn(M + 9, K, device=DEV)
+    w = torch.randn(K, device=DEV)
+    b = torch.randn(1, device=DEV)
+    ar = torch.randperm(M + 9, device=DEV)[:M].int().contiguous() if gather else None
+    cr = torch.randperm(M + 4, device=DEV)[:M].int().contiguous() if gather else None
+    xs = X[ar.long()] if gather else X[:M]
+    ref = xs.double() @ w.double() + b.double()
+    if relu:
+        ref = ref.relu()
+    out = torch.full((M + 4, 2), 4.0, device=DEV)
+    lib.call("tm_rowdot", M, K, X, K, ar, w, b, out, 2, cr, 1 if relu else 0, lib.stream())
+    got = out[cr.long(), 0] if gather else out[:M, 0]
+    assert_close(got, ref, 1e-5, 1e-5, "rowdot")
+    assert bool((out[:, 1] == 4.0).all())
