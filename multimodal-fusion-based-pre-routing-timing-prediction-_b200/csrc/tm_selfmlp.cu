@@ -919,7 +919,9 @@ constexpr uint32_t L1_SBO = (L1_K / 8) * 128;                                   
 constexpr uint32_t L1_A_PLANE = (TM / 8) * L1_SBO, L1_W_PLANE = (HIDF / 8) * L1_SBO;   // 12 KB, 24 KB
 constexpr uint32_t L1_OFF_W = 0, L1_OFF_A = 2 * L1_W_PLANE, L1_OFF_B = L1_OFF_A + 2 * L1_A_PLANE;
 constexpr uint32_t L1_OFF_INV = L1_OFF_B + HIDF * 4, L1_OFF_BAR = L1_OFF_INV + 2 * TM * 4;
-constexpr uint32_t L1_SMEM = L1_OFF_BAR + 8 * 8 + 16;
+// (requested size: more than half an SM's shared memory, so that two of these CTAs -- each allocates all 512 TMEM
+//  columns -- can never be resident on one SM)
+constexpr uint32_t L1_SMEM = (L1_OFF_BAR + 8 * 8 + 16) > 120 * 1024 ? (L1_OFF_BAR + 8 * 8 + 16) : 120 * 1024;
 constexpr int L1_LOAD_W = TM / 32;                                              // loader warps that own rows
 
 __global__ void selfmlp_pack_w1_kernel(const float* __restrict__ W1, int kin, uint8_t* __restrict__ out) {
