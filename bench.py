@@ -707,7 +707,11 @@ def main():
                                "" if world <= 1 else " with the bucketed NCCL all-reduces captured inside"
                                if os.environ.get("TM_DP_GRAPH", "1") != "0" else " + NCCL gradient all-reduce after each replay (TM_DP_GRAPH=0)"))
                            if use_graph else "eager launches",
-                           "l2": "working set per step (~1.5 GB of activations) exceeds the 126 MB L2; no flush needed"},
+                           "l2": "working set per step (~1.5 GB of activations) exceeds the 126 MB L2; no flush needed",
+                           "arithmetic": "fp32 storage and accumulation everywhere; tensor-core products at >= 21 significant bits "
+                                         "(3xTF32 tcgen05 GEMMs / convolutions; fp16 two-term split with power-of-two scales in "
+                                         "the propagation's tile MLP and the fused self-term MLP kernels): rtol 1e-3 against the "
+                                         "fp32 oracle on predictions, loss and every gradient"},
                 "e2e": {"value": world * args.steps / e2e_s, "unit": "designs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "note": e2e_note},
                 "gpu_launches": launches, "clocks": clocks, "loss": lv, "sustained": sustained, "allreduce": allreduce,
