@@ -439,10 +439,16 @@ int tm_selfmlp_gen_bwd1(int64_t M, const float* G, int64_t ldg, const int32_t* g
 /* The same product for an MLP whose hidden activations H were STORED (fc_cell_self, 36 inputs): the hidden-layer
  * gradient DH[r] = (G[g_rows[m]] @ W2) * (H[r] > 0), r = h_rows ? h_rows[m] : m, written out (it feeds the first-layer
  * weight gradient).  Replaces the masked data-gradient GEMM of the general MLP backward. */
-/* First layer of such an MLP: HID[m, 0:256] = relu(X[x_rows[m], 0:kin] @ W1^T + b1), kin % 4 == 0, kin <= 48. */
+/* First layer of such an MLP: HID[m, 0:256] = relu(X[x_rows[m], 0:kin] @ W1^T + b1), kin % 4 == 0, kin <= 48;
+ * rowmax (optional, [M]): max of row m's outputs.  Second layer: out[out_rows[m], 0:128] = HID[h_rows[m]] @ W2^T + b2
+ * with the per-row operand scale taken from rowmax (ws: tm_selfmlp_ws_bytes()). */
 size_t tm_selfmlp_lin1_ws_bytes(void);
 int tm_selfmlp_lin1_relu(int64_t M, const float* X, int64_t ldx, const int32_t* x_rows, int64_t kin, const float* W1,
-                         const float* b1, float* HID, int64_t ldh, void* ws, size_t ws_bytes, void* stream);
+                         const float* b1, float* HID, int64_t ldh, float* rowmax, void* ws, size_t ws_bytes,
+                         void* stream);
+int tm_selfmlp_rows_forward(int64_t M, const float* H, int64_t ldh, const int32_t* h_rows, const float* rowmax,
+                            const float* W2, const float* b2, float* out, int64_t ldo, const int32_t* out_rows,
+                            void* ws, size_t ws_bytes, void* stream);
 size_t tm_selfmlp_rows_dh_ws_bytes(void);
 int tm_selfmlp_rows_dh(int64_t M, const float* G, int64_t ldg, const int32_t* g_rows, const float* W2, const float* H,
                        int64_t ldh, const int32_t* h_rows, float* DH, int64_t lddh, void* ws, size_t ws_bytes,

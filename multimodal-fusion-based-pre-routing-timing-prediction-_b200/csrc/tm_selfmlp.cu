@@ -161,8 +161,16 @@ struct Args {
   float* out;
   int64_t ldo;
   const int* out_rows;
+  // LOADED form (tm_selfmlp_rows_forward): the hidden layer is read, not generated
+  const float* H;         // [.][ldh] stored hidden activations
+  int64_t ldh;
+  const int* h_rows;      // row of H (and of rowmax) for row m (NULL: m)
+  const float* rowmax;    // max |H[r]| per row (tm_selfmlp_lin1_relu writes it): the per-row operand scale
 };
 
+// LOADED == false: the hidden layer is generated from 1-2 inputs (fc_net_self).  LOADED == true: second layer of an MLP
+// whose hidden activations are stored (fc_cell_self): the same pipeline with loaders in place of the generators.
+template <bool LOADED>
 __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* w0_s = reinterpret_cast<float*>(smem + OFF_P);
@@ -193,9 +201,9 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
                    : "memory");
   }
   for (int j = tid; j < HIDF; j += THREADS) {
-    w0_s[j] = a.W1[(size_t)j * a.kx];
-    w1_s[j] = a.kx > 1 ? a.W1[(size_t)j * a.kx + 1] : 0.f;
-    b1_s[j] = a.b1[j];
+    w0_s[j] = LOADED ? 0.f : a.W1[(size_t)j * a.kx];
+    w1_s[j] = (!LOADED && a.kx > 1) ? a.W1[(size_t)j * a.kx + 1] : 0.f;
+    b1_s[j] = LOADED ? 0.f : a.b1[j];
   }
   for (int j = tid; j < NOUT; j += THREADS) b2_s[j] = a.b2 ? a.b2[j] : 0.f;
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, TM_COLS);
@@ -225,7 +233,67 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
     }
   };
 
-  if (warp >= GEN_WARP0) {
+  if (LOADED && warp >= GEN_WARP0) {
+    // ======================= loaders: stored hidden rows -> operand planes =======================
+    // Same ownership as the generators below: warp gw = k-group gw of every chunk (32 bytes of a row per chunk), a lane
+    // = four rows; the next chunk's eight 16-byte loads are issued before the current chunk is split and stored.
+    const int gw = warp - GEN_WARP0;
+    uint32_t g = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const float* hp[4];
+      float sc[4];
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) {
+        const int64_t m = t * TM + rb * 32 + lane;
+        hp[rb] = nullptr; sc[rb] = 1.f;
+        if (m < a.M) {
+          const int64_t r = a.h_rows ? (int64_t)a.h_rows[m] : m;
+          hp[rb] = a.H + r * a.ldh + gw * 8;
+          float inv;
+          bound_scale(a.rowmax[r], sc[rb], inv);
+        }
+      }
+      float4 cur[4][2], nxt[4][2];
+      auto fetch = [&](int c, float4 (&v)[4][2]) {
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+          v[rb][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[rb][1] = v[rb][0];
+          if (hp[rb]) {
+            v[rb][0] = __ldg(reinterpret_cast<const float4*>(hp[rb] + c * KC));
+            v[rb][1] = __ldg(reinterpret_cast<const float4*>(hp[rb] + c * KC + 4));
+          }
+        }
+      };
+      fetch(0, cur);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c, ++g) {
+        if (c + 1 < NCH) fetch(c + 1, nxt);
+        const uint32_t buf = g & 1u;
+        mbar_wait(&h_empty[buf], ((g >> 1) & 1u) ^ 1u);
+        uint8_t* hi_p = smem + OFF_H + buf * 2 * H_PLANE + (uint32_t)gw * H_LBO;
+        uint8_t* lo_p = hi_p + H_PLANE;
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+          const int row = rb * 32 + lane;
+          uint32_t hw[4], lw[4];
+          split_pair(cur[rb][0].x * sc[rb], cur[rb][0].y * sc[rb], hw[0], lw[0]);
+          split_pair(cur[rb][0].z * sc[rb], cur[rb][0].w * sc[rb], hw[1], lw[1]);
+          split_pair(cur[rb][1].x * sc[rb], cur[rb][1].y * sc[rb], hw[2], lw[2]);
+          split_pair(cur[rb][1].z * sc[rb], cur[rb][1].w * sc[rb], hw[3], lw[3]);
+          const uint32_t off = (uint32_t)(row >> 3) * H_SBO + (uint32_t)(row & 7) * 16;
+          *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_full[buf]);
+        if (c + 1 < NCH) {
+#pragma unroll
+          for (int rb = 0; rb < 4; ++rb) { cur[rb][0] = nxt[rb][0]; cur[rb][1] = nxt[rb][1]; }
+        }
+      }
+    }
+  } else if (warp >= GEN_WARP0) {
     // ======================= generators: hidden chunks -> operand planes =======================
     // Warp gw owns k-group gw of EVERY chunk (hidden units c*64 + 8 gw .. + 7): their first-layer parameters live in
     // registers for the whole kernel (96 values, identical in every lane), a lane owns four rows of the tile.  No
@@ -313,10 +381,15 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
       const uint32_t ab = (uint32_t)li & 1u;
       const int64_t m = t * TM + warp * 32 + lane;
-      float x0, x1;
-      row_x(m, x0, x1);
       float s, inv;
-      bound_scale(fmaf(fabsf(x0), wm0, fmaf(fabsf(x1), wm1, bm)), s, inv);
+      if constexpr (LOADED) {
+        s = 1.f; inv = 1.f;
+        if (m < a.M) bound_scale(a.rowmax[a.h_rows ? (int64_t)a.h_rows[m] : m], s, inv);
+      } else {
+        float x0, x1;
+        row_x(m, x0, x1);
+        bound_scale(fmaf(fabsf(x0), wm0, fmaf(fabsf(x1), wm1, bm)), s, inv);
+      }
       float* op = nullptr;
       if (m < a.M) op = a.out + (a.out_rows ? (int64_t)a.out_rows[m] : m) * a.ldo;
       mbar_wait(&acc_full[ab], ((uint32_t)li >> 1) & 1u);
@@ -945,6 +1018,7 @@ struct L1Args {
   const uint8_t* wplanes;
   float* out;
   int64_t ldo;
+  float* rowmax;          // optional: max over the row's 256 outputs (the scale of tm_selfmlp_rows_forward)
 };
 
 __global__ void __launch_bounds__(THREADS, 1) selfmlp_lin1_kernel(L1Args a) {
@@ -1055,6 +1129,7 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_lin1_kernel(L1Args a) {
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
       const int64_t m = t * TM + warp * 32 + lane;
       float* op = m < a.M ? a.out + m * a.ldo : nullptr;
+      float rmax = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         mbar_wait(&acc_full[half], li & 1u);
@@ -1076,6 +1151,7 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_lin1_kernel(L1Args a) {
               o.y = fmaxf(fmaf(fmaf(vc[4 * e + 1], LO_INV, vm[4 * e + 1]), inv, b.y), 0.f);
               o.z = fmaxf(fmaf(fmaf(vc[4 * e + 2], LO_INV, vm[4 * e + 2]), inv, b.z), 0.f);
               o.w = fmaxf(fmaf(fmaf(vc[4 * e + 3], LO_INV, vm[4 * e + 3]), inv, b.w), 0.f);
+              rmax = fmaxf(fmaxf(rmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
               st4(op + j0 + 4 * e, o);
             }
           }
@@ -1084,6 +1160,7 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_lin1_kernel(L1Args a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[half]);
       }
+      if (a.rowmax && op) a.rowmax[m] = rmax;
     }
   }
   tc_fence_before();
@@ -1107,11 +1184,11 @@ extern "C" int tm_selfmlp_gen_forward(int64_t M, const float* X, int64_t ldx, co
   uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   selfmlp_pack_kernel<<<(NOUT * HIDF + 255) / 256, 256, 0, st>>>(W2, planes);
   TM_TRY(check_launch("selfmlp_pack"));
-  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES + 1024));
-  Args a{M, X, ldx, x_rows, (int)kx, W1, b1, b2, planes, out, ldo, out_rows};
+  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES + 1024));
+  Args a{M, X, ldx, x_rows, (int)kx, W1, b1, b2, planes, out, ldo, out_rows, nullptr, 0, nullptr, nullptr};
   const int64_t ntiles = (M + TM - 1) / TM;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  selfmlp_gen_fwd_kernel<<<grid, THREADS, SMEM_BYTES + 1024, st>>>(a);
+  selfmlp_gen_fwd_kernel<false><<<grid, THREADS, SMEM_BYTES + 1024, st>>>(a);
   return check_launch("selfmlp_gen_fwd");
 }
 
@@ -1201,7 +1278,8 @@ extern "C" size_t tm_selfmlp_lin1_ws_bytes() { return 2 * (size_t)L1_W_PLANE + 2
 
 /* HID[m, 0:256] = relu(X[x_rows[m], 0:kin] @ W1^T + b1) for m < M (W1 [256][kin] as stored; kin % 4 == 0, kin <= 48). */
 extern "C" int tm_selfmlp_lin1_relu(int64_t M, const float* X, int64_t ldx, const int32_t* x_rows, int64_t kin, const float* W1,
-                                    const float* b1, float* HID, int64_t ldh, void* ws, size_t ws_bytes, void* stream) {
+                                    const float* b1, float* HID, int64_t ldh, float* rowmax, void* ws, size_t ws_bytes,
+                                    void* stream) {
   TM_REQUIRE(kin > 0 && kin <= L1_K && (kin & 3) == 0, "tm_selfmlp_lin1_relu: kin must be a multiple of 4, <= 48");
   TM_REQUIRE(ws && ws_bytes >= tm_selfmlp_lin1_ws_bytes(), "tm_selfmlp_lin1_relu: workspace too small (tm_selfmlp_lin1_ws_bytes)");
   TM_REQUIRE((ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (ldh & 3) == 0 && (reinterpret_cast<uintptr_t>(HID) & 15) == 0,
@@ -1214,7 +1292,29 @@ extern "C" int tm_selfmlp_lin1_relu(int64_t M, const float* X, int64_t ldx, cons
   TM_CUDA(cudaFuncSetAttribute(selfmlp_lin1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1_SMEM + 1024));
   const int64_t ntiles = (M + TM - 1) / TM;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  L1Args a{M, X, ldx, x_rows, (int)kin, b1, planes, HID, ldh};
+  L1Args a{M, X, ldx, x_rows, (int)kin, b1, planes, HID, ldh, rowmax};
   selfmlp_lin1_kernel<<<grid, THREADS, L1_SMEM + 1024, st>>>(a);
   return check_launch("selfmlp_lin1");
+}
+
+/* out[out_rows[m], 0:128] = H[h_rows[m], 0:256] @ W2^T + b2: second layer of an MLP whose hidden activations are stored;
+ * rowmax[r] >= max |H[r, :]| (tm_selfmlp_lin1_relu writes it).  ws: tm_selfmlp_ws_bytes(). */
+extern "C" int tm_selfmlp_rows_forward(int64_t M, const float* H, int64_t ldh, const int32_t* h_rows, const float* rowmax,
+                                       const float* W2, const float* b2, float* out, int64_t ldo, const int32_t* out_rows,
+                                       void* ws, size_t ws_bytes, void* stream) {
+  TM_REQUIRE(ws && ws_bytes >= tm_selfmlp_ws_bytes(), "tm_selfmlp_rows_forward: workspace too small (tm_selfmlp_ws_bytes)");
+  TM_REQUIRE(rowmax, "tm_selfmlp_rows_forward: rowmax missing");
+  TM_REQUIRE((ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldh & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0,
+             "tm_selfmlp_rows_forward: H and out rows must be 16-byte aligned");
+  if (M <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  selfmlp_pack_kernel<<<(NOUT * HIDF + 255) / 256, 256, 0, st>>>(W2, planes);
+  TM_TRY(check_launch("selfmlp_pack"));
+  TM_CUDA(cudaFuncSetAttribute(selfmlp_gen_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES + 1024));
+  Args a{M, nullptr, 0, nullptr, 1, nullptr, nullptr, b2, planes, out, ldo, out_rows, H, ldh, h_rows, rowmax};
+  const int64_t ntiles = (M + TM - 1) / TM;
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  selfmlp_gen_fwd_kernel<true><<<grid, THREADS, SMEM_BYTES + 1024, st>>>(a);
+  return check_launch("selfmlp_rows_fwd");
 }

@@ -200,8 +200,15 @@ def mlp2_forward(x, ldx, rows, n_rows, w1, b1, w2, b2, out, ldo, out_rows=None, 
             and n_rows > 0):
         # fc_cell_self's first layer (36 inputs): output-bound, fp16 two-term split on tcgen05 (tm_selfmlp.cu)
         nb = tm_lib.ws_bytes("tm_selfmlp_lin1_ws_bytes")
-        call("tm_selfmlp_lin1_relu", n_rows, x, ldx, rows, kin, _f32c(w1), _f32c(b1), h, hid, tm_lib.workspace(nb, out.device),
-             nb, stream())
+        fuse2 = nout == 128 and ldo % 4 == 0 and out.data_ptr() % 16 == 0
+        rowmax = torch.empty(n_rows, dtype=torch.float32, device=out.device) if fuse2 else None
+        call("tm_selfmlp_lin1_relu", n_rows, x, ldx, rows, kin, _f32c(w1), _f32c(b1), h, hid, rowmax,
+             tm_lib.workspace(nb, out.device), nb, stream())
+        if fuse2:                                   # second layer on the same machinery, per-row scale from rowmax
+            nb = tm_lib.ws_bytes("tm_selfmlp_ws_bytes")
+            call("tm_selfmlp_rows_forward", n_rows, h, hid, None, rowmax, _f32c(w2), _f32c(b2), out, ldo, out_rows,
+                 tm_lib.workspace(nb, out.device), nb, stream())
+            return h
     else:
         gemm_nn(n_rows, hid, kin, x, ldx, _f32c(w1), kin, h, hid, a_rows=rows, bias=b1, flags=RELU, b_is_nk=True, math=math)
     gemm_nn(n_rows, nout, hid, h, hid, _f32c(w2), hid, out, ldo, c_rows=out_rows, bias=b2, b_is_nk=True, math=math)

@@ -60,8 +60,12 @@ for M in (1, 2, 7, 31, 63, 64, 65, 127, 128, 129, 255, 300, 1025, 9473, 18945):
         note("rows_dh", rel(sel(DH), (sel(G).double() @ W2.double()) * (sel(H) > 0)))
         # lin1
         nb = lib.ws_bytes("tm_selfmlp_lin1_ws_bytes"); HH = torch.zeros(M, 256, device=DEV)
-        lib.call("tm_selfmlp_lin1_relu", M, X36, 36, r, 36, W136, b1, HH, 256, lib.workspace(nb, DEV), nb, st)
+        rmx = torch.empty(M, device=DEV)
+        lib.call("tm_selfmlp_lin1_relu", M, X36, 36, r, 36, W136, b1, HH, 256, rmx, lib.workspace(nb, DEV), nb, st)
         note("lin1", rel(HH, (sel(X36).double() @ W136.double().t() + b1.double()).relu()))
+        nb = lib.ws_bytes("tm_selfmlp_ws_bytes"); o2 = torch.zeros(n, 128, device=DEV)
+        lib.call("tm_selfmlp_rows_forward", M, HH, 256, None, rmx, W2, b2, o2, 128, r, lib.workspace(nb, DEV), nb, st)
+        note("rows_forward", rel(sel(o2), HH.double() @ W2.double().t() + b2.double()))
 torch.cuda.synchronize()
 print({k: f"{v:.2e}" for k, v in worst.items()})
 bad = {k: v for k, v in worst.items() if v > (2e-3 if k.startswith("bwd1") else 1e-4)}

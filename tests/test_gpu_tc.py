@@ -282,9 +282,23 @@ def test_selfmlp_lin1_relu(lib, M, kin, gather, xscale):
     ref = (xs.double() @ W1.double().t() + b1.double()).relu()
     H = torch.full((M + 5, 256), -3.0, device=DEV)
     nb = lib.ws_bytes("tm_selfmlp_lin1_ws_bytes")
-    lib.call("tm_selfmlp_lin1_relu", M, X, kin, xr, kin, W1, b1, H, 256, lib.workspace(nb, DEV), nb, lib.stream())
+    rowmax = torch.full((M,), -1.0, device=DEV)
+    lib.call("tm_selfmlp_lin1_relu", M, X, kin, xr, kin, W1, b1, H, 256, rowmax, lib.workspace(nb, DEV), nb, lib.stream())
     assert_close(H[:M], ref, 1e-4, 2e-5, "lin1")
     assert bool((H[M:] == -3.0).all())
+    assert torch.equal(rowmax, H[:M].max(dim=1).values)
+    # second layer from the stored hidden rows, scattered output
+    W2 = torch.randn(128, 256, device=DEV) * 0.1
+    b2 = torch.randn(128, device=DEV) * 0.1
+    orow = torch.randperm(M + 7, device=DEV)[:M].int().contiguous() if gather else None
+    out = torch.full((M + 7, 128), 6.0, device=DEV)
+    nb2 = lib.ws_bytes("tm_selfmlp_ws_bytes")
+    lib.call("tm_selfmlp_rows_forward", M, H, 256, None, rowmax, W2, b2, out, 128, orow, lib.workspace(nb2, DEV), nb2, lib.stream())
+    ref2 = H[:M].double() @ W2.double().t() + b2.double()
+    assert_close(out[orow.long()] if gather else out[:M], ref2, 1e-4, 2e-5, "rows_forward")
+    touched = torch.zeros(M + 7, dtype=torch.bool, device=DEV)
+    touched[orow.long() if gather else torch.arange(M, device=DEV)] = True
+    assert bool((out[~touched] == 6.0).all())
 
 
 @pytest.mark.parametrize("M,K,gather,relu", [(1350, 256, False, False), (77, 130, True, True), (5, 3, False, False)])
