@@ -293,9 +293,6 @@ __device__ __forceinline__ void mlp_tile(const Tiles& T, const float* Wa, const 
 // unchanged): chunk c < 8 = k16 step c of Wa as [plane hi | lo'][8 k-pairs][264 words], chunk 8 + c = two k16 steps of
 // Wb as [plane][16 k-pairs][136 words].
 // =============================================================================================
-#ifndef TM_H16_PAIRSYNC
-#define TM_H16_PAIRSYNC 0
-#endif
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
@@ -389,18 +386,8 @@ __device__ __forceinline__ void mlp_tile_h(const Tiles& T, const float* Wa, cons
 #pragma unroll
     for (int c = 0; c < 4; ++c) { m2[j][c] = 0.f; c2[j][c] = 0.f; }
   for (int c = 0; c < NCHUNK; ++c) {
-#if TM_H16_PAIRSYNC
-    if (!(c & 1)) {                       // one CTA barrier per TWO chunks: everybody is done with chunks <= c-1, so the
-      __syncthreads();                    // two oldest slots are free (and, at c = 0 / 8, the input / hidden tiles are visible)
-      if (tid == 0) {
-        if (c) issue_chunk(T, Wa, Wb, c + NSTAGE - 2);
-        issue_chunk(T, Wa, Wb, c + NSTAGE - 1);
-      }
-    }
-#else
     __syncthreads();                      // everybody is done with chunk c-1 (its slot is free); tiles visible
-    if (tid == 0) issue_chunk(T, Wa, Wb, c + NSTAGE - 1);
-#endif
+    if (tid == 0) issue_chunk(T, Wa, Wb, c + NSTAGE - 1);         // (one barrier per TWO chunks measured the same: not kept)
     wait_chunk(T, c);
     const uint32_t* w = reinterpret_cast<const uint32_t*>(T.wbuf + (c % NSTAGE) * SLOT);
     if (c < 8) {                          // GEMM1: k16 step c of Wa
