@@ -43,7 +43,9 @@ static_assert(GEN_W == KC / 8, "one generator warp per k-group of a chunk");
 // K-major SWIZZLE_NONE operand planes (core matrix = 8 rows x 16 bytes):
 //   off(row, k) = (row / 8) * SBO + (k / 8) * LBO + (row % 8) * 16 + (k % 8) * 2          [bytes, fp16]
 constexpr uint32_t W_LBO = 128, W_SBO = (HIDF / 8) * W_LBO, W_PLANE = (NOUT / 8) * W_SBO;   // 64 KB
-constexpr uint32_t H_LBO = 128, H_SBO = (KC / 8) * H_LBO, H_PLANE = (TM / 8) * H_SBO;      // 16 KB
+// (hidden chunk planes: the k-group stride is padded by 16 bytes so that the 8-byte stores of the loaders -- a lane
+//  holds four consecutive k of one row -- spread over the banks)
+constexpr uint32_t H_LBO = 144, H_SBO = (KC / 8) * H_LBO, H_PLANE = (TM / 8) * H_SBO;      // 18 KB
 constexpr uint32_t OFF_W = 0;                              // Whi, Wlo
 constexpr uint32_t OFF_H = OFF_W + 2 * W_PLANE;            // [buffer 2][hi, lo]
 constexpr uint32_t OFF_P = OFF_H + 4 * H_PLANE;            // w0[256], w1[256], b1[256], b2[128], maxima[4]
@@ -235,33 +237,33 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
 
   if (LOADED && warp >= GEN_WARP0) {
     // ======================= loaders: stored hidden rows -> operand planes =======================
-    // Same ownership as the generators below: warp gw = k-group gw of every chunk (32 bytes of a row per chunk), a lane
-    // = four rows; the next chunk's eight 16-byte loads are issued before the current chunk is split and stored.
+    // Warp gw owns rows 16 gw .. 16 gw + 15 of the tile.  Per chunk (64 hidden units = 256 bytes of a row) a load
+    // instruction reads TWO whole 256-byte row pieces (half a warp each, 16 bytes per lane), so a lane holds four
+    // consecutive k of one row: one 8-byte store per plane.  The next chunk's eight loads are issued before the
+    // current chunk is split and stored.
     const int gw = warp - GEN_WARP0;
+    const int sub = lane >> 4, kq = lane & 15;                 // which of the two rows of a load; 4-wide k piece
     uint32_t g = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const float* hp[4];
-      float sc[4];
+      const float* hp[8];
+      float sc[8];
 #pragma unroll
-      for (int rb = 0; rb < 4; ++rb) {
-        const int64_t m = t * TM + rb * 32 + lane;
-        hp[rb] = nullptr; sc[rb] = 1.f;
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = t * TM + gw * 16 + 2 * i + sub;
+        hp[i] = nullptr; sc[i] = 1.f;
         if (m < a.M) {
           const int64_t r = a.h_rows ? (int64_t)a.h_rows[m] : m;
-          hp[rb] = a.H + r * a.ldh + gw * 8;
+          hp[i] = a.H + r * a.ldh + kq * 4;
           float inv;
-          bound_scale(a.rowmax[r], sc[rb], inv);
+          bound_scale(a.rowmax[r], sc[i], inv);
         }
       }
-      float4 cur[4][2], nxt[4][2];
-      auto fetch = [&](int c, float4 (&v)[4][2]) {
+      float4 cur[8], nxt[8];
+      auto fetch = [&](int c, float4 (&v)[8]) {
 #pragma unroll
-        for (int rb = 0; rb < 4; ++rb) {
-          v[rb][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[rb][1] = v[rb][0];
-          if (hp[rb]) {
-            v[rb][0] = __ldg(reinterpret_cast<const float4*>(hp[rb] + c * KC));
-            v[rb][1] = __ldg(reinterpret_cast<const float4*>(hp[rb] + c * KC + 4));
-          }
+        for (int i = 0; i < 8; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (hp[i]) v[i] = __ldg(reinterpret_cast<const float4*>(hp[i] + c * KC));
         }
       };
       fetch(0, cur);
@@ -270,26 +272,24 @@ __global__ void __launch_bounds__(THREADS, 1) selfmlp_gen_fwd_kernel(Args a) {
         if (c + 1 < NCH) fetch(c + 1, nxt);
         const uint32_t buf = g & 1u;
         mbar_wait(&h_empty[buf], ((g >> 1) & 1u) ^ 1u);
-        uint8_t* hi_p = smem + OFF_H + buf * 2 * H_PLANE + (uint32_t)gw * H_LBO;
+        uint8_t* hi_p = smem + OFF_H + buf * 2 * H_PLANE + (uint32_t)(kq >> 1) * H_LBO + (uint32_t)(kq & 1) * 8;
         uint8_t* lo_p = hi_p + H_PLANE;
 #pragma unroll
-        for (int rb = 0; rb < 4; ++rb) {
-          const int row = rb * 32 + lane;
-          uint32_t hw[4], lw[4];
-          split_pair(cur[rb][0].x * sc[rb], cur[rb][0].y * sc[rb], hw[0], lw[0]);
-          split_pair(cur[rb][0].z * sc[rb], cur[rb][0].w * sc[rb], hw[1], lw[1]);
-          split_pair(cur[rb][1].x * sc[rb], cur[rb][1].y * sc[rb], hw[2], lw[2]);
-          split_pair(cur[rb][1].z * sc[rb], cur[rb][1].w * sc[rb], hw[3], lw[3]);
+        for (int i = 0; i < 8; ++i) {
+          const int row = gw * 16 + 2 * i + sub;
+          uint32_t h0, l0, h1, l1;
+          split_pair(cur[i].x * sc[i], cur[i].y * sc[i], h0, l0);
+          split_pair(cur[i].z * sc[i], cur[i].w * sc[i], h1, l1);
           const uint32_t off = (uint32_t)(row >> 3) * H_SBO + (uint32_t)(row & 7) * 16;
-          *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          *reinterpret_cast<uint2*>(hi_p + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(lo_p + off) = make_uint2(l0, l1);
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&h_full[buf]);
         if (c + 1 < NCH) {
 #pragma unroll
-          for (int rb = 0; rb < 4; ++rb) { cur[rb][0] = nxt[rb][0]; cur[rb][1] = nxt[rb][1]; }
+          for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
       }
     }
