@@ -19,7 +19,7 @@ excluded).  Prints ONE JSON line on rank 0.
 * roofline: the level-wise propagation forward (the HBM-bound kernel family), algorithmic bytes of
            SURVEY.md 8d / its CUDA-event time, against MEASURED_PEAKS.json;
 * cpu_baseline: the oracle (a port of the reference arithmetic) on the host cores.
-Under torchrun the three bucketed NCCL gradient all-reduces are captured inside each rank's CUDA graph and
+Under torchrun the two bucketed NCCL gradient all-reduces (head + fusion early; GNN + U-Net after the last kernel) are captured inside each rank's CUDA graph and
 overlap the backward; `allreduce` reports their stand-alone time, the exposed part and the overlap fraction,
 `config5` the 64-design run of SURVEY.md 8d (seeds 0..63 sharded round-robin over the ranks).
 """
@@ -483,7 +483,7 @@ def main():
         allreduce = {"buckets": {k: int(b.flat.numel()) * 4 for k, b in step._buckets.items()},
                      "ms_standalone": ar_ms, "step_ms_without_exchange": local_ms, "exposed_ms": exposed,
                      "overlap_frac": max(0.0, min(1.0, 1.0 - exposed / ar_ms)) if ar_ms > 0 else None,
-                     "where": "three bucketed ncclAllReduce (head+fusion, GNN, U-Net) on a side stream INSIDE the captured graph"}
+                     "where": "two bucketed ncclAllReduce (head + fusion as soon as they exist; GNN + U-Net as one exchange after the last kernel) on a side stream INSIDE the captured graph"}
 
     # ---- BASELINE config 5: 64 designs of config-2 shape, seeds 0..63, round-robin over the ranks
     config5 = None

@@ -277,15 +277,17 @@ class DesignStep:
         ggrads = tm_ops.gnn_backward(sched, saved, gp, G)
         pairs = list(zip(self.gnn_params, ggrads))
         self._assign(pairs)
-        self._post_allreduce("gnn", [p for p, _ in pairs])
         with torch.cuda.stream(side):
             old_cap = tm_lib.lib().tm_tc_set_grid_cap(img_cap)
             ug = tm_unet.unet_backward(cnn, ust, dF.reshape(fmap.shape))
             tm_lib.lib().tm_tc_set_grid_cap(old_cap)
             upairs = [(self.cnn_params[k], ug[k]) for k in self.cnn_names]
             self._assign(upairs)
-            self._post_allreduce("unet", [p for p, _ in upairs])
         main.wait_stream(side)                               # join: every gradient exists on `main`
+        # The GNN and U-Net gradients go out as ONE exchange after the join (2.5 MB): posted separately they were two
+        # latency-bound all-reduces queued behind each other on the communication stream at the very end of the step
+        # (the U-Net's could not start before the GNN's, which waits for the last weight-gradient kernel)
+        self._post_allreduce("tail", [p for p, _ in pairs] + [p for p, _ in upairs])
         self._wait_allreduce()
         # a tensor-core kernel whose barrier timed out leaves garbage: the step's loss becomes NaN (loud in any
         # training loop, also under graph replay); tm_lib.check_err_flags() names the cause on the host
