@@ -1,9 +1,9 @@
 """Design-level data parallelism: shard designs across ranks, all-reduce gradients.
 
 The reference trains one design at a time on one device (train.py:461); designs are independent
-samples, so the only exchange is one gradient SUM per step (11.6 MB of fp32), posted in three buckets
-as soon as each group of gradients exists (head + fusion -> GNN -> U-Net) so that the NCCL transfers
-over NVLink overlap the remaining backward kernels.
+samples, so the only exchange is one gradient SUM per step (11.6 MB of fp32), posted in two buckets:
+head + fusion (9 MB) as soon as those gradients exist, so that the NCCL transfer over NVLink overlaps the
+remaining backward kernels, and GNN + U-Net (2.5 MB) as one exchange after the last kernel.
 
 ``FlatBucket`` owns ONE persistent flat fp32 buffer per group, allocated on first use.  Every step:
 

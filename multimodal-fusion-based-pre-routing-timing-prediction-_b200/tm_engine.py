@@ -300,7 +300,7 @@ class DesignStep:
         tensors become the graph's static inputs: refresh them in place (``tensor.copy_``) and call
         the returned function, which replays the graph and returns the same (loss, pred) tensors;
         ``param.grad`` tensors are rewritten in place by every replay.  On the data-parallel path the
-        three bucketed NCCL all-reduces are captured INSIDE the graph (persistent flat buffers,
+        bucketed NCCL all-reduces (head + fusion early, GNN + U-Net after the join) are captured INSIDE the graph (persistent flat buffers,
         ``tm_dp.FlatBucket``), where they overlap the backward as in the eager schedule; with
         ``TM_DP_GRAPH=0`` the graph holds the rank's compute only and one exchange is posted after each
         replay.  ``pool``: a ``torch.cuda.graph_pool_handle()`` shared by graphs that are replayed one
